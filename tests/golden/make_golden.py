@@ -1,0 +1,242 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REAL REFERENCE.
+
+Run in the build container only (needs /root/reference and oracle/_ref, see oracle/build_ref.py):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed; small):
+  ds1.npz        DS1 alignment (27 taxa, 934 patterns) as tip masks + weights, the MrBayes tree and
+                 the NJ tree of the reference's own tests as (peel, blens), and the reference's
+                 lnL / gradients on them (pins -6904.632, test/test_phylo.py:214-273, and
+                 -7130.96813417, test/test_bito.py:35).
+  pdm.npz        Chyp_torch.get_pdm / Chyp_np.get_pdm outputs + torch-autograd gradients.
+  nj_hard.npz    Cpeeler.nj_np outputs.
+  nj_soft.npz    peeler.nj_torch outputs + autograd gradient of a random linear functional of blens.
+  prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
+
+The tests never read /root/reference; they read these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refload  # noqa: E402
+from dodonaphy_b200 import newick, synth  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+REF = "/root/reference"
+
+
+class _TN:
+    def __init__(self, labels):
+        self._l = labels
+
+    def labels(self):
+        return self._l
+
+
+class _Aln:
+    def __init__(self, labels, seqs):
+        self.taxon_namespace = _TN(labels)
+        self._s = seqs
+
+    def sequences(self):
+        return self._s
+
+
+def masks_from_partials(parts):
+    out = []
+    for p in parts:
+        a = p.numpy()
+        out.append((a[0] + 2 * a[1] + 4 * a[2] + 8 * a[3]).astype(np.uint8))
+    return np.stack(out)
+
+
+def ref_partials(r, masks):
+    from oracle.phylo import mask_to_partial
+
+    S, L = masks.shape
+    parts = [torch.tensor(mask_to_partial(m)) for m in masks]
+    parts += [torch.zeros((1, 4, L)) for _ in range(S - 1)]
+    return parts
+
+
+def ref_ll_and_grads(r, masks, weights, peel, blens, model, rates=None, freqs=None):
+    """lnL + autograd gradients through the reference's own functions."""
+    b = torch.tensor(blens, requires_grad=True)
+    pm = r.phylomodel.PhyloModel(model)
+    if model == "GTR":
+        # set the constrained parameters directly on the transforms' inverse (phylomodel.py:23-45)
+        pm._freqs = pm.freqs_transform.inv(torch.tensor(freqs)).clone().detach().requires_grad_(True)
+        pm._sub_rates = pm.sub_rates_transform.inv(torch.tensor(rates)).clone().detach().requires_grad_(True)
+    mats = pm.get_transition_mats(b)
+    mats.retain_grad()
+    fr = pm.freqs
+    if model == "GTR":
+        fr.retain_grad()
+    ll = r.phylo.calculate_treelikelihood(ref_partials(r, masks), torch.tensor(weights), peel, mats, fr)
+    ll.backward()
+    out = dict(lnL=ll.item(), g_blens=b.grad.numpy().copy(), g_mats=mats.grad.numpy().copy(),
+               mats=mats.detach().numpy().copy())
+    if model == "GTR":
+        out["g_raw_freqs"] = pm._freqs.grad.numpy().copy()
+        out["g_raw_rates"] = pm._sub_rates.grad.numpy().copy()
+        out["raw_freqs"] = pm._freqs.detach().numpy().copy()
+        out["raw_rates"] = pm._sub_rates.detach().numpy().copy()
+    return out
+
+
+def make_ds1(r):
+    labels, seqs = newick.read_nexus_alignment(f"{REF}/test/data/ds1/dna.nex")
+    parts, w = r.phylo.compress_alignment(_Aln(labels, seqs))
+    masks = masks_from_partials(parts)
+    weights = w.numpy().astype(np.int64)
+    out = dict(masks=masks, weights=weights)
+    nwk, tr = newick.read_nexus_tree(f"{REF}/test/data/ds1/mb_tree300000.nex")
+    trees = {"mb": newick.newick_to_peel(nwk, labels, tr),
+             "nj": newick.newick_to_peel(open(f"{REF}/test/data/ds1/dna.nj.newick").read(), labels)}
+    rng = np.random.default_rng(20)
+    rates, freqs = synth.gtr_params(rng)
+    out["gtr_rates"], out["gtr_freqs"] = rates, freqs
+    for name, (peel, blens) in trees.items():
+        out[f"{name}_peel"], out[f"{name}_blens"] = peel, blens
+        pn = [p.numpy() for p in parts] + [np.zeros((1, 4, masks.shape[1])) for _ in range(26)]
+        out[f"{name}_lnL_cython"] = float(r.Cphylo.compute_LL_np(pn, weights, peel, blens))
+        jc = ref_ll_and_grads(r, masks, weights, peel, blens, "JC69")
+        out[f"{name}_lnL_torch"] = jc["lnL"]
+        out[f"{name}_g_blens"] = jc["g_blens"]
+        g = ref_ll_and_grads(r, masks, weights, peel, blens, "GTR", rates, freqs)
+        for k, v in g.items():
+            out[f"{name}_gtr_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "ds1.npz"), **out)
+    print("ds1:", out["mb_lnL_torch"], out["nj_lnL_torch"], out["mb_gtr_lnL"])
+
+
+def make_pdm(r):
+    rng = np.random.default_rng(31)
+    out = {}
+    cases = [(5, 2, -1.0, False), (12, 3, -1.0, False), (27, 3, -0.5, False), (64, 5, -1.0, False),
+             (17, 4, -2.3, True), (64, 5, -1.0, True), (130, 5, -1.0, False)]
+    out["n"] = len(cases)
+    for i, (S, D, curv, mats) in enumerate(cases):
+        x = rng.normal(0, 0.05 if i % 2 == 0 else 0.3, (S, D))
+        if i == 1:
+            x[3] = x[2]  # coincident points: clamp + zero-gradient path
+        C = rng.normal(size=(S, S))
+        out[f"{i}_x"], out[f"{i}_curv"], out[f"{i}_matsumoto"], out[f"{i}_C"] = x, curv, mats, C
+        for proj in ("up", "wrap"):
+            xt = torch.tensor(x, requires_grad=True)
+            ct = torch.tensor([curv], requires_grad=True)
+            Dm = r.Chyp_torch.get_pdm(xt, curvature=ct, matsumoto=mats, projection=proj)
+            (Dm * torch.tensor(C)).sum().backward()
+            out[f"{i}_pdm_torch_{proj}"] = Dm.detach().numpy().copy()
+            out[f"{i}_gx_{proj}"] = xt.grad.numpy().copy()
+            out[f"{i}_gc_{proj}"] = ct.grad.numpy().copy()
+        out[f"{i}_pdm_np"] = r.Chyp_np.get_pdm(x, curvature=curv, matsumoto=mats)
+    np.savez_compressed(os.path.join(HERE, "pdm.npz"), **out)
+    print("pdm cases:", len(cases))
+
+
+def make_nj_hard(r):
+    rng = np.random.default_rng(32)
+    out = {}
+    sizes = [2, 3, 4, 5, 8, 13, 27, 40, 64, 100]
+    out["n"] = len(sizes) + 2
+    for i, S in enumerate(sizes):
+        x = rng.normal(0, 0.05, (S, 3 if S < 30 else 5))
+        pdm = np.ascontiguousarray(r.Chyp_np.get_pdm(x))
+        peel, blens = r.Cpeeler.nj_np(pdm)
+        out[f"{i}_pdm"], out[f"{i}_peel"], out[f"{i}_blens"] = pdm, np.asarray(peel, dtype=np.int64), blens
+    # exact-tie inputs: equidistant taxa, and an integer matrix (test/test_peeler.py:228-303)
+    i = len(sizes)
+    pdm = np.ones((6, 6)) - np.eye(6)
+    peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(pdm))
+    out[f"{i}_pdm"], out[f"{i}_peel"], out[f"{i}_blens"] = pdm, np.asarray(peel, dtype=np.int64), blens
+    i += 1
+    pdm = np.array([[0, 5, 9, 9, 8], [5, 0, 10, 10, 9], [9, 10, 0, 8, 7], [9, 10, 8, 0, 3], [8, 9, 7, 3, 0]], dtype=np.float64)
+    peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(pdm))
+    out[f"{i}_pdm"], out[f"{i}_peel"], out[f"{i}_blens"] = pdm, np.asarray(peel, dtype=np.int64), blens
+    np.savez_compressed(os.path.join(HERE, "nj_hard.npz"), **out)
+    print("nj_hard cases:", out["n"])
+
+
+def make_nj_soft(r):
+    rng = np.random.default_rng(33)
+    out = {}
+    cases = [(3, 1e-8), (4, 1e-8), (5, 1e-8), (8, 1e-8), (12, 1e-8), (12, 1e-4), (17, 1e-8), (21, 1e-8), (27, 1e-8)]
+    n = 0
+    for S, tau in cases:
+        x = rng.normal(0, 0.05, (S, 3))
+        pdm = r.Chyp_torch.get_pdm(torch.tensor(x)).detach().clone().requires_grad_(True)
+        peel, blens = r.peeler.nj_torch(pdm, tau=tau)
+        c = rng.normal(size=2 * S - 2)
+        (blens * torch.tensor(c)).sum().backward()
+        out[f"{n}_pdm"], out[f"{n}_tau"], out[f"{n}_peel"] = pdm.detach().numpy().copy(), tau, np.asarray(peel, dtype=np.int64)
+        out[f"{n}_blens"], out[f"{n}_c"], out[f"{n}_g_pdm"] = blens.detach().numpy().copy(), c, pdm.grad.numpy().copy()
+        n += 1
+    # all-ties case of test/test_peeler.py:343-348 and the 17-taxon matrix of test/test_peel_data.txt
+    pdm = torch.tensor(np.ones((6, 6)) - np.eye(6), requires_grad=True)
+    peel, blens = r.peeler.nj_torch(pdm, tau=1e-8)
+    c = rng.normal(size=10)
+    (blens * torch.tensor(c)).sum().backward()
+    out[f"{n}_pdm"], out[f"{n}_tau"], out[f"{n}_peel"] = pdm.detach().numpy().copy(), 1e-8, np.asarray(peel, dtype=np.int64)
+    out[f"{n}_blens"], out[f"{n}_c"], out[f"{n}_g_pdm"] = blens.detach().numpy().copy(), c, pdm.grad.numpy().copy()
+    n += 1
+    d1 = np.genfromtxt(f"{REF}/test/test_peel_data.txt", dtype=np.double, delimiter=", ")
+    til = np.tril_indices(17, -1)
+    d2 = np.zeros((17, 17))
+    d2[til[0], til[1]] = d1
+    d2[til[1], til[0]] = d1
+    for tau in (1e-8, 1e-20):
+        pdm = torch.tensor(d2, requires_grad=True)
+        peel, blens = r.peeler.nj_torch(pdm, tau=tau)
+        c = rng.normal(size=2 * 17 - 2)
+        (blens * torch.tensor(c)).sum().backward()
+        out[f"{n}_pdm"], out[f"{n}_tau"], out[f"{n}_peel"] = pdm.detach().numpy().copy(), tau, np.asarray(peel, dtype=np.int64)
+        out[f"{n}_blens"], out[f"{n}_c"], out[f"{n}_g_pdm"] = blens.detach().numpy().copy(), c, pdm.grad.numpy().copy()
+        n += 1
+    out["n"] = n
+    np.savez_compressed(os.path.join(HERE, "nj_soft.npz"), **out)
+    print("nj_soft cases:", n)
+
+
+def make_prune(r):
+    out = {}
+    cases = [(4, 40, 41), (8, 120, 42), (27, 300, 43), (64, 500, 44), (130, 200, 45)]
+    n = 0
+    for S, L, seed in cases:
+        prob = synth.make_problem(S, L, B=1, D=5, seed=seed)
+        pdm = np.ascontiguousarray(r.Chyp_np.get_pdm(prob["xs"][0]))
+        peel, blens = r.Cpeeler.nj_np(pdm)
+        peel = np.asarray(peel, dtype=np.int64)
+        out[f"{n}_masks"], out[f"{n}_weights"], out[f"{n}_peel"], out[f"{n}_blens"] = prob["masks"], prob["weights"], peel, blens
+        out[f"{n}_rates"], out[f"{n}_freqs"] = prob["rates"], prob["freqs"]
+        jc = ref_ll_and_grads(r, prob["masks"], prob["weights"], peel, blens, "JC69")
+        for k, v in jc.items():
+            out[f"{n}_jc_{k}"] = v
+        g = ref_ll_and_grads(r, prob["masks"], prob["weights"], peel, blens, "GTR", prob["rates"], prob["freqs"])
+        for k, v in g.items():
+            out[f"{n}_gtr_{k}"] = v
+        # MCMC twin
+        pn = [p.numpy() for p in ref_partials(r, prob["masks"])]
+        out[f"{n}_lnL_cython"] = float(r.Cphylo.compute_LL_np(pn, prob["weights"], peel, blens))
+        n += 1
+    out["n"] = n
+    np.savez_compressed(os.path.join(HERE, "prune.npz"), **out)
+    print("prune cases:", n)
+
+
+if __name__ == "__main__":
+    r = refload.load()
+    assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
+    make_ds1(r)
+    make_pdm(r)
+    make_nj_hard(r)
+    make_nj_soft(r)
+    make_prune(r)
