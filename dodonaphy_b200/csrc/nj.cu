@@ -1,0 +1,560 @@
+// K2: batched neighbour joining -- one tree per CTA, sm_100a.
+//
+// dodo_nj_hard   replaces Cpeeler.nj_np (dodonaphy/cython/Cpeeler.pyx:15-125).  Bit-identical peel
+//                and blens: the running row sums (_nj_xsub) are updated with the reference's
+//                operation order using explicitly rounded adds/multiplies (no FMA contraction), the
+//                new node's row sum is accumulated sequentially in pool order, and the join is the
+//                FIRST strict minimum of q in pool order (pool order == ascending node id).
+// dodo_nj_soft   replaces peeler.nj_torch (dodonaphy/peeler.py:155-220): compute_Q (:223-248),
+//                soft.argmin (dodonaphy/soft.py:38-53) evaluated from the last row of each SoftSort
+//                matrix only (O(entries) instead of O(entries^2)), get_new_dist_soft (:251-265).
+// dodo_nj_soft_bwd  vector-Jacobian product d blens / d pdm (what torch autograd computes through
+//                the one-hot row selections of peeler.py:196-213): a reverse replay of the joins.
+//
+// Matrix state lives in the caller's workspace (L2-resident: 8 S^2 bytes per tree); the active list
+// and per-node scalars live in shared memory.  Storage slot of a new node = slot of its left child.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace dodo {
+
+constexpr double LARGE = 1e9;  // peeler.py:11
+
+struct QKey {
+    double q;
+    unsigned long long key;
+};
+
+__device__ __forceinline__ QKey qmin(QKey a, QKey b) {
+    return (b.q < a.q || (b.q == a.q && b.key < a.key)) ? b : a;
+}
+
+__device__ __forceinline__ QKey warp_qmin(QKey v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        QKey o;
+        o.q = __shfl_xor_sync(0xffffffffu, v.q, m);
+        o.key = __shfl_xor_sync(0xffffffffu, v.key, m);
+        v = qmin(v, o);
+    }
+    return v;
+}
+
+// workspace per tree (doubles): Dm[S*S] | Ab[S*S] ; ints are in shared memory
+__host__ __device__ inline size_t nj_ws_doubles(int S) { return 2 * (size_t)S * S + 4 * (size_t)S; }
+
+// ------------------------------------------------------------------------------------------ hard
+__global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
+                                                       int64_t *__restrict__ peel, double *__restrict__ blens) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    double *Dm = ws + (size_t)b * nj_ws_doubles(S);
+    const double *P = pdm + (size_t)b * S * S;
+    double *xs = reinterpret_cast<double *>(smem_raw);  // [S] by storage slot
+    double *newd = xs + S;                              // [S]
+    int *act = reinterpret_cast<int *>(newd + S);       // [S] pool position -> storage slot
+    int *act2 = act + S;                                // [S]
+    int *id_of = act2 + S;                              // [S] storage slot -> node id
+    __shared__ QKey wbest[32];
+    __shared__ int sh_pa, sh_pb;
+    int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    double *bl = blens + (size_t)b * (2 * S - 2);
+
+    for (size_t i = tid; i < (size_t)S * S; i += T) Dm[i] = P[i];
+    for (int s = tid; s < S; s += T) {
+        act[s] = s;
+        id_of[s] = s;
+        // Cpeeler.pyx:46-54: sequential sum over the other pool members, in pool order
+        double acc = 0.0;
+        const double *row = P + (size_t)s * S;
+        for (int j = 0; j < S; ++j)
+            if (j != s) acc = __dadd_rn(acc, row[j]);
+        xs[s] = acc;
+    }
+    __syncthreads();
+
+    for (int n = S; n > 1; --n) {
+        const double nm2 = (double)n - 2.0;
+        // ---- first strict minimum of q over pairs (pa < pb) in pool order (Cpeeler.pyx:58-66)
+        QKey best;
+        best.q = DBL_MAX;
+        best.key = ~0ull;
+        for (int pa = warp; pa < n - 1; pa += nwarp) {
+            const int sa = act[pa];
+            const double xa = xs[sa];
+            const double *row = Dm + (size_t)sa * S;
+            for (int pb = pa + 1 + lane; pb < n; pb += 32) {
+                const int sb = act[pb];
+                double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, row[sb]), xa), xs[sb]);
+                if (q < best.q) {
+                    best.q = q;
+                    best.key = ((unsigned long long)pa << 32) | (unsigned)pb;
+                }
+            }
+        }
+        best = warp_qmin(best);
+        if (lane == 0) wbest[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            QKey v = lane < nwarp ? wbest[lane] : QKey{DBL_MAX, ~0ull};
+            v = warp_qmin(v);
+            if (lane == 0) {
+                sh_pa = (int)(v.key >> 32);
+                sh_pb = (int)(v.key & 0xffffffffu);
+            }
+        }
+        __syncthreads();
+        const int pa = sh_pa, pb = sh_pb;
+        const int sa = act[pa], sb = act[pb];
+        const int n1 = id_of[sa], n2 = id_of[sb];
+        const int parent = S + (S - n);
+        const double d12 = Dm[(size_t)sa * S + sb];
+        // ---- distances of the new node, running row sums (Cpeeler.pyx:81-95)
+        for (int p = tid; p < n; p += T) {
+            if (p == pa || p == pb) continue;
+            const int sx = act[p];
+            const double *rx = Dm + (size_t)sx * S;
+            double v1 = __dadd_rn(__dadd_rn(0.0, rx[sa]), rx[sb]);
+            double dist = __dmul_rn(0.5, __dsub_rn(v1, d12));
+            newd[sx] = dist;
+            double x = __dadd_rn(xs[sx], dist);
+            x = __dsub_rn(x, Dm[(size_t)sa * S + sx]);
+            x = __dsub_rn(x, Dm[(size_t)sb * S + sx]);
+            xs[sx] = x;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // branch lengths (Cpeeler.pyx:98-112) with the joined nodes' row sums as they stand
+            double df, dg;
+            if (n > 2) {
+                double v1 = __dmul_rn(0.5, d12);
+                double v4 = __dmul_rn(__ddiv_rn(1.0, __dmul_rn(2.0, nm2)), __dsub_rn(xs[sa], xs[sb]));
+                df = __dadd_rn(v1, v4);
+                dg = __dsub_rn(d12, df);
+            } else {
+                df = __ddiv_rn(d12, 2.0);
+                dg = df;
+            }
+            bl[n1] = fmax(df, DBL_EPSILON);  // Cpeeler.pyx:124
+            bl[n2] = fmax(dg, DBL_EPSILON);
+            pl[(S - n) * 3 + 0] = n1;
+            pl[(S - n) * 3 + 1] = n2;
+            pl[(S - n) * 3 + 2] = parent;
+            // new node's row sum: sequential in pool order (Cpeeler.pyx:92)
+            double acc = 0.0;
+            for (int p = 0; p < n; ++p) {
+                if (p == pa || p == pb) continue;
+                acc = __dadd_rn(acc, newd[act[p]]);
+            }
+            xs[sa] = acc;
+            id_of[sa] = parent;
+        }
+        // new node takes the storage slot of n1; pool = survivors in order, then the new node
+        for (int p = tid; p < n; p += T) {
+            if (p == pa || p == pb) continue;
+            const int sx = act[p];
+            const double dist = newd[sx];
+            Dm[(size_t)sa * S + sx] = dist;
+            Dm[(size_t)sx * S + sa] = dist;
+            act2[p - (p > pa) - (p > pb)] = sx;
+        }
+        if (tid == 0) act2[n - 2] = sa;
+        __syncthreads();
+        for (int p = tid; p < n - 1; p += T) act[p] = act2[p];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ soft
+// Entry enumeration for the soft argmin.  The reference flattens tril(Q) of the padded N x N matrix
+// row-major (peeler.py:194): flat = row*N + col.  Active mode visits only active pairs row > col in
+// that order; inactive entries (strict upper triangle = 0, masked/diagonal = 1e9) are provably
+// negligible under the guard computed below, and their contribution to the second softmax is added
+// in closed form.  Full mode visits all N^2 entries (exact in every regime).
+struct SoftCtx {
+    const double *Dm;
+    const double *rs;    // row sums by storage slot
+    const int *act;      // pool position -> storage slot (ascending node id)
+    const int *id_of;    // storage slot -> node id
+    const int *pos_of;   // node id -> pool position or -1
+    int S, N, n;
+    double nm2;
+};
+
+__device__ __forceinline__ double soft_Q(const SoftCtx &c, int srow, int scol) {
+    // compute_Q (peeler.py:223-248): Q' = (n-2) d - r_i - r_j ; Q = (Q' + Q'^T)/2
+    double a = (c.nm2 * c.Dm[(size_t)srow * c.S + scol] - c.rs[srow]) - c.rs[scol];
+    double b = (c.nm2 * c.Dm[(size_t)scol * c.S + srow] - c.rs[scol]) - c.rs[srow];
+    return 0.5 * (a + b);
+}
+
+// l-th active pair in row-major lower-triangle order -> (prow, pcol)
+__device__ __forceinline__ void tri_unrank(long long l, int &prow, int &pcol) {
+    int r = (int)((1.0 + sqrt(1.0 + 8.0 * (double)l)) * 0.5);
+    while ((long long)r * (r - 1) / 2 > l) --r;
+    while ((long long)(r + 1) * r / 2 <= l) ++r;
+    prow = r;
+    pcol = (int)(l - (long long)r * (r - 1) / 2);
+}
+
+template <bool FULL>
+struct EntryIter {
+    const SoftCtx &c;
+    long long l, end;
+    int prow, pcol;
+    __device__ EntryIter(const SoftCtx &c_, long long l0, long long l1) : c(c_), l(l0), end(l1) {
+        prow = 0; pcol = 0;
+        if (!FULL && l0 < l1) tri_unrank(l0, prow, pcol);
+    }
+    __device__ __forceinline__ bool valid() const { return l < end; }
+    __device__ __forceinline__ void get(double &s, double &flat) const {
+        if (FULL) {
+            int row = (int)(l / c.N), col = (int)(l - (long long)row * c.N);
+            flat = (double)l;
+            if (row < col) { s = 0.0; return; }
+            int pr = c.pos_of[row], pc = c.pos_of[col];
+            if (row == col || pr < 0 || pc < 0) { s = LARGE; return; }
+            s = soft_Q(c, c.act[pr], c.act[pc]);
+        } else {
+            int srow = c.act[prow], scol = c.act[pcol];
+            flat = (double)c.id_of[srow] * (double)c.N + (double)c.id_of[scol];
+            s = soft_Q(c, srow, scol);
+        }
+    }
+    __device__ __forceinline__ void next() {
+        ++l;
+        if (!FULL) {
+            if (++pcol == prow) { ++prow; pcol = 0; }
+        }
+    }
+};
+
+__device__ __forceinline__ double block_reduce(double v, double *sh, int op /*0 sum,1 min,2 max*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        double o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = op == 0 ? v + o : (op == 1 ? fmin(v, o) : fmax(v, o));
+    }
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = sh[0];
+    for (int w = 1; w < nwarp; ++w) r = op == 0 ? r + sh[w] : (op == 1 ? fmin(r, sh[w]) : fmax(r, sh[w]));
+    return r;
+}
+
+// exclusive prefix over threads (by thread id) of v; also returns the total
+__device__ __forceinline__ double block_excl_scan(double v, double *sh, double &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads();
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    double off = 0.0, tot = 0.0;
+    for (int w = 0; w < nwarp; ++w) {
+        if (w < warp) off += sh[w];
+        tot += sh[w];
+    }
+    total = tot;
+    return off + inc - v;
+}
+
+template <bool FULL>
+__device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const long long P = FULL ? (long long)c.N * c.N : (long long)c.n * (c.n - 1) / 2;
+    const long long chunk = (P + T - 1) / T;
+    const long long l0 = min(P, (long long)tid * chunk), l1 = min(P, l0 + chunk);
+    // pass 1: min
+    double m = DBL_MAX;
+    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+        double s, f;
+        it.get(s, f);
+        m = fmin(m, s);
+    }
+    if (!FULL) m = fmin(m, 0.0);  // the strict upper triangle holds zeros (torch.tril)
+    m = block_reduce(m, sh, 1);
+    // pass 2: sum of exp(-|s-m|/tau) in flat order
+    double loc = 0.0;
+    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+        double s, f;
+        it.get(s, f);
+        loc += exp(-fabs(s - m) / tau);
+    }
+    double Z;
+    double off = block_excl_scan(loc, sh, Z);
+    double NN = (double)c.N * (double)c.N;
+    if (!FULL) {
+        // inactive entries: zeros and 1e9 -- require their softmax mass to be invisible in fp64
+        double worst = exp(-fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
+        guard_ok = (NN * worst <= 1e-18 * fmin(1.0, tau) * Z);
+    } else {
+        guard_ok = true;
+    }
+    // pass 3: c_j = p_j * cumsum(p)_j ; M = max c
+    double run = off, M = 0.0;
+    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+        double s, f;
+        it.get(s, f);
+        double e = exp(-fabs(s - m) / tau);
+        run += e;
+        M = fmax(M, (e / Z) * (run / Z));
+    }
+    M = block_reduce(M, sh, 2);
+    // pass 4: second softmax on -c, soft index = sum p'_j * flat_j
+    run = off;
+    double z2 = 0.0, isum = 0.0, fsum = 0.0;
+    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+        double s, f;
+        it.get(s, f);
+        double e = exp(-fabs(s - m) / tau);
+        run += e;
+        double cj = (e / Z) * (run / Z);
+        double e2 = exp(-fabs(M - cj) / tau);
+        z2 += e2;
+        isum = fma(e2, f, isum);
+        fsum += f;
+    }
+    z2 = block_reduce(z2, sh, 0);
+    isum = block_reduce(isum, sh, 0);
+    if (!FULL) {
+        fsum = block_reduce(fsum, sh, 0);
+        double e0 = exp(-M / tau);  // entries with c_j == 0
+        double cnt = NN - (double)P;
+        z2 += cnt * e0;
+        isum += e0 * (NN * (NN - 1.0) * 0.5 - fsum);
+    }
+    idx_out = isum / z2;
+}
+
+__global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
+                                                       double *__restrict__ ws, int64_t *__restrict__ peel,
+                                                       double *__restrict__ blens, int32_t *__restrict__ flags) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int N = 2 * S - 1;
+    double *Dm = ws + (size_t)b * nj_ws_doubles(S);
+    const double *P = pdm + (size_t)b * S * S;
+    double *rs = reinterpret_cast<double *>(smem_raw);  // [S]
+    double *newd = rs + S;                              // [S]
+    double *sh = newd + S;                              // [32]
+    int *act = reinterpret_cast<int *>(sh + 32);        // [S]
+    int *act2 = act + S;                                // [S]
+    int *id_of = act2 + S;                              // [S]
+    int *pos_of = id_of + S;                            // [N]
+    int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    double *bl = blens + (size_t)b * (2 * S - 2);
+    int32_t *fl = flags + (size_t)b * (S - 1);
+
+    for (size_t i = tid; i < (size_t)S * S; i += T) {
+        int r = (int)(i / S), cc = (int)(i - (size_t)r * S);
+        Dm[i] = (r == cc) ? 0.0 : P[i];  // dists.fill_diagonal_(0.0), peeler.py:178
+    }
+    for (int s = tid; s < S; s += T) { act[s] = s; id_of[s] = s; }
+    for (int i = tid; i < N; i += T) pos_of[i] = i < S ? i : -1;
+    __syncthreads();
+
+    for (int n = S; n > 1; --n) {
+        // fresh row sums over the active set (peeler.py:240, :261)
+        for (int p = warp; p < n; p += nwarp) {
+            const int sx = act[p];
+            const double *row = Dm + (size_t)sx * S;
+            double acc = 0.0;
+            for (int q = lane; q < n; q += 32) {
+                int sy = act[q];
+                if (sy != sx) acc += row[sy];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) rs[sx] = acc;
+        }
+        __syncthreads();
+        SoftCtx c{Dm, rs, act, id_of, pos_of, S, N, n, (double)(n - 2)};
+        double idx;
+        bool ok;
+        if (full) soft_argmin_block<true>(c, tau, sh, idx, ok);
+        else soft_argmin_block<false>(c, tau, sh, idx, ok);
+        // unravel (soft.py:7-10) and round (peeler.py:196-198)
+        double rowf = trunc(idx / (double)N), colf = fmod(idx, (double)N);
+        int right = (int)rint(rowf), left = (int)rint(colf);
+        int fbits = ok ? 0 : 4;
+        bool bad = !(idx == idx) || right < 0 || right >= N || left < 0 || left >= N || right == left;
+        int pr = bad ? -1 : pos_of[right], pc = bad ? -1 : pos_of[left];
+        if (pr < 0 || pc < 0) {
+            // the reference would index a masked node here (garbage); flag it and stop this tree
+            if (tid == 0) {
+                for (int t = S - n; t < S - 1; ++t) fl[t] = 8;
+            }
+            return;
+        }
+        const int sl = act[pc], sr = act[pr];
+        const int parent = S + (S - n);
+        const double d_lr = Dm[(size_t)sl * S + sr];
+        const double nact = fmax((double)n, 3.0);
+        double d_pl = 0.5 * d_lr + (rs[sl] - rs[sr]) / (2.0 * (nact - 2.0));
+        if (!(d_pl > DBL_EPSILON)) { fbits |= (d_pl == DBL_EPSILON) ? 0 : 1; d_pl = DBL_EPSILON; }
+        double d_pr = d_lr - d_pl;
+        if (!(d_pr > DBL_EPSILON)) { fbits |= (d_pr == DBL_EPSILON) ? 0 : 2; d_pr = DBL_EPSILON; }
+        for (int p = tid; p < n; p += T) {
+            if (p == pc || p == pr) continue;
+            const int sx = act[p];
+            newd[sx] = 0.5 * ((Dm[(size_t)sl * S + sx] + Dm[(size_t)sr * S + sx]) - d_lr);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            pl[(S - n) * 3 + 0] = left;
+            pl[(S - n) * 3 + 1] = right;
+            pl[(S - n) * 3 + 2] = parent;
+            bl[left] = d_pl;
+            bl[right] = d_pr;
+            fl[S - n] = fbits;
+            id_of[sl] = parent;
+            pos_of[left] = -1;
+            pos_of[right] = -1;
+        }
+        const int plo = min(pc, pr), phi = max(pc, pr);
+        for (int p = tid; p < n; p += T) {
+            if (p == pc || p == pr) continue;
+            const int sx = act[p];
+            const double u = newd[sx];
+            Dm[(size_t)sl * S + sx] = u;
+            Dm[(size_t)sx * S + sl] = u;
+            act2[p - (p > plo) - (p > phi)] = sx;
+        }
+        if (tid == 0) act2[n - 2] = sl;
+        __syncthreads();
+        for (int p = tid; p < n - 1; p += T) {
+            act[p] = act2[p];
+            pos_of[id_of[act2[p]]] = p;
+        }
+        __syncthreads();
+    }
+}
+
+// reverse replay: adjoint of blens w.r.t. the input distance matrix
+__global__ void __launch_bounds__(1024) nj_soft_bwd_kernel(const int64_t *__restrict__ peel,
+                                                           const int32_t *__restrict__ flags,
+                                                           const double *__restrict__ gblens, int S,
+                                                           double *__restrict__ ws, double *__restrict__ gpdm) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int N = 2 * S - 1;
+    double *Ab = ws + (size_t)b * nj_ws_doubles(S) + (size_t)S * S;
+    double *sh = reinterpret_cast<double *>(smem_raw);  // [32]
+    int *st_of = reinterpret_cast<int *>(sh + 32);      // [N] node id -> storage slot
+    int *active = st_of + N;                            // [S] storage slot active?
+    const int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    const int32_t *fl = flags + (size_t)b * (S - 1);
+    const double *gb = gblens + (size_t)b * (2 * S - 2);
+    double *out = gpdm + (size_t)b * S * S;
+
+    for (size_t i = tid; i < (size_t)S * S; i += T) Ab[i] = 0.0;
+    for (int s = tid; s < S; s += T) { st_of[s] = s; active[s] = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < S - 1; ++t) st_of[(int)pl[t * 3 + 2]] = st_of[(int)pl[t * 3 + 0]];
+        active[st_of[(int)pl[(S - 2) * 3 + 2]]] = 1;
+    }
+    __syncthreads();
+    for (int t = S - 2; t >= 0; --t) {
+        const int left = (int)pl[t * 3 + 0], right = (int)pl[t * 3 + 1];
+        const int sl = st_of[left], sr = st_of[right];
+        const int n = S - t;
+        const int f = fl[t];
+        const double nact = fmax((double)n, 3.0);
+        // un-join: slot sl (currently the parent) becomes `left`, slot sr becomes active as `right`
+        double usum = 0.0;
+        for (int sx = tid; sx < S; sx += T) {
+            if (!active[sx] || sx == sl) continue;
+            usum += Ab[(size_t)sl * S + sx] + Ab[(size_t)sx * S + sl];
+        }
+        usum = block_reduce(usum, sh, 0);
+        double g_pl = gb[left], g_pr = gb[right];
+        double g_lr = 0.0, g_rl = 0.0, g_rr = 0.0;
+        if (!(f & 2)) { g_lr += g_pr; g_pl -= g_pr; }
+        if (!(f & 1)) {
+            g_lr += 0.5 * g_pl;
+            g_rl = g_pl / (2.0 * (nact - 2.0));
+            g_rr = -g_rl;
+        }
+        for (int sx = tid; sx < S; sx += T) {
+            if (!active[sx] || sx == sl) continue;
+            double ub = Ab[(size_t)sl * S + sx] + Ab[(size_t)sx * S + sl];
+            Ab[(size_t)sl * S + sx] = 0.5 * ub + g_rl;
+            Ab[(size_t)sr * S + sx] = 0.5 * ub + g_rr;
+            Ab[(size_t)sx * S + sl] = 0.0;
+            Ab[(size_t)sx * S + sr] = 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            Ab[(size_t)sl * S + sr] = -0.5 * usum + g_lr + g_rl;
+            Ab[(size_t)sr * S + sl] = g_rr;
+            active[sr] = 1;
+        }
+        __syncthreads();
+    }
+    for (size_t i = tid; i < (size_t)S * S; i += T) {
+        int r = (int)(i / S), c = (int)(i - (size_t)r * S);
+        out[i] = (r == c) ? 0.0 : 0.5 * (Ab[(size_t)r * S + c] + Ab[(size_t)c * S + r]);
+    }
+}
+
+}  // namespace dodo
+
+using namespace dodo;
+
+extern "C" uint64_t dodo_nj_workspace_bytes(int B, int S) {
+    return (uint64_t)B * nj_ws_doubles(S) * sizeof(double);
+}
+
+static int nj_threads(int S) { return S <= 48 ? 128 : (S <= 160 ? 256 : (S <= 600 ? 512 : 1024)); }
+
+extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
+                            void *stream_) {
+    DODO_CHECK_ARG(d_pdm && d_ws && d_peel && d_blens, "dodo_nj_hard: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_hard: need B>=1, S>=2");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t smem = 2 * (size_t)S * sizeof(double) + 3 * (size_t)S * sizeof(int);
+    if (smem > 48 * 1024)
+        DODO_CUDA(cudaFuncSetAttribute(nj_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nj_hard_kernel<<<B, nj_threads(S), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void *d_ws, int64_t *d_peel,
+                            double *d_blens, int32_t *d_flags, void *stream_) {
+    DODO_CHECK_ARG(d_pdm && d_ws && d_peel && d_blens && d_flags, "dodo_nj_soft: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_soft: need B>=1, S>=2");
+    DODO_CHECK_ARG(tau != 0.0 && tau == tau, "dodo_nj_soft: tau must be a non-zero number");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int full = tau < 0.0 ? 1 : 0;  // negative tau selects the exhaustive N^2 enumeration
+    const double t = fabs(tau);
+    size_t smem = (2 * (size_t)S + 32) * sizeof(double) + (3 * (size_t)S + 2 * (size_t)S) * sizeof(int);
+    if (smem > 48 * 1024)
+        DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nj_soft_kernel<<<B, nj_threads(S), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+extern "C" int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, const double *d_grad_blens, int B,
+                                int S, void *d_ws, double *d_grad_pdm, void *stream_) {
+    DODO_CHECK_ARG(d_peel && d_flags && d_grad_blens && d_ws && d_grad_pdm, "dodo_nj_soft_bwd: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_soft_bwd: need B>=1, S>=2");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t smem = 32 * sizeof(double) + (2 * (size_t)S + (size_t)S) * sizeof(int);
+    if (smem > 48 * 1024)
+        DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nj_soft_bwd_kernel<<<B, nj_threads(S), smem, stream>>>(d_peel, d_flags, d_grad_blens, S, (double *)d_ws, d_grad_pdm);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}

@@ -1,0 +1,311 @@
+"""Batched device engine for the hot path (the B200-first API the reference-shaped shims sit on).
+
+``SubstModel``   host-side substitution-model parameters -> ``dodo_model_t``
+                 (PhyloModel, dodonaphy/phylomodel.py:76-128)
+``PruneEngine``  tips resident in HBM as packed IUPAC masks, workspace cached per batch shape,
+                 one call = lnL (and d lnL / d blens) for a whole batch of trees
+                 (phylo.calculate_treelikelihood, dodonaphy/phylo.py:132-139, + autograd;
+                 Cphylo.compute_LL_np, dodonaphy/cython/Cphylo.pyx:9-23)
+
+Everything here is plumbing around the C ABI (include/dodonaphy_b200.h): torch is used for device
+memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SubstModel:
+    """JC69 or GTR substitution model (host side, tiny).  The eigen-system is obtained exactly as
+    the reference does (phylomodel.py:96-114): eigh of sqrt(pi) Q sqrt(pi)^-1."""
+
+    def __init__(self, kind, U, lam, Uinv, Q, pi):
+        self.kind = kind
+        self.U, self.lam, self.Uinv, self.Q, self.pi = (np.ascontiguousarray(a, dtype=np.float64) for a in (U, lam, Uinv, Q, pi))
+
+    @staticmethod
+    def jc69(freqs=None):
+        Q = np.full((4, 4), 1.0 / 3.0)
+        np.fill_diagonal(Q, -1.0)
+        pi = np.full(4, 0.25) if freqs is None else np.asarray(freqs, dtype=np.float64)
+        return SubstModel(_lib.MODEL_JC69, np.eye(4), np.zeros(4), np.eye(4), Q, pi)
+
+    @staticmethod
+    def gtr_q(rates, freqs):
+        """compute_Q_martix + norm (phylomodel.py:116-128)."""
+        rates = np.asarray(rates, dtype=np.float64)
+        freqs = np.asarray(freqs, dtype=np.float64)
+        if rates.shape != (6,) or freqs.shape != (4,):
+            raise ValueError("GTR needs 6 exchangeabilities and 4 frequencies")
+        iu = np.triu_indices(4, 1)
+        Q = np.zeros((4, 4))
+        Q[iu[0], iu[1]] = rates
+        Q[iu[1], iu[0]] = rates
+        Q = Q * freqs[None, :]
+        Q = Q + np.diag(-np.sum(Q, axis=1))
+        return Q / (-np.sum(np.diagonal(Q) * freqs))
+
+    @staticmethod
+    def gtr(rates, freqs, root_freqs=None):
+        freqs = np.asarray(freqs, dtype=np.float64)
+        Q = SubstModel.gtr_q(rates, freqs)
+        sp = np.diag(np.sqrt(freqs))
+        spi = np.diag(1.0 / np.sqrt(freqs))
+        lam, V = np.linalg.eigh(sp @ Q @ spi)
+        pi = freqs if root_freqs is None else np.asarray(root_freqs, dtype=np.float64)
+        return SubstModel(_lib.MODEL_EIGEN, spi @ V, lam, np.linalg.inv(V) @ sp, Q, pi)
+
+    def c_struct(self):
+        m = _lib.Model()
+        for i in range(16):
+            m.U[i] = self.U.reshape(-1)[i]
+            m.Uinv[i] = self.Uinv.reshape(-1)[i]
+            m.Q[i] = self.Q.reshape(-1)[i]
+        for i in range(4):
+            m.lam[i] = self.lam[i]
+            m.pi[i] = self.pi[i]
+        m.kind = self.kind
+        return m
+
+
+def pack_tip_partials(partials):
+    """Tip partials as the reference holds them (list of S arrays/tensors (4, L) with 0/1 entries,
+    phylo.py:27-46) -> uint8 mask array (S, L).  Raises ValueError for non-0/1 values."""
+    rows = []
+    for p in partials:
+        a = p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
+        a = a.reshape(4, -1)
+        if not np.all((a == 0.0) | (a == 1.0)):
+            raise ValueError("tip partials must be 0/1 indicator vectors")
+        rows.append((a[0] + 2 * a[1] + 4 * a[2] + 8 * a[3]).astype(np.uint8))
+    return np.stack(rows)
+
+
+def validate_peel(peel, S):
+    """Host-side check of a peel array (raises ValueError like the reference would fail)."""
+    peel = np.asarray(peel)
+    if peel.shape[-2:] != (S - 1, 3):
+        raise ValueError(f"peel must have shape (..., {S - 1}, 3), got {peel.shape}")
+    flat = peel.reshape(-1, S - 1, 3)
+    for pl in flat:
+        seen = set(range(S))
+        for l, r, p in pl:
+            if l not in seen or r not in seen or l == r or not (S <= p < 2 * S - 1) or p in seen:
+                raise ValueError("peel is not a valid post-order of a binary tree")
+            seen.discard(int(l))
+            seen.discard(int(r))
+            seen.add(int(p))
+        if len(seen) != 1:
+            raise ValueError("peel does not describe a single tree")
+
+
+class PruneEngine:
+    """Felsenstein pruning over a batch of trees on one GPU.
+
+    tipmask : (S, L) uint8 IUPAC masks (bit j <-> state j in order A,C,G,T)
+    weights : (L,) pattern weights (int64 or float64)
+    """
+
+    def __init__(self, tipmask, weights, device=None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        tm = torch.as_tensor(np.ascontiguousarray(tipmask) if isinstance(tipmask, np.ndarray) else tipmask)
+        if tm.dtype != torch.uint8 or tm.dim() != 2:
+            raise TypeError("tipmask must be a (S, L) uint8 array")
+        self.S, self.L = int(tm.shape[0]), int(tm.shape[1])
+        self.E = 2 * self.S - 2
+        self.tipmask = tm.to(self.device).contiguous()
+        w = torch.as_tensor(weights)
+        if w.numel() != self.L:
+            raise ValueError("weights must have one entry per site pattern")
+        self.weights = w.to(self.device, dtype=torch.float64).contiguous()
+        self._plans = {}
+        self.grid_hint = 0
+        self.threads_hint = 0
+
+    def _plan(self, B, K, flags):
+        key = (B, K, flags, self.grid_hint, self.threads_hint)
+        hit = self._plans.get(key)
+        if hit is None:
+            plan = _lib.PrunePlan()
+            _lib.check(self.lib.dodo_prune_plan(B, self.S, self.L, K, flags, self.grid_hint, self.threads_hint, C.byref(plan)))
+            ws = torch.empty(int(plan.ws_bytes), dtype=torch.uint8, device=self.device)
+            hit = (plan, ws)
+            self._plans[key] = hit
+        return hit
+
+    def loglik(self, peel, blens, model, rates=None, mix=False, grad=False, out=None, mats=None):
+        """lnL for a batch.
+
+        peel  : int64 device tensor (B, S-1, 3) or (S-1, 3) (one topology shared by the batch)
+        blens : float64 device tensor (B, 2S-2) (or (2S-2,) for B = 1); ignored if ``mats`` given
+        mats  : optional float64 device tensor (B, 2S-2, K, 4, 4): caller-supplied P matrices
+        rates : K category rates (host); None => K = 1
+        Returns (lnL (B,), grad_blens (B, 2S-2) or None), both device tensors.
+        """
+        with torch.cuda.device(self.device):
+            if mats is not None:
+                mats = mats.to(self.device, dtype=torch.float64).contiguous()
+                B, K = int(mats.shape[0]), int(mats.shape[2])
+                blens_t = None
+                rates_arr = np.ones(K)
+            else:
+                blens_t = blens.to(self.device, dtype=torch.float64)
+                if blens_t.dim() == 1:
+                    blens_t = blens_t.unsqueeze(0)
+                blens_t = blens_t.contiguous()
+                B = int(blens_t.shape[0])
+                rates_arr = np.ones(1) if rates is None else np.ascontiguousarray(rates, dtype=np.float64)
+                K = int(rates_arr.shape[0])
+                if blens_t.shape[1] != self.E:
+                    raise ValueError(f"blens must have {self.E} entries per tree")
+            peel_t = peel.to(self.device, dtype=torch.int64)
+            if peel_t.dim() == 2:
+                peel_t = peel_t.unsqueeze(0)
+            peel_t = peel_t.contiguous()
+            if tuple(peel_t.shape[1:]) != (self.S - 1, 3) or peel_t.shape[0] not in (1, B):
+                raise ValueError("peel must have shape (B or 1, S-1, 3)")
+            flags = (_lib.PRUNE_GRAD if grad else 0) | (_lib.PRUNE_MIX if (mix and K > 1) else 0)
+            plan, ws = self._plan(B, K, flags)
+            ll = torch.empty(B, dtype=torch.float64, device=self.device)
+            g = torch.empty((B, self.E), dtype=torch.float64, device=self.device) if grad else None
+            cm = model.c_struct()
+            rates_c = (C.c_double * K)(*rates_arr.tolist())
+            _lib.check(self.lib.dodo_prune(C.byref(plan), C.byref(cm), rates_c, _ptr(self.tipmask), self.L,
+                                           _ptr(self.weights), _ptr(peel_t), int(peel_t.shape[0]), _ptr(blens_t),
+                                           _ptr(mats), _ptr(ws), _ptr(ll), _ptr(g), None, None, _stream()))
+            return ll, g
+
+
+# --------------------------------------------------------------------------------------------
+# K1 / K2 batched device functions
+# --------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(tag, nbytes, device):
+    key = (tag, device)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _as_batch(x, ndim):
+    x = x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+    if not x.is_cuda:
+        _lib.require_cuda()
+        x = x.cuda()
+    x = x.to(torch.float64)
+    squeeze = x.dim() == ndim - 1
+    if squeeze:
+        x = x.unsqueeze(0)
+    if x.dim() != ndim:
+        raise ValueError(f"expected a {ndim - 1}- or {ndim}-dimensional tensor")
+    return x.contiguous(), squeeze
+
+
+def _curv_tensor(curvature, device):
+    if isinstance(curvature, torch.Tensor):
+        return curvature.detach().to(device=device, dtype=torch.float64).reshape(-1)[:1].contiguous()
+    return torch.tensor([float(curvature)], dtype=torch.float64, device=device)
+
+
+def pdm_forward(x, curvature=-1.0, variant="torch", lift="up", matsumoto=False):
+    """Batched pairwise hyperbolic distances.  x: (B,S,D) or (S,D) -> (B,S,S) or (S,S) on device."""
+    lib = _lib.load()
+    x, squeeze = _as_batch(x, 3)
+    B, S, D = (int(v) for v in x.shape)
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, S, S), dtype=torch.float64, device=x.device)
+        ws = _workspace("pdm", lib.dodo_pdm_workspace_bytes(B, S, D), x.device)
+        cv = _curv_tensor(curvature, x.device)
+        _lib.check(lib.dodo_pdm_fwd(_ptr(x), B, S, D, _ptr(cv), _lib.PDM_TORCH if variant == "torch" else _lib.PDM_NUMPY,
+                                    _lib.LIFT_UP if lift == "up" else _lib.LIFT_WRAP, int(bool(matsumoto)),
+                                    _ptr(ws), _ptr(out), _stream()))
+    return out[0] if squeeze else out
+
+
+def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False):
+    """VJP of pdm_forward (torch variant).  Returns (grad_x like x, grad_curvature (B,))."""
+    lib = _lib.load()
+    x, squeeze = _as_batch(x, 3)
+    g, _ = _as_batch(grad_pdm, 3)
+    B, S, D = (int(v) for v in x.shape)
+    if tuple(g.shape) != (B, S, S):
+        raise ValueError("grad_pdm must have shape (B,S,S)")
+    with torch.cuda.device(x.device):
+        gx = torch.empty_like(x)
+        gc = torch.empty(B, dtype=torch.float64, device=x.device)
+        ws = _workspace("pdm", lib.dodo_pdm_workspace_bytes(B, S, D), x.device)
+        cv = _curv_tensor(curvature, x.device)
+        _lib.check(lib.dodo_pdm_bwd(_ptr(x), B, S, D, _ptr(cv), _lib.PDM_TORCH,
+                                    _lib.LIFT_UP if lift == "up" else _lib.LIFT_WRAP, int(bool(matsumoto)),
+                                    _ptr(ws), _ptr(g), _ptr(gx), _ptr(gc), _stream()))
+    return (gx[0] if squeeze else gx), gc
+
+
+def nj_hard(pdm):
+    """Batched hard NJ (Cpeeler.nj_np).  pdm (B,S,S) or (S,S) -> peel int64 (B,S-1,3), blens (B,2S-2)."""
+    lib = _lib.load()
+    pdm, squeeze = _as_batch(pdm, 3)
+    B, S = int(pdm.shape[0]), int(pdm.shape[1])
+    if pdm.shape[2] != S or S < 2:
+        raise ValueError("pdm must be square with at least 2 taxa")
+    with torch.cuda.device(pdm.device):
+        peel = torch.empty((B, S - 1, 3), dtype=torch.int64, device=pdm.device)
+        blens = torch.empty((B, 2 * S - 2), dtype=torch.float64, device=pdm.device)
+        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device)
+        _lib.check(lib.dodo_nj_hard(_ptr(pdm), B, S, _ptr(ws), _ptr(peel), _ptr(blens), _stream()))
+    return (peel[0], blens[0]) if squeeze else (peel, blens)
+
+
+def nj_soft(pdm, tau, exhaustive=False, return_flags=False):
+    """Batched soft NJ (peeler.nj_torch with tau).  Returns peel, blens[, flags (B,S-1) int32].
+    ``exhaustive`` evaluates soft.argmin over all N^2 padded entries instead of the active pairs."""
+    lib = _lib.load()
+    pdm, squeeze = _as_batch(pdm, 3)
+    B, S = int(pdm.shape[0]), int(pdm.shape[1])
+    if pdm.shape[2] != S or S < 2:
+        raise ValueError("pdm must be square with at least 2 taxa")
+    tau = float(tau)
+    if not tau > 0.0:
+        raise ValueError("tau must be positive")
+    with torch.cuda.device(pdm.device):
+        peel = torch.zeros((B, S - 1, 3), dtype=torch.int64, device=pdm.device)
+        blens = torch.zeros((B, 2 * S - 2), dtype=torch.float64, device=pdm.device)
+        flags = torch.zeros((B, S - 1), dtype=torch.int32, device=pdm.device)
+        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device)
+        _lib.check(lib.dodo_nj_soft(_ptr(pdm), B, S, -tau if exhaustive else tau, _ptr(ws), _ptr(peel), _ptr(blens),
+                                    _ptr(flags), _stream()))
+    if squeeze:
+        peel, blens, flags = peel[0], blens[0], flags[0]
+    return (peel, blens, flags) if return_flags else (peel, blens)
+
+
+def nj_soft_backward(peel, flags, grad_blens):
+    """VJP of soft-NJ branch lengths w.r.t. the distance matrix: returns symmetric (B,S,S)."""
+    lib = _lib.load()
+    g, squeeze = _as_batch(grad_blens, 2)
+    B = int(g.shape[0])
+    S = int(g.shape[1]) // 2 + 1
+    peel = peel.reshape(B, S - 1, 3).to(device=g.device, dtype=torch.int64).contiguous()
+    flags = flags.reshape(B, S - 1).to(device=g.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(g.device):
+        out = torch.empty((B, S, S), dtype=torch.float64, device=g.device)
+        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), g.device)
+        _lib.check(lib.dodo_nj_soft_bwd(_ptr(peel), _ptr(flags), _ptr(g), B, S, _ptr(ws), _ptr(out), _stream()))
+    return out[0] if squeeze else out

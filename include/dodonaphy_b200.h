@@ -1,0 +1,149 @@
+/*
+ * dodonaphy_b200 -- C ABI of the B200-native Dodonaphy hot path.
+ *
+ * Plain C: raw device pointers, explicit sizes, a CUDA stream passed as void*.  No torch types.
+ * Every entry point returns 0 on success and a negative DODO_E* code otherwise;
+ * dodo_last_error() gives a human-readable message for the calling thread.
+ *
+ * All floating point is IEEE fp64.  Index data (peel) is int64, exactly like the reference
+ * (Cpeeler.pyx:28, peeler.py:180).  Batch axis B = VI samples or MCMC chains; S taxa; L site
+ * patterns; K rate categories; E = 2S-2 branches; D embedding dimension.
+ *
+ * Each function names the reference interface it replaces (paths relative to the reference
+ * repository mattapow/dodonaphy).
+ */
+#ifndef DODONAPHY_B200_H
+#define DODONAPHY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DODO_OK 0
+#define DODO_EINVAL (-1)  /* bad argument (reference raises ValueError)            */
+#define DODO_ECUDA (-2)   /* CUDA runtime error                                    */
+#define DODO_ENOTIMPL (-3) /* combination not implemented (NotImplementedError)    */
+#define DODO_EINEXACT (-4) /* soft-NJ exactness guard tripped (see dodo_nj_soft)   */
+
+const char *dodo_last_error(void);
+int dodo_version(void);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+uint64_t dodo_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Substitution model.  P(t) = U diag(exp(lam t)) Uinv, dP/dt = Q P.
+ * Replaces PhyloModel.get_transition_mats / JC69_p_t / GTR_p_t (dodonaphy/phylomodel.py:76-114)
+ * and Cphylo.JC69_p_t (dodonaphy/cython/Cphylo.pyx:45-51): P(t) is formed on the device.
+ * kind = DODO_MODEL_JC69 uses the reference's closed form a = 1/4 + 3/4 e^{-4t/3},
+ * b = 1/4 - 1/4 e^{-4t/3} (U, Uinv, lam ignored); kind = DODO_MODEL_EIGEN uses the eigen-system
+ * (the caller obtains it as the reference does, eigh of sqrt(pi) Q sqrt(pi)^-1).
+ * ------------------------------------------------------------------------------------------ */
+#define DODO_MODEL_JC69 0
+#define DODO_MODEL_EIGEN 1
+typedef struct {
+    double U[16];    /* row-major 4x4 */
+    double Uinv[16]; /* row-major 4x4 */
+    double lam[4];
+    double Q[16]; /* row-major rate matrix, rows sum to 0 */
+    double pi[4]; /* root frequencies ("freqs" argument of calculate_treelikelihood) */
+    int32_t kind;
+    int32_t _pad;
+} dodo_model_t;
+
+/* ------------------------------------------------------------------------------------------
+ * K3: fused P(t) + Felsenstein pruning, forward and (optionally) gradient.
+ * Replaces phylo.calculate_treelikelihood (dodonaphy/phylo.py:132-139) + torch autograd,
+ * Cphylo.calculate_treelikelihood / compute_LL_np (dodonaphy/cython/Cphylo.pyx:9-42) and the
+ * backend slot BaseModel.compute_LL dispatches to (dodonaphy/base_model.py:219-247); shaped like
+ * the reference's own native plugin phylo.TreeLikelihood (dodonaphy/phylo.py:177-226): value and
+ * gradient in one call.
+ * ------------------------------------------------------------------------------------------ */
+#define DODO_PRUNE_GRAD 1u     /* also produce d lnL / d blens                                   */
+#define DODO_PRUNE_MIX 2u      /* K>1: lnL = sum_p w_p log(mean_k f_k)  (discrete-gamma mixture) */
+                               /* without it K categories are independent and their lnL are      */
+                               /* summed -- what the reference's broadcasting does (phylo.py:137) */
+#define DODO_PRUNE_SCALE 4u    /* power-of-two rescaling (bit-identical where the unscaled       */
+                               /* computation stays finite)                                       */
+#define DODO_PRUNE_GMATS 8u    /* also produce d lnL / d P[b,e,k,:,:] and d lnL / d pi          */
+
+typedef struct {
+    int32_t B, S, L, K;
+    uint32_t flags;
+    int32_t threads;       /* CTA size                                                    */
+    int32_t grid;          /* persistent CTAs                                             */
+    int32_t tile_patterns; /* site patterns per CTA work item                             */
+    int32_t n_tiles;       /* ceil(L / tile_patterns)                                     */
+    int32_t n_items;       /* B * n_tiles                                                 */
+    int32_t _pad;
+    uint64_t ws_bytes;     /* device workspace the caller must provide                    */
+    /* offsets (bytes) of the sub-buffers inside the workspace                            */
+    uint64_t off_ops, off_sched, off_pmat, off_tiptab, off_scratch, off_ll_part, off_g_part, off_gm_part;
+} dodo_prune_plan_t;
+
+/* Fill *plan for a problem size.  grid_hint/threads_hint = 0 picks the defaults. */
+int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int grid_hint, int threads_hint,
+                    dodo_prune_plan_t *plan);
+
+/*
+ * d_tipmask : uint8 [S][ld_mask], bit j set <=> state j (A,C,G,T) compatible with the tip
+ *             (the 0/1 tip partials of phylo.compress_alignment, dodonaphy/phylo.py:27-46, packed)
+ * d_weights : double [L] pattern weights
+ * d_peel    : int64 [B or 1][S-1][3] rows [left,right,parent], post-order; peel_batch = 1 shares one
+ *             topology across the batch
+ * d_blens   : double [B][2S-2]; blens[i] = branch above node i
+ * rates     : host double [K] category rates (1.0 for K = 1)
+ * d_P_in    : optional double [B][2S-2][K][16] transition matrices supplied by the caller
+ *             (the "mats" argument of calculate_treelikelihood); NULL => formed on device
+ * outputs   : d_loglik [B]; d_grad_blens [B][2S-2] (flag GRAD, else NULL);
+ *             d_grad_P [B][2S-2][K][16] and d_grad_pi [B][4] (flag GMATS, else NULL)
+ */
+int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
+               const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights,
+               const int64_t *d_peel, int peel_batch, const double *d_blens, const double *d_P_in,
+               void *d_ws, double *d_loglik, double *d_grad_blens, double *d_grad_P,
+               double *d_grad_pi, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1: batched pairwise hyperbolic distance.
+ * Replaces Chyp_torch.get_pdm (dodonaphy/cython/Chyp_torch.pyx:399-423; lifts :486-504 "up",
+ * :387-396 "wrap") and Chyp_np.get_pdm (dodonaphy/cython/Chyp_np.pyx:321-367).
+ * ------------------------------------------------------------------------------------------ */
+#define DODO_PDM_TORCH 0 /* clamp H at -1.0000001, zero diagonal       (Chyp_torch.pyx:418,422) */
+#define DODO_PDM_NUMPY 1 /* clamp H at -(1+eps), diagonal kept, curvature 0 => Euclidean        */
+#define DODO_LIFT_UP 0
+#define DODO_LIFT_WRAP 1
+
+uint64_t dodo_pdm_workspace_bytes(int B, int S, int D);
+/* d_x [B][S][D]; d_curvature: device double [1] (shared) ; d_pdm [B][S][S] */
+int dodo_pdm_fwd(const double *d_x, int B, int S, int D, const double *d_curvature, int variant,
+                 int lift, int matsumoto, void *d_ws, double *d_pdm, void *stream);
+/* VJP: d_grad_pdm [B][S][S] -> d_grad_x [B][S][D], d_grad_curv [B] (one partial per sample) */
+int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double *d_curvature, int variant,
+                 int lift, int matsumoto, void *d_ws, const double *d_grad_pdm, double *d_grad_x,
+                 double *d_grad_curv, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2: batched neighbour joining, one tree per CTA.
+ * dodo_nj_hard replaces Cpeeler.nj_np (dodonaphy/cython/Cpeeler.pyx:15-125): bit-identical peel
+ * and blens (same operation order, no FMA contraction, first strict minimum in pool order).
+ * dodo_nj_soft replaces peeler.nj_torch (dodonaphy/peeler.py:155-220) with soft.argmin
+ * (dodonaphy/soft.py:38-53) evaluated in O(active pairs) per join.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t dodo_nj_workspace_bytes(int B, int S);
+/* d_pdm [B][S][S] (not modified); d_peel int64 [B][S-1][3]; d_blens [B][2S-2] */
+int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
+                 void *stream);
+/* d_flags int32 [B][S-1]: bit0 = d_pl clamped, bit1 = d_pr clamped, bit2 = exactness guard tripped */
+int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void *d_ws, int64_t *d_peel,
+                 double *d_blens, int32_t *d_flags, void *stream);
+/* VJP of blens w.r.t. pdm given the recorded joins: d_grad_pdm [B][S][S] (symmetric) */
+int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, const double *d_grad_blens,
+                     int B, int S, void *d_ws, double *d_grad_pdm, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DODONAPHY_B200_H */

@@ -1,0 +1,142 @@
+"""GPU parity: K3 (fused P(t) + pruning forward/backward) through the C ABI against
+(1) fixtures produced by the real reference (tests/golden), (2) the CPU oracle on seeded inputs.
+Tolerance: 1e-9 relative (BASELINE.json north_star) on lnL and on the gradient (relative to the
+largest gradient component of the tree)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _engine(masks, weights):
+    from dodonaphy_b200.engine import PruneEngine
+
+    return PruneEngine(masks, weights)
+
+
+def _dev(a, dtype=None):
+    return torch.as_tensor(a, dtype=dtype).cuda()
+
+
+def _assert_grad(ours, ref):
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(ours, ref, rtol=RTOL, atol=RTOL * scale)
+
+
+@pytest.mark.parametrize("tree", ["mb", "nj"])
+def test_ds1_known_answers(tree):
+    """-6904.632 (test/test_phylo.py:239) and -7130.96813417 (test/test_bito.py:35)."""
+    from dodonaphy_b200.engine import SubstModel
+
+    g = load_golden("ds1.npz")
+    eng = _engine(g["masks"], g["weights"])
+    ll, grad = eng.loglik(_dev(g[f"{tree}_peel"]), _dev(g[f"{tree}_blens"]), SubstModel.jc69(), grad=True)
+    expect = {"mb": -6904.632, "nj": -7130.96813417}[tree]
+    assert ll.item() == pytest.approx(expect, abs=1e-3 if tree == "mb" else 1e-7)
+    assert ll.item() == pytest.approx(float(g[f"{tree}_lnL_torch"]), rel=RTOL)
+    _assert_grad(grad[0].cpu().numpy(), g[f"{tree}_g_blens"])
+    # forward-only kernel gives the same value
+    ll2, none = eng.loglik(_dev(g[f"{tree}_peel"]), _dev(g[f"{tree}_blens"]), SubstModel.jc69(), grad=False)
+    assert none is None
+    assert ll2.item() == pytest.approx(ll.item(), rel=1e-14)
+    # GTR
+    m = SubstModel.gtr(g["gtr_rates"], g["gtr_freqs"])
+    ll, grad = eng.loglik(_dev(g[f"{tree}_peel"]), _dev(g[f"{tree}_blens"]), m, grad=True)
+    assert ll.item() == pytest.approx(float(g[f"{tree}_gtr_lnL"]), rel=RTOL)
+    _assert_grad(grad[0].cpu().numpy(), g[f"{tree}_gtr_g_blens"])
+
+
+def test_reference_fixtures():
+    from dodonaphy_b200.engine import SubstModel
+
+    g = load_golden("prune.npz")
+    for i in range(int(g["n"])):
+        eng = _engine(g[f"{i}_masks"], g[f"{i}_weights"])
+        peel, blens = _dev(g[f"{i}_peel"]), _dev(g[f"{i}_blens"])
+        ll, grad = eng.loglik(peel, blens, SubstModel.jc69(), grad=True)
+        assert ll.item() == pytest.approx(float(g[f"{i}_jc_lnL"]), rel=RTOL), i
+        assert ll.item() == pytest.approx(float(g[f"{i}_lnL_cython"]), rel=RTOL), i
+        _assert_grad(grad[0].cpu().numpy(), g[f"{i}_jc_g_blens"])
+        m = SubstModel.gtr(g[f"{i}_rates"], g[f"{i}_freqs"])
+        ll, grad = eng.loglik(peel, blens, m, grad=True)
+        assert ll.item() == pytest.approx(float(g[f"{i}_gtr_lnL"]), rel=RTOL), i
+        _assert_grad(grad[0].cpu().numpy(), g[f"{i}_gtr_g_blens"])
+        # caller-supplied matrices (the "mats" argument of calculate_treelikelihood)
+        mats = _dev(g[f"{i}_gtr_mats"]).reshape(1, -1, 1, 4, 4)
+        ll3, _ = eng.loglik(peel, None, m, mats=mats)
+        assert ll3.item() == pytest.approx(float(g[f"{i}_gtr_lnL"]), rel=RTOL), i
+
+
+@pytest.mark.parametrize("S,L,B,K", [(2, 5, 1, 1), (3, 33, 2, 1), (8, 100, 5, 1), (16, 257, 4, 4), (64, 1000, 6, 4), (40, 70, 3, 2)])
+def test_batched_vs_oracle(S, L, B, K):
+    """Seeded synthetic batches (different topology per sample), JC69 and GTR, K categories in both
+    semantics (reference broadcasting = independent categories summed; MIX = discrete gamma)."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import hyp, nj, phylo
+
+    prob = synth.make_problem(S, L, B, D=3, seed=100 + S)
+    tips = [phylo.mask_to_partial(m) for m in prob["masks"]]
+    peels, blens = [], []
+    for b in range(B):
+        p, bl = nj.nj_hard(hyp.get_pdm_np(prob["xs"][b]))
+        peels.append(p)
+        blens.append(bl)
+    peels, blens = np.stack(peels), np.stack(blens)
+    eng = _engine(prob["masks"], prob["weights"])
+    rates = phylo.discrete_gamma_rates(0.5, K)
+    for model_name in ("JC69", "GTR"):
+        if model_name == "JC69":
+            m = SubstModel.jc69()
+            pfun = lambda t: phylo.jc69_p_t_torch(t)
+            freqs = np.full(4, 0.25)
+        else:
+            m = SubstModel.gtr(prob["rates"], prob["freqs"])
+            pfun = lambda t: phylo.gtr_p_t_torch(t, torch.tensor(prob["rates"]), torch.tensor(prob["freqs"]))
+            freqs = prob["freqs"]
+        for mix in ((False, True) if K > 1 else (False,)):
+            ll, grad = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=True)
+            ll_f, _ = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=False)
+            for b in range(B):
+                bt = torch.tensor(blens[b], requires_grad=True)
+                mats = pfun(bt[:, None] * torch.tensor(rates)[None, :])
+                ref = phylo.treelikelihood_torch([torch.tensor(t) for t in tips], torch.tensor(prob["weights"]),
+                                                 peels[b], mats, torch.tensor(freqs), gamma_mix=mix)
+                ref.backward()
+                assert ll[b].item() == pytest.approx(ref.item(), rel=RTOL), (model_name, mix, b)
+                assert ll_f[b].item() == pytest.approx(ref.item(), rel=RTOL)
+                _assert_grad(grad[b].cpu().numpy(), bt.grad.numpy())
+
+
+def test_shared_topology_and_determinism():
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import hyp, nj
+
+    prob = synth.make_problem(24, 300, 4, D=3, seed=7)
+    peel, bl = nj.nj_hard(hyp.get_pdm_np(prob["x"]))
+    eng = _engine(prob["masks"], prob["weights"])
+    blens = np.stack([bl * (1 + 0.1 * b) for b in range(4)])
+    m = SubstModel.gtr(prob["rates"], prob["freqs"])
+    ll1, g1 = eng.loglik(_dev(peel), _dev(blens), m, grad=True)
+    ll2, g2 = eng.loglik(_dev(np.stack([peel] * 4)), _dev(blens), m, grad=True)
+    assert torch.equal(ll1, ll2) and torch.equal(g1, g2)
+    ll3, g3 = eng.loglik(_dev(peel), _dev(blens), m, grad=True)
+    assert torch.equal(ll1, ll3) and torch.equal(g1, g3)  # run-to-run bit reproducible
+
+
+def test_argument_errors():
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    eng = PruneEngine(np.ones((4, 10), dtype=np.uint8), np.ones(10))
+    with pytest.raises(ValueError):
+        eng.loglik(_dev(np.zeros((3, 3), dtype=np.int64)), _dev(np.ones(5)), SubstModel.jc69())
+    with pytest.raises(ValueError):
+        eng.loglik(_dev(np.zeros((2, 3), dtype=np.int64)), _dev(np.ones(6)), SubstModel.jc69())
+    with pytest.raises(ValueError):
+        PruneEngine(np.ones((4, 10), dtype=np.uint8), np.ones(9))

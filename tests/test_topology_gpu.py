@@ -1,0 +1,142 @@
+"""GPU parity: K1 (pairwise hyperbolic distance) and K2 (hard / soft neighbour joining) through
+the C ABI, against fixtures produced by the real reference (tests/golden) and the CPU oracle.
+
+Bars (BASELINE.json north_star): NJ peels bit-exact; hard-NJ branch lengths bit-exact too (same
+operation order); floating point elsewhere within 1e-9 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+# ------------------------------------------------------------------ K1
+def test_pdm_reference_fixtures():
+    from dodonaphy_b200 import engine
+
+    g = load_golden("pdm.npz")
+    for i in range(int(g["n"])):
+        x, curv, mats, C = g[f"{i}_x"], float(g[f"{i}_curv"]), bool(g[f"{i}_matsumoto"]), g[f"{i}_C"]
+        for lift in ("up", "wrap"):
+            ours = engine.pdm_forward(_dev(x), curv, "torch", lift, mats).cpu().numpy()
+            np.testing.assert_allclose(ours, g[f"{i}_pdm_torch_{lift}"], rtol=1e-9, atol=1e-12)
+            assert np.array_equal(ours, ours.T)
+            gx, gc = engine.pdm_backward(_dev(x), _dev(C), curv, lift, mats)
+            ref = g[f"{i}_gx_{lift}"]
+            np.testing.assert_allclose(gx.cpu().numpy(), ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+            assert gc.item() == pytest.approx(float(g[f"{i}_gc_{lift}"][0]), rel=1e-9)
+        ours = engine.pdm_forward(_dev(x), curv, "numpy", "up", mats).cpu().numpy()
+        ref = g[f"{i}_pdm_np"]
+        off = ~np.eye(len(x), dtype=bool)
+        near = ref < 1e-6  # coincident points: acosh(1 + O(eps)) is rounding noise of size sqrt(eps)
+        np.testing.assert_allclose(ours[off & ~near], ref[off & ~near], rtol=1e-9, atol=1e-13)
+        # the NumPy twin leaves acosh(1+eps) ~ 2e-8 rounding noise on the diagonal (never read by NJ)
+        np.testing.assert_allclose(ours[~off | near], ref[~off | near], rtol=0, atol=1e-7)
+
+
+def test_pdm_batched_and_euclidean():
+    from dodonaphy_b200 import engine
+    from oracle import hyp
+
+    rng = np.random.default_rng(11)
+    x = rng.normal(0, 0.2, (5, 33, 4))
+    ours = engine.pdm_forward(_dev(x), -0.7).cpu().numpy()
+    for b in range(5):
+        np.testing.assert_allclose(ours[b], hyp.get_pdm_torch(x[b], -0.7), rtol=1e-10, atol=1e-13)
+    eu = engine.pdm_forward(_dev(x[0]), 0.0, "numpy").cpu().numpy()
+    np.testing.assert_allclose(eu, hyp.get_pdm_np(x[0], 0.0), rtol=1e-12, atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        engine.pdm_forward(_dev(x[0]), -1.0, "numpy", "wrap")
+    with pytest.raises(ValueError):
+        engine.pdm_forward(_dev(np.zeros((3, 40))), -1.0)
+
+
+# ------------------------------------------------------------------ K2 hard
+def test_nj_hard_reference_fixtures_bit_exact():
+    from dodonaphy_b200 import engine
+
+    g = load_golden("nj_hard.npz")
+    for i in range(int(g["n"])):
+        peel, blens = engine.nj_hard(_dev(g[f"{i}_pdm"]))
+        assert np.array_equal(peel.cpu().numpy(), g[f"{i}_peel"]), i
+        assert np.array_equal(blens.cpu().numpy(), g[f"{i}_blens"]), i
+
+
+@pytest.mark.parametrize("S,B", [(7, 9), (64, 16), (150, 3), (300, 2)])
+def test_nj_hard_batched_vs_oracle_bit_exact(S, B):
+    from dodonaphy_b200 import engine
+    from oracle import hyp, nj
+
+    rng = np.random.default_rng(S)
+    xs = rng.normal(0, 0.05, (B, S, 5))
+    pd = np.stack([hyp.get_pdm_np(x) for x in xs])
+    peel, blens = engine.nj_hard(_dev(pd))
+    for b in range(B if S <= 150 else 1):
+        p_ref, b_ref = nj.nj_hard(pd[b])
+        assert np.array_equal(peel[b].cpu().numpy(), p_ref)
+        assert np.array_equal(blens[b].cpu().numpy(), b_ref)
+    # every peel is a valid tree
+    from dodonaphy_b200.engine import validate_peel
+
+    validate_peel(peel.cpu().numpy(), S)
+
+
+# ------------------------------------------------------------------ K2 soft
+@pytest.mark.parametrize("exhaustive", [False, True])
+def test_nj_soft_reference_fixtures(exhaustive):
+    from dodonaphy_b200 import engine
+
+    g = load_golden("nj_soft.npz")
+    for i in range(int(g["n"])):
+        tau = float(g[f"{i}_tau"])
+        if tau < 1e-12 and not exhaustive:
+            continue  # tau = 1e-20: rounding-level ties, only the exhaustive enumeration is claimed
+        peel, blens, flags = engine.nj_soft(_dev(g[f"{i}_pdm"]), tau, exhaustive=exhaustive, return_flags=True)
+        if tau >= 1e-12:
+            assert int((flags & 12).sum().item()) == 0, (i, flags)
+        assert np.array_equal(peel.cpu().numpy(), g[f"{i}_peel"]), (i, tau)
+        np.testing.assert_allclose(blens.cpu().numpy(), g[f"{i}_blens"], rtol=1e-9, atol=1e-15)
+        gp = engine.nj_soft_backward(peel, flags, _dev(g[f"{i}_c"])).cpu().numpy()
+        ref = g[f"{i}_g_pdm"]
+        np.testing.assert_allclose(2 * gp, ref + ref.T, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("S,B", [(27, 4), (64, 8), (130, 2)])
+def test_nj_soft_batched_vs_oracle(S, B):
+    from dodonaphy_b200 import engine
+    from oracle import hyp, nj
+
+    rng = np.random.default_rng(1000 + S)
+    xs = rng.normal(0, 0.05, (B, S, 5))
+    pd = np.stack([hyp.get_pdm_torch(x) for x in xs])
+    peel, blens, flags = engine.nj_soft(_dev(pd), 1e-8, return_flags=True)
+    assert int((flags & 12).sum().item()) == 0
+    c = rng.normal(size=(B, 2 * S - 2))
+    gp = engine.nj_soft_backward(peel, flags, _dev(c)).cpu().numpy()
+    for b in range(B):
+        p_ref, b_ref = nj.nj_soft(pd[b], 1e-8)
+        assert np.array_equal(peel[b].cpu().numpy(), p_ref)
+        np.testing.assert_allclose(blens[b].cpu().numpy(), b_ref, rtol=1e-9, atol=1e-15)
+        if b == 0 and S <= 64:
+            t = torch.tensor(pd[b], requires_grad=True)
+            _, bt = nj.nj_soft_torch(t, 1e-8)
+            (bt * torch.tensor(c[b])).sum().backward()
+            ref = t.grad.numpy()
+            np.testing.assert_allclose(2 * gp[b], ref + ref.T, rtol=1e-9, atol=1e-12)
+
+
+def test_nj_soft_all_ties():
+    """test/test_peeler.py:343-348: six equidistant taxa must still give a valid peel."""
+    from dodonaphy_b200 import engine
+    from dodonaphy_b200.engine import validate_peel
+
+    pd = np.ones((6, 6)) - np.eye(6)
+    peel, blens = engine.nj_soft(_dev(pd), 1e-8)
+    validate_peel(peel.cpu().numpy(), 6)
+    assert peel.cpu().numpy().tolist() == [[4, 5, 6], [3, 6, 7], [2, 7, 8], [1, 8, 9], [0, 9, 10]]
