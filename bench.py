@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dodonaphy_b200 hot path (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): VI on a synthetic 64-taxon x 10 000-site-pattern alignment,
+GTR + Gamma4, 128 samples per step and per GPU, embedding dimension 5.  One *step* = one pass of the
+whole hot path over the batch:
+
+    locations -> pairwise hyperbolic distance -> soft NJ -> P(t) + pruning lnL -> d lnL/d blens
+              -> soft-NJ backward -> distance backward -> d lnL / d locations
+
+metric  = log-lik+grad evaluations per second expressed as taxa x site-patterns x samples / s.
+value   = device-timed (CUDA events, max over ranks), inputs resident in HBM.
+e2e     = the same through the public API with HOST buffers: pinned H2D of the step's locations and
+          D2H of lnL + gradients inside the timed region.
+roofline= algorithmic bytes of the pruning fwd+bwd kernel (V(5S-8)+2S per pattern and
+          sample, V = 32K) / that kernel's duration measured with CUDA events around the launch.
+cpu_baseline / --impl reference = the reference's CPU arithmetic (oracle port of its torch path, its
+          own compiled Cython modules from oracle/_ref where they exist) on this box's host cores,
+          on a bounded sample of the same workload.
+
+N > 1 (torchrun, one rank per GPU): samples are sharded, every rank holds its own 128 samples (weak
+scaling); the only exchange is an all_gather of the per-sample lnL (the IWAE logsumexp needs all of
+them).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "log-lik+grad evals/sec (taxa x sites x samples / s)"
+UNIT = "taxa*sites*samples/s"
+WORKLOADS = {
+    # name: S, L, B per GPU, D, K, gamma alpha, seed
+    "c2": dict(S=64, L=10000, B=128, D=5, K=4, alpha=0.5, seed=1002, tau=1e-8,
+               desc="VI, synthetic 64 taxa x 10k site patterns, GTR+G4, 128 samples/step, d5 (BASELINE.json configs[1])"),
+    "tiny": dict(S=16, L=500, B=8, D=3, K=4, alpha=0.5, seed=1, tau=1e-8, desc="debug"),
+}
+
+
+def algorithmic_bytes_fwd_bwd(S, K):
+    """bytes per (pattern, sample) of a fwd+bwd evaluation that materialises every
+    partial once: V(5S-8) + 2S with V = 32 K."""
+    V = 32 * K
+    return V * (5 * S - 8) + 2 * S
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        top = max(sm)
+        loaded = [v for v in sm if v >= 0.5 * top]
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm (the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(prob, cfg, n_trees, repeats=1):
+    """Reference CPU arithmetic for n_trees samples of the workload; returns (seconds per pass,
+    description).  Topology stage: the reference's soft NJ needs 209 s and 18.8 GB per 64-taxon tree
+    (SURVEY.md Appendix B), so its hard NJ (compiled Cpeeler.nj_np when available) stands in."""
+    import torch
+
+    from oracle import hyp, nj, phylo, refload
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = refload.load()
+    rates = torch.tensor(phylo.discrete_gamma_rates(cfg["alpha"], cfg["K"]))
+    tips = [torch.tensor(phylo.mask_to_partial(m)) for m in prob["masks"]]
+    w = torch.tensor(prob["weights"])
+    sub = torch.tensor(prob["rates"])
+    fr = torch.tensor(prob["freqs"])
+    kind = "port"
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for b in range(n_trees):
+            x = prob["xs"][b % prob["xs"].shape[0]]
+            if ref.compiled:
+                pdm = np.ascontiguousarray(ref.Chyp_np.get_pdm(x))
+                peel, blens = ref.Cpeeler.nj_np(pdm)
+                peel = np.asarray(peel)
+            else:
+                peel, blens = nj.nj_hard(hyp.get_pdm_np(x))
+            bt = torch.tensor(blens, requires_grad=True)
+            mats = phylo.gtr_p_t_torch(bt[:, None] * rates[None, :], sub, fr)
+            ll = phylo.treelikelihood_torch(tips, w, peel, mats, fr, gamma_mix=cfg["K"] > 1)
+            ll.backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    desc = (f"{n_trees} of {cfg['B']} samples: pdm + hard NJ ({'reference Cython modules (oracle/_ref)' if ref.compiled else 'oracle port'}; "
+            f"the reference's soft NJ is infeasible at {cfg['S']} taxa) + GTR P(t) + pruning lnL + autograd gradient "
+            f"(torch float64 port of phylo.py:132-139 / phylomodel.py:96-114), {torch.get_num_threads()} threads")
+    return best, desc, kind, torch.get_num_threads()
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dodonaphy_b200 import synth
+
+    prob = synth.make_problem(cfg["S"], cfg["L"], cfg["B"], D=cfg["D"], seed=cfg["seed"])
+    n_trees = args.cpu_trees
+    for _ in range(args.warmup):
+        cpu_reference(prob, cfg, max(1, n_trees // 4))
+    times = []
+    desc = kind = None
+    cores = 1
+    for _ in range(args.steps):
+        dt, desc, kind, cores = cpu_reference(prob, cfg, n_trees)
+        times.append(dt)
+    sec = sum(times) / len(times)
+    value = cfg["S"] * cfg["L"] * n_trees / sec
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "taxa": cfg["S"], "site_patterns": cfg["L"], "samples_per_step": n_trees,
+                       "rate_categories": cfg["K"], "model": "GTR+G4"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: dodonaphy_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from dodonaphy_b200 import _lib, synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    S, L, B, D, K = cfg["S"], cfg["L"], cfg["B"], cfg["D"], cfg["K"]
+    prob = synth.make_problem(S, L, B * world, D=D, seed=cfg["seed"])
+    xs = prob["xs"][rank * B:(rank + 1) * B]
+    model = SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(cfg["alpha"], K)
+    hp = HotPath(prob["masks"], prob["weights"], model, rates=rates, mix=K > 1, tau=cfg["tau"])
+    if args.grid:
+        hp.prune.grid_hint = args.grid
+    if args.threads:
+        hp.prune.threads_hint = args.threads
+    lib = _lib.load()
+    x_dev = torch.as_tensor(xs).cuda()
+    x_pin = torch.as_tensor(xs).pin_memory()
+    ll_pin = torch.empty(B, dtype=torch.float64).pin_memory()
+    gx_pin = torch.empty((B, S, D), dtype=torch.float64).pin_memory()
+    gathered = torch.empty(B * world, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step():
+        r = hp.value_and_grad(x_dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, r["lnL"])
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+    barrier()
+    assert torch.isfinite(r["lnL"]).all(), "non-finite lnL in warm-up"
+    assert int((r["flags"] & 12).sum().item()) == 0, "soft-NJ exactness guard tripped"
+
+    # ---- device-timed region: exactly K steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b_ in evs:  # instantiate the handles
+        a.record()
+        b_.record()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.2)
+    launches0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        lib.dodo_set_timing_events(evs[i][0].cuda_event, evs[i][1].cuda_event)
+        step()
+    t_end.record()
+    barrier()
+    lib.dodo_set_timing_events(None, None)
+    launches = _lib.launch_count() - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    kern_ms = [a.elapsed_time(b_) for a, b_ in evs]
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end region: host buffers in, host buffers out, every step
+    for _ in range(2):
+        hp.value_and_grad_host(x_pin, ll_pin, gx_pin)
+        torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        rr = hp.value_and_grad_host(x_pin, ll_pin, gx_pin)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rr["lnL"])
+        torch.cuda.current_stream().synchronize()  # the caller reads ll_pin / gx_pin now
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    ms_step = ms_total / args.steps
+    units = S * L * B * world
+    value = units / (ms_step * 1e-3)
+    e2e_value = units / (ms_e2e / args.steps * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = algorithmic_bytes_fwd_bwd(S, K) * L * B
+        k_ms = sum(kern_ms) / len(kern_ms)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            if tj.get("workload") == args.workload:
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": cfg["desc"], "taxa": S, "site_patterns": L, "samples_per_step_per_gpu": B,
+                           "global_samples_per_step": B * world, "rate_categories": K, "model": "GTR+G4", "embedding_dim": D,
+                           "soft_nj_tau": cfg["tau"], "sharding": "by sample; all_gather of per-sample lnL" if world > 1 else "single GPU",
+                           "l2": "pruning scratch streams ~20 GB/step through HBM (>> 126 MB L2); no flush needed"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 8),
+                        "d2h_bytes_per_step": int((ll_pin.numel() + gx_pin.numel()) * 8), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "dodo::prune_kernel<true> (fused pruning fwd+bwd)", "achieved": achieved,
+                             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                             "kernel_share_of_step": k_ms / ms_step, "traffic": traffic},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            from dodonaphy_b200 import synth as _s  # noqa: F401
+
+            dt, desc, kind, cores = cpu_reference(prob, cfg, args.cpu_trees)
+            line["cpu_baseline"] = {"value": S * L * args.cpu_trees / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": desc, "seconds": dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-trees", type=int, default=32, help="samples in the bounded CPU-baseline pass")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--grid", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "dodo_last_error": (C.c_char_p, []),
     "dodo_version": (C.c_int, []),
     "dodo_launch_count": (C.c_uint64, []),
+    "dodo_set_timing_events": (None, [C.c_void_p, C.c_void_p]),
     "dodo_prune_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
                                   C.POINTER(PrunePlan)]),
     "dodo_prune": (C.c_int, [C.POINTER(PrunePlan), C.POINTER(Model), C.POINTER(C.c_double), C.c_void_p,

@@ -18,6 +18,8 @@ STAMP = os.path.join(OUT_DIR, "build.stamp")
 SOURCES = ["common.cu", "prune.cu", "pdm.cu", "nj.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
+# tuning knobs (compile-time), e.g. DODO_DEFINES="-DDODO_PRUNE_MINBLOCKS=3"
+NVCC_FLAGS += os.environ.get("DODO_DEFINES", "").split()
 
 
 def nvcc_path():

@@ -8,6 +8,9 @@ namespace dodo {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+
+void timing_events(cudaEvent_t *a, cudaEvent_t *b) { *a = g_ev_start; *b = g_ev_stop; }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -35,4 +38,8 @@ int sm_count() {
 
 extern "C" const char *dodo_last_error(void) { return dodo::g_err; }
 extern "C" int dodo_version(void) { return 100; }
+extern "C" void dodo_set_timing_events(void *start, void *stop) {
+    dodo::g_ev_start = (cudaEvent_t)start;
+    dodo::g_ev_stop = (cudaEvent_t)stop;
+}
 extern "C" uint64_t dodo_launch_count(void) { return dodo::g_launches.load(); }

@@ -11,6 +11,7 @@ namespace dodo {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+void timing_events(cudaEvent_t *start, cudaEvent_t *stop);
 
 #define DODO_CHECK_ARG(cond, ...)            \
     do {                                     \

@@ -25,6 +25,9 @@
 namespace dodo {
 
 constexpr int MAX_K = 8;
+#ifndef DODO_PRUNE_MINBLOCKS
+#define DODO_PRUNE_MINBLOCKS 4
+#endif
 
 struct ModelDev {
     double U[16], Uinv[16], lam[4], Q[16], pi[4];
@@ -133,11 +136,16 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
 }
 
 // ------------------------------------------------------------------------------------------
-// Transition tables: P[b][e][k] (16 doubles) and, for tip edges, tiptab[b][t][k][mask][4] =
-// sum over the states allowed by the mask of the columns of P (== P . tip_partial exactly).
+// Transition tables, laid out so that one (sample, category) slab is contiguous and can be staged
+// into shared memory with coalesced 16-byte copies:
+//   tab[b][k] = { Pint[S-1][16] : P of the edge above internal node S+i (row-major; root row unused)
+//                 Ttip[S][5][4] : for tip edge t, the four columns of P and the row sums
+//                                 (== P . tip_partial for the masks A,C,G,T and N/?/-) }
 // ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t tab_doubles(int S) { return (size_t)(S - 1) * 16 + (size_t)S * 20; }
+
 __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens, const double *__restrict__ P_in,
-                                  int B, int S, int K, double *__restrict__ Pmat, double *__restrict__ tiptab) {
+                                  int B, int S, int K, double *__restrict__ tab) {
     const int E = 2 * S - 2;
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * E * K;
@@ -174,31 +182,28 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
                 }
         }
     }
-    {
-        double2 *out = reinterpret_cast<double2 *>(Pmat + gid * 16);
+    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S);
+    if (e >= S) {
+        double2 *out = reinterpret_cast<double2 *>(slab + (size_t)(e - S) * 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) out[i] = make_double2(P[2 * i], P[2 * i + 1]);
-    }
-    if (e < S) {
-        double2 *tt = reinterpret_cast<double2 *>(tiptab + (((size_t)b * S + e) * K + k) * 64);
-        for (int m = 0; m < 16; ++m) {
-            double v[4];
+    } else {
+        double2 *tt = reinterpret_cast<double2 *>(slab + (size_t)(S - 1) * 16 + (size_t)e * 20);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                double acc = 0.0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (m & (1 << j)) acc += P[i * 4 + j];
-                v[i] = acc;
-            }
-            tt[m * 2 + 0] = make_double2(v[0], v[1]);
-            tt[m * 2 + 1] = make_double2(v[2], v[3]);
+        for (int j = 0; j < 4; ++j) {
+            tt[j * 2 + 0] = make_double2(P[0 + j], P[4 + j]);
+            tt[j * 2 + 1] = make_double2(P[8 + j], P[12 + j]);
         }
+        double rs[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rs[i] = ((P[i * 4 + 0] + P[i * 4 + 1]) + P[i * 4 + 2]) + P[i * 4 + 3];
+        tt[8] = make_double2(rs[0], rs[1]);
+        tt[9] = make_double2(rs[2], rs[3]);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Main kernel
+// Main kernel: one thread = one site pattern; it walks the tree once per rate category.
 // ------------------------------------------------------------------------------------------
 struct PruneArgs {
     const uint8_t *tipmask;
@@ -206,118 +211,222 @@ struct PruneArgs {
     const double *weights;
     const int4 *ops;
     int ops_batch;  // 1 => shared topology
-    const double *Pmat;
-    const double *tiptab;
+    const double *tab;
     double2 *scratch;
     double *ll_part;  // [n_items]
     double *g_part;   // [n_items][E]
-    double *gm_part;  // [n_items][...] (GMATS)  -- reserved
     int B, S, L, K;
     int n_tiles, n_items, tile_patterns;
     int mix;
 };
 
+__host__ __device__ inline size_t prune_smem_bytes(int threads, int S, int K) {
+    const size_t nwarp = threads / 32, E = 2 * (size_t)S - 2;
+    size_t dbl = nwarp * E + (size_t)K * threads + nwarp + tab_doubles(S);
+    dbl = (dbl + 1) & ~(size_t)1;  // keep the int4 schedule 16-byte aligned
+    return dbl * sizeof(double) + (size_t)(S - 1) * sizeof(int4);
+}
+
+__device__ __forceinline__ V4 lds4(const double *p) {
+    double2 x = *reinterpret_cast<const double2 *>(p), y = *reinterpret_cast<const double2 *>(p + 2);
+    return V4{x.x, x.y, y.x, y.y};
+}
+
+// y = P x / y = P^T x with P (row-major) in shared memory (warp-uniform address -> broadcast)
+__device__ __forceinline__ V4 matvec_s(const double *P, const V4 &x) {
+    V4 r0 = lds4(P), r1 = lds4(P + 4), r2 = lds4(P + 8), r3 = lds4(P + 12);
+    V4 y;
+    y.a = fma(r0.d, x.d, fma(r0.c, x.c, fma(r0.b, x.b, r0.a * x.a)));
+    y.b = fma(r1.d, x.d, fma(r1.c, x.c, fma(r1.b, x.b, r1.a * x.a)));
+    y.c = fma(r2.d, x.d, fma(r2.c, x.c, fma(r2.b, x.b, r2.a * x.a)));
+    y.d = fma(r3.d, x.d, fma(r3.c, x.c, fma(r3.b, x.b, r3.a * x.a)));
+    return y;
+}
+
+__device__ __forceinline__ V4 matvecT_s(const double *P, const V4 &x) {
+    V4 r = lds4(P);
+    V4 y{r.a * x.a, r.b * x.a, r.c * x.a, r.d * x.a};
+    r = lds4(P + 4);
+    y.a = fma(r.a, x.b, y.a), y.b = fma(r.b, x.b, y.b), y.c = fma(r.c, x.b, y.c), y.d = fma(r.d, x.b, y.d);
+    r = lds4(P + 8);
+    y.a = fma(r.a, x.c, y.a), y.b = fma(r.b, x.c, y.b), y.c = fma(r.c, x.c, y.c), y.d = fma(r.d, x.c, y.d);
+    r = lds4(P + 12);
+    y.a = fma(r.a, x.d, y.a), y.b = fma(r.b, x.d, y.b), y.c = fma(r.c, x.d, y.c), y.d = fma(r.d, x.d, y.d);
+    return y;
+}
+
+// message of a tip: P . (indicator of the states allowed by the 4-bit mask)
+__device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, int m) {
+    const bool fast = (m == 15) || ((m & (m - 1)) == 0 && m != 0);
+    const int j = (m == 15) ? 4 : (__ffs(m | 16) - 1) & 3;
+    V4 v = lds4(T + j * 4);
+    if (__any_sync(0xffffffffu, !fast)) {
+        if (!fast) {  // IUPAC two/three-state codes: add the columns in state order (m == 0: nothing allowed)
+            v = V4{0, 0, 0, 0};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (m & (1 << jj)) {
+                    V4 c = lds4(T + jj * 4);
+                    v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d;
+                }
+        }
+    }
+    return v;
+}
+
+// an operand that is either a tip (mask byte prefetched) or an internal message (vector prefetched)
+struct Operand {
+    V4 v;
+    int m;
+};
+
 template <bool GRAD>
-__global__ void __launch_bounds__(256) prune_kernel(PruneArgs A, ModelDev md) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(256, DODO_PRUNE_MINBLOCKS) prune_kernel(PruneArgs A, ModelDev md) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nwarp = nthr >> 5;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
-    const int k = warp % K;
-    const int pg = warp / K;
-    double *gacc = smem;                     // [nwarp][E]
-    double *fx = smem + (size_t)nwarp * E;   // [nwarp][32]
-    double *red = fx + nwarp * 32;           // [nwarp]
+    const size_t tabn = tab_doubles(S);
+    double *tab_sm = reinterpret_cast<double *>(smem_raw);  // Pint[S-1][16] | Ttip[S][20]
+    double *T_sm = tab_sm + (size_t)(S - 1) * 16;
+    double *gacc = tab_sm + tabn;                           // [nwarp][E]
+    double *fx = gacc + (size_t)nwarp * E;                  // [K][nthr]
+    double *red = fx + (size_t)K * nthr;                    // [nwarp]
+    int4 *ops_sm = reinterpret_cast<int4 *>(smem_raw + (((tabn + (size_t)nwarp * E + (size_t)K * nthr + nwarp + 1) & ~(size_t)1) * sizeof(double)));  // [nops]
     if (GRAD) {
         for (int i = tid; i < nwarp * E; i += nthr) gacc[i] = 0.0;
     }
-    __syncthreads();
-    double2 *scr = A.scratch + (size_t)blockIdx.x * (size_t)(S - 1) * 2 * nthr;
-    const double rate_k = md.rates[k];
+    // scratch ring of this CTA: [k][node][half][thread]
+    double2 *scr0 = A.scratch + (size_t)blockIdx.x * (size_t)K * (S - 1) * 2 * nthr;
 
     for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int b = item / A.n_tiles;
         const int tile = item - b * A.n_tiles;
-        int p = tile * A.tile_patterns + pg * 32 + lane;
+        const int p = tile * A.tile_patterns + tid;
         const bool valid = p < A.L;
-        if (!valid) p = A.L - 1;
         const double wt = valid ? __ldg(A.weights + p) : 0.0;
-        const int4 *ops_b = A.ops + (size_t)(A.ops_batch == 1 ? 0 : b) * nops;
-        const double *Pm = A.Pmat + ((size_t)b * E * K + k) * 16;
-        const double *tt = A.tiptab + (((size_t)b * S) * K + k) * 64;
-        const uint8_t *tm = A.tipmask + p;
-
-        auto tip_msg = [&](int t) -> V4 {
-            int m = __ldg(tm + (size_t)t * A.ld_mask) & 15;
-            const double *row = tt + ((size_t)t * K) * 64 + m * 4;
-            double2 x = ldg2(row), y = ldg2(row + 2);
-            return V4{x.x, x.y, y.x, y.y};
+        const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
+        const double *tab_b = A.tab + (size_t)b * K * tabn;
+        __syncthreads();
+        {
+            const int4 *ops_b = A.ops + (size_t)(A.ops_batch == 1 ? 0 : b) * nops;
+            for (int i = tid; i < nops; i += nthr) ops_sm[i] = __ldg(ops_b + i);
+        }
+        auto stage_tables = [&](int k) {
+            __syncthreads();  // everyone is done with the previous slab
+            const double2 *src = reinterpret_cast<const double2 *>(tab_b + (size_t)k * tabn);
+            double2 *dst = reinterpret_cast<double2 *>(tab_sm);
+            for (int i = tid; i < (int)(tabn / 2); i += nthr) dst[i] = __ldg(src + i);
+            __syncthreads();
         };
-        auto ld_scr = [&](int idx) -> V4 {
-            double2 x = __ldcg(scr + ((size_t)idx * 2 + 0) * nthr + tid);
-            double2 y = __ldcg(scr + ((size_t)idx * 2 + 1) * nthr + tid);
-            return V4{x.x, x.y, y.x, y.y};
+        auto fetch = [&](int node, const double2 *scr) -> Operand {
+            Operand o;
+            if (node < S) {
+                o.m = __ldg(tm + (size_t)node * A.ld_mask) & 15;
+                o.v = V4{0, 0, 0, 0};
+            } else {
+                double2 x = __ldcg(scr + ((size_t)(node - S) * 2 + 0) * nthr + tid);
+                double2 y = __ldcg(scr + ((size_t)(node - S) * 2 + 1) * nthr + tid);
+                o.v = V4{x.x, x.y, y.x, y.y};
+                o.m = 0;
+            }
+            return o;
         };
-        auto st_scr = [&](int idx, const V4 &v) {
+        auto resolve = [&](int node, const Operand &o) -> V4 {
+            return node < S ? tip_message(T_sm + (size_t)node * 20, o.m) : o.v;
+        };
+        auto st_scr = [&](double2 *scr, int idx, const V4 &v) {
             __stcg(scr + ((size_t)idx * 2 + 0) * nthr + tid, make_double2(v.a, v.b));
             __stcg(scr + ((size_t)idx * 2 + 1) * nthr + tid, make_double2(v.c, v.d));
         };
 
-        // ---------------- forward (post-order) ----------------
-        V4 prev = V4{0, 0, 0, 0};
-        V4 rootL = prev;
-        for (int i = 0; i < nops; ++i) {
-            const int4 op = __ldg(ops_b + i);
-            V4 a = (op.x < S) ? tip_msg(op.x) : ld_scr(op.x - S);
-            V4 bv = (op.y < S) ? tip_msg(op.y) : prev;
-            V4 Lv = vmul(a, bv);
-            if (i == nops - 1) {
-                rootL = Lv;
-            } else {
-                prev = matvec_g(Pm + (size_t)op.z * K * 16, Lv);
-                if (GRAD || (op.w & 1)) st_scr(op.z - S, prev);
+        // ---------------- forward (post-order), one pass per rate category ----------------
+        double fsum = 0.0, ll = 0.0;
+        for (int k = 0; k < K; ++k) {
+            stage_tables(k);
+            double2 *scr = scr0 + (size_t)k * (S - 1) * 2 * nthr;
+            V4 prev = V4{0, 0, 0, 0};
+            V4 rootL = prev;
+            int4 opc = ops_sm[0];
+            Operand a_c = fetch(opc.x, scr), b_c = fetch(opc.y < S ? opc.y : 0, scr);
+            for (int i = 0; i < nops; ++i) {
+                int4 opn = opc;
+                Operand a_n = a_c, b_n = b_c;
+                if (i + 1 < nops) {
+                    // operands of the next join: an internal `a` was stored >= 2 joins ago
+                    opn = ops_sm[i + 1];
+                    a_n = fetch(opn.x, scr);
+                    if (opn.y < S) b_n = fetch(opn.y, scr);
+                }
+                V4 av = resolve(opc.x, a_c);
+                V4 bv = (opc.y < S) ? resolve(opc.y, b_c) : prev;
+                V4 Lv = vmul(av, bv);
+                if (i == nops - 1) {
+                    rootL = Lv;
+                } else {
+                    prev = matvec_s(tab_sm + (size_t)(opc.z - S) * 16, Lv);
+                    if (GRAD || (opc.w & 1)) st_scr(scr, opc.z - S, prev);
+                }
+                opc = opn; a_c = a_n; b_c = b_n;
             }
+            double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
+            if (GRAD) fx[(size_t)k * nthr + tid] = fk;
+            fsum += fk;
+            if (!A.mix) ll += wt * log(fk);
         }
-        double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
-        double f = fk;
-        if (A.mix && K > 1) {
-            fx[warp * 32 + lane] = fk;
-            __syncthreads();
-            double s = 0.0;
-            for (int kk = 0; kk < K; ++kk) s += fx[(pg * K + kk) * 32 + lane];
-            f = s / (double)K;
-        }
-        double ll = 0.0;
-        if (!(A.mix && K > 1) || k == 0) ll = wt * log(f);
+        const double f = fsum / (double)K;
+        if (A.mix) ll = wt * log(f);
         ll = warp_sum(ll);
         if (lane == 0) red[warp] = ll;
 
         // ---------------- backward (the same schedule reversed = pre-order) ----------------
         if (GRAD) {
-            const double sc = (A.mix && K > 1) ? wt / (f * (double)K) : wt / f;
-            V4 wprev = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
             double *gw = gacc + (size_t)warp * E;
-            for (int i = nops - 1; i >= 0; --i) {
-                const int4 op = __ldg(ops_b + i);
-                V4 w = (op.w & 1) ? ld_scr(op.z - S) : wprev;
-                const bool ai = op.x >= S, bi = op.y >= S;
-                V4 a = ai ? ld_scr(op.x - S) : tip_msg(op.x);
-                V4 bv = bi ? ld_scr(op.y - S) : tip_msg(op.y);
-                V4 ua = vmul(w, bv);
-                V4 ub = vmul(w, a);
-                double ga = rate_k * uQx(md.Q, ua, a);
-                double gb = rate_k * uQx(md.Q, ub, bv);
-                ga = warp_sum(ga);
-                gb = warp_sum(gb);
-                if (lane == 0) {
-                    gw[op.x] += ga;
-                    gw[op.y] += gb;
+            for (int k = 0; k < K; ++k) {
+                stage_tables(k);
+                double2 *scr = scr0 + (size_t)k * (S - 1) * 2 * nthr;
+                const double rate_k = md.rates[k];
+                const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(size_t)k * nthr + tid];
+                V4 wprev = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
+                int4 opc = ops_sm[nops - 1];
+                Operand a_c = fetch(opc.x, scr), b_c = fetch(opc.y, scr);
+                V4 w_c = wprev;
+                for (int i = nops - 1; i >= 0; --i) {
+                    int4 opn = opc;
+                    Operand a_n = a_c, b_n = b_c;
+                    V4 w_n = w_c;
+                    if (i > 0) {
+                        // nothing stored in this iteration is read by join i-1 (its own upper message,
+                        // when it comes from scratch, was stored by an ancestor's join)
+                        opn = ops_sm[i - 1];
+                        a_n = fetch(opn.x, scr);
+                        b_n = fetch(opn.y, scr);
+                        if (opn.w & 1) {
+                            double2 x = __ldcg(scr + ((size_t)(opn.z - S) * 2 + 0) * nthr + tid);
+                            double2 y = __ldcg(scr + ((size_t)(opn.z - S) * 2 + 1) * nthr + tid);
+                            w_n = V4{x.x, x.y, y.x, y.y};
+                        }
+                    }
+                    const V4 w = (opc.w & 1) ? w_c : wprev;
+                    const bool ai = opc.x >= S, bi = opc.y >= S;
+                    const V4 av = resolve(opc.x, a_c), bv = resolve(opc.y, b_c);
+                    V4 ua = vmul(w, bv);
+                    V4 ub = vmul(w, av);
+                    double ga = rate_k * uQx(md.Q, ua, av);
+                    double gb = rate_k * uQx(md.Q, ub, bv);
+                    ga = warp_sum(ga);
+                    gb = warp_sum(gb);
+                    if (lane == 0) {
+                        gw[opc.x] += ga;
+                        gw[opc.y] += gb;
+                    }
+                    if (ai) st_scr(scr, opc.x - S, matvecT_s(tab_sm + (size_t)(opc.x - S) * 16, ua));
+                    if (bi) wprev = matvecT_s(tab_sm + (size_t)(opc.y - S) * 16, ub);
+                    opc = opn; a_c = a_n; b_c = b_n; w_c = w_n;
                 }
-                if (ai) st_scr(op.x - S, matvecT_g(Pm + (size_t)op.x * K * 16, ua));
-                if (bi) wprev = matvecT_g(Pm + (size_t)op.y * K * 16, ub);
             }
         }
         __syncthreads();
@@ -337,7 +446,6 @@ __global__ void __launch_bounds__(256) prune_kernel(PruneArgs A, ModelDev md) {
                 gp[e] = s;
             }
         }
-        __syncthreads();
     }
 }
 
@@ -379,31 +487,53 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     }
     memset(plan, 0, sizeof(*plan));
     plan->B = B; plan->S = S; plan->L = L; plan->K = K; plan->flags = flags;
-    int groups = K <= 8 ? 8 / K : 1;
-    if (groups < 1) groups = 1;
-    int threads = 32 * K * groups;
+    int threads = 256;
     if (threads_hint > 0) {
-        DODO_CHECK_ARG(threads_hint % (32 * K) == 0 && threads_hint <= 256,
-                       "dodo_prune_plan: threads must be a multiple of 32*K and <= 256");
+        DODO_CHECK_ARG(threads_hint % 32 == 0 && threads_hint <= 256, "dodo_prune_plan: threads must be a multiple of 32, <= 256");
         threads = threads_hint;
-        groups = threads / (32 * K);
+    }
+    while (threads > 32 && L <= threads / 2) threads /= 2;  // tiny alignments: do not idle most of a CTA
+    size_t smem = prune_smem_bytes(threads, S, K);
+    while (smem > 227 * 1024 && threads > 32) {
+        threads /= 2;
+        smem = prune_smem_bytes(threads, S, K);
+    }
+    if (smem > 227 * 1024) {
+        set_error("dodo_prune_plan: %d taxa need %zu bytes of shared memory per CTA (limit 227 KB)", S, smem);
+        return DODO_ENOTIMPL;
     }
     plan->threads = threads;
-    plan->tile_patterns = 32 * groups;
+    plan->tile_patterns = threads;
     plan->n_tiles = (L + plan->tile_patterns - 1) / plan->tile_patterns;
     long long items = (long long)B * plan->n_tiles;
     DODO_CHECK_ARG(items < (1ll << 31), "dodo_prune_plan: too many work items");
     plan->n_items = (int)items;
-    int grid = grid_hint > 0 ? grid_hint : 2 * sm_count();
+    int grid = grid_hint;
+    if (grid <= 0) {
+        // persistent grid: every CTA the SMs can hold at once (a multiple of the SM count)
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(prune_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        int per_sm = 0;
+        cudaError_t e = (flags & DODO_PRUNE_GRAD)
+                            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true>, threads, smem)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false>, threads, smem);
+        if (e != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        grid = per_sm * sm_count();
+    }
     if (grid > plan->n_items) grid = plan->n_items;
     plan->grid = grid;
     const uint64_t E = 2ull * S - 2, nI = S - 1;
     uint64_t off = 0;
     plan->off_ops = off;     off = align_up(off + (uint64_t)B * nI * sizeof(int4), 256);
     plan->off_sched = off;   off = align_up(off + (uint64_t)B * 6 * S * sizeof(int), 256);
-    plan->off_pmat = off;    off = align_up(off + (uint64_t)B * E * K * 16 * sizeof(double), 256);
-    plan->off_tiptab = off;  off = align_up(off + (uint64_t)B * S * K * 64 * sizeof(double), 256);
-    plan->off_scratch = off; off = align_up(off + (uint64_t)grid * nI * 2 * threads * sizeof(double2), 256);
+    plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S) * sizeof(double), 256);
+    plan->off_tiptab = off;
+    plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * 2 * threads * sizeof(double2), 256);
     plan->off_ll_part = off; off = align_up(off + (uint64_t)plan->n_items * sizeof(double), 256);
     plan->off_g_part = off;
     if (flags & DODO_PRUNE_GRAD) off = align_up(off + (uint64_t)plan->n_items * E * sizeof(double), 256);
@@ -441,8 +571,7 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
 
     int4 *ops = (int4 *)(ws + plan->off_ops);
     int *sched = (int *)(ws + plan->off_sched);
-    double *Pmat = (double *)(ws + plan->off_pmat);
-    double *tiptab = (double *)(ws + plan->off_tiptab);
+    double *tab = (double *)(ws + plan->off_pmat);
 
     {
         int nb = peel_batch;
@@ -451,21 +580,22 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     }
     {
         size_t total = (size_t)B * E * K;
-        transition_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(md, d_blens, d_P_in, B, S, K, Pmat, tiptab);
+        transition_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(md, d_blens, d_P_in, B, S, K, tab);
         DODO_LAUNCH_CHECK();
     }
     PruneArgs A;
     A.tipmask = d_tipmask; A.ld_mask = ld_mask; A.weights = d_weights;
-    A.ops = ops; A.ops_batch = peel_batch; A.Pmat = Pmat; A.tiptab = tiptab;
+    A.ops = ops; A.ops_batch = peel_batch; A.tab = tab;
     A.scratch = (double2 *)(ws + plan->off_scratch);
     A.ll_part = (double *)(ws + plan->off_ll_part);
     A.g_part = (double *)(ws + plan->off_g_part);
-    A.gm_part = nullptr;
     A.B = B; A.S = S; A.L = L; A.K = K;
     A.n_tiles = plan->n_tiles; A.n_items = plan->n_items; A.tile_patterns = plan->tile_patterns;
-    A.mix = (plan->flags & DODO_PRUNE_MIX) ? 1 : 0;
-    const int nwarp = plan->threads / 32;
-    size_t smem = ((size_t)nwarp * E + (size_t)nwarp * 32 + nwarp) * sizeof(double);
+    A.mix = ((plan->flags & DODO_PRUNE_MIX) && K > 1) ? 1 : 0;
+    size_t smem = prune_smem_bytes(plan->threads, S, K);
+    cudaEvent_t ev0, ev1;
+    timing_events(&ev0, &ev1);
+    if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
     if (grad) {
         if (smem > 48 * 1024)
             DODO_CUDA(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -476,6 +606,7 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
         prune_kernel<false><<<plan->grid, plan->threads, smem, stream>>>(A, md);
     }
     DODO_LAUNCH_CHECK();
+    if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev1, stream));
     {
         int total = B * (E + 1);
         prune_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(A.ll_part, A.g_part, B, plan->n_tiles, E, d_loglik,

@@ -66,6 +66,19 @@ class SubstModel:
         pi = freqs if root_freqs is None else np.asarray(root_freqs, dtype=np.float64)
         return SubstModel(_lib.MODEL_EIGEN, spi @ V, lam, np.linalg.inv(V) @ sp, Q, pi)
 
+    @staticmethod
+    def discrete_gamma(alpha, K):
+        """Yang (1994) mean-rate discrete gamma categories (shape = rate = alpha; mean 1).
+        New functionality: the reference has no rate heterogeneity."""
+        if K == 1:
+            return np.ones(1)
+        from scipy.special import gammainc
+        from scipy.stats import gamma
+
+        cuts = gamma.ppf(np.arange(1, K) / K, a=alpha, scale=1.0 / alpha)
+        cdf = np.concatenate([[0.0], gammainc(alpha + 1.0, cuts * alpha), [1.0]])
+        return (cdf[1:] - cdf[:-1]) * K
+
     def c_struct(self):
         m = _lib.Model()
         for i in range(16):

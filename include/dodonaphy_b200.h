@@ -32,6 +32,10 @@ const char *dodo_last_error(void);
 int dodo_version(void);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t dodo_launch_count(void);
+/* Measurement hook: when both handles (cudaEvent_t) are non-NULL, dodo_prune records `start`
+ * immediately before and `stop` immediately after its main pruning kernel on the caller's stream,
+ * so that a benchmark can time that kernel alone without a profiler.  Pass NULLs to switch off. */
+void dodo_set_timing_events(void *start, void *stop);
 
 /* ------------------------------------------------------------------------------------------
  * Substitution model.  P(t) = U diag(exp(lam t)) Uinv, dP/dt = Q P.
