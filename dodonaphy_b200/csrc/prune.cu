@@ -26,7 +26,7 @@ namespace dodo {
 
 constexpr int MAX_K = 8;
 #ifndef DODO_PRUNE_MINBLOCKS
-#define DODO_PRUNE_MINBLOCKS 4
+#define DODO_PRUNE_MINBLOCKS 3
 #endif
 
 struct ModelDev {
@@ -220,16 +220,29 @@ struct PruneArgs {
     int mix;
 };
 
-__host__ __device__ inline size_t prune_smem_bytes(int threads, int S, int K) {
+// shared memory: tables | gacc[nwarp][E] | fx[K][threads] | red[nwarp] | ops int4[S+2] | sel u8[S][threads]
+__host__ __device__ inline size_t prune_smem_dbl(int threads, int S, int K) {
     const size_t nwarp = threads / 32, E = 2 * (size_t)S - 2;
     size_t dbl = nwarp * E + (size_t)K * threads + nwarp + tab_doubles(S);
-    dbl = (dbl + 1) & ~(size_t)1;  // keep the int4 schedule 16-byte aligned
-    return dbl * sizeof(double) + (size_t)(S - 1) * sizeof(int4);
+    return (dbl + 1) & ~(size_t)1;  // keep the int4 schedule 16-byte aligned
+}
+__host__ __device__ inline size_t prune_smem_bytes(int threads, int S, int K) {
+    return prune_smem_dbl(threads, S, K) * sizeof(double) + (size_t)(S + 2) * sizeof(int4) + (size_t)S * threads;
 }
 
 __device__ __forceinline__ V4 lds4(const double *p) {
     double2 x = *reinterpret_cast<const double2 *>(p), y = *reinterpret_cast<const double2 *>(p + 2);
     return V4{x.x, x.y, y.x, y.y};
+}
+
+// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100), L1-bypassing: one message per access
+__device__ __forceinline__ V4 ldg256(const V4 *p) {
+    V4 r;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(V4 *p, const V4 &v) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
 
 // y = P x / y = P^T x with P (row-major) in shared memory (warp-uniform address -> broadcast)
@@ -255,17 +268,24 @@ __device__ __forceinline__ V4 matvecT_s(const double *P, const V4 &x) {
     return y;
 }
 
-// message of a tip: P . (indicator of the states allowed by the 4-bit mask)
-__device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, int m) {
-    const bool fast = (m == 15) || ((m & (m - 1)) == 0 && m != 0);
-    const int j = (m == 15) ? 4 : (__ffs(m | 16) - 1) & 3;
-    V4 v = lds4(T + j * 4);
-    if (__any_sync(0xffffffffu, !fast)) {
-        if (!fast) {  // IUPAC two/three-state codes: add the columns in state order (m == 0: nothing allowed)
+// tip selector byte: low nibble = IUPAC mask; high nibble = row of Ttip (0..3 one-hot state, 4 = all
+// four states) or 7 = any other combination (handled by summing columns)
+__device__ __forceinline__ unsigned encode_sel(unsigned m) {
+    m &= 15u;
+    unsigned j = (m == 15u) ? 4u : ((m != 0u && (m & (m - 1u)) == 0u) ? (unsigned)(__ffs(m) - 1) : 7u);
+    return m | (j << 4);
+}
+
+// message of a tip = P . (indicator of the states allowed by its mask)
+__device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, unsigned sel) {
+    const unsigned j = sel >> 4;
+    V4 v = lds4(T + (j & 3u) * 4 + (j & 4u) * 4);
+    if (__any_sync(0xffffffffu, j == 7u)) {
+        if (j == 7u) {  // two/three-state codes: add the columns in state order (mask 0: nothing allowed)
             v = V4{0, 0, 0, 0};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-                if (m & (1 << jj)) {
+                if (sel & (1u << jj)) {
                     V4 c = lds4(T + jj * 4);
                     v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d;
                 }
@@ -274,106 +294,119 @@ __device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, int m) {
     return v;
 }
 
-// an operand that is either a tip (mask byte prefetched) or an internal message (vector prefetched)
-struct Operand {
-    V4 v;
-    int m;
-};
+// sum x over the warp into lane 0 and y into lane 16 with 5 shuffles (fixed order)
+__device__ __forceinline__ double warp_sum2(double x, double y, int lane) {
+    const bool hi = lane & 16;
+    double keep = hi ? y : x, send = hi ? x : y;
+    keep += shfl_xor_d(send, 16);
+    keep += shfl_xor_d(keep, 8);
+    keep += shfl_xor_d(keep, 4);
+    keep += shfl_xor_d(keep, 2);
+    keep += shfl_xor_d(keep, 1);
+    return keep;
+}
 
 template <bool GRAD>
 __global__ void __launch_bounds__(256, DODO_PRUNE_MINBLOCKS) prune_kernel(PruneArgs A, ModelDev md) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int nwarp = nthr >> 5;
+    const unsigned tid = threadIdx.x;
+    const unsigned nthr = blockDim.x;
+    const unsigned lane = tid & 31u;
+    const unsigned warp = tid >> 5;
+    const unsigned nwarp = nthr >> 5;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
-    const size_t tabn = tab_doubles(S);
+    const unsigned tabn = (unsigned)tab_doubles(S);
     double *tab_sm = reinterpret_cast<double *>(smem_raw);  // Pint[S-1][16] | Ttip[S][20]
-    double *T_sm = tab_sm + (size_t)(S - 1) * 16;
-    double *gacc = tab_sm + tabn;                           // [nwarp][E]
-    double *fx = gacc + (size_t)nwarp * E;                  // [K][nthr]
-    double *red = fx + (size_t)K * nthr;                    // [nwarp]
-    int4 *ops_sm = reinterpret_cast<int4 *>(smem_raw + (((tabn + (size_t)nwarp * E + (size_t)K * nthr + nwarp + 1) & ~(size_t)1) * sizeof(double)));  // [nops]
+    double *T_sm = tab_sm + (unsigned)(S - 1) * 16u;
+    double *gacc = tab_sm + tabn;                            // [nwarp][E]
+    double *fx = gacc + nwarp * (unsigned)E;                 // [K][nthr]
+    double *red = fx + (unsigned)K * nthr;                   // [nwarp]
+    int4 *ops_sm = reinterpret_cast<int4 *>(smem_raw + prune_smem_dbl(nthr, S, K) * sizeof(double));  // [S+2]
+    uint8_t *sel_sm = reinterpret_cast<uint8_t *>(ops_sm + (S + 2)) + tid;                            // [S][nthr]
     if (GRAD) {
-        for (int i = tid; i < nwarp * E; i += nthr) gacc[i] = 0.0;
+        for (unsigned i = tid; i < nwarp * (unsigned)E; i += nthr) gacc[i] = 0.0;
     }
-    // scratch ring of this CTA: [k][node][half][thread]
-    double2 *scr0 = A.scratch + (size_t)blockIdx.x * (size_t)K * (S - 1) * 2 * nthr;
+    // scratch ring of this CTA: [k][node][thread] x 32 B
+    V4 *scr0 = reinterpret_cast<V4 *>(A.scratch) + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid;
+    double *gw = gacc + warp * (unsigned)E;
 
+    auto tipmsg = [&](int t) -> V4 { return tip_message(T_sm + (unsigned)t * 20u, sel_sm[(unsigned)t * nthr]); };
+
+#pragma unroll 1
     for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int b = item / A.n_tiles;
         const int tile = item - b * A.n_tiles;
-        const int p = tile * A.tile_patterns + tid;
+        const int p = tile * A.tile_patterns + (int)tid;
         const bool valid = p < A.L;
         const double wt = valid ? __ldg(A.weights + p) : 0.0;
-        const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
         const double *tab_b = A.tab + (size_t)b * K * tabn;
         __syncthreads();
         {
+            // schedule of this sample, re-encoded: child code < 0 -> tip ~code, else internal index;
+            // entries 0 and nops+1 are harmless dummies so that the one-ahead prefetch needs no bounds test
             const int4 *ops_b = A.ops + (size_t)(A.ops_batch == 1 ? 0 : b) * nops;
-            for (int i = tid; i < nops; i += nthr) ops_sm[i] = __ldg(ops_b + i);
+            for (int i = tid; i < nops + 2; i += nthr) {
+                int4 o = make_int4(~0, ~0, 0, 4);
+                if (i >= 1 && i <= nops) {
+                    o = __ldg(ops_b + (i - 1));
+                    o.x = o.x < S ? ~o.x : o.x - S;
+                    o.y = o.y < S ? ~o.y : o.y - S;
+                    o.z -= S;
+                }
+                ops_sm[i] = o;
+            }
+            // tip selectors of this thread's pattern (thread-private column of sel_sm)
+            const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
+            for (int t = 0; t < S; ++t) sel_sm[(unsigned)t * nthr] = (uint8_t)encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
         }
         auto stage_tables = [&](int k) {
-            __syncthreads();  // everyone is done with the previous slab
+            __syncthreads();  // everyone is done with the previous slab (and the schedule is visible)
             const double2 *src = reinterpret_cast<const double2 *>(tab_b + (size_t)k * tabn);
             double2 *dst = reinterpret_cast<double2 *>(tab_sm);
-            for (int i = tid; i < (int)(tabn / 2); i += nthr) dst[i] = __ldg(src + i);
+            for (unsigned i = tid; i < tabn / 2; i += nthr) dst[i] = __ldg(src + i);
             __syncthreads();
-        };
-        auto fetch = [&](int node, const double2 *scr) -> Operand {
-            Operand o;
-            if (node < S) {
-                o.m = __ldg(tm + (size_t)node * A.ld_mask) & 15;
-                o.v = V4{0, 0, 0, 0};
-            } else {
-                double2 x = __ldcg(scr + ((size_t)(node - S) * 2 + 0) * nthr + tid);
-                double2 y = __ldcg(scr + ((size_t)(node - S) * 2 + 1) * nthr + tid);
-                o.v = V4{x.x, x.y, y.x, y.y};
-                o.m = 0;
-            }
-            return o;
-        };
-        auto resolve = [&](int node, const Operand &o) -> V4 {
-            return node < S ? tip_message(T_sm + (size_t)node * 20, o.m) : o.v;
-        };
-        auto st_scr = [&](double2 *scr, int idx, const V4 &v) {
-            __stcg(scr + ((size_t)idx * 2 + 0) * nthr + tid, make_double2(v.a, v.b));
-            __stcg(scr + ((size_t)idx * 2 + 1) * nthr + tid, make_double2(v.c, v.d));
         };
 
         // ---------------- forward (post-order), one pass per rate category ----------------
         double fsum = 0.0, ll = 0.0;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
             stage_tables(k);
-            double2 *scr = scr0 + (size_t)k * (S - 1) * 2 * nthr;
+            V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
             V4 prev = V4{0, 0, 0, 0};
             V4 rootL = prev;
-            int4 opc = ops_sm[0];
-            Operand a_c = fetch(opc.x, scr), b_c = fetch(opc.y < S ? opc.y : 0, scr);
-            for (int i = 0; i < nops; ++i) {
-                int4 opn = opc;
-                Operand a_n = a_c, b_n = b_c;
-                if (i + 1 < nops) {
-                    // operands of the next join: an internal `a` was stored >= 2 joins ago
-                    opn = ops_sm[i + 1];
-                    a_n = fetch(opn.x, scr);
-                    if (opn.y < S) b_n = fetch(opn.y, scr);
-                }
-                V4 av = resolve(opc.x, a_c);
-                V4 bv = (opc.y < S) ? resolve(opc.y, b_c) : prev;
-                V4 Lv = vmul(av, bv);
-                if (i == nops - 1) {
+            // join i uses (Ac, Bc); the operands of join i+1 are fetched into (An, Bn) meanwhile.
+            auto step = [&](int i, const V4 &Ac, const V4 &Bc, V4 &An, V4 &Bn) {
+                const int4 o = ops_sm[i];
+                const int4 on = ops_sm[i + 1];
+                if (on.x < 0) An = tipmsg(~on.x);
+                else An = ldg256(scr + (unsigned)on.x * nthr);  // stored >= 2 joins ago (schedule_kernel)
+                if (on.y < 0) Bn = tipmsg(~on.y);
+                const V4 bv = (o.y < 0) ? Bc : prev;
+                const V4 Lv = vmul(Ac, bv);
+                if (i == nops) {
                     rootL = Lv;
                 } else {
-                    prev = matvec_s(tab_sm + (size_t)(opc.z - S) * 16, Lv);
-                    if (GRAD || (opc.w & 1)) st_scr(scr, opc.z - S, prev);
+                    prev = matvec_s(tab_sm + (unsigned)o.z * 16u, Lv);
+                    if (GRAD || (o.w & 1)) stg256(scr + (unsigned)o.z * nthr, prev);
                 }
-                opc = opn; a_c = a_n; b_c = b_n;
+            };
+            V4 A0, B0, A1, B1;
+            {
+                const int4 o1 = ops_sm[1];
+                A0 = o1.x < 0 ? tipmsg(~o1.x) : ldg256(scr + (unsigned)o1.x * nthr);
+                B0 = tipmsg(o1.y < 0 ? ~o1.y : 0);
+                A1 = A0; B1 = B0;
             }
+            int i = 1;
+#pragma unroll 1
+            for (; i + 1 <= nops; i += 2) {
+                step(i, A0, B0, A1, B1);
+                step(i + 1, A1, B1, A0, B0);
+            }
+            if (i <= nops) step(i, A0, B0, A1, B1);
             double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
-            if (GRAD) fx[(size_t)k * nthr + tid] = fk;
+            if (GRAD) fx[(unsigned)k * nthr + tid] = fk;
             fsum += fk;
             if (!A.mix) ll += wt * log(fk);
         }
@@ -384,64 +417,65 @@ __global__ void __launch_bounds__(256, DODO_PRUNE_MINBLOCKS) prune_kernel(PruneA
 
         // ---------------- backward (the same schedule reversed = pre-order) ----------------
         if (GRAD) {
-            double *gw = gacc + (size_t)warp * E;
+#pragma unroll 1
             for (int k = 0; k < K; ++k) {
                 stage_tables(k);
-                double2 *scr = scr0 + (size_t)k * (S - 1) * 2 * nthr;
+                V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
                 const double rate_k = md.rates[k];
-                const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(size_t)k * nthr + tid];
+                const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(unsigned)k * nthr + tid];
                 V4 wprev = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
-                int4 opc = ops_sm[nops - 1];
-                Operand a_c = fetch(opc.x, scr), b_c = fetch(opc.y, scr);
-                V4 w_c = wprev;
-                for (int i = nops - 1; i >= 0; --i) {
-                    int4 opn = opc;
-                    Operand a_n = a_c, b_n = b_c;
-                    V4 w_n = w_c;
-                    if (i > 0) {
-                        // nothing stored in this iteration is read by join i-1 (its own upper message,
-                        // when it comes from scratch, was stored by an ancestor's join)
-                        opn = ops_sm[i - 1];
-                        a_n = fetch(opn.x, scr);
-                        b_n = fetch(opn.y, scr);
-                        if (opn.w & 1) {
-                            double2 x = __ldcg(scr + ((size_t)(opn.z - S) * 2 + 0) * nthr + tid);
-                            double2 y = __ldcg(scr + ((size_t)(opn.z - S) * 2 + 1) * nthr + tid);
-                            w_n = V4{x.x, x.y, y.x, y.y};
-                        }
+                // join i uses (Ac, Bc, Wc); operands of join i-1 are fetched into (An, Bn, Wn) meanwhile:
+                // nothing stored by join i is read by join i-1 (its upper message, when it comes from
+                // scratch, was stored by an ancestor's join; its children are other nodes)
+                auto step = [&](int i, const V4 &Ac, const V4 &Bc, const V4 &Wc, V4 &An, V4 &Bn, V4 &Wn) {
+                    const int4 o = ops_sm[i];
+                    const int4 on = ops_sm[i - 1];
+                    if (on.x < 0) An = tipmsg(~on.x); else An = ldg256(scr + (unsigned)on.x * nthr);
+                    if (on.y < 0) Bn = tipmsg(~on.y); else Bn = ldg256(scr + (unsigned)on.y * nthr);
+                    if (on.w & 1) Wn = ldg256(scr + (unsigned)on.z * nthr);
+                    const V4 w = (o.w & 1) ? Wc : wprev;
+                    const V4 ua = vmul(w, Bc);
+                    const V4 ub = vmul(w, Ac);
+                    const double ga = rate_k * uQx(md.Q, ua, Ac);
+                    const double gb = rate_k * uQx(md.Q, ub, Bc);
+                    const double g2 = warp_sum2(ga, gb, lane);
+                    if ((lane & 15u) == 0u) {
+                        const int c = lane ? o.y : o.x;
+                        gw[c < 0 ? ~c : c + S] += g2;
                     }
-                    const V4 w = (opc.w & 1) ? w_c : wprev;
-                    const bool ai = opc.x >= S, bi = opc.y >= S;
-                    const V4 av = resolve(opc.x, a_c), bv = resolve(opc.y, b_c);
-                    V4 ua = vmul(w, bv);
-                    V4 ub = vmul(w, av);
-                    double ga = rate_k * uQx(md.Q, ua, av);
-                    double gb = rate_k * uQx(md.Q, ub, bv);
-                    ga = warp_sum(ga);
-                    gb = warp_sum(gb);
-                    if (lane == 0) {
-                        gw[opc.x] += ga;
-                        gw[opc.y] += gb;
-                    }
-                    if (ai) st_scr(scr, opc.x - S, matvecT_s(tab_sm + (size_t)(opc.x - S) * 16, ua));
-                    if (bi) wprev = matvecT_s(tab_sm + (size_t)(opc.y - S) * 16, ub);
-                    opc = opn; a_c = a_n; b_c = b_n; w_c = w_n;
+                    if (o.x >= 0) stg256(scr + (unsigned)o.x * nthr, matvecT_s(tab_sm + (unsigned)o.x * 16u, ua));
+                    if (o.y >= 0) wprev = matvecT_s(tab_sm + (unsigned)o.y * 16u, ub);
+                };
+                V4 A0, B0, W0, A1, B1, W1;
+                {
+                    const int4 o1 = ops_sm[nops];
+                    A0 = o1.x < 0 ? tipmsg(~o1.x) : ldg256(scr + (unsigned)o1.x * nthr);
+                    B0 = o1.y < 0 ? tipmsg(~o1.y) : ldg256(scr + (unsigned)o1.y * nthr);
+                    W0 = wprev;
+                    A1 = A0; B1 = B0; W1 = W0;
                 }
+                int i = nops;
+#pragma unroll 1
+                for (; i - 1 >= 1; i -= 2) {
+                    step(i, A0, B0, W0, A1, B1, W1);
+                    step(i - 1, A1, B1, W1, A0, B0, W0);
+                }
+                if (i >= 1) step(i, A0, B0, W0, A1, B1, W1);
             }
         }
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
-            for (int w2 = 0; w2 < nwarp; ++w2) s += red[w2];
+            for (unsigned w2 = 0; w2 < nwarp; ++w2) s += red[w2];
             A.ll_part[item] = s;
         }
         if (GRAD) {
             double *gp = A.g_part + (size_t)item * E;
-            for (int e = tid; e < E; e += nthr) {
+            for (unsigned e = tid; e < (unsigned)E; e += nthr) {
                 double s = 0.0;
-                for (int w2 = 0; w2 < nwarp; ++w2) {
-                    s += gacc[(size_t)w2 * E + e];
-                    gacc[(size_t)w2 * E + e] = 0.0;
+                for (unsigned w2 = 0; w2 < nwarp; ++w2) {
+                    s += gacc[w2 * (unsigned)E + e];
+                    gacc[w2 * (unsigned)E + e] = 0.0;
                 }
                 gp[e] = s;
             }
@@ -533,7 +567,7 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     plan->off_sched = off;   off = align_up(off + (uint64_t)B * 6 * S * sizeof(int), 256);
     plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S) * sizeof(double), 256);
     plan->off_tiptab = off;
-    plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * 2 * threads * sizeof(double2), 256);
+    plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * threads * 32, 256);
     plan->off_ll_part = off; off = align_up(off + (uint64_t)plan->n_items * sizeof(double), 256);
     plan->off_g_part = off;
     if (flags & DODO_PRUNE_GRAD) off = align_up(off + (uint64_t)plan->n_items * E * sizeof(double), 256);
