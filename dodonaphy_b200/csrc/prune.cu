@@ -241,6 +241,7 @@ __device__ __forceinline__ V4 ldg256(const V4 *p) {
     asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void stg256(V4 *p, const V4 &v) {
     asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
@@ -306,11 +307,11 @@ __device__ __forceinline__ double warp_sum2(double x, double y, int lane) {
     return keep;
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(256, DODO_PRUNE_MINBLOCKS) prune_kernel(PruneArgs A, ModelDev md) {
+template <bool GRAD, int NTHR>
+__global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) prune_kernel(PruneArgs A, ModelDev md) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned tid = threadIdx.x;
-    const unsigned nthr = blockDim.x;
+    constexpr unsigned nthr = NTHR;
     const unsigned lane = tid & 31u;
     const unsigned warp = tid >> 5;
     const unsigned nwarp = nthr >> 5;
@@ -382,8 +383,9 @@ __global__ void __launch_bounds__(256, DODO_PRUNE_MINBLOCKS) prune_kernel(PruneA
                 if (on.x < 0) An = tipmsg(~on.x);
                 else An = ldg256(scr + (unsigned)on.x * nthr);  // stored >= 2 joins ago (schedule_kernel)
                 if (on.y < 0) Bn = tipmsg(~on.y);
-                const V4 bv = (o.y < 0) ? Bc : prev;
-                const V4 Lv = vmul(Ac, bv);
+                V4 Lv;
+                if (o.y < 0) Lv = vmul(Ac, Bc);
+                else Lv = vmul(Ac, prev);
                 if (i == nops) {
                     rootL = Lv;
                 } else {
@@ -433,9 +435,15 @@ __global__ void __launch_bounds__(256, DODO_PRUNE_MINBLOCKS) prune_kernel(PruneA
                     if (on.x < 0) An = tipmsg(~on.x); else An = ldg256(scr + (unsigned)on.x * nthr);
                     if (on.y < 0) Bn = tipmsg(~on.y); else Bn = ldg256(scr + (unsigned)on.y * nthr);
                     if (on.w & 1) Wn = ldg256(scr + (unsigned)on.z * nthr);
-                    const V4 w = (o.w & 1) ? Wc : wprev;
-                    const V4 ua = vmul(w, Bc);
-                    const V4 ub = vmul(w, Ac);
+                    {
+                        // pull the messages needed three joins from now out of HBM into L2
+                        const int4 of = ops_sm[i > 3 ? i - 3 : 0];
+                        if (of.x >= 0) prefetch_l2(scr + (unsigned)of.x * nthr);
+                        if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
+                    }
+                    V4 ua, ub;
+                    if (o.w & 1) { ua = vmul(Wc, Bc); ub = vmul(Wc, Ac); }
+                    else { ua = vmul(wprev, Bc); ub = vmul(wprev, Ac); }
                     const double ga = rate_k * uQx(md.Q, ua, Ac);
                     const double gb = rate_k * uQx(md.Q, ub, Bc);
                     const double g2 = warp_sum2(ga, gb, lane);
@@ -502,6 +510,17 @@ __global__ void prune_reduce_kernel(const double *__restrict__ ll_part, const do
     }
 }
 
+typedef void (*prune_fn_t)(PruneArgs, ModelDev);
+static prune_fn_t prune_entry(bool grad, int threads) {
+    switch (threads) {
+        case 256: return grad ? prune_kernel<true, 256> : prune_kernel<false, 256>;
+        case 128: return grad ? prune_kernel<true, 128> : prune_kernel<false, 128>;
+        case 64: return grad ? prune_kernel<true, 64> : prune_kernel<false, 64>;
+        case 32: return grad ? prune_kernel<true, 32> : prune_kernel<false, 32>;
+    }
+    return nullptr;
+}
+
 }  // namespace dodo
 
 using namespace dodo;
@@ -523,7 +542,8 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     plan->B = B; plan->S = S; plan->L = L; plan->K = K; plan->flags = flags;
     int threads = 256;
     if (threads_hint > 0) {
-        DODO_CHECK_ARG(threads_hint % 32 == 0 && threads_hint <= 256, "dodo_prune_plan: threads must be a multiple of 32, <= 256");
+        DODO_CHECK_ARG(threads_hint == 32 || threads_hint == 64 || threads_hint == 128 || threads_hint == 256,
+                       "dodo_prune_plan: threads must be 32, 64, 128 or 256");
         threads = threads_hint;
     }
     while (threads > 32 && L <= threads / 2) threads /= 2;  // tiny alignments: do not idle most of a CTA
@@ -545,14 +565,12 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     int grid = grid_hint;
     if (grid <= 0) {
         // persistent grid: every CTA the SMs can hold at once (a multiple of the SM count)
-        if (smem > 48 * 1024) {
-            cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(prune_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(prune_entry((flags & DODO_PRUNE_GRAD) != 0, threads),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
-        cudaError_t e = (flags & DODO_PRUNE_GRAD)
-                            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<true>, threads, smem)
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_kernel<false>, threads, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_entry((flags & DODO_PRUNE_GRAD) != 0, threads),
+                                                                      threads, smem);
         if (e != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 1;
@@ -630,14 +648,11 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
-    if (grad) {
-        if (smem > 48 * 1024)
-            DODO_CUDA(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prune_kernel<true><<<plan->grid, plan->threads, smem, stream>>>(A, md);
-    } else {
-        if (smem > 48 * 1024)
-            DODO_CUDA(cudaFuncSetAttribute(prune_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prune_kernel<false><<<plan->grid, plan->threads, smem, stream>>>(A, md);
+    {
+        prune_fn_t fn = prune_entry(grad, plan->threads);
+        DODO_CHECK_ARG(fn != nullptr, "dodo_prune: unsupported CTA size %d", plan->threads);
+        if (smem > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<plan->grid, plan->threads, smem, stream>>>(A, md);
     }
     DODO_LAUNCH_CHECK();
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev1, stream));
