@@ -1,0 +1,59 @@
+"""NumPy-facing hyperboloid utilities of the MCMC path (dodonaphy/cython/Chyp_np.pyx).
+
+``get_pdm`` (Chyp_np.pyx:321-367) runs the CUDA distance kernel (NumPy variant: clamp -(1+eps),
+diagonal kept, curvature 0 => Euclidean).  The single-point helpers are O(D) host arithmetic kept
+for API parity (project_up :253-277, hyperbolic_distance :279-296, lorentz_product :298-319,
+poincare_to_hyper(_2d) :413-439).
+"""
+import numpy as np
+import torch
+
+from . import engine as _engine
+
+eps = np.finfo(np.double).eps
+
+
+def get_pdm(x, curvature=-1.0, matsumoto=False, get_jacobian=False):
+    """(S,D) ndarray -> (S,S) ndarray of pairwise distances; a leading batch axis is accepted."""
+    if get_jacobian:
+        if matsumoto:
+            raise NotImplementedError("Jacobian is not implemented for Matsumoto metric.")
+        raise NotImplementedError("get_jacobian: use Chyp_torch.get_pdm + autograd (analytic VJP on device)")
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = _engine.pdm_forward(torch.from_numpy(x), float(curvature), "numpy", "up", bool(matsumoto))
+    return out.cpu().numpy()
+
+
+def project_up(loc):
+    loc = np.asarray(loc, dtype=np.float64)
+    return np.concatenate(([np.sqrt(np.sum(loc * loc) + 1.0)], loc))
+
+
+def project_up_2d(loc):
+    loc = np.asarray(loc, dtype=np.float64)
+    return np.concatenate((np.sqrt(np.sum(loc * loc, axis=1, keepdims=True) + 1.0), loc), axis=1)
+
+
+def lorentz_product(x, y):
+    return -x[0] * y[0] + np.dot(x[1:], y[1:])
+
+
+def hyperbolic_distance(x1, x2, curvature=-1.0):
+    """Distance between two points given WITHOUT their time coordinate (Chyp_np.pyx:279-296)."""
+    s1, s2 = project_up(x1), project_up(x2)
+    if np.isclose(curvature, 0.0):
+        return np.linalg.norm(s2 - s1)
+    inner = np.maximum(-lorentz_product(s1, s2), 1.0 + eps)
+    return 1.0 / np.sqrt(-curvature) * np.arccosh(inner)
+
+
+def poincare_to_hyper(location):
+    location = np.asarray(location, dtype=np.float64)
+    a = np.sum(location * location)
+    return np.concatenate(([(1 + a) / (1 - a)], 2 * location / (1 - a + eps)))
+
+
+def poincare_to_hyper_2d(location):
+    location = np.asarray(location, dtype=np.float64)
+    a = np.sum(location * location, axis=-1, keepdims=True)
+    return np.concatenate(((1 + a) / (1 - a), 2 * location / (1 - a + eps)), axis=1)

@@ -1,0 +1,136 @@
+"""The part of the reference's ``BaseModel`` that sits on the hot path
+(dodonaphy/base_model.py): construction from tip partials + weights (:35-107), the learnable
+curvature leaf (:109-124), the tree-decoding ``connect`` step its subclasses implement
+(vi.py:467-491, chain.py:171-221) and the likelihood dispatch ``compute_LL`` (:219-247).
+
+Two ways in:
+
+* one tree at a time, with the reference's signatures (``compute_LL(peel, blen)``,
+  ``connect(locs)``) -- what the unmodified VI / MCMC loops call per sample;
+* a whole batch at once (``log_likelihood_batch``, ``log_likelihood_batch_np``) -- the batching
+  glue for ``DodonaphyVI.elbo_siwae`` (importance x boosts samples, vi.py:328-333) and
+  ``DodonaphyMCMC.learn`` (one proposal per chain, mcmc.py:136-146): every sample / chain of a step
+  goes through the kernels in a single pass.
+
+Priors, logging, checkpointing and the alternative research losses of the reference class are host
+code outside the path and are not reproduced here.
+"""
+import numpy as np
+import torch
+
+from . import Chyp_np, Chyp_torch, Cpeeler, peeler
+from .phylo import LikelihoodInstance, TreeLikelihood
+from .phylomodel import PhyloModel
+from .pipeline import HotPath
+
+
+class _BatchedLogLik(torch.autograd.Function):
+    """lnL of B embeddings in one fused pass; gradients to locations and curvature."""
+
+    @staticmethod
+    def forward(ctx, locs, curvature_leaf, hot):
+        # the leaf is log(-kappa) (base_model.py:109-124): kappa = -exp(leaf), d kappa / d leaf = kappa
+        hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
+        ctx.kappa = hot.curvature
+        x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
+        out = hot.value_and_grad(x)
+        ctx.save_for_backward(out["grad_x"].to(locs.device), out["grad_curvature"].to(curvature_leaf.device))
+        ctx.cshape = curvature_leaf.shape
+        ctx.mark_non_differentiable(out["peel"])
+        return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device)
+
+    @staticmethod
+    def backward(ctx, g_ll, _g_peel, g_blens):
+        gx, gc = ctx.saved_tensors
+        if g_blens is not None and bool((g_blens != 0).any()):
+            raise NotImplementedError("use connect()/compute_LL() when the loss depends on blens directly")
+        return g_ll.reshape(-1, 1, 1) * gx, ((g_ll * gc).sum() * ctx.kappa).reshape(ctx.cshape), None
+
+
+class BaseModel:
+    def __init__(self, inference_name, partials, weights, dim, soft_temp, curvature=-1.0, embedder="up",
+                 connector="nj", normalise_leaf=False, loss_fn="likelihood", require_grad=True, matsumoto=False,
+                 tip_labels=None, model_name="JC69", freqs=None, gamma_shape=None, n_rate_categories=1):
+        if embedder not in ("wrap", "up"):
+            raise AssertionError("embedder must be 'wrap' or 'up'")
+        if connector not in ("geodesics", "nj", "nj-r", "fix"):
+            raise AssertionError("unknown connector")
+        self.inference_name = inference_name
+        n_tips = len(partials) if tip_labels is None else len(tip_labels)
+        self.partials = list(partials[:n_tips])
+        self.weights = weights
+        self.S = n_tips
+        self.L = int(self.partials[0].shape[-1])
+        self.D = dim
+        self.bcount = 2 * self.S - 2
+        self.soft_temp = soft_temp
+        self.require_grad = require_grad
+        self.embedder, self.connector = embedder, connector
+        self.normalise_leaf, self.loss_fn, self.matsumoto = normalise_leaf, loss_fn, matsumoto
+        self.tip_labels = tip_labels or [f"T{i + 1}" for i in range(self.S)]
+        self.name_id = {name: i for i, name in enumerate(self.tip_labels)}
+        self.curvature = curvature
+        self.phylomodel = PhyloModel(model_name, freqs=None if freqs is None else torch.as_tensor(freqs))
+        from .engine import SubstModel
+
+        self.rates = None if n_rate_categories <= 1 else SubstModel.discrete_gamma(gamma_shape or 0.5, n_rate_categories)
+        self._inst = LikelihoodInstance(self.partials, weights, None, rates=self.rates, mix=self.rates is not None)
+        self._hot = None
+        self.use_bito = False
+
+    # -- curvature: kappa = -exp(_curvature), the leaf is learnable on the VI path ------------------
+    @property
+    def curvature(self):
+        return -torch.exp(self._curvature) if self.require_grad else -np.exp(self._curvature)
+
+    @curvature.setter
+    def curvature(self, value):
+        if self.require_grad:
+            v = torch.as_tensor(value, dtype=torch.float64)
+            leaf = torch.log(-v).clone().detach()
+            self._curvature = leaf.requires_grad_(True) if not hasattr(self, "_curvature") else leaf
+        else:
+            self._curvature = np.log(-np.asarray(value, dtype=np.float64))
+
+    # -- one tree -------------------------------------------------------------------------------
+    def compute_LL(self, peel, blen):
+        """lnL of one tree; ``blen`` a torch tensor (gradient flows) or an ndarray (MCMC)."""
+        self._inst.model = self.phylomodel.device_model()
+        if isinstance(blen, torch.Tensor):
+            return TreeLikelihood.apply(blen, peel, self._inst)
+        out = TreeLikelihood.apply(torch.as_tensor(np.asarray(blen, dtype=np.float64)), peel, self._inst)
+        return np.float64(out.item())
+
+    def connect(self, locs):
+        """Decode one embedding into (peel, blens, pdm) by neighbour joining."""
+        if self.connector not in ("nj",):
+            raise NotImplementedError(f"connector {self.connector!r} is outside the NJ hot path")
+        if self.require_grad:
+            pdm = Chyp_torch.get_pdm(locs, curvature=self.curvature, matsumoto=self.matsumoto, projection=self.embedder)
+            peel, blens = peeler.nj_torch(pdm, tau=self.soft_temp)
+        else:
+            pdm = Chyp_np.get_pdm(locs, curvature=float(self.curvature), matsumoto=self.matsumoto)
+            peel, blens = Cpeeler.nj_np(pdm)
+        return peel, blens, pdm
+
+    # -- a batch of trees -------------------------------------------------------------------------
+    def _hotpath(self):
+        model = self.phylomodel.device_model()
+        if self._hot is None:
+            self._hot = HotPath.from_engine(self._inst.engine, model, rates=self.rates, mix=self.rates is not None,
+                                            tau=self.soft_temp, lift=self.embedder, matsumoto=self.matsumoto)
+        self._hot.model = model
+        self._hot.tau = self.soft_temp
+        return self._hot
+
+    def log_likelihood_batch(self, locs):
+        """VI: (B,S,D) sampled locations -> (lnL (B,), peel (B,S-1,3), blens (B,2S-2)); lnL carries
+        gradient to ``locs`` and to the curvature leaf."""
+        return _BatchedLogLik.apply(locs, self._curvature, self._hotpath())
+
+    def log_likelihood_batch_np(self, locs):
+        """MCMC: (B,S,D) proposals (one per chain) -> (lnL, peel, blens) as NumPy arrays, no gradient."""
+        hot = self._hotpath()
+        hot.curvature = float(self.curvature)
+        out = hot.value(torch.as_tensor(np.ascontiguousarray(locs, dtype=np.float64)).to(hot.device))
+        return out["lnL"].cpu().numpy(), out["peel"].cpu().numpy(), out["blens"].cpu().numpy()

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict_
             if (lane == 0) {
                 sh_pa = (int)(v.key >> 32);
                 sh_pb = (int)(v.key & 0xffffffffu);
+                if (v.key == ~0ull) { sh_pa = 0; sh_pb = 1; }  // all-NaN distances: stay memory-safe
             }
         }
         __syncthreads();

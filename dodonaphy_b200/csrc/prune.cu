@@ -98,7 +98,10 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
     int *Lc = sched + (size_t)b * 6 * S;
     int *Rc = Lc + S, *st = Rc + S, *isz = st + S, *start = isz + S, *afl = start + S;
     int4 *op = ops + (size_t)b * nI;
-    for (int i = 0; i < nI; ++i) { isz[i] = 0; afl[i] = 0; start[i] = 0; }
+    for (int i = 0; i < nI; ++i) {
+        isz[i] = 0; afl[i] = 0; start[i] = 0; Lc[i] = 0; Rc[i] = 0; st[i] = 1;
+        op[i] = make_int4(0, 0, S + i, i == nI - 1 ? 2 : 0);  // memory-safe default for malformed peels
+    }
     const int Nn = 2 * S - 1;
     for (int i = 0; i < nI; ++i) {
         int l = (int)pl[i * 3 + 0], r = (int)pl[i * 3 + 1], p = (int)pl[i * 3 + 2];
@@ -215,6 +218,8 @@ struct PruneArgs {
     double2 *scratch;
     double *ll_part;  // [n_items]
     double *g_part;   // [n_items][E]
+    double *gm_part;  // [n_items][K][nwarp][E][16]
+    double *gpi_part; // [n_items][nwarp][4]
     int B, S, L, K;
     int n_tiles, n_items, tile_patterns;
     int mix;
@@ -307,8 +312,57 @@ __device__ __forceinline__ double warp_sum2(double x, double y, int lane) {
     return keep;
 }
 
-template <bool GRAD, int NTHR>
+// sum over the warp of the 4x4 outer products u (x) v; entry (i,j) ends in lane 2*(4i+j) and is
+// written to dst[4i+j].  Halving butterfly: 16 double shuffles instead of 80, fixed order.
+__device__ __forceinline__ void outer_reduce_store(const V4 &u, const V4 &v, double *dst, unsigned lane) {
+    double x[16];
+    const double uu[4] = {u.a, u.b, u.c, u.d}, vv[4] = {v.a, v.b, v.c, v.d};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[i * 4 + j] = uu[i] * vv[j];
+    double y[8];
+    {
+        const bool hi = lane & 16u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double keep = hi ? x[i + 8] : x[i], send = hi ? x[i] : x[i + 8];
+            y[i] = keep + shfl_xor_d(send, 16);
+        }
+    }
+    double z[4];
+    {
+        const bool hi = lane & 8u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double keep = hi ? y[i + 4] : y[i], send = hi ? y[i] : y[i + 4];
+            z[i] = keep + shfl_xor_d(send, 8);
+        }
+    }
+    double t[2];
+    {
+        const bool hi = lane & 4u;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double keep = hi ? z[i + 2] : z[i], send = hi ? z[i] : z[i + 2];
+            t[i] = keep + shfl_xor_d(send, 4);
+        }
+    }
+    double r;
+    {
+        const bool hi = lane & 2u;
+        double keep = hi ? t[1] : t[0], send = hi ? t[0] : t[1];
+        r = keep + shfl_xor_d(send, 2);
+    }
+    r += shfl_xor_d(r, 1);
+    if (!(lane & 1u)) dst[lane >> 1] = r;
+}
+
+// MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
+template <int MODE, int NTHR>
 __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) prune_kernel(PruneArgs A, ModelDev md) {
+    constexpr bool GRAD = MODE == 1;
+    constexpr bool GMATS = MODE == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned tid = threadIdx.x;
     constexpr unsigned nthr = NTHR;
@@ -390,7 +444,7 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
                     rootL = Lv;
                 } else {
                     prev = matvec_s(tab_sm + (unsigned)o.z * 16u, Lv);
-                    if (GRAD || (o.w & 1)) stg256(scr + (unsigned)o.z * nthr, prev);
+                    if (MODE != 0 || (o.w & 1)) stg256(scr + (unsigned)o.z * nthr, prev);
                 }
             };
             V4 A0, B0, A1, B1;
@@ -408,7 +462,7 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
             }
             if (i <= nops) step(i, A0, B0, A1, B1);
             double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
-            if (GRAD) fx[(unsigned)k * nthr + tid] = fk;
+            if (MODE != 0) fx[(unsigned)k * nthr + tid] = fk;
             fsum += fk;
             if (!A.mix) ll += wt * log(fk);
         }
@@ -471,6 +525,58 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
                 if (i >= 1) step(i, A0, B0, W0, A1, B1, W1);
             }
         }
+        if (GMATS) {
+            // Node-centric reverse sweep: join i receives u_n (upper message on the PARENT side of the
+            // edge above n), forms w_n = P_n^T u_n and L_n = msg_a * msg_b, emits
+            // dlnL/dP_n = sum_patterns u_n (x) L_n, and hands u_a = w_n * msg_b, u_b = w_n * msg_a down.
+            // A tip child's edge is emitted here too: dlnL/dP_t = sum u_t (x) indicator(mask_t).
+            double gpi0 = 0.0, gpi1 = 0.0, gpi2 = 0.0, gpi3 = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                stage_tables(k);
+                V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
+                const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(unsigned)k * nthr + tid];
+                double *gpart = A.gm_part + ((((size_t)item * K + k) * nwarp + warp) * (size_t)E) * 16;
+                V4 uprev = V4{0, 0, 0, 0};
+#pragma unroll 1
+                for (int i = nops; i >= 1; --i) {
+                    const int4 o = ops_sm[i];
+                    const V4 av = o.x < 0 ? tipmsg(~o.x) : ldg256(scr + (unsigned)o.x * nthr);
+                    const V4 bv = o.y < 0 ? tipmsg(~o.y) : ldg256(scr + (unsigned)o.y * nthr);
+                    const V4 Lv = vmul(av, bv);
+                    V4 w;
+                    if (i == nops) {
+                        w = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
+                        gpi0 = fma(sc, Lv.a, gpi0); gpi1 = fma(sc, Lv.b, gpi1);
+                        gpi2 = fma(sc, Lv.c, gpi2); gpi3 = fma(sc, Lv.d, gpi3);
+                    } else {
+                        const V4 u = (o.w & 1) ? ldg256(scr + (unsigned)o.z * nthr) : uprev;
+                        outer_reduce_store(u, Lv, gpart + (size_t)(o.z + S) * 16, lane);
+                        w = matvecT_s(tab_sm + (unsigned)o.z * 16u, u);
+                    }
+                    const V4 ua = vmul(w, bv), ub = vmul(w, av);
+                    if (o.x < 0) {
+                        const unsigned m = sel_sm[(unsigned)(~o.x) * nthr];
+                        outer_reduce_store(ua, V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)},
+                                           gpart + (size_t)(~o.x) * 16, lane);
+                    } else {
+                        stg256(scr + (unsigned)o.x * nthr, ua);
+                    }
+                    if (o.y < 0) {
+                        const unsigned m = sel_sm[(unsigned)(~o.y) * nthr];
+                        outer_reduce_store(ub, V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)},
+                                           gpart + (size_t)(~o.y) * 16, lane);
+                    } else {
+                        uprev = ub;
+                    }
+                }
+            }
+            gpi0 = warp_sum(gpi0); gpi1 = warp_sum(gpi1); gpi2 = warp_sum(gpi2); gpi3 = warp_sum(gpi3);
+            if (lane == 0) {
+                double *gq = A.gpi_part + ((size_t)item * nwarp + warp) * 4;
+                gq[0] = gpi0; gq[1] = gpi1; gq[2] = gpi2; gq[3] = gpi3;
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
@@ -510,16 +616,42 @@ __global__ void prune_reduce_kernel(const double *__restrict__ ll_part, const do
     }
 }
 
+// fixed-order reduction of the per-(tile, warp) outer-product partials
+__global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, const double *__restrict__ gpi_part,
+                                          int B, int n_tiles, int K, int nwarp, int E, double *__restrict__ grad_P,
+                                          double *__restrict__ grad_pi) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nP = (size_t)B * E * K * 16;
+    if (gid < nP) {
+        const int ij = gid % 16;
+        const int k = (gid / 16) % K;
+        const int e = (gid / (16 * (size_t)K)) % E;
+        const int b = gid / (16 * (size_t)K * E);
+        double s = 0.0;
+        for (int t = 0; t < n_tiles; ++t)
+            for (int w = 0; w < nwarp; ++w)
+                s += gm_part[(((((size_t)b * n_tiles + t) * K + k) * nwarp + w) * E + e) * 16 + ij];
+        grad_P[gid] = s;
+    } else if (gid < nP + (size_t)B * 4) {
+        const int i = (gid - nP) % 4, b = (gid - nP) / 4;
+        double s = 0.0;
+        for (int t = 0; t < n_tiles; ++t)
+            for (int w = 0; w < nwarp; ++w) s += gpi_part[(((size_t)b * n_tiles + t) * nwarp + w) * 4 + i];
+        grad_pi[(size_t)b * 4 + i] = s;
+    }
+}
+
 typedef void (*prune_fn_t)(PruneArgs, ModelDev);
-static prune_fn_t prune_entry(bool grad, int threads) {
+static prune_fn_t prune_entry(int mode, int threads) {
     switch (threads) {
-        case 256: return grad ? prune_kernel<true, 256> : prune_kernel<false, 256>;
-        case 128: return grad ? prune_kernel<true, 128> : prune_kernel<false, 128>;
-        case 64: return grad ? prune_kernel<true, 64> : prune_kernel<false, 64>;
-        case 32: return grad ? prune_kernel<true, 32> : prune_kernel<false, 32>;
+        case 256: return mode == 0 ? prune_kernel<0, 256> : (mode == 1 ? prune_kernel<1, 256> : prune_kernel<2, 256>);
+        case 128: return mode == 0 ? prune_kernel<0, 128> : (mode == 1 ? prune_kernel<1, 128> : prune_kernel<2, 128>);
+        case 64: return mode == 0 ? prune_kernel<0, 64> : (mode == 1 ? prune_kernel<1, 64> : prune_kernel<2, 64>);
+        case 32: return mode == 0 ? prune_kernel<0, 32> : (mode == 1 ? prune_kernel<1, 32> : prune_kernel<2, 32>);
     }
     return nullptr;
 }
+static int prune_mode(uint32_t flags) { return (flags & DODO_PRUNE_GMATS) ? 2 : ((flags & DODO_PRUNE_GRAD) ? 1 : 0); }
 
 }  // namespace dodo
 
@@ -530,10 +662,8 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     DODO_CHECK_ARG(plan != nullptr, "dodo_prune_plan: plan is NULL");
     DODO_CHECK_ARG(B >= 1 && S >= 2 && L >= 1, "dodo_prune_plan: need B>=1, S>=2, L>=1 (got %d,%d,%d)", B, S, L);
     DODO_CHECK_ARG(K >= 1 && K <= MAX_K, "dodo_prune_plan: K must be in [1,%d] (got %d)", MAX_K, K);
-    if (flags & DODO_PRUNE_GMATS) {
-        set_error("dodo_prune_plan: DODO_PRUNE_GMATS not implemented yet");
-        return DODO_ENOTIMPL;
-    }
+    DODO_CHECK_ARG(!((flags & DODO_PRUNE_GMATS) && (flags & DODO_PRUNE_GRAD)),
+                   "dodo_prune_plan: GRAD and GMATS are separate calls");
     if (flags & DODO_PRUNE_SCALE) {
         set_error("dodo_prune_plan: DODO_PRUNE_SCALE not implemented yet");
         return DODO_ENOTIMPL;
@@ -566,10 +696,10 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     if (grid <= 0) {
         // persistent grid: every CTA the SMs can hold at once (a multiple of the SM count)
         if (smem > 48 * 1024)
-            cudaFuncSetAttribute(prune_entry((flags & DODO_PRUNE_GRAD) != 0, threads),
+            cudaFuncSetAttribute(prune_entry(prune_mode(flags), threads),
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_entry((flags & DODO_PRUNE_GRAD) != 0, threads),
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_entry(prune_mode(flags), threads),
                                                                       threads, smem);
         if (e != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
@@ -590,6 +720,11 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     plan->off_g_part = off;
     if (flags & DODO_PRUNE_GRAD) off = align_up(off + (uint64_t)plan->n_items * E * sizeof(double), 256);
     plan->off_gm_part = off;
+    if (flags & DODO_PRUNE_GMATS) {
+        const uint64_t nwarp = threads / 32;
+        off = align_up(off + (uint64_t)plan->n_items * K * nwarp * E * 16 * sizeof(double), 256);
+        off = align_up(off + (uint64_t)plan->n_items * nwarp * 4 * sizeof(double), 256);
+    }
     plan->ws_bytes = off;
     return DODO_OK;
 }
@@ -607,7 +742,8 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     const bool grad = plan->flags & DODO_PRUNE_GRAD;
     DODO_CHECK_ARG(!grad || d_grad_blens, "dodo_prune: GRAD requested but d_grad_blens is NULL");
     DODO_CHECK_ARG(!(grad && d_P_in), "dodo_prune: blens gradient needs device-formed P(t) (use GMATS for explicit mats)");
-    (void)d_grad_P; (void)d_grad_pi;
+    const bool gmats = plan->flags & DODO_PRUNE_GMATS;
+    DODO_CHECK_ARG(!gmats || (d_grad_P && d_grad_pi), "dodo_prune: GMATS requested but d_grad_P / d_grad_pi is NULL");
     cudaStream_t stream = (cudaStream_t)stream_;
     char *ws = (char *)d_ws;
     const int E = 2 * S - 2;
@@ -641,6 +777,8 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.scratch = (double2 *)(ws + plan->off_scratch);
     A.ll_part = (double *)(ws + plan->off_ll_part);
     A.g_part = (double *)(ws + plan->off_g_part);
+    A.gm_part = (double *)(ws + plan->off_gm_part);
+    A.gpi_part = A.gm_part + (align_up((uint64_t)plan->n_items * K * (plan->threads / 32) * E * 16 * sizeof(double), 256) / sizeof(double));
     A.B = B; A.S = S; A.L = L; A.K = K;
     A.n_tiles = plan->n_tiles; A.n_items = plan->n_items; A.tile_patterns = plan->tile_patterns;
     A.mix = ((plan->flags & DODO_PRUNE_MIX) && K > 1) ? 1 : 0;
@@ -649,7 +787,7 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
     {
-        prune_fn_t fn = prune_entry(grad, plan->threads);
+        prune_fn_t fn = prune_entry(prune_mode(plan->flags), plan->threads);
         DODO_CHECK_ARG(fn != nullptr, "dodo_prune: unsupported CTA size %d", plan->threads);
         if (smem > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<plan->grid, plan->threads, smem, stream>>>(A, md);
@@ -660,6 +798,12 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
         int total = B * (E + 1);
         prune_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(A.ll_part, A.g_part, B, plan->n_tiles, E, d_loglik,
                                                                       grad ? d_grad_blens : nullptr);
+        DODO_LAUNCH_CHECK();
+    }
+    if (gmats) {
+        size_t total = (size_t)B * E * K * 16 + (size_t)B * 4;
+        prune_reduce_gmats_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(
+            A.gm_part, A.gpi_part, B, plan->n_tiles, K, plan->threads / 32, E, d_grad_P, d_grad_pi);
         DODO_LAUNCH_CHECK();
     }
     return DODO_OK;

@@ -201,6 +201,35 @@ class PruneEngine:
                                            _ptr(mats), _ptr(ws), _ptr(ll), _ptr(g), None, None, _stream()))
             return ll, g
 
+    def loglik_mats(self, peel, mats, pi, grad=False, mix=False):
+        """lnL from caller-supplied transition matrices (the ``mats`` / ``freqs`` arguments of
+        phylo.calculate_treelikelihood).  mats: (B, 2S-2, K, 4, 4) device tensor; pi: 4 root
+        frequencies (host).  Returns dict(lnL (B,), grad_mats like mats, grad_pi (B,4)) -- the
+        gradients only when ``grad``."""
+        with torch.cuda.device(self.device):
+            mats = mats.to(self.device, dtype=torch.float64).contiguous()
+            if mats.dim() != 5 or mats.shape[1] != self.E or tuple(mats.shape[3:]) != (4, 4):
+                raise ValueError(f"mats must have shape (B, {self.E}, K, 4, 4)")
+            B, K = int(mats.shape[0]), int(mats.shape[2])
+            peel_t = peel.to(self.device, dtype=torch.int64)
+            if peel_t.dim() == 2:
+                peel_t = peel_t.unsqueeze(0)
+            peel_t = peel_t.contiguous()
+            if tuple(peel_t.shape[1:]) != (self.S - 1, 3) or peel_t.shape[0] not in (1, B):
+                raise ValueError("peel must have shape (B or 1, S-1, 3)")
+            flags = (_lib.PRUNE_GMATS if grad else 0) | (_lib.PRUNE_MIX if (mix and K > 1) else 0)
+            plan, ws = self._plan(B, K, flags)
+            model = SubstModel(_lib.MODEL_EIGEN, np.eye(4), np.zeros(4), np.eye(4), np.zeros((4, 4)), np.asarray(pi, dtype=np.float64))
+            ll = torch.empty(B, dtype=torch.float64, device=self.device)
+            gP = torch.empty_like(mats) if grad else None
+            gpi = torch.empty((B, 4), dtype=torch.float64, device=self.device) if grad else None
+            cm = model.c_struct()
+            rates_c = (C.c_double * K)(*([1.0] * K))
+            _lib.check(self.lib.dodo_prune(C.byref(plan), C.byref(cm), rates_c, _ptr(self.tipmask), self.L,
+                                           _ptr(self.weights), _ptr(peel_t), int(peel_t.shape[0]), None,
+                                           _ptr(mats), _ptr(ws), _ptr(ll), None, _ptr(gP), _ptr(gpi), _stream()))
+            return dict(lnL=ll, grad_mats=gP, grad_pi=gpi)
+
 
 # --------------------------------------------------------------------------------------------
 # K1 / K2 batched device functions

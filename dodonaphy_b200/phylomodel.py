@@ -1,0 +1,137 @@
+"""Substitution-model front end with the reference's ``PhyloModel`` surface for the hot path
+(``get_transition_mats`` / ``JC69_p_t`` / ``GTR_p_t`` / ``compute_Q_martix`` / ``norm``,
+dodonaphy/phylomodel.py:76-128, and the unconstrained ``_sub_rates`` (5) / ``_freqs`` (3) leaves of
+:19-45 that the optimisers differentiate).
+
+The likelihood kernels never consume P(t) tensors: they form P(t) on the device from
+``device_model()``.  The tensor-returning methods exist so that callers written against the
+reference (and its tests, test/test_phylo.py:276-300) keep working; they are 4x4 host arithmetic.
+Priors, file output and the rest of the reference class are outside the hot path.
+"""
+import torch
+from torch.distributions.transforms import StickBreakingTransform
+
+from .engine import SubstModel
+
+_SIMPLEX = StickBreakingTransform()
+_EYE4 = torch.eye(4, dtype=torch.float64)
+
+
+class _SimplexLeaf:
+    """A point on the simplex stored as an unconstrained leaf tensor (what Adam updates)."""
+
+    def __init__(self, value, learnable):
+        raw = _SIMPLEX.inv(torch.as_tensor(value, dtype=torch.float64)).clone().detach()
+        self.raw = raw.requires_grad_(True) if learnable else raw
+
+    def value(self):
+        return _SIMPLEX(self.raw)
+
+
+class PhyloModel:
+    MODELS = ("JC69", "GTR")
+
+    def __init__(self, name, sub_rates=None, freqs=None):
+        self.name = name
+        learn = name == "GTR"
+        self.fix_sub_rates = self.fix_freqs = not learn
+        if name == "JC69":
+            sub_rates, freqs = torch.full((6,), 1.0 / 6.0), torch.full((4,), 0.25)
+        elif name == "GTR":
+            if sub_rates is None:
+                sub_rates = torch.distributions.Dirichlet(torch.ones(6, dtype=torch.float64)).sample()
+            if freqs is None:
+                freqs = torch.distributions.Dirichlet(torch.ones(4, dtype=torch.float64)).sample()
+        self._rates_leaf = _SimplexLeaf(sub_rates, learn) if name in self.MODELS else None
+        self._freqs_leaf = _SimplexLeaf(freqs, learn) if name in self.MODELS else None
+
+    def __eq__(self, other):
+        return self.name == (other if isinstance(other, str) else other.name)
+
+    __hash__ = None
+
+    # unconstrained leaves, named as in the reference so params_optim dictionaries line up
+    @property
+    def _sub_rates(self):
+        return self._rates_leaf.raw
+
+    @_sub_rates.setter
+    def _sub_rates(self, raw):
+        self._rates_leaf.raw = raw
+
+    @property
+    def _freqs(self):
+        return self._freqs_leaf.raw
+
+    @_freqs.setter
+    def _freqs(self, raw):
+        self._freqs_leaf.raw = raw
+
+    @property
+    def sub_rates(self):
+        return self._rates_leaf.value()
+
+    @sub_rates.setter
+    def sub_rates(self, value):
+        if self.name != "JC69":
+            self._rates_leaf = _SimplexLeaf(value, not self.fix_sub_rates)
+
+    @property
+    def freqs(self):
+        return self._freqs_leaf.value()
+
+    @freqs.setter
+    def freqs(self, value):
+        if self.name != "JC69":
+            self._freqs_leaf = _SimplexLeaf(value, not self.fix_freqs)
+
+    # ------------------------------------------------------------------ P(t) as tensors
+    def get_transition_mats(self, blens):
+        if self.name == "JC69":
+            return self.JC69_p_t(blens)
+        if self.name == "GTR":
+            return self.GTR_p_t(blens)
+        raise ValueError(f"Model {self.name} has no transition matrix implementation.")
+
+    @staticmethod
+    def JC69_p_t(branch_lengths):
+        """(E,) or (E,K) -> (E,K,4,4): diagonal 1/4 + 3/4 e^{-4t/3}, off-diagonal 1/4 - 1/4 e^{-4t/3}."""
+        branch_lengths = branch_lengths.to(torch.float64)
+        t = branch_lengths if branch_lengths.dim() > 1 else branch_lengths.unsqueeze(-1)
+        decay = torch.exp(-4.0 / 3.0 * t)[..., None, None]
+        same = 0.25 + 3.0 / 4.0 * decay
+        diff = 0.25 - 0.25 * decay
+        return torch.where(_EYE4.bool(), same, diff)
+
+    def compute_Q_martix(self):
+        """Rate matrix: symmetric exchangeabilities (upper-triangle order 01,02,03,12,13,23) times
+        the column frequencies, rows summing to zero, one expected substitution per unit time."""
+        r, pi = self.sub_rates, self.freqs
+        iu = torch.triu_indices(4, 4, 1)
+        R = torch.zeros((4, 4), dtype=torch.float64).index_put((iu[0], iu[1]), r)
+        Q = (R + R.T) * pi
+        Q = Q - torch.diag(Q.sum(dim=1))
+        return Q / self.norm(Q)
+
+    def norm(self, Q):
+        return -(torch.diagonal(Q, dim1=-2, dim2=-1) * self.freqs).sum(-1)
+
+    def _eigensystem(self):
+        pi = self.freqs
+        root, inv_root = torch.diag(pi.sqrt()), torch.diag(pi.rsqrt())
+        lam, V = torch.linalg.eigh(root @ self.compute_Q_martix() @ inv_root)
+        return inv_root @ V, lam, torch.linalg.inv(V) @ root
+
+    def GTR_p_t(self, branch_lengths):
+        """(E,) -> (E,4,4); (E,K) -> (E,K,4,4):  U diag(exp(lam t)) U^-1."""
+        U, lam, Uinv = self._eigensystem()
+        growth = torch.exp(branch_lengths.to(torch.float64).unsqueeze(-1) * lam)
+        return (U * growth.unsqueeze(-2)) @ Uinv
+
+    # ------------------------------------------------------------------ what the kernels consume
+    def device_model(self):
+        if self.name == "JC69":
+            return SubstModel.jc69()
+        if self.name == "GTR":
+            return SubstModel.gtr(self.sub_rates.detach().cpu().numpy(), self.freqs.detach().cpu().numpy())
+        raise ValueError(f"Model {self.name} has no transition matrix implementation.")

@@ -26,6 +26,17 @@ class HotPath:
         self.lift = lift
         self.matsumoto = matsumoto
 
+    @classmethod
+    def from_engine(cls, prune_engine, model, rates=None, mix=False, tau=1e-8, curvature=-1.0, lift="up", matsumoto=False):
+        """Share an existing PruneEngine (tips already resident on the device)."""
+        self = cls.__new__(cls)
+        self.prune = prune_engine
+        self.device = prune_engine.device
+        self.model = model
+        self.rates = None if rates is None else np.ascontiguousarray(rates, dtype=np.float64)
+        self.mix, self.tau, self.curvature, self.lift, self.matsumoto = bool(mix), tau, curvature, lift, matsumoto
+        return self
+
     def value_and_grad(self, x):
         """x: (B,S,D) device tensor.  Returns dict(lnL (B,), grad_x (B,S,D), grad_curvature (B,),
         peel (B,S-1,3), blens (B,2S-2)) -- soft-NJ (VI) path."""

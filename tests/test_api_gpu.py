@@ -1,0 +1,163 @@
+"""GPU parity through the reference-shaped Python API (same names/arguments as the reference's
+modules): these read like the reference's own tests (test/test_phylo.py, test/test_peeler.py,
+test/test_bito.py, test/test_chyp_np.py) with the CUDA path underneath."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _partials(masks):
+    from oracle.phylo import mask_to_partial
+
+    S, L = masks.shape
+    parts = [torch.tensor(mask_to_partial(m)) for m in masks]
+    return parts + [torch.zeros((1, 4, L), dtype=torch.float64) for _ in range(S - 1)]
+
+
+def test_likelihood_mrbayes_torch_and_numpy():
+    """test/test_phylo.py:214-273."""
+    from dodonaphy_b200 import Cphylo, phylo
+    from dodonaphy_b200.phylomodel import PhyloModel
+
+    g = load_golden("ds1.npz")
+    partials = _partials(g["masks"])
+    weights = torch.tensor(g["weights"])
+    blens = torch.tensor(g["mb_blens"])
+    mats = PhyloModel.JC69_p_t(blens)
+    freqs = torch.full([4], 0.25, dtype=torch.float64)
+    ln_p = phylo.calculate_treelikelihood(partials, weights, g["mb_peel"], mats, freqs)
+    assert ln_p.item() == pytest.approx(-6904.632, abs=1e-3)
+    assert ln_p.item() == pytest.approx(float(g["mb_lnL_torch"]), rel=1e-9)
+    pn = [p.numpy() for p in partials]
+    ln_np = Cphylo.calculate_treelikelihood(pn, g["weights"], g["mb_peel"], mats.numpy(), np.full(4, 0.25))
+    assert ln_np == pytest.approx(-6904.632, abs=1e-3)
+    assert Cphylo.compute_LL_np(pn, g["weights"], g["nj_peel"], g["nj_blens"]) == pytest.approx(-7130.96813417, abs=1e-7)
+
+
+@pytest.mark.parametrize("tree", ["mb", "nj"])
+def test_calculate_treelikelihood_autograd_matches_reference(tree):
+    """Gradients the reference gets from torch autograd: d lnL/d mats, d lnL/d blens (through the
+    model's own P(t)), d lnL/d GTR parameters."""
+    from dodonaphy_b200 import phylo
+    from dodonaphy_b200.phylomodel import PhyloModel
+
+    g = load_golden("ds1.npz")
+    partials = _partials(g["masks"])
+    weights = torch.tensor(g["weights"])
+    pm = PhyloModel("GTR", torch.tensor(g["gtr_rates"]), torch.tensor(g["gtr_freqs"]))
+    np.testing.assert_allclose(pm._sub_rates.detach().numpy(), g[f"{tree}_gtr_raw_rates"], rtol=1e-12)
+    blens = torch.tensor(g[f"{tree}_blens"], requires_grad=True)
+    mats = pm.get_transition_mats(blens)
+    mats.retain_grad()
+    ll = phylo.calculate_treelikelihood(partials, weights, g[f"{tree}_peel"], mats, pm.freqs)
+    ll.backward()
+    assert ll.item() == pytest.approx(float(g[f"{tree}_gtr_lnL"]), rel=1e-9)
+    for ours, ref in ((mats.grad.numpy(), g[f"{tree}_gtr_g_mats"]), (blens.grad.numpy(), g[f"{tree}_gtr_g_blens"]),
+                      (pm._sub_rates.grad.numpy(), g[f"{tree}_gtr_g_raw_rates"]), (pm._freqs.grad.numpy(), g[f"{tree}_gtr_g_raw_freqs"])):
+        np.testing.assert_allclose(ours, ref, rtol=1e-8, atol=1e-9 * np.abs(ref).max())
+
+
+def test_reference_broadcast_semantics_with_category_axis():
+    """mats (E,K,4,4): the reference sums the K per-category log-likelihoods (phylo.py:137-139)."""
+    from dodonaphy_b200 import phylo
+    from dodonaphy_b200.phylomodel import PhyloModel
+    from oracle import phylo as ophylo
+
+    g = load_golden("prune.npz")
+    i = 2
+    partials = _partials(g[f"{i}_masks"])
+    blens = torch.tensor(g[f"{i}_blens"])
+    mats = PhyloModel.JC69_p_t(torch.stack([blens, 2.0 * blens, 0.5 * blens], dim=1))
+    ll = phylo.calculate_treelikelihood(partials, torch.tensor(g[f"{i}_weights"]), g[f"{i}_peel"], mats, torch.full([4], 0.25, dtype=torch.float64))
+    tips = [ophylo.mask_to_partial(m) for m in g[f"{i}_masks"]]
+    ref = ophylo.treelikelihood(tips, g[f"{i}_weights"], g[f"{i}_peel"], mats.numpy(), np.full(4, 0.25))
+    assert ll.item() == pytest.approx(ref, rel=1e-9)
+
+
+def test_tree_likelihood_plugin_and_base_model():
+    """The native-plugin shape (phylo.TreeLikelihood, phylo.py:177-226) via BaseModel.compute_LL."""
+    from dodonaphy_b200.base_model import BaseModel
+
+    g = load_golden("ds1.npz")
+    partials = _partials(g["masks"])[:27]
+    model = BaseModel("vi", partials, torch.tensor(g["weights"]), dim=3, soft_temp=1e-8, model_name="JC69")
+    blens = torch.tensor(g["nj_blens"], requires_grad=True)
+    ll = model.compute_LL(g["nj_peel"], blens)
+    (2.0 * ll).backward()
+    assert ll.item() == pytest.approx(-7130.96813417, abs=1e-7)
+    np.testing.assert_allclose(blens.grad.numpy(), 2.0 * g["nj_g_blens"], rtol=1e-8, atol=1e-8 * np.abs(g["nj_g_blens"]).max())
+    assert model.compute_LL(g["mb_peel"], g["mb_blens"]) == pytest.approx(-6904.632, abs=1e-3)
+
+
+def test_get_pdm_and_nj_torch_autograd_chain():
+    """VI connect step (vi.py:467-491): x -> pdm -> soft NJ -> blens, gradient back to x and curvature,
+    against the oracle's torch restatement of the same chain."""
+    from dodonaphy_b200 import Chyp_torch, peeler
+    from oracle import hyp, nj
+
+    rng = np.random.default_rng(77)
+    x_np = rng.normal(0, 0.05, (14, 3))
+    c = rng.normal(size=26)
+    x = torch.tensor(x_np, requires_grad=True)
+    curv = torch.tensor([-1.3], dtype=torch.float64, requires_grad=True)
+    pdm = Chyp_torch.get_pdm(x, curvature=curv)
+    peel, blens = peeler.nj_torch(pdm, tau=1e-8)
+    (blens * torch.tensor(c)).sum().backward()
+    pdm_ref = hyp.get_pdm_torch(x_np, -1.3)
+    np.testing.assert_allclose(pdm.detach().numpy(), pdm_ref, rtol=1e-10, atol=1e-13)
+    p_ref, b_ref = nj.nj_soft(pdm_ref, 1e-8)
+    assert np.array_equal(peel, p_ref)
+    t = torch.tensor(pdm_ref, requires_grad=True)
+    _, bt = nj.nj_soft_torch(t, 1e-8)
+    (bt * torch.tensor(c)).sum().backward()
+    gx_ref, gc_ref = hyp.get_pdm_torch_vjp(x_np, t.grad.numpy(), -1.3)
+    np.testing.assert_allclose(x.grad.numpy(), gx_ref, rtol=1e-7, atol=1e-9 * np.abs(gx_ref).max())
+    assert curv.grad.item() == pytest.approx(gc_ref, rel=1e-8)
+
+
+def test_numpy_path_names():
+    """MCMC connect step (chain.py:171-221): Chyp_np.get_pdm -> Cpeeler.nj_np."""
+    from dodonaphy_b200 import Chyp_np, Cpeeler
+    from oracle import nj
+
+    x = np.random.default_rng(3).normal(0, 0.05, (20, 3))
+    pdm = Chyp_np.get_pdm(x)
+    peel, blens = Cpeeler.nj_np(pdm)
+    p_ref, b_ref = nj.nj_hard(pdm)
+    assert np.array_equal(peel, p_ref) and np.array_equal(blens, b_ref)
+    assert peel.dtype == np.int64 and blens.dtype == np.float64
+    assert Chyp_np.hyperbolic_distance(x[0], x[1]) == pytest.approx(pdm[0, 1], rel=1e-10)
+    with pytest.raises(NotImplementedError):
+        Chyp_np.get_pdm(x, matsumoto=True, get_jacobian=True)
+
+
+def test_batched_model_entry_points():
+    """Batching glue: B samples / chains per call agree with the one-tree-at-a-time API."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.base_model import BaseModel
+    from oracle.phylo import mask_to_partial
+
+    prob = synth.make_problem(10, 120, 5, D=3, seed=9)
+    partials = [torch.tensor(mask_to_partial(m)) for m in prob["masks"]]
+    vi = BaseModel("vi", partials, torch.tensor(prob["weights"]), dim=3, soft_temp=1e-8, model_name="JC69")
+    locs = torch.tensor(prob["xs"], requires_grad=True)
+    ll, peel, blens = vi.log_likelihood_batch(locs)
+    ll.sum().backward()
+    g_batch = locs.grad.clone()
+    for b in range(5):
+        xb = torch.tensor(prob["xs"][b], requires_grad=True)
+        pl, bl, _ = vi.connect(xb)
+        assert np.array_equal(pl, peel[b].cpu().numpy())
+        llb = vi.compute_LL(pl, bl)
+        llb.backward()
+        assert llb.item() == pytest.approx(ll[b].item(), rel=1e-12)
+        np.testing.assert_allclose(xb.grad.numpy(), g_batch[b].numpy(), rtol=1e-8, atol=1e-9 * g_batch[b].abs().max().item())
+    mc = BaseModel("mcmc", partials, prob["weights"], dim=3, soft_temp=None, require_grad=False, model_name="JC69")
+    ll_np, peel_np, blens_np = mc.log_likelihood_batch_np(prob["xs"])
+    pl, bl, _ = mc.connect(prob["xs"][2])
+    assert np.array_equal(pl, peel_np[2]) and np.array_equal(bl, blens_np[2])
+    assert mc.compute_LL(pl, bl) == pytest.approx(ll_np[2], rel=1e-12)
