@@ -1,0 +1,234 @@
+"""CPU tests (no GPU): host-side logic of the package, the C-ABI library's exported symbols, the
+no-CPU-fallback contract, and the multi-process sharding logic on the gloo backend (world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_builds_and_exports_every_declared_symbol():
+    from dodonaphy_b200 import _lib, build
+
+    lib_path = build.build()
+    handle = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "dodonaphy_b200.h")).read()
+    declared = set(re.findall(r"\b(dodo_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    for name in declared:
+        assert hasattr(handle, name), f"{name} is declared in include/dodonaphy_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert handle.dodo_version() >= 100
+
+
+def test_plan_and_argument_validation_without_gpu():
+    """dodo_prune_plan is pure host arithmetic: sizes, tiling, error codes."""
+    from dodonaphy_b200 import _lib
+
+    lib = _lib.load()
+    plan = _lib.PrunePlan()
+    assert lib.dodo_prune_plan(128, 64, 10000, 4, _lib.PRUNE_GRAD | _lib.PRUNE_MIX, 444, 0, ctypes.byref(plan)) == 0
+    assert (plan.threads, plan.tile_patterns, plan.grid) == (256, 256, 444)
+    assert plan.n_tiles == 40 and plan.n_items == 128 * 40
+    assert plan.ws_bytes > plan.off_scratch > plan.off_pmat > 0
+    assert lib.dodo_prune_plan(1, 1, 10, 1, 0, 1, 0, ctypes.byref(plan)) == _lib.DODO_EINVAL
+    assert b"S>=2" in lib.dodo_last_error()
+    assert lib.dodo_prune_plan(1, 8, 10, 9, 0, 1, 0, ctypes.byref(plan)) == _lib.DODO_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(lib.dodo_prune_plan(1, 8, 10, 1, _lib.PRUNE_GRAD | _lib.PRUNE_GMATS, 1, 0, ctypes.byref(plan)))
+    assert lib.dodo_nj_workspace_bytes(3, 10) == 3 * (2 * 100 + 40) * 8
+    assert lib.dodo_pdm_workspace_bytes(2, 5, 3) == 2 * 5 * 5 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box without CUDA")
+def test_no_cpu_fallback():
+    from dodonaphy_b200 import engine
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        engine.PruneEngine(np.ones((4, 8), dtype=np.uint8), np.ones(8))
+    with pytest.raises(RuntimeError):
+        engine.pdm_forward(torch.zeros(4, 3, dtype=torch.float64))
+
+
+def test_product_code_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dodonaphy_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports oracle/"
+
+
+# ------------------------------------------------------------------ host helpers
+def test_pack_tips_and_validate_peel():
+    from dodonaphy_b200.engine import pack_tip_partials, validate_peel
+    from oracle.phylo import mask_to_partial
+
+    masks = np.array([[1, 2, 4, 8, 15, 5], [3, 9, 6, 12, 14, 7]], dtype=np.uint8)
+    assert np.array_equal(pack_tip_partials([mask_to_partial(m) for m in masks]), masks)
+    assert np.array_equal(pack_tip_partials([torch.tensor(mask_to_partial(m)) for m in masks]), masks)
+    with pytest.raises(ValueError):
+        pack_tip_partials([np.full((4, 3), 0.5)])
+    validate_peel(np.array([[0, 1, 4], [2, 3, 5], [4, 5, 6]]), 4)
+    for bad in ([[0, 1, 4], [2, 3, 5], [4, 4, 6]], [[0, 1, 4], [2, 3, 4], [4, 5, 6]], [[0, 1, 9], [2, 3, 5], [4, 5, 6]]):
+        with pytest.raises(ValueError):
+            validate_peel(np.array(bad), 4)
+    with pytest.raises(ValueError):
+        validate_peel(np.zeros((2, 3)), 4)
+
+
+def test_subst_model_matches_oracle():
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import phylo as ophylo
+
+    rng = np.random.default_rng(0)
+    rates, freqs = rng.dirichlet(np.ones(6)), rng.dirichlet(np.ones(4))
+    m = SubstModel.gtr(rates, freqs)
+    np.testing.assert_allclose(m.Q, ophylo.gtr_q(rates, freqs), rtol=1e-14)
+    t = 0.37
+    P = (m.U * np.exp(m.lam * t)) @ m.Uinv
+    np.testing.assert_allclose(P, ophylo.gtr_p_t(np.array([t]), rates, freqs)[0], rtol=1e-12)
+    np.testing.assert_allclose(SubstModel.discrete_gamma(0.5, 4), ophylo.discrete_gamma_rates(0.5, 4), rtol=1e-14)
+    jc = SubstModel.jc69()
+    np.testing.assert_allclose(jc.Q.sum(axis=1), 0.0, atol=1e-15)
+    with pytest.raises(ValueError):
+        SubstModel.gtr(np.ones(5), freqs)
+
+
+def test_phylomodel_surface():
+    """test/test_phylo.py:276-300 against the host-side PhyloModel mirror."""
+    from dodonaphy_b200.phylomodel import PhyloModel
+
+    b = torch.tensor([0.1], dtype=torch.double)
+    pm = PhyloModel("GTR", freqs=torch.full([4], 0.25, dtype=torch.double), sub_rates=torch.full([6], 1 / 6, dtype=torch.double))
+    assert torch.allclose(pm.JC69_p_t(b)[:, 0], pm.GTR_p_t(b))
+    for blens_in, size in (([[1.0, 1.0]], [1, 2, 4, 4]), ([[1.0]], [1, 1, 4, 4]), ([[1.0], [1.0]], [2, 1, 4, 4])):
+        assert list(PhyloModel("GTR").GTR_p_t(torch.tensor(blens_in, dtype=torch.double)).shape) == size
+    with pytest.raises(ValueError):
+        PhyloModel("HKY").get_transition_mats(b)
+    assert pm._sub_rates.shape == (5,) and pm._freqs.shape == (3,) and pm._freqs.requires_grad
+    assert PhyloModel("JC69") == "JC69"
+
+
+def test_compress_alignment_matches_oracle():
+    from dodonaphy_b200 import phylo
+    from oracle import phylo as ophylo
+
+    class _NS:
+        def labels(self):
+            return ["a", "b", "c"]
+
+    class _Aln:
+        taxon_namespace = _NS()
+
+        def sequences(self):
+            return ["ACGTNACGT-", "ACGTRACGTY", "AAGTNAAGT?"]
+
+    parts, w = phylo.compress_alignment(_Aln())
+    tips, w_ref, _ = ophylo.compress_alignment(_Aln().sequences())
+    assert w.tolist() == w_ref.tolist()
+    for p, t in zip(parts, tips):
+        assert np.array_equal(p.numpy(), t)
+
+
+def test_newick_round_trip_and_reference_convention():
+    """test/test_tree.py:19-43: peel/blens of the reference's 6-taxon example."""
+    from dodonaphy_b200 import newick
+
+    data = ("(bird:6.000000e-02,((chimp:5.000000e-02,dog:2.000000e-02):17.000000e-02,"
+            "(crocodile:4.000000e-02,emu:3.000000e-02):18.000000e-02):19.000000e-02,kangaroo:1.000000e-02);")
+    labels = ["bird", "chimp", "dog", "crocodile", "emu", "kangaroo"]
+    peel, blens = newick.newick_to_peel(data, labels)
+    assert peel.tolist() == [[1, 2, 6], [3, 4, 7], [6, 7, 8], [0, 8, 9], [5, 9, 10]]
+    np.testing.assert_allclose(blens, [0.06, 0.05, 0.02, 0.04, 0.03, 0.01, 0.17, 0.18, 0.19, 0.0])
+    again, b2 = newick.newick_to_peel(newick.peel_to_newick(peel, blens, labels), labels)
+    assert again.shape == peel.shape and sorted(b2.tolist()) == sorted(blens.tolist())
+
+
+def test_parent_id_vector():
+    from dodonaphy_b200.phylo import get_parent_id_vector
+
+    peel = np.array([[0, 1, 4], [2, 4, 5], [3, 5, 6]])
+    assert get_parent_id_vector(peel, rooted=False) == [4, 4, 5, 5, 5]
+    assert get_parent_id_vector(peel, rooted=True) == [4, 4, 5, 6, 5, 6]
+
+
+def test_shard_bounds_cover_everything():
+    from dodonaphy_b200.dist import shard_bounds
+
+    for n in (1, 7, 128, 1000003):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_generator_is_seeded_and_consistent():
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import validate_peel
+
+    a = synth.make_problem(12, 50, 3, D=3, seed=4)
+    b = synth.make_problem(12, 50, 3, D=3, seed=4)
+    assert np.array_equal(a["masks"], b["masks"]) and np.array_equal(a["xs"], b["xs"])
+    validate_peel(a["guide_peel"], 12)
+    assert a["masks"].dtype == np.uint8 and set(np.unique(a["masks"])) <= {1, 2, 4, 8, 15}
+    assert (a["guide_blens"] > 0).all() and a["weights"].min() >= 1
+
+
+# ------------------------------------------------------------------ world_size 2 over gloo
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from dodonaphy_b200 import dist as ddist, synth
+from oracle import hyp, nj, phylo
+
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+prob = synth.make_problem(9, 101, 5, D=3, seed=21)
+tips_full = [phylo.mask_to_partial(m) for m in prob["masks"]]
+peels, blens = zip(*[nj.nj_hard(hyp.get_pdm_np(x)) for x in prob["xs"]])
+full = np.array([phylo.compute_LL_np(tips_full, prob["weights"], p, b) for p, b in zip(peels, blens)])
+
+# (1) sample sharding: each rank evaluates its slice, all_gather reassembles the batch in order
+lo, hi = ddist.shard_bounds(5, rank, 2)
+mine = ddist.shard_samples(torch.arange(5))
+assert mine.tolist() == list(range(lo, hi))
+local = torch.tensor(full[lo:hi])
+got = ddist.gather_samples(local, 5)
+assert np.array_equal(got.numpy(), full), (got, full)
+
+# (2) site sharding: per-block lnL (+ gradient vector) summed with one all_reduce
+masks_blk, w_blk = ddist.shard_sites(prob["masks"], prob["weights"])
+tips_blk = [phylo.mask_to_partial(m) for m in masks_blk]
+part = torch.tensor([phylo.compute_LL_np(tips_blk, w_blk, p, b) for p, b in zip(peels, blens)], dtype=torch.float64)
+gpart = torch.full((5, 16), float(rank + 1), dtype=torch.float64)
+tot, gtot = ddist.reduce_site_blocks(part, gpart)
+np.testing.assert_allclose(tot.numpy(), full, rtol=1e-12)
+assert torch.equal(gtot, torch.full((5, 16), 3.0, dtype=torch.float64))
+tot_only, none = ddist.reduce_site_blocks(part)
+assert none is None
+np.testing.assert_allclose(tot_only.numpy(), full, rtol=1e-12)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT, "port": port})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{out}"
+        assert f"rank {r} ok" in out
