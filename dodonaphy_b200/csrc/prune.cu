@@ -216,6 +216,7 @@ struct PruneArgs {
     int ops_batch;  // 1 => shared topology
     const double *tab;
     double2 *scratch;
+    int *cscratch;    // rescaling counters, same indexing as scratch (SCALE only)
     double *ll_part;  // [n_items]
     double *g_part;   // [n_items][E]
     double *gm_part;  // [n_items][K][nwarp][E][16]
@@ -225,18 +226,28 @@ struct PruneArgs {
     int mix;
 };
 
-// shared memory: tables | gacc[nwarp][E] | fx[K][threads] | red[nwarp] | ops int4[S+2] | sel u8[S][threads]
-__host__ __device__ inline size_t prune_smem_dbl(int threads, int S, int K) {
-    const size_t nwarp = threads / 32, E = 2 * (size_t)S - 2;
-    size_t dbl = nwarp * E + (size_t)K * threads + nwarp + tab_doubles(S);
-    return (dbl + 1) & ~(size_t)1;  // keep the int4 schedule 16-byte aligned
+constexpr int NT = 256;  // threads per CTA = site patterns per work item
+
+// Shared memory.  SMALL (tables and tip selectors resident): tables | gacc | fx | red | cx | ops | sel.
+// LARGE (big S: tables and masks stay in global memory, read through L1): gacc | fx | red | cx | ops.
+__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small) {
+    const size_t nwarp = NT / 32, E = 2 * (size_t)S - 2;
+    size_t dbl = nwarp * E + (size_t)K * NT + nwarp + (small ? tab_doubles(S) : 0);
+    return (dbl + 1) & ~(size_t)1;  // keep what follows 16-byte aligned
 }
-__host__ __device__ inline size_t prune_smem_bytes(int threads, int S, int K) {
-    return prune_smem_dbl(threads, S, K) * sizeof(double) + (size_t)(S + 2) * sizeof(int4) + (size_t)S * threads;
+__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small) {
+    return prune_smem_dbl(S, K, small) * sizeof(double) + (size_t)K * NT * sizeof(int) +
+           (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT : 0);
 }
 
 __device__ __forceinline__ V4 lds4(const double *p) {
     double2 x = *reinterpret_cast<const double2 *>(p), y = *reinterpret_cast<const double2 *>(p + 2);
+    return V4{x.x, x.y, y.x, y.y};
+}
+template <bool SMALL>
+__device__ __forceinline__ V4 ld4t(const double *p) {
+    if (SMALL) return lds4(p);
+    double2 x = ldg2(p), y = ldg2(p + 2);
     return V4{x.x, x.y, y.x, y.y};
 }
 
@@ -251,9 +262,10 @@ __device__ __forceinline__ void stg256(V4 *p, const V4 &v) {
     asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
 
-// y = P x / y = P^T x with P (row-major) in shared memory (warp-uniform address -> broadcast)
-__device__ __forceinline__ V4 matvec_s(const double *P, const V4 &x) {
-    V4 r0 = lds4(P), r1 = lds4(P + 4), r2 = lds4(P + 8), r3 = lds4(P + 12);
+// y = P x / y = P^T x with P (row-major, warp-uniform address -> broadcast)
+template <bool SMALL>
+__device__ __forceinline__ V4 matvec_t(const double *P, const V4 &x) {
+    V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL>(P + 4), r2 = ld4t<SMALL>(P + 8), r3 = ld4t<SMALL>(P + 12);
     V4 y;
     y.a = fma(r0.d, x.d, fma(r0.c, x.c, fma(r0.b, x.b, r0.a * x.a)));
     y.b = fma(r1.d, x.d, fma(r1.c, x.c, fma(r1.b, x.b, r1.a * x.a)));
@@ -261,15 +273,15 @@ __device__ __forceinline__ V4 matvec_s(const double *P, const V4 &x) {
     y.d = fma(r3.d, x.d, fma(r3.c, x.c, fma(r3.b, x.b, r3.a * x.a)));
     return y;
 }
-
-__device__ __forceinline__ V4 matvecT_s(const double *P, const V4 &x) {
-    V4 r = lds4(P);
+template <bool SMALL>
+__device__ __forceinline__ V4 matvecT_t(const double *P, const V4 &x) {
+    V4 r = ld4t<SMALL>(P);
     V4 y{r.a * x.a, r.b * x.a, r.c * x.a, r.d * x.a};
-    r = lds4(P + 4);
+    r = ld4t<SMALL>(P + 4);
     y.a = fma(r.a, x.b, y.a), y.b = fma(r.b, x.b, y.b), y.c = fma(r.c, x.b, y.c), y.d = fma(r.d, x.b, y.d);
-    r = lds4(P + 8);
+    r = ld4t<SMALL>(P + 8);
     y.a = fma(r.a, x.c, y.a), y.b = fma(r.b, x.c, y.b), y.c = fma(r.c, x.c, y.c), y.d = fma(r.d, x.c, y.d);
-    r = lds4(P + 12);
+    r = ld4t<SMALL>(P + 12);
     y.a = fma(r.a, x.d, y.a), y.b = fma(r.b, x.d, y.b), y.c = fma(r.c, x.d, y.c), y.d = fma(r.d, x.d, y.d);
     return y;
 }
@@ -283,16 +295,17 @@ __device__ __forceinline__ unsigned encode_sel(unsigned m) {
 }
 
 // message of a tip = P . (indicator of the states allowed by its mask)
+template <bool SMALL>
 __device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, unsigned sel) {
     const unsigned j = sel >> 4;
-    V4 v = lds4(T + (j & 3u) * 4 + (j & 4u) * 4);
+    V4 v = ld4t<SMALL>(T + (j & 3u) * 4 + (j & 4u) * 4);
     if (__any_sync(0xffffffffu, j == 7u)) {
         if (j == 7u) {  // two/three-state codes: add the columns in state order (mask 0: nothing allowed)
             v = V4{0, 0, 0, 0};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
                 if (sel & (1u << jj)) {
-                    V4 c = lds4(T + jj * 4);
+                    V4 c = ld4t<SMALL>(T + jj * 4);
                     v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d;
                 }
         }
@@ -301,8 +314,8 @@ __device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, unsigned s
 }
 
 // sum x over the warp into lane 0 and y into lane 16 with 5 shuffles (fixed order)
-__device__ __forceinline__ double warp_sum2(double x, double y, int lane) {
-    const bool hi = lane & 16;
+__device__ __forceinline__ double warp_sum2(double x, double y, unsigned lane) {
+    const bool hi = lane & 16u;
     double keep = hi ? y : x, send = hi ? x : y;
     keep += shfl_xor_d(send, 16);
     keep += shfl_xor_d(keep, 8);
@@ -358,43 +371,71 @@ __device__ __forceinline__ void outer_reduce_store(const V4 &u, const V4 &v, dou
     if (!(lane & 1u)) dst[lane >> 1] = r;
 }
 
+// Power-of-two rescaling (exact: mantissas untouched, so results are bit-identical to the unscaled
+// computation wherever that one stays in range).  true value = stored * 2^(-256 * count).
+constexpr double SC_LO = 0x1p-256, SC_LO2 = 0x1p-512, SC_UP = 0x1p256, SC_UP2 = 0x1p512;
+__device__ __forceinline__ void scale_up(V4 &v, int &count) {  // keep max(v) >= 2^-256 (v >= 0)
+    const double m = fmax(fmax(fabs(v.a), fabs(v.b)), fmax(fabs(v.c), fabs(v.d)));
+    if (m < SC_LO && m > 0.0) {
+        const bool two = m < SC_LO2;
+        const double f = two ? SC_UP2 : SC_UP;
+        v.a *= f; v.b *= f; v.c *= f; v.d *= f;
+        count += two ? 2 : 1;
+    }
+}
+__device__ __forceinline__ void scale_both(V4 &v, int &count) {  // upper messages can also grow
+    const double m = fmax(fmax(fabs(v.a), fabs(v.b)), fmax(fabs(v.c), fabs(v.d)));
+    if (m < SC_LO && m > 0.0) {
+        v.a *= SC_UP; v.b *= SC_UP; v.c *= SC_UP; v.d *= SC_UP;
+        count += 1;
+    } else if (m > SC_UP) {
+        v.a *= SC_LO; v.b *= SC_LO; v.c *= SC_LO; v.d *= SC_LO;
+        count -= 1;
+    }
+}
+__device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0 / saturating
+    d = max(-5, min(3, d));
+    return scalbn(1.0, 256 * d);
+}
+
 // MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
-template <int MODE, int NTHR>
-__global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) prune_kernel(PruneArgs A, ModelDev md) {
+template <int MODE, bool SMALL, bool SCALE>
+__global__ void __launch_bounds__(NT, 3) prune_kernel(PruneArgs A, ModelDev md) {
     constexpr bool GRAD = MODE == 1;
     constexpr bool GMATS = MODE == 2;
+    static_assert(!(GMATS && SCALE), "GMATS is built without rescaling");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned tid = threadIdx.x;
-    constexpr unsigned nthr = NTHR;
+    constexpr unsigned nthr = NT;
     const unsigned lane = tid & 31u;
     const unsigned warp = tid >> 5;
-    const unsigned nwarp = nthr >> 5;
+    constexpr unsigned nwarp = NT / 32;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
     const unsigned tabn = (unsigned)tab_doubles(S);
-    double *tab_sm = reinterpret_cast<double *>(smem_raw);  // Pint[S-1][16] | Ttip[S][20]
-    double *T_sm = tab_sm + (unsigned)(S - 1) * 16u;
-    double *gacc = tab_sm + tabn;                            // [nwarp][E]
-    double *fx = gacc + nwarp * (unsigned)E;                 // [K][nthr]
-    double *red = fx + (unsigned)K * nthr;                   // [nwarp]
-    int4 *ops_sm = reinterpret_cast<int4 *>(smem_raw + prune_smem_dbl(nthr, S, K) * sizeof(double));  // [S+2]
-    uint8_t *sel_sm = reinterpret_cast<uint8_t *>(ops_sm + (S + 2)) + tid;                            // [S][nthr]
+    double *tab_sm = reinterpret_cast<double *>(smem_raw);       // SMALL: Pint[S-1][16] | Ttip[S][20]
+    double *gacc = tab_sm + (SMALL ? tabn : 0u);                 // [nwarp][E]
+    double *fx = gacc + nwarp * (unsigned)E;                     // [K][nthr]
+    double *red = fx + (unsigned)K * nthr;                       // [nwarp]
+    int *cx = reinterpret_cast<int *>(smem_raw + prune_smem_dbl(S, K, SMALL) * sizeof(double));  // [K][nthr]
+    int4 *ops_sm = reinterpret_cast<int4 *>(cx + (unsigned)K * nthr);                            // [S+2]
+    uint8_t *sel_sm = reinterpret_cast<uint8_t *>(ops_sm + (S + 2)) + tid;                       // SMALL: [S][nthr]
     if (GRAD) {
         for (unsigned i = tid; i < nwarp * (unsigned)E; i += nthr) gacc[i] = 0.0;
     }
-    // scratch ring of this CTA: [k][node][thread] x 32 B
+    // scratch ring of this CTA: [k][node][thread] x 32 B (+ 4 B rescaling counters)
     V4 *scr0 = reinterpret_cast<V4 *>(A.scratch) + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid;
+    int *cscr0 = SCALE ? A.cscratch + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid : nullptr;
     double *gw = gacc + warp * (unsigned)E;
-
-    auto tipmsg = [&](int t) -> V4 { return tip_message(T_sm + (unsigned)t * 20u, sel_sm[(unsigned)t * nthr]); };
 
 #pragma unroll 1
     for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int b = item / A.n_tiles;
         const int tile = item - b * A.n_tiles;
-        const int p = tile * A.tile_patterns + (int)tid;
+        const int p = tile * NT + (int)tid;
         const bool valid = p < A.L;
         const double wt = valid ? __ldg(A.weights + p) : 0.0;
         const double *tab_b = A.tab + (size_t)b * K * tabn;
+        const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
         __syncthreads();
         {
             // schedule of this sample, re-encoded: child code < 0 -> tip ~code, else internal index;
@@ -410,16 +451,25 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
                 }
                 ops_sm[i] = o;
             }
-            // tip selectors of this thread's pattern (thread-private column of sel_sm)
-            const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
-            for (int t = 0; t < S; ++t) sel_sm[(unsigned)t * nthr] = (uint8_t)encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+            if (SMALL) {  // tip selectors of this thread's pattern (thread-private column of sel_sm)
+                for (int t = 0; t < S; ++t) sel_sm[(unsigned)t * nthr] = (uint8_t)encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+            }
         }
+        const double *tabk = tab_sm;  // tables of the current category (shared or global)
         auto stage_tables = [&](int k) {
             __syncthreads();  // everyone is done with the previous slab (and the schedule is visible)
-            const double2 *src = reinterpret_cast<const double2 *>(tab_b + (size_t)k * tabn);
-            double2 *dst = reinterpret_cast<double2 *>(tab_sm);
-            for (unsigned i = tid; i < tabn / 2; i += nthr) dst[i] = __ldg(src + i);
-            __syncthreads();
+            if (SMALL) {
+                const double2 *src = reinterpret_cast<const double2 *>(tab_b + (size_t)k * tabn);
+                double2 *dst = reinterpret_cast<double2 *>(tab_sm);
+                for (unsigned i = tid; i < tabn / 2; i += nthr) dst[i] = __ldg(src + i);
+                __syncthreads();
+            } else {
+                tabk = tab_b + (size_t)k * tabn;
+            }
+        };
+        auto tipmsg = [&](int t) -> V4 {
+            const unsigned sel = SMALL ? (unsigned)sel_sm[(unsigned)t * nthr] : encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+            return tip_message<SMALL>(tabk + (unsigned)(S - 1) * 16u + (unsigned)t * 20u, sel);
         };
 
         // ---------------- forward (post-order), one pass per rate category ----------------
@@ -428,46 +478,72 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
         for (int k = 0; k < K; ++k) {
             stage_tables(k);
             V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
+            int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * nthr : nullptr;
             V4 prev = V4{0, 0, 0, 0};
             V4 rootL = prev;
+            int pc = 0, rootc = 0;
             // join i uses (Ac, Bc); the operands of join i+1 are fetched into (An, Bn) meanwhile.
-            auto step = [&](int i, const V4 &Ac, const V4 &Bc, V4 &An, V4 &Bn) {
+            auto step = [&](int i, const V4 &Ac, const V4 &Bc, int Acc, V4 &An, V4 &Bn, int &Anc) {
                 const int4 o = ops_sm[i];
                 const int4 on = ops_sm[i + 1];
-                if (on.x < 0) An = tipmsg(~on.x);
-                else An = ldg256(scr + (unsigned)on.x * nthr);  // stored >= 2 joins ago (schedule_kernel)
+                Anc = 0;
+                if (on.x < 0) {
+                    An = tipmsg(~on.x);
+                } else {  // stored >= 2 joins ago (schedule_kernel)
+                    An = ldg256(scr + (unsigned)on.x * nthr);
+                    if (SCALE) Anc = __ldcg(cscr + (unsigned)on.x * nthr);
+                }
                 if (on.y < 0) Bn = tipmsg(~on.y);
                 V4 Lv;
+                int cnt = Acc;
                 if (o.y < 0) Lv = vmul(Ac, Bc);
-                else Lv = vmul(Ac, prev);
+                else { Lv = vmul(Ac, prev); cnt += pc; }
+                if (SCALE) scale_up(Lv, cnt);
                 if (i == nops) {
                     rootL = Lv;
+                    rootc = cnt;
                 } else {
-                    prev = matvec_s(tab_sm + (unsigned)o.z * 16u, Lv);
-                    if (MODE != 0 || (o.w & 1)) stg256(scr + (unsigned)o.z * nthr, prev);
+                    prev = matvec_t<SMALL>(tabk + (unsigned)o.z * 16u, Lv);
+                    pc = cnt;
+                    if (MODE != 0 || (o.w & 1)) {
+                        stg256(scr + (unsigned)o.z * nthr, prev);
+                        if (SCALE) __stcg(cscr + (unsigned)o.z * nthr, cnt);
+                    }
                 }
             };
             V4 A0, B0, A1, B1;
+            int A0c = 0, A1c = 0;
             {
                 const int4 o1 = ops_sm[1];
-                A0 = o1.x < 0 ? tipmsg(~o1.x) : ldg256(scr + (unsigned)o1.x * nthr);
+                A0 = o1.x < 0 ? tipmsg(~o1.x) : ldg256(scr + (unsigned)o1.x * nthr);  // first join: both tips
                 B0 = tipmsg(o1.y < 0 ? ~o1.y : 0);
                 A1 = A0; B1 = B0;
             }
             int i = 1;
 #pragma unroll 1
             for (; i + 1 <= nops; i += 2) {
-                step(i, A0, B0, A1, B1);
-                step(i + 1, A1, B1, A0, B0);
+                step(i, A0, B0, A0c, A1, B1, A1c);
+                step(i + 1, A1, B1, A1c, A0, B0, A0c);
             }
-            if (i <= nops) step(i, A0, B0, A1, B1);
+            if (i <= nops) step(i, A0, B0, A0c, A1, B1, A1c);
             double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
-            if (MODE != 0) fx[(unsigned)k * nthr + tid] = fk;
+            if (MODE != 0 || SCALE) fx[(unsigned)k * nthr + tid] = fk;
+            if (SCALE) cx[(unsigned)k * nthr + tid] = rootc;
             fsum += fk;
-            if (!A.mix) ll += wt * log(fk);
+            if (!A.mix) ll += SCALE ? wt * (log(fk) - (double)rootc * (256.0 * 0.6931471805599453)) : wt * log(fk);
         }
-        const double f = fsum / (double)K;
-        if (A.mix) ll = wt * log(f);
+        double f = fsum / (double)K;
+        int cmin = 0;
+        if (SCALE) {
+            cmin = cx[tid];
+            for (int k = 1; k < K; ++k) cmin = min(cmin, cx[(unsigned)k * nthr + tid]);
+            if (A.mix) {
+                double s = 0.0;
+                for (int k = 0; k < K; ++k) s += fx[(unsigned)k * nthr + tid] * pow2_256(cmin - cx[(unsigned)k * nthr + tid]);
+                f = s / (double)K;
+            }
+        }
+        if (A.mix) ll = SCALE ? wt * (log(f) - (double)cmin * (256.0 * 0.6931471805599453)) : wt * log(f);
         ll = warp_sum(ll);
         if (lane == 0) red[warp] = ll;
 
@@ -477,18 +553,28 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
             for (int k = 0; k < K; ++k) {
                 stage_tables(k);
                 V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
+                int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * nthr : nullptr;
                 const double rate_k = md.rates[k];
                 const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(unsigned)k * nthr + tid];
                 V4 wprev = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
+                // true upper message = stored * 2^(256 * we)
+                int we = SCALE ? (A.mix ? cmin : cx[(unsigned)k * nthr + tid]) : 0;
                 // join i uses (Ac, Bc, Wc); operands of join i-1 are fetched into (An, Bn, Wn) meanwhile:
                 // nothing stored by join i is read by join i-1 (its upper message, when it comes from
                 // scratch, was stored by an ancestor's join; its children are other nodes)
-                auto step = [&](int i, const V4 &Ac, const V4 &Bc, const V4 &Wc, V4 &An, V4 &Bn, V4 &Wn) {
+                auto step = [&](int i, const V4 &Ac, const V4 &Bc, const V4 &Wc, int Acc, int Bcc, int Wcc,
+                                V4 &An, V4 &Bn, V4 &Wn, int &Anc, int &Bnc, int &Wnc) {
                     const int4 o = ops_sm[i];
                     const int4 on = ops_sm[i - 1];
-                    if (on.x < 0) An = tipmsg(~on.x); else An = ldg256(scr + (unsigned)on.x * nthr);
-                    if (on.y < 0) Bn = tipmsg(~on.y); else Bn = ldg256(scr + (unsigned)on.y * nthr);
-                    if (on.w & 1) Wn = ldg256(scr + (unsigned)on.z * nthr);
+                    Anc = 0; Bnc = 0;
+                    if (on.x < 0) An = tipmsg(~on.x);
+                    else { An = ldg256(scr + (unsigned)on.x * nthr); if (SCALE) Anc = __ldcg(cscr + (unsigned)on.x * nthr); }
+                    if (on.y < 0) Bn = tipmsg(~on.y);
+                    else { Bn = ldg256(scr + (unsigned)on.y * nthr); if (SCALE) Bnc = __ldcg(cscr + (unsigned)on.y * nthr); }
+                    if (on.w & 1) {
+                        Wn = ldg256(scr + (unsigned)on.z * nthr);
+                        if (SCALE) Wnc = __ldcg(cscr + (unsigned)on.z * nthr);
+                    }
                     {
                         // pull the messages needed three joins from now out of HBM into L2
                         const int4 of = ops_sm[i > 3 ? i - 3 : 0];
@@ -496,33 +582,51 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
                         if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
                     }
                     V4 ua, ub;
-                    if (o.w & 1) { ua = vmul(Wc, Bc); ub = vmul(Wc, Ac); }
-                    else { ua = vmul(wprev, Bc); ub = vmul(wprev, Ac); }
-                    const double ga = rate_k * uQx(md.Q, ua, Ac);
-                    const double gb = rate_k * uQx(md.Q, ub, Bc);
+                    int ew;
+                    if (o.w & 1) { ua = vmul(Wc, Bc); ub = vmul(Wc, Ac); ew = Wcc; }
+                    else { ua = vmul(wprev, Bc); ub = vmul(wprev, Ac); ew = we; }
+                    double ga = rate_k * uQx(md.Q, ua, Ac);
+                    double gb = rate_k * uQx(md.Q, ub, Bc);
+                    if (SCALE) {
+                        const double sf = pow2_256(ew - Acc - Bcc);
+                        ga *= sf; gb *= sf;
+                    }
                     const double g2 = warp_sum2(ga, gb, lane);
                     if ((lane & 15u) == 0u) {
                         const int c = lane ? o.y : o.x;
                         gw[c < 0 ? ~c : c + S] += g2;
                     }
-                    if (o.x >= 0) stg256(scr + (unsigned)o.x * nthr, matvecT_s(tab_sm + (unsigned)o.x * 16u, ua));
-                    if (o.y >= 0) wprev = matvecT_s(tab_sm + (unsigned)o.y * 16u, ub);
+                    if (o.x >= 0) {
+                        V4 wa = matvecT_t<SMALL>(tabk + (unsigned)o.x * 16u, ua);
+                        int ea = ew - Bcc;
+                        if (SCALE) { int neg = -ea; scale_both(wa, neg); ea = -neg; }
+                        stg256(scr + (unsigned)o.x * nthr, wa);
+                        if (SCALE) __stcg(cscr + (unsigned)o.x * nthr, ea);
+                    }
+                    if (o.y >= 0) {
+                        wprev = matvecT_t<SMALL>(tabk + (unsigned)o.y * 16u, ub);
+                        we = ew - Acc;
+                        if (SCALE) { int neg = -we; scale_both(wprev, neg); we = -neg; }
+                    }
                 };
                 V4 A0, B0, W0, A1, B1, W1;
+                int A0c = 0, B0c = 0, W0c = 0, A1c = 0, B1c = 0, W1c = 0;
                 {
                     const int4 o1 = ops_sm[nops];
-                    A0 = o1.x < 0 ? tipmsg(~o1.x) : ldg256(scr + (unsigned)o1.x * nthr);
-                    B0 = o1.y < 0 ? tipmsg(~o1.y) : ldg256(scr + (unsigned)o1.y * nthr);
+                    if (o1.x < 0) A0 = tipmsg(~o1.x);
+                    else { A0 = ldg256(scr + (unsigned)o1.x * nthr); if (SCALE) A0c = __ldcg(cscr + (unsigned)o1.x * nthr); }
+                    if (o1.y < 0) B0 = tipmsg(~o1.y);
+                    else { B0 = ldg256(scr + (unsigned)o1.y * nthr); if (SCALE) B0c = __ldcg(cscr + (unsigned)o1.y * nthr); }
                     W0 = wprev;
                     A1 = A0; B1 = B0; W1 = W0;
                 }
                 int i = nops;
 #pragma unroll 1
                 for (; i - 1 >= 1; i -= 2) {
-                    step(i, A0, B0, W0, A1, B1, W1);
-                    step(i - 1, A1, B1, W1, A0, B0, W0);
+                    step(i, A0, B0, W0, A0c, B0c, W0c, A1, B1, W1, A1c, B1c, W1c);
+                    step(i - 1, A1, B1, W1, A1c, B1c, W1c, A0, B0, W0, A0c, B0c, W0c);
                 }
-                if (i >= 1) step(i, A0, B0, W0, A1, B1, W1);
+                if (i >= 1) step(i, A0, B0, W0, A0c, B0c, W0c, A1, B1, W1, A1c, B1c, W1c);
             }
         }
         if (GMATS) {
@@ -538,6 +642,10 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
                 const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(unsigned)k * nthr + tid];
                 double *gpart = A.gm_part + ((((size_t)item * K + k) * nwarp + warp) * (size_t)E) * 16;
                 V4 uprev = V4{0, 0, 0, 0};
+                auto maskvec = [&](int t) -> V4 {
+                    const unsigned m = SMALL ? (unsigned)sel_sm[(unsigned)t * nthr] : (unsigned)__ldg(tm + (size_t)t * A.ld_mask);
+                    return V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)};
+                };
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = ops_sm[i];
@@ -552,23 +660,13 @@ __global__ void __launch_bounds__(NTHR, (DODO_PRUNE_MINBLOCKS * 256) / NTHR) pru
                     } else {
                         const V4 u = (o.w & 1) ? ldg256(scr + (unsigned)o.z * nthr) : uprev;
                         outer_reduce_store(u, Lv, gpart + (size_t)(o.z + S) * 16, lane);
-                        w = matvecT_s(tab_sm + (unsigned)o.z * 16u, u);
+                        w = matvecT_t<SMALL>(tabk + (unsigned)o.z * 16u, u);
                     }
                     const V4 ua = vmul(w, bv), ub = vmul(w, av);
-                    if (o.x < 0) {
-                        const unsigned m = sel_sm[(unsigned)(~o.x) * nthr];
-                        outer_reduce_store(ua, V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)},
-                                           gpart + (size_t)(~o.x) * 16, lane);
-                    } else {
-                        stg256(scr + (unsigned)o.x * nthr, ua);
-                    }
-                    if (o.y < 0) {
-                        const unsigned m = sel_sm[(unsigned)(~o.y) * nthr];
-                        outer_reduce_store(ub, V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)},
-                                           gpart + (size_t)(~o.y) * 16, lane);
-                    } else {
-                        uprev = ub;
-                    }
+                    if (o.x < 0) outer_reduce_store(ua, maskvec(~o.x), gpart + (size_t)(~o.x) * 16, lane);
+                    else stg256(scr + (unsigned)o.x * nthr, ua);
+                    if (o.y < 0) outer_reduce_store(ub, maskvec(~o.y), gpart + (size_t)(~o.y) * 16, lane);
+                    else uprev = ub;
                 }
             }
             gpi0 = warp_sum(gpi0); gpi1 = warp_sum(gpi1); gpi2 = warp_sum(gpi2); gpi3 = warp_sum(gpi3);
@@ -642,15 +740,17 @@ __global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, co
 }
 
 typedef void (*prune_fn_t)(PruneArgs, ModelDev);
-static prune_fn_t prune_entry(int mode, int threads) {
-    switch (threads) {
-        case 256: return mode == 0 ? prune_kernel<0, 256> : (mode == 1 ? prune_kernel<1, 256> : prune_kernel<2, 256>);
-        case 128: return mode == 0 ? prune_kernel<0, 128> : (mode == 1 ? prune_kernel<1, 128> : prune_kernel<2, 128>);
-        case 64: return mode == 0 ? prune_kernel<0, 64> : (mode == 1 ? prune_kernel<1, 64> : prune_kernel<2, 64>);
-        case 32: return mode == 0 ? prune_kernel<0, 32> : (mode == 1 ? prune_kernel<1, 32> : prune_kernel<2, 32>);
+static prune_fn_t prune_entry(int mode, bool small, bool scale) {
+    if (mode == 2) return small ? prune_kernel<2, true, false> : prune_kernel<2, false, false>;
+    if (mode == 1) {
+        if (small) return scale ? prune_kernel<1, true, true> : prune_kernel<1, true, false>;
+        return scale ? prune_kernel<1, false, true> : prune_kernel<1, false, false>;
     }
-    return nullptr;
+    if (small) return scale ? prune_kernel<0, true, true> : prune_kernel<0, true, false>;
+    return scale ? prune_kernel<0, false, true> : prune_kernel<0, false, false>;
 }
+// tables + selectors live in shared memory when that still leaves room for 3 CTAs per SM
+static bool prune_small(int S, int K) { return prune_smem_bytes(S, K, true) <= 74 * 1024; }
 static int prune_mode(uint32_t flags) { return (flags & DODO_PRUNE_GMATS) ? 2 : ((flags & DODO_PRUNE_GRAD) ? 1 : 0); }
 
 }  // namespace dodo
@@ -664,24 +764,15 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     DODO_CHECK_ARG(K >= 1 && K <= MAX_K, "dodo_prune_plan: K must be in [1,%d] (got %d)", MAX_K, K);
     DODO_CHECK_ARG(!((flags & DODO_PRUNE_GMATS) && (flags & DODO_PRUNE_GRAD)),
                    "dodo_prune_plan: GRAD and GMATS are separate calls");
-    if (flags & DODO_PRUNE_SCALE) {
-        set_error("dodo_prune_plan: DODO_PRUNE_SCALE not implemented yet");
-        return DODO_ENOTIMPL;
-    }
+    DODO_CHECK_ARG(!((flags & DODO_PRUNE_GMATS) && (flags & DODO_PRUNE_SCALE)),
+                   "dodo_prune_plan: GMATS is not available with rescaling");
     memset(plan, 0, sizeof(*plan));
     plan->B = B; plan->S = S; plan->L = L; plan->K = K; plan->flags = flags;
-    int threads = 256;
-    if (threads_hint > 0) {
-        DODO_CHECK_ARG(threads_hint == 32 || threads_hint == 64 || threads_hint == 128 || threads_hint == 256,
-                       "dodo_prune_plan: threads must be 32, 64, 128 or 256");
-        threads = threads_hint;
-    }
-    while (threads > 32 && L <= threads / 2) threads /= 2;  // tiny alignments: do not idle most of a CTA
-    size_t smem = prune_smem_bytes(threads, S, K);
-    while (smem > 227 * 1024 && threads > 32) {
-        threads /= 2;
-        smem = prune_smem_bytes(threads, S, K);
-    }
+    (void)threads_hint;
+    const int threads = NT;
+    const bool small = prune_small(S, K);
+    const bool scale = (flags & DODO_PRUNE_SCALE) != 0;
+    const size_t smem = prune_smem_bytes(S, K, small);
     if (smem > 227 * 1024) {
         set_error("dodo_prune_plan: %d taxa need %zu bytes of shared memory per CTA (limit 227 KB)", S, smem);
         return DODO_ENOTIMPL;
@@ -695,12 +786,10 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     int grid = grid_hint;
     if (grid <= 0) {
         // persistent grid: every CTA the SMs can hold at once (a multiple of the SM count)
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(prune_entry(prune_mode(flags), threads),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        prune_fn_t fn = prune_entry(prune_mode(flags), small, scale);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prune_entry(prune_mode(flags), threads),
-                                                                      threads, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
         if (e != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 1;
@@ -714,8 +803,9 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     plan->off_ops = off;     off = align_up(off + (uint64_t)B * nI * sizeof(int4), 256);
     plan->off_sched = off;   off = align_up(off + (uint64_t)B * 6 * S * sizeof(int), 256);
     plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S) * sizeof(double), 256);
-    plan->off_tiptab = off;
     plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * threads * 32, 256);
+    plan->off_tiptab = off;  // rescaling counters (int32 per stored message)
+    if (scale) off = align_up(off + (uint64_t)grid * K * nI * threads * sizeof(int), 256);
     plan->off_ll_part = off; off = align_up(off + (uint64_t)plan->n_items * sizeof(double), 256);
     plan->off_g_part = off;
     if (flags & DODO_PRUNE_GRAD) off = align_up(off + (uint64_t)plan->n_items * E * sizeof(double), 256);
@@ -775,6 +865,7 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.tipmask = d_tipmask; A.ld_mask = ld_mask; A.weights = d_weights;
     A.ops = ops; A.ops_batch = peel_batch; A.tab = tab;
     A.scratch = (double2 *)(ws + plan->off_scratch);
+    A.cscratch = (int *)(ws + plan->off_tiptab);
     A.ll_part = (double *)(ws + plan->off_ll_part);
     A.g_part = (double *)(ws + plan->off_g_part);
     A.gm_part = (double *)(ws + plan->off_gm_part);
@@ -782,13 +873,13 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.B = B; A.S = S; A.L = L; A.K = K;
     A.n_tiles = plan->n_tiles; A.n_items = plan->n_items; A.tile_patterns = plan->tile_patterns;
     A.mix = ((plan->flags & DODO_PRUNE_MIX) && K > 1) ? 1 : 0;
-    size_t smem = prune_smem_bytes(plan->threads, S, K);
+    const bool small = prune_small(S, K);
+    size_t smem = prune_smem_bytes(S, K, small);
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
     {
-        prune_fn_t fn = prune_entry(prune_mode(plan->flags), plan->threads);
-        DODO_CHECK_ARG(fn != nullptr, "dodo_prune: unsupported CTA size %d", plan->threads);
+        prune_fn_t fn = prune_entry(prune_mode(plan->flags), small, (plan->flags & DODO_PRUNE_SCALE) != 0);
         if (smem > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<plan->grid, plan->threads, smem, stream>>>(A, md);
     }

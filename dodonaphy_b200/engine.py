@@ -159,13 +159,15 @@ class PruneEngine:
             self._plans[key] = hit
         return hit
 
-    def loglik(self, peel, blens, model, rates=None, mix=False, grad=False, out=None, mats=None):
+    def loglik(self, peel, blens, model, rates=None, mix=False, grad=False, out=None, mats=None, scale=None):
         """lnL for a batch.
 
         peel  : int64 device tensor (B, S-1, 3) or (S-1, 3) (one topology shared by the batch)
         blens : float64 device tensor (B, 2S-2) (or (2S-2,) for B = 1); ignored if ``mats`` given
         mats  : optional float64 device tensor (B, 2S-2, K, 4, 4): caller-supplied P matrices
         rates : K category rates (host); None => K = 1
+        scale : power-of-two rescaling against underflow (bit-identical to the unscaled result where
+                that one is finite); None => on for >= 200 taxa
         Returns (lnL (B,), grad_blens (B, 2S-2) or None), both device tensors.
         """
         with torch.cuda.device(self.device):
@@ -190,7 +192,9 @@ class PruneEngine:
             peel_t = peel_t.contiguous()
             if tuple(peel_t.shape[1:]) != (self.S - 1, 3) or peel_t.shape[0] not in (1, B):
                 raise ValueError("peel must have shape (B or 1, S-1, 3)")
-            flags = (_lib.PRUNE_GRAD if grad else 0) | (_lib.PRUNE_MIX if (mix and K > 1) else 0)
+            if scale is None:
+                scale = self.S >= 200
+            flags = (_lib.PRUNE_GRAD if grad else 0) | (_lib.PRUNE_MIX if (mix and K > 1) else 0) | (_lib.PRUNE_SCALE if scale else 0)
             plan, ws = self._plan(B, K, flags)
             ll = torch.empty(B, dtype=torch.float64, device=self.device)
             g = torch.empty((B, self.E), dtype=torch.float64, device=self.device) if grad else None

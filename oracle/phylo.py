@@ -180,3 +180,27 @@ def gtr_p_t_torch(blens, rates, freqs):
     lam, V = torch.linalg.eigh(sp @ Q @ spi)
     ex = torch.exp(lam * blens.unsqueeze(-1))
     return ((spi @ V) * ex.unsqueeze(-2)) @ (V.inverse() @ sp)
+
+
+def treelikelihood_rescaled_torch(tip_partials, weights, post_indexing, mats, freqs, gamma_mix=False):
+    """Underflow-safe twin of ``treelikelihood_torch``: every internal partial is divided by its
+    per-pattern maximum and the logs are accumulated.  Mathematically identical to phylo.py:132-139;
+    used as the oracle where the reference's unscaled product underflows."""
+    import torch
+
+    S = len(tip_partials)
+    K = mats.shape[1] if mats.dim() == 4 else 1
+    m4 = mats if mats.dim() == 4 else mats.unsqueeze(1)
+    partials = [p.unsqueeze(0).expand(K, -1, -1) for p in tip_partials] + [None] * (S - 1)
+    logs = [torch.zeros((K, p.shape[-1]), dtype=torch.float64) for p in tip_partials] + [None] * (S - 1)
+    for left, right, node in post_indexing:
+        v = torch.matmul(m4[left], partials[left]) * torch.matmul(m4[right], partials[right])
+        mx = v.detach().max(dim=1, keepdim=True).values.clamp_min(1e-300)
+        partials[node] = v / mx
+        logs[node] = logs[left] + logs[right] + torch.log(mx.squeeze(1))
+    root = post_indexing[-1][-1]
+    site = torch.einsum("i,kil->kl", freqs, partials[root])
+    lsite = torch.log(site) + logs[root]
+    if gamma_mix:
+        return torch.sum((torch.logsumexp(lsite, dim=0) - np.log(K)) * weights)
+    return torch.sum(lsite * weights)

@@ -140,3 +140,60 @@ def test_argument_errors():
         eng.loglik(_dev(np.zeros((2, 3), dtype=np.int64)), _dev(np.ones(6)), SubstModel.jc69())
     with pytest.raises(ValueError):
         PruneEngine(np.ones((4, 10), dtype=np.uint8), np.ones(9))
+
+
+def _nj_batch(prob):
+    from oracle import hyp, nj
+
+    peels, blens = zip(*[nj.nj_hard(hyp.get_pdm_np(x)) for x in prob["xs"]])
+    return np.stack(peels), np.stack(blens)
+
+
+@pytest.mark.parametrize("S,L,K", [(12, 300, 1), (64, 700, 4), (130, 260, 2)])
+def test_rescaling_is_bit_identical_when_nothing_underflows(S, L, K):
+    """Power-of-two rescaling never touches a mantissa: with and without it the results are equal
+    bit for bit (small-table and large-table kernel variants, all rate-category modes)."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+
+    prob = synth.make_problem(S, L, 3, D=3, seed=300 + S)
+    peels, blens = _nj_batch(prob)
+    eng = _engine(prob["masks"], prob["weights"])
+    m = SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(0.5, K)
+    for mix in (False, True):
+        a, ga = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=True, scale=False)
+        b, gb = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=True, scale=True)
+        assert torch.equal(a, b) and torch.equal(ga, gb)
+        c, _ = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=False, scale=True)
+        assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("K,mix", [(1, False), (4, True), (3, False)])
+def test_rescaling_where_the_reference_underflows(K, mix):
+    """Long branches on 400 taxa: the unscaled product (the reference's arithmetic) underflows to
+    -inf; the rescaled kernel must agree with the log-space oracle (lnL and gradient)."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import phylo
+
+    S, L = 400, 40
+    prob = synth.make_problem(S, L, 1, D=4, seed=77)
+    rng = np.random.default_rng(5)
+    masks = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)  # i.i.d. columns: tiny site likelihoods
+    peels, blens = _nj_batch(prob)
+    blens = blens * 40.0 + 0.5
+    eng = _engine(masks, prob["weights"])
+    m = SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(0.5, K)
+    raw, _ = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=False, scale=False)
+    assert not torch.isfinite(raw).all(), "test input no longer underflows without rescaling"
+    ll, g = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=True, scale=True)
+    bt = torch.tensor(blens[0], requires_grad=True)
+    mats = phylo.gtr_p_t_torch(bt[:, None] * torch.tensor(rates)[None, :], torch.tensor(prob["rates"]), torch.tensor(prob["freqs"]))
+    ref = phylo.treelikelihood_rescaled_torch([torch.tensor(phylo.mask_to_partial(x)) for x in masks], torch.tensor(prob["weights"]),
+                                              peels[0], mats, torch.tensor(prob["freqs"]), gamma_mix=mix)
+    ref.backward()
+    assert torch.isfinite(ll).all()
+    assert ll.item() == pytest.approx(ref.item(), rel=RTOL)
+    _assert_grad(g[0].cpu().numpy(), bt.grad.numpy())
