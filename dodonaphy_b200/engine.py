@@ -264,10 +264,23 @@ def _as_batch(x, ndim):
     return x.contiguous(), squeeze
 
 
+_curv_cache = {}
+
+
 def _curv_tensor(curvature, device):
     if isinstance(curvature, torch.Tensor):
-        return curvature.detach().to(device=device, dtype=torch.float64).reshape(-1)[:1].contiguous()
-    return torch.tensor([float(curvature)], dtype=torch.float64, device=device)
+        if curvature.is_cuda:
+            return curvature.detach().to(device=device, dtype=torch.float64).reshape(-1)[:1].contiguous()
+        curvature = float(curvature.detach().reshape(-1)[0])
+    # a pageable host->device copy synchronises the stream: keep one device scalar per value
+    key = (float(curvature), str(device))
+    t = _curv_cache.get(key)
+    if t is None:
+        if len(_curv_cache) > 64:
+            _curv_cache.clear()
+        t = torch.tensor([float(curvature)], dtype=torch.float64, device=device)
+        _curv_cache[key] = t
+    return t
 
 
 def pdm_forward(x, curvature=-1.0, variant="torch", lift="up", matsumoto=False):
