@@ -268,6 +268,9 @@ __device__ __forceinline__ double block_excl_scan(double v, double *sh, double &
     return off + inc - v;
 }
 
+// exp(-a) for a >= 0; exactly 0 beyond the fp64 underflow point, without paying for the call
+__device__ __forceinline__ double exp_neg(double a) { return a > 750.0 ? 0.0 : exp(-a); }
+
 template <bool FULL>
 __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
     const int tid = threadIdx.x, T = blockDim.x;
@@ -288,14 +291,14 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
-        loc += exp(-fabs(s - m) / tau);
+        loc += exp_neg(fabs(s - m) / tau);
     }
     double Z;
     double off = block_excl_scan(loc, sh, Z);
     double NN = (double)c.N * (double)c.N;
     if (!FULL) {
         // inactive entries: zeros and 1e9 -- require their softmax mass to be invisible in fp64
-        double worst = exp(-fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
+        double worst = exp_neg(fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
         guard_ok = (NN * worst <= 1e-18 * fmin(1.0, tau) * Z);
     } else {
         guard_ok = true;
@@ -305,21 +308,27 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
-        double e = exp(-fabs(s - m) / tau);
-        run += e;
-        M = fmax(M, (e / Z) * (run / Z));
+        double e = exp_neg(fabs(s - m) / tau);
+        if (e != 0.0) {
+            run += e;
+            M = fmax(M, (e / Z) * (run / Z));
+        }
     }
     M = block_reduce(M, sh, 2);
     // pass 4: second softmax on -c, soft index = sum p'_j * flat_j
     run = off;
+    const double e0 = exp_neg(M / tau);  // entries with c_j == 0
     double z2 = 0.0, isum = 0.0, fsum = 0.0;
     for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
-        double e = exp(-fabs(s - m) / tau);
-        run += e;
-        double cj = (e / Z) * (run / Z);
-        double e2 = exp(-fabs(M - cj) / tau);
+        double e = exp_neg(fabs(s - m) / tau);
+        double e2 = e0;
+        if (e != 0.0) {
+            run += e;
+            double cj = (e / Z) * (run / Z);
+            e2 = exp_neg(fabs(M - cj) / tau);
+        }
         z2 += e2;
         isum = fma(e2, f, isum);
         fsum += f;
@@ -328,7 +337,6 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     isum = block_reduce(isum, sh, 0);
     if (!FULL) {
         fsum = block_reduce(fsum, sh, 0);
-        double e0 = exp(-M / tau);  // entries with c_j == 0
         double cnt = NN - (double)P;
         z2 += cnt * e0;
         isum += e0 * (NN * (NN - 1.0) * 0.5 - fsum);

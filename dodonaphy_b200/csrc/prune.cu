@@ -89,53 +89,58 @@ __device__ __forceinline__ double uQx(const double *Q, const V4 &u, const V4 &x)
 // Strahler number is evaluated first, which bounds the number of simultaneously pending a-children
 // by log2(S).
 // ------------------------------------------------------------------------------------------
-__global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S, int4 *__restrict__ ops,
-                                int *__restrict__ sched) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S, int4 *__restrict__ ops) {
+    // one warp per sample: the peel is staged into shared memory by the warp, lane 0 runs the two
+    // (inherently sequential) passes there, the warp writes the schedule back coalesced
+    extern __shared__ __align__(16) int sched_sm[];
+    const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= nb) return;
-    const int nI = S - 1;
+    const int nI = S - 1, Nn = 2 * S - 1;
     const int64_t *pl = peel + (size_t)b * nI * 3;
-    int *Lc = sched + (size_t)b * 6 * S;
-    int *Rc = Lc + S, *st = Rc + S, *isz = st + S, *start = isz + S, *afl = start + S;
-    int4 *op = ops + (size_t)b * nI;
-    for (int i = 0; i < nI; ++i) {
-        isz[i] = 0; afl[i] = 0; start[i] = 0; Lc[i] = 0; Rc[i] = 0; st[i] = 1;
-        op[i] = make_int4(0, 0, S + i, i == nI - 1 ? 2 : 0);  // memory-safe default for malformed peels
-    }
-    const int Nn = 2 * S - 1;
-    for (int i = 0; i < nI; ++i) {
-        int l = (int)pl[i * 3 + 0], r = (int)pl[i * 3 + 1], p = (int)pl[i * 3 + 2];
+    int4 *op = reinterpret_cast<int4 *>(sched_sm);               // [S-1] schedule being built
+    int *Pl = reinterpret_cast<int *>(op + nI), *Pr = Pl + S, *Pp = Pr + S;  // peel rows
+    int *Lc = Pp + S, *Rc = Lc + S, *st = Rc + S, *isz = st + S, *start = isz + S, *afl = start + S;
+    for (int i = lane; i < nI; i += 32) {
         // memory safety for malformed input (the host shim validates and raises)
-        l = min(max(l, 0), Nn - 1); r = min(max(r, 0), Nn - 1); p = min(max(p, S), Nn - 1);
-        int idx = p - S;
-        Lc[idx] = l; Rc[idx] = r;
-        int sl = l < S ? 1 : st[l - S], sr = r < S ? 1 : st[r - S];
-        st[idx] = (sl == sr) ? sl + 1 : max(sl, sr);
-        isz[idx] = 1 + (l >= S ? isz[l - S] : 0) + (r >= S ? isz[r - S] : 0);
+        Pl[i] = min(max((int)pl[i * 3 + 0], 0), Nn - 1);
+        Pr[i] = min(max((int)pl[i * 3 + 1], 0), Nn - 1);
+        Pp[i] = min(max((int)pl[i * 3 + 2], S), Nn - 1);
+        isz[i] = 0; afl[i] = 0; start[i] = 0; Lc[i] = 0; Rc[i] = 0; st[i] = 1;
+        op[i] = make_int4(0, 0, S + i, i == nI - 1 ? 2 : 0);
     }
-    for (int i = nI - 1; i >= 0; --i) {
-        int p = min(max((int)pl[i * 3 + 2], S), Nn - 1);
-        int idx = p - S;
-        int l = Lc[idx], r = Rc[idx];
-        int a, bb;
-        bool li = l >= S, ri = r >= S;
-        if (li && ri) {
-            if (st[l - S] >= st[r - S]) { a = l; bb = r; } else { a = r; bb = l; }
-        } else if (li) { a = r; bb = l; }
-        else { a = l; bb = r; }
-        int s0 = (i == nI - 1) ? 0 : start[idx];
-        int oi = s0 + isz[idx] - 1;
-        oi = min(max(oi, 0), nI - 1);
-        int flags = afl[idx] | ((i == nI - 1) ? 2 : 0);
-        op[oi] = make_int4(a, bb, p, flags);
-        if (li && ri) {
-            start[a - S] = s0;
-            start[bb - S] = s0 + isz[a - S];
-            afl[a - S] = 1;
-        } else if (bb >= S) {
-            start[bb - S] = s0;
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < nI; ++i) {
+            const int l = Pl[i], r = Pr[i], idx = Pp[i] - S;
+            Lc[idx] = l; Rc[idx] = r;
+            const int sl = l < S ? 1 : st[l - S], sr = r < S ? 1 : st[r - S];
+            st[idx] = (sl == sr) ? sl + 1 : max(sl, sr);
+            isz[idx] = 1 + (l >= S ? isz[l - S] : 0) + (r >= S ? isz[r - S] : 0);
+        }
+        for (int i = nI - 1; i >= 0; --i) {
+            const int p = Pp[i], idx = p - S;
+            const int l = Lc[idx], r = Rc[idx];
+            int a, bb;
+            const bool li = l >= S, ri = r >= S;
+            if (li && ri) {
+                if (st[l - S] >= st[r - S]) { a = l; bb = r; } else { a = r; bb = l; }
+            } else if (li) { a = r; bb = l; }
+            else { a = l; bb = r; }
+            const int s0 = (i == nI - 1) ? 0 : start[idx];
+            const int oi = min(max(s0 + isz[idx] - 1, 0), nI - 1);
+            op[oi] = make_int4(a, bb, p, afl[idx] | ((i == nI - 1) ? 2 : 0));
+            if (li && ri) {
+                start[a - S] = s0;
+                start[bb - S] = s0 + isz[a - S];
+                afl[a - S] = 1;
+            } else if (bb >= S) {
+                start[bb - S] = s0;
+            }
         }
     }
+    __syncwarp();
+    int4 *out = ops + (size_t)b * nI;
+    for (int i = lane; i < nI; i += 32) out[i] = op[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -853,7 +858,10 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
 
     {
         int nb = peel_batch;
-        schedule_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(d_peel, nb, S, ops, sched);
+        (void)sched;
+        size_t sm = ((size_t)9 * S + 4) * sizeof(int) + (size_t)(S - 1) * sizeof(int4);
+        if (sm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        schedule_kernel<<<nb, 32, sm, stream>>>(d_peel, nb, S, ops);
         DODO_LAUNCH_CHECK();
     }
     {
