@@ -1,0 +1,113 @@
+"""GPU parity at the shapes of BASELINE.json's other configurations (sizes the oracle finishes in
+seconds) plus size-independent properties at the full shapes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+def test_c3_shape_mcmc_chains_forward_only():
+    """configs[2]: 200 taxa, JC69, independent chains, gradient-free path
+    (Chyp_np.get_pdm -> Cpeeler.nj_np -> Cphylo.compute_LL_np)."""
+    from dodonaphy_b200 import engine, synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+    from oracle import cbuild, phylo
+
+    S, L, B = 200, 3000, 4
+    prob = synth.make_problem(S, L, B, D=5, seed=1003)
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69())
+    out = hp.value(_dev(prob["xs"]))
+    tips = [phylo.mask_to_partial(m) for m in prob["masks"]]
+    pdm = engine.pdm_forward(_dev(prob["xs"]), -1.0, "numpy").cpu().numpy()
+    for b in range(B):
+        peel, blens = cbuild.nj_hard_c(pdm[b])
+        assert np.array_equal(out["peel"][b].cpu().numpy(), peel)
+        assert np.array_equal(out["blens"][b].cpu().numpy(), blens)
+        assert out["lnL"][b].item() == pytest.approx(phylo.compute_LL_np(tips, prob["weights"], peel, blens), rel=1e-9)
+
+
+@pytest.mark.parametrize("S,B", [(700, 2), (2000, 2)])
+def test_c4_shape_topology_stress_hard_nj_bit_exact(S, B):
+    """configs[3]: pairwise distance + batched NJ at up to 2000 taxa; hard NJ bit-exact against the
+    C restatement of Cpeeler.nj_np (the Cython original needs ~4 min per 2000-taxon tree)."""
+    from dodonaphy_b200 import engine
+    from dodonaphy_b200.engine import validate_peel
+    from oracle import cbuild, hyp
+
+    rng = np.random.default_rng(1004)
+    xs = rng.normal(0, 0.05, (B, S, 5))
+    pdm = engine.pdm_forward(_dev(xs), -1.0, "numpy")
+    off = ~np.eye(S, dtype=bool)
+    np.testing.assert_allclose(pdm[0].cpu().numpy()[off], hyp.get_pdm_np(xs[0])[off], rtol=1e-10, atol=1e-14)
+    peel, blens = engine.nj_hard(pdm)
+    p_ref, b_ref = cbuild.nj_hard_c(pdm[0].cpu().numpy())
+    assert np.array_equal(peel[0].cpu().numpy(), p_ref)
+    assert np.array_equal(blens[0].cpu().numpy(), b_ref)
+    validate_peel(peel.cpu().numpy(), S)
+
+
+def test_c4_shape_soft_nj_medium_vs_oracle_and_large_properties():
+    from dodonaphy_b200 import engine
+    from dodonaphy_b200.engine import validate_peel
+    from oracle import hyp, nj
+
+    rng = np.random.default_rng(1005)
+    S = 300
+    x = rng.normal(0, 0.05, (S, 5))
+    pdm = hyp.get_pdm_torch(x)
+    peel, blens, flags = engine.nj_soft(_dev(pdm), 1e-8, return_flags=True)
+    assert int((flags & 12).sum().item()) == 0
+    p_ref, b_ref = nj.nj_soft(pdm, 1e-8)
+    assert np.array_equal(peel.cpu().numpy(), p_ref)
+    np.testing.assert_allclose(blens.cpu().numpy(), b_ref, rtol=1e-9, atol=1e-15)
+    # 2000 taxa: the reference cannot run at all (its SoftSort matrix would hold (3999^2)^2 doubles);
+    # check what does not depend on size: a valid tree, exactness guard silent, and the NJ identity
+    # that the two branches of every join add up to the distance between the joined nodes.
+    S = 2000
+    xs = rng.normal(0, 0.05, (1, S, 5))
+    pdm = engine.pdm_forward(_dev(xs), -1.0, "torch")
+    peel, blens, flags = engine.nj_soft(pdm, 1e-8, return_flags=True)
+    assert int((flags & 12).sum().item()) == 0
+    validate_peel(peel.cpu().numpy(), S)
+    pl, bl, d = peel[0].cpu().numpy(), blens[0].cpu().numpy(), pdm[0].cpu().numpy()
+    first = pl[0]
+    assert bl[first[0]] + bl[first[1]] == pytest.approx(d[first[0], first[1]], rel=1e-12)
+    assert (bl > 0).all()
+
+
+def test_c5_shape_long_alignment_site_blocks():
+    """configs[4]: 500 taxa, one tree, long alignment split into site blocks: per-block lnL and
+    gradients add up to the whole (what the NCCL all_reduce does across GPUs), rescaling on, and the
+    whole agrees with the log-space oracle."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.dist import shard_bounds
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+    from oracle import cbuild, hyp, phylo
+
+    S, L = 500, 6000
+    prob = synth.make_problem(S, L, 1, D=5, seed=1006)
+    peel, blens = cbuild.nj_hard_c(hyp.get_pdm_np(prob["xs"][0]))
+    m = SubstModel.jc69()
+    whole = PruneEngine(prob["masks"], prob["weights"])
+    ll, g = whole.loglik(_dev(peel), _dev(blens), m, grad=True)
+    parts_ll, parts_g = 0.0, 0.0
+    for r in range(4):
+        lo, hi = shard_bounds(L, r, 4)
+        eng = PruneEngine(np.ascontiguousarray(prob["masks"][:, lo:hi]), prob["weights"][lo:hi])
+        l, gg = eng.loglik(_dev(peel), _dev(blens), m, grad=True)
+        parts_ll = parts_ll + l
+        parts_g = parts_g + gg
+    assert parts_ll.item() == pytest.approx(ll.item(), rel=1e-12)
+    np.testing.assert_allclose(parts_g.cpu().numpy(), g.cpu().numpy(), rtol=1e-10, atol=1e-10 * g.abs().max().item())
+    bt = torch.tensor(blens, requires_grad=True)
+    ref = phylo.treelikelihood_rescaled_torch([torch.tensor(phylo.mask_to_partial(x)) for x in prob["masks"]],
+                                              torch.tensor(prob["weights"]), peel, phylo.jc69_p_t_torch(bt), torch.full([4], 0.25, dtype=torch.float64))
+    ref.backward()
+    assert ll.item() == pytest.approx(ref.item(), rel=1e-9)
+    np.testing.assert_allclose(g[0].cpu().numpy(), bt.grad.numpy(), rtol=1e-9, atol=1e-9 * np.abs(bt.grad.numpy()).max())
