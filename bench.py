@@ -46,6 +46,13 @@ WORKLOADS = {
                desc="VI, synthetic 64 taxa x 10k site patterns, GTR+G4, 128 samples/step, d5 (BASELINE.json configs[1])"),
     "tiny": dict(S=16, L=500, B=8, D=3, K=4, alpha=0.5, seed=1, tau=1e-8, desc="debug"),
 }
+# the other BASELINE.json configurations: parity-test shapes, timed by `bench.py --side NAME` into
+# profiles/ (NOT the headline line; they print their own small JSON)
+SIDE = {
+    "c3": dict(S=200, L=50000, B=64, D=5, desc="MCMC, 64 chains, 200 taxa x 50k patterns, JC69, forward only (configs[2])"),
+    "c4": dict(S=2000, B=256, D=5, desc="pairwise distance + batched NJ, 2000 taxa x 256 embeddings (configs[3])"),
+    "c5": dict(S=500, L=1000000, B=1, D=5, desc="long alignment, 500 taxa x 1M patterns, fwd+grad (configs[4]; one GPU holds L/world)"),
+}
 
 
 def algorithmic_bytes_fwd_bwd(S, K):
@@ -329,6 +336,76 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+def run_side(args):
+    """Timings of the non-headline configurations (device time, CUDA events)."""
+    import torch
+
+    from dodonaphy_b200 import dist as ddist, engine, synth
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    cfg = SIDE[args.side]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {"side": args.side, "config": cfg["desc"], "n_gpus": world}
+    S, B, D = cfg["S"], cfg["B"], cfg["D"]
+    rng = np.random.default_rng(7)
+    if args.side == "c4":
+        lo, hi = ddist.shard_bounds(B, rank, world)
+        xs = torch.as_tensor(rng.normal(0, 0.05, (B, S, D))[lo:hi]).cuda()
+        pdm = engine.pdm_forward(xs, -1.0, "torch")
+        out["pdm_ms"] = timed(lambda: engine.pdm_forward(xs, -1.0, "torch"), 5)
+        out["nj_hard_ms"] = timed(lambda: engine.nj_hard(pdm), 1)
+        out["nj_soft_ms"] = timed(lambda: engine.nj_soft(pdm, 1e-8), 1)
+        out["trees_per_gpu"] = hi - lo
+        out["nj_hard_GBps_algorithmic"] = (hi - lo) * 4 * (S ** 3 - S) / 3 / (out["nj_hard_ms"] * 1e-3) / 1e9
+    else:
+        L = cfg["L"]
+        prob = synth.make_problem(S, min(L, 20000), B * (world if args.side == "c3" else 1), D=D, seed=1003)
+        reps = -(-L // prob["masks"].shape[1])
+        masks = np.tile(prob["masks"], (1, reps))[:, :L]  # columns repeated to reach the full length
+        weights = np.tile(prob["weights"], reps)[:L]
+        if args.side == "c3":
+            hp = HotPath(masks, weights, SubstModel.jc69())
+            lo, hi = ddist.shard_bounds(B * world, rank, world)
+            xs = torch.as_tensor(prob["xs"][lo:hi]).cuda()
+            ms = timed(lambda: hp.value(xs), 3)
+            out.update(ms_per_sweep=ms, value=S * L * B * world / (ms * 1e-3), unit=UNIT)
+        else:
+            lo, hi = ddist.shard_bounds(L, rank, world)
+            eng = PruneEngine(np.ascontiguousarray(masks[:, lo:hi]), weights[lo:hi])
+            peel, blens = engine.nj_hard(engine.pdm_forward(torch.as_tensor(prob["xs"][0]).cuda(), -1.0, "numpy"))
+
+            def ev():
+                ll, g = eng.loglik(peel, blens, SubstModel.jc69(), grad=True)
+                if world > 1:
+                    ddist.reduce_site_blocks(ll, g)
+
+            ms = timed(ev, 3)
+            out.update(ms_per_eval=ms, value=S * L / (ms * 1e-3), unit=UNIT, patterns_per_gpu=hi - lo)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,7 +417,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--side", default=None, choices=sorted(SIDE), help="time a non-headline configuration instead")
     args = ap.parse_args()
+    if args.side:
+        return run_side(args)
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)
