@@ -182,6 +182,7 @@ struct SoftCtx {
     const int *pos_of;   // node id -> pool position or -1
     int S, N, n;
     double nm2;
+    long long dense_n;   // MODE 2: Dm is a dense row-major array of dense_n entries with N columns
 };
 
 __device__ __forceinline__ double soft_Q(const SoftCtx &c, int srow, int scol) {
@@ -200,8 +201,10 @@ __device__ __forceinline__ void tri_unrank(long long l, int &prow, int &pcol) {
     pcol = (int)(l - (long long)r * (r - 1) / 2);
 }
 
-template <bool FULL>
+// MODE 0: active pairs of the NJ state; 1: all N^2 entries of the padded NJ matrix; 2: a dense array
+template <int MODE>
 struct EntryIter {
+    static constexpr bool FULL = MODE != 0;
     const SoftCtx &c;
     long long l, end;
     int prow, pcol;
@@ -211,7 +214,10 @@ struct EntryIter {
     }
     __device__ __forceinline__ bool valid() const { return l < end; }
     __device__ __forceinline__ void get(double &s, double &flat) const {
-        if (FULL) {
+        if (MODE == 2) {
+            s = c.Dm[l];
+            flat = (double)l;
+        } else if (FULL) {
             int row = (int)(l / c.N), col = (int)(l - (long long)row * c.N);
             flat = (double)l;
             if (row < col) { s = 0.0; return; }
@@ -271,15 +277,16 @@ __device__ __forceinline__ double block_excl_scan(double v, double *sh, double &
 // exp(-a) for a >= 0; exactly 0 beyond the fp64 underflow point, without paying for the call
 __device__ __forceinline__ double exp_neg(double a) { return a > 750.0 ? 0.0 : exp(-a); }
 
-template <bool FULL>
+template <int MODE>
 __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
+    constexpr bool FULL = MODE != 0;
     const int tid = threadIdx.x, T = blockDim.x;
-    const long long P = FULL ? (long long)c.N * c.N : (long long)c.n * (c.n - 1) / 2;
+    const long long P = MODE == 2 ? c.dense_n : (FULL ? (long long)c.N * c.N : (long long)c.n * (c.n - 1) / 2);
     const long long chunk = (P + T - 1) / T;
     const long long l0 = min(P, (long long)tid * chunk), l1 = min(P, l0 + chunk);
     // pass 1: min
     double m = DBL_MAX;
-    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+    for (EntryIter<MODE> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
         m = fmin(m, s);
@@ -288,7 +295,7 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     m = block_reduce(m, sh, 1);
     // pass 2: sum of exp(-|s-m|/tau) in flat order
     double loc = 0.0;
-    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+    for (EntryIter<MODE> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
         loc += exp_neg(fabs(s - m) / tau);
@@ -305,7 +312,7 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     }
     // pass 3: c_j = p_j * cumsum(p)_j ; M = max c
     double run = off, M = 0.0;
-    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+    for (EntryIter<MODE> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
         double e = exp_neg(fabs(s - m) / tau);
@@ -319,7 +326,7 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     run = off;
     const double e0 = exp_neg(M / tau);  // entries with c_j == 0
     double z2 = 0.0, isum = 0.0, fsum = 0.0;
-    for (EntryIter<FULL> it(c, l0, l1); it.valid(); it.next()) {
+    for (EntryIter<MODE> it(c, l0, l1); it.valid(); it.next()) {
         double s, f;
         it.get(s, f);
         double e = exp_neg(fabs(s - m) / tau);
@@ -386,11 +393,11 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
             if (lane == 0) rs[sx] = acc;
         }
         __syncthreads();
-        SoftCtx c{Dm, rs, act, id_of, pos_of, S, N, n, (double)(n - 2)};
+        SoftCtx c{Dm, rs, act, id_of, pos_of, S, N, n, (double)(n - 2), 0};
         double idx;
         bool ok;
-        if (full) soft_argmin_block<true>(c, tau, sh, idx, ok);
-        else soft_argmin_block<false>(c, tau, sh, idx, ok);
+        if (full) soft_argmin_block<1>(c, tau, sh, idx, ok);
+        else soft_argmin_block<0>(c, tau, sh, idx, ok);
         // unravel (soft.py:7-10) and round (peeler.py:196-198)
         double rowf = trunc(idx / (double)N), colf = fmod(idx, (double)N);
         int right = (int)rint(rowf), left = (int)rint(colf);
@@ -516,9 +523,33 @@ __global__ void __launch_bounds__(1024) nj_soft_bwd_kernel(const int64_t *__rest
     }
 }
 
+// soft.argmin on arbitrary matrices (dodonaphy/soft.py:38-53), one CTA per matrix
+__global__ void __launch_bounds__(256) soft_argmin_kernel(const double *__restrict__ Q, int rows, int cols, double tau,
+                                                          double *__restrict__ out) {
+    __shared__ double sh[32];
+    const long long n = (long long)rows * cols;
+    SoftCtx c{Q + (size_t)blockIdx.x * n, nullptr, nullptr, nullptr, nullptr, 0, cols, 0, 0.0, n};
+    double idx;
+    bool ok;
+    soft_argmin_block<2>(c, tau, sh, idx, ok);
+    if (threadIdx.x == 0) {
+        out[blockIdx.x * 2 + 0] = trunc(idx / (double)cols);  // unravel_index (soft.py:7-10)
+        out[blockIdx.x * 2 + 1] = fmod(idx, (double)cols);
+    }
+}
+
 }  // namespace dodo
 
 using namespace dodo;
+
+extern "C" int dodo_soft_argmin(const double *d_Q, int B, int rows, int cols, double tau, double *d_rowcol, void *stream_) {
+    DODO_CHECK_ARG(d_Q && d_rowcol, "dodo_soft_argmin: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && rows >= 1 && cols >= 1, "dodo_soft_argmin: need B, rows, cols >= 1");
+    DODO_CHECK_ARG(tau > 0.0, "dodo_soft_argmin: tau must be positive");
+    soft_argmin_kernel<<<B, 256, 0, (cudaStream_t)stream_>>>(d_Q, rows, cols, tau, d_rowcol);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
 
 extern "C" uint64_t dodo_nj_workspace_bytes(int B, int S) {
     return (uint64_t)B * nj_ws_doubles(S) * sizeof(double);

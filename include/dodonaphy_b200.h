@@ -143,6 +143,10 @@ int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel,
 /* d_flags int32 [B][S-1]: bit0 = d_pl clamped, bit1 = d_pr clamped, bit2 = exactness guard tripped */
 int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void *d_ws, int64_t *d_peel,
                  double *d_blens, int32_t *d_flags, void *stream);
+/* soft.argmin (dodonaphy/soft.py:38-53) on B dense row-major matrices [B][rows][cols]:
+ * d_rowcol [B][2] = (soft_row, soft_col) as doubles, ties resolved towards the last entry. */
+int dodo_soft_argmin(const double *d_Q, int B, int rows, int cols, double tau, double *d_rowcol,
+                     void *stream);
 /* VJP of blens w.r.t. pdm given the recorded joins: d_grad_pdm [B][S][S] (symmetric) */
 int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, const double *d_grad_blens,
                      int B, int S, void *d_ws, double *d_grad_pdm, void *stream);

@@ -161,3 +161,24 @@ def test_batched_model_entry_points():
     pl, bl, _ = mc.connect(prob["xs"][2])
     assert np.array_equal(pl, peel_np[2]) and np.array_equal(bl, blens_np[2])
     assert mc.compute_LL(pl, bl) == pytest.approx(ll_np[2], rel=1e-12)
+
+
+def test_soft_module():
+    """test/test_soft.py (values) + soft.argmin against the reference-pinned closed form."""
+    from dodonaphy_b200 import soft
+    from oracle import nj
+
+    s = torch.tensor([5, 2, 4.4, 0.5, 10], dtype=torch.double, requires_grad=True)
+    assert torch.isclose(soft.min(s, 1e-3), torch.tensor(0.5, dtype=torch.double))
+    assert torch.isclose(soft.clamp_pos(torch.tensor(-3.0, dtype=torch.double), 1e-3, epsilon=torch.tensor(0.0001)), torch.tensor(0.0001, dtype=torch.double))
+    perm = soft.sort(torch.tensor([3, 2, 1], dtype=torch.double).reshape(1, 3, 1), 0.5)
+    assert torch.allclose((perm @ torch.tensor([3, 2, 1], dtype=torch.double)).squeeze(), torch.tensor([2.8509, 2.0, 1.1491], dtype=torch.double), rtol=1e-3)
+    rng = np.random.default_rng(8)
+    for n, m in ((3, 3), (7, 7), (40, 40), (5, 9)):
+        for tau in (1e-8, 1e-4, 0.3):
+            Q = np.tril(rng.normal(size=(n, m)))
+            Q[rng.integers(1, n), 0] = Q.min()  # exact tie
+            r, c = soft.argmin(torch.tensor(Q), tau)
+            rr, cc = nj.soft_argmin(Q, tau)
+            assert r.item() == pytest.approx(rr, abs=1e-9) and c.item() == pytest.approx(cc, rel=1e-9, abs=1e-9)
+    assert soft.index_to_hard_one_hot(torch.tensor(2.2), 4).tolist() == [0, 0, 1, 0]
