@@ -183,12 +183,15 @@ struct SoftCtx {
     int S, N, n;
     double nm2;
     long long dense_n;   // MODE 2: Dm is a dense row-major array of dense_n entries with N columns
+    int symmetric;       // Dm[i][j] == Dm[j][i] bit for bit: the transposed load can be skipped
 };
 
 __device__ __forceinline__ double soft_Q(const SoftCtx &c, int srow, int scol) {
     // compute_Q (peeler.py:223-248): Q' = (n-2) d - r_i - r_j ; Q = (Q' + Q'^T)/2
-    double a = (c.nm2 * c.Dm[(size_t)srow * c.S + scol] - c.rs[srow]) - c.rs[scol];
-    double b = (c.nm2 * c.Dm[(size_t)scol * c.S + srow] - c.rs[scol]) - c.rs[srow];
+    const double dij = c.Dm[(size_t)srow * c.S + scol];
+    const double dji = c.symmetric ? dij : c.Dm[(size_t)scol * c.S + srow];
+    double a = (c.nm2 * dij - c.rs[srow]) - c.rs[scol];
+    double b = (c.nm2 * dji - c.rs[scol]) - c.rs[srow];
     return 0.5 * (a + b);
 }
 
@@ -277,8 +280,127 @@ __device__ __forceinline__ double block_excl_scan(double v, double *sh, double &
 // exp(-a) for a >= 0; exactly 0 beyond the fp64 underflow point, without paying for the call
 __device__ __forceinline__ double exp_neg(double a) { return a > 750.0 ? 0.0 : exp(-a); }
 
+// Fast path of the soft argmin.  With a small temperature only the handful of entries within
+// W = 750 tau of the minimum have a non-zero softmax weight in fp64 (exp underflows to exactly 0 beyond
+// that), so ONE sweep suffices: every thread tracks its running minimum and the entries inside the
+// window below it; after the block-wide minimum is known the survivors are gathered (<= CAND_CAP),
+// ordered by flat index and the two softmaxes of soft.py:42-52 are evaluated on them, all other
+// entries entering in closed form (c_j = 0 => weight exp(-max c / tau) each).  Any overflow falls
+// back to the general multi-pass evaluation below, so the result is the same in every regime.
+constexpr int CAND_LOCAL = 4, CAND_CAP = 128;
+
+template <int MODE>
+__device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
+    constexpr bool FULL = MODE != 0;
+    __shared__ double cand_s[CAND_CAP], cand_f[CAND_CAP];
+    __shared__ int cand_n, cand_over;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const long long P = MODE == 2 ? c.dense_n : (FULL ? (long long)c.N * c.N : (long long)c.n * (c.n - 1) / 2);
+    const long long chunk = (P + T - 1) / T;
+    const long long l0 = min(P, (long long)tid * chunk), l1 = min(P, l0 + chunk);
+    const double W = 750.0 * tau;
+    double bs[CAND_LOCAL], bf[CAND_LOCAL];
+    int nb = 0;
+    bool over = false;
+    double lm = DBL_MAX;
+    auto visit = [&](double s, double f) {
+        if (s < lm) lm = s;
+        if (s <= lm + W) {
+            if (nb == CAND_LOCAL) {  // drop what has fallen out of the window
+                int w = 0;
+#pragma unroll
+                for (int i = 0; i < CAND_LOCAL; ++i)
+                    if (bs[i] <= lm + W) { bs[w] = bs[i]; bf[w] = bf[i]; ++w; }
+                nb = w;
+            }
+            if (nb == CAND_LOCAL) over = true;
+            else {
+#pragma unroll
+                for (int i = 0; i < CAND_LOCAL; ++i)
+                    if (i == nb) { bs[i] = s; bf[i] = f; }
+                ++nb;
+            }
+        }
+    };
+    if (MODE == 0) {
+        // one matrix row per warp, lanes across its columns: coalesced reads of the row
+        const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+        for (int prow = 1 + warp; prow < c.n; prow += nwarp) {
+            const int srow = c.act[prow];
+            const double frow = (double)c.id_of[srow] * (double)c.N;
+            for (int pcol = lane; pcol < prow; pcol += 32) {
+                const int scol = c.act[pcol];
+                visit(soft_Q(c, srow, scol), frow + (double)c.id_of[scol]);
+            }
+        }
+    } else {
+        for (EntryIter<MODE> it(c, l0, l1); it.valid(); it.next()) {
+            double s, f;
+            it.get(s, f);
+            visit(s, f);
+        }
+    }
+    if (tid == 0) { cand_n = 0; cand_over = 0; }
+    double m = lm;
+    if (!FULL) m = fmin(m, 0.0);  // the strict upper triangle holds zeros (torch.tril)
+    m = block_reduce(m, sh, 1);   // (contains the barriers that publish cand_n / cand_over)
+    if (over) cand_over = 1;
+#pragma unroll
+    for (int i = 0; i < CAND_LOCAL; ++i)
+        if (i < nb && bs[i] <= m + W) {
+            int slot = atomicAdd(&cand_n, 1);
+            if (slot < CAND_CAP) { cand_s[slot] = bs[i]; cand_f[slot] = bf[i]; }
+        }
+    __syncthreads();
+    const int n = cand_n;
+    const bool ok = !cand_over && n <= CAND_CAP && n >= 1;
+    if (!ok) { __syncthreads(); return false; }
+    const double NN = MODE == 0 ? (double)c.N * (double)c.N : (double)P;
+    if (tid == 0) {
+        for (int i = 1; i < n; ++i) {  // order by flat index (the reference's cumsum order)
+            double ks = cand_s[i], kf = cand_f[i];
+            int j = i - 1;
+            while (j >= 0 && cand_f[j] > kf) { cand_s[j + 1] = cand_s[j]; cand_f[j + 1] = cand_f[j]; --j; }
+            cand_s[j + 1] = ks; cand_f[j + 1] = kf;
+        }
+        double Z = 0.0;
+        for (int i = 0; i < n; ++i) Z += exp_neg(fabs(cand_s[i] - m) / tau);
+        double run = 0.0, M = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double e = exp_neg(fabs(cand_s[i] - m) / tau);
+            run += e;
+            M = fmax(M, (e / Z) * (run / Z));
+        }
+        const double e0 = exp_neg(M / tau);
+        double z2 = 0.0, isum = 0.0, fs = 0.0;
+        run = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double e = exp_neg(fabs(cand_s[i] - m) / tau);
+            double e2 = e0;
+            if (e != 0.0) {
+                run += e;
+                e2 = exp_neg(fabs(M - (e / Z) * (run / Z)) / tau);
+            }
+            z2 += e2;
+            isum = fma(e2, cand_f[i], isum);
+            fs += cand_f[i];
+        }
+        z2 += (NN - (double)n) * e0;
+        isum += e0 * (NN * (NN - 1.0) * 0.5 - fs);
+        sh[0] = isum / z2;
+        double worst = FULL ? 0.0 : exp_neg(fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
+        sh[1] = (FULL || NN * worst <= 1e-18 * fmin(1.0, tau) * Z) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    idx_out = sh[0];
+    guard_ok = sh[1] != 0.0;
+    __syncthreads();
+    return true;
+}
+
 template <int MODE>
 __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
+    if (soft_argmin_fast<MODE>(c, tau, sh, idx_out, guard_ok)) return;
     constexpr bool FULL = MODE != 0;
     const int tid = threadIdx.x, T = blockDim.x;
     const long long P = MODE == 2 ? c.dense_n : (FULL ? (long long)c.N * c.N : (long long)c.n * (c.n - 1) / 2);
@@ -371,10 +493,14 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
     double *bl = blens + (size_t)b * (2 * S - 2);
     int32_t *fl = flags + (size_t)b * (S - 1);
 
+    int asym = 0;
     for (size_t i = tid; i < (size_t)S * S; i += T) {
         int r = (int)(i / S), cc = (int)(i - (size_t)r * S);
-        Dm[i] = (r == cc) ? 0.0 : P[i];  // dists.fill_diagonal_(0.0), peeler.py:178
+        const double v = P[i];
+        Dm[i] = (r == cc) ? 0.0 : v;  // dists.fill_diagonal_(0.0), peeler.py:178
+        if (r != cc && v != P[(size_t)cc * S + r]) asym = 1;
     }
+    const int symmetric = __syncthreads_or(asym) ? 0 : 1;  // new rows/columns are written symmetrically
     for (int s = tid; s < S; s += T) { act[s] = s; id_of[s] = s; }
     for (int i = tid; i < N; i += T) pos_of[i] = i < S ? i : -1;
     __syncthreads();
@@ -393,7 +519,7 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
             if (lane == 0) rs[sx] = acc;
         }
         __syncthreads();
-        SoftCtx c{Dm, rs, act, id_of, pos_of, S, N, n, (double)(n - 2), 0};
+        SoftCtx c{Dm, rs, act, id_of, pos_of, S, N, n, (double)(n - 2), 0, symmetric};
         double idx;
         bool ok;
         if (full) soft_argmin_block<1>(c, tau, sh, idx, ok);
@@ -528,7 +654,7 @@ __global__ void __launch_bounds__(256) soft_argmin_kernel(const double *__restri
                                                           double *__restrict__ out) {
     __shared__ double sh[32];
     const long long n = (long long)rows * cols;
-    SoftCtx c{Q + (size_t)blockIdx.x * n, nullptr, nullptr, nullptr, nullptr, 0, cols, 0, 0.0, n};
+    SoftCtx c{Q + (size_t)blockIdx.x * n, nullptr, nullptr, nullptr, nullptr, 0, cols, 0, 0.0, n, 0};
     double idx;
     bool ok;
     soft_argmin_block<2>(c, tau, sh, idx, ok);
