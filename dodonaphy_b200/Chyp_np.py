@@ -15,13 +15,37 @@ eps = np.finfo(np.double).eps
 
 def get_pdm(x, curvature=-1.0, matsumoto=False, get_jacobian=False):
     """(S,D) ndarray -> (S,S) ndarray of pairwise distances; a leading batch axis is accepted."""
-    if get_jacobian:
-        if matsumoto:
-            raise NotImplementedError("Jacobian is not implemented for Matsumoto metric.")
-        raise NotImplementedError("get_jacobian: use Chyp_torch.get_pdm + autograd (analytic VJP on device)")
+    if get_jacobian and matsumoto:
+        raise NotImplementedError("Jacobian is not implemented for Matsumoto metric.")
     x = np.ascontiguousarray(x, dtype=np.float64)
-    out = _engine.pdm_forward(torch.from_numpy(x), float(curvature), "numpy", "up", bool(matsumoto))
-    return out.cpu().numpy()
+    xd = torch.from_numpy(x).cuda() if torch.cuda.is_available() else torch.from_numpy(x)
+    out = _engine.pdm_forward(xd, float(curvature), "numpy", "up", bool(matsumoto))
+    if not get_jacobian:
+        return out.cpu().numpy()
+    if curvature == 0.0:
+        return out.cpu().numpy(), np.eye(x.shape[0])
+    return out.cpu().numpy(), _pair_jacobian(xd, float(curvature)).cpu().numpy()
+
+
+def _pair_jacobian(x, curvature):
+    """Analytic Jacobian of the n(n-1)/2 pair distances (row-major pairs i<j) w.r.t. the n*(D+1) sheet
+    coordinates (Chyp_np.pyx:369-410), vectorised on the device the points live on:
+    row k=(i,j): block i = A_ij (B_ij s_i - s_j), block j = A_ji (B_ji s_j - s_i),
+    A = 1/sqrt(-kappa (H^2-1)), B_ij = u_j/u_i."""
+    n, dim = x.shape
+    s = torch.cat((torch.sqrt((x * x).sum(1, keepdim=True) + 1.0), x), dim=1)
+    X = s @ s.T
+    u = torch.sqrt(torch.diagonal(X) + 1.0)
+    H = torch.minimum(X - torch.outer(u, u), torch.tensor(-(1.0 + eps), dtype=torch.float64, device=x.device))
+    A = 1.0 / torch.sqrt(-curvature * (H * H - 1.0))
+    Bm = torch.outer(1.0 / u, u)
+    i, j = torch.triu_indices(n, n, 1, device=x.device)
+    npair = i.numel()
+    G = torch.zeros((npair, n, dim + 1), dtype=torch.float64, device=x.device)
+    k = torch.arange(npair, device=x.device)
+    G[k, i] = A[i, j, None] * (Bm[i, j, None] * s[i] - s[j])
+    G[k, j] = A[j, i, None] * (Bm[j, i, None] * s[j] - s[i])
+    return G.reshape(npair, n * (dim + 1))
 
 
 def project_up(loc):

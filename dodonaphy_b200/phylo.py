@@ -42,6 +42,27 @@ def compress_alignment(alignment, get_namespace=False, get_freqs=False):
     return partials, weights
 
 
+def compress_alignment_device(sequences, device="cuda"):
+    """Alignment ingestion on the device: the same unique-sorted-pattern compression as
+    ``compress_alignment`` (phylo.py:16-58) for a list of equal-length strings, but the column
+    sort/unique runs on the GPU and the result is what the kernels consume directly:
+    (tip masks uint8 (S, L) on ``device``, pattern weights int64 (L,) on ``device``).
+    Patterns are ordered like the reference's ``sorted(Counter(zip(*sequences)))`` (byte order of the
+    raw characters); the character -> state-set map is case-insensitive."""
+    S = len(sequences)
+    n = len(sequences[0])
+    if any(len(q) != n for q in sequences):
+        raise ValueError("sequences must have equal length")
+    raw = torch.frombuffer(bytearray("".join(sequences), "ascii"), dtype=torch.uint8).reshape(S, n).to(device)
+    cols, counts = torch.unique(raw.T.contiguous(), dim=0, return_counts=True)  # lexicographic, like sorted()
+    lut = torch.full((256,), 15, dtype=torch.uint8)
+    for ch, m in _IUPAC.items():
+        lut[ord(ch)] = m
+        lut[ord(ch.lower())] = m
+    masks = lut.to(device)[cols.T.contiguous().long()]
+    return masks.contiguous(), counts.to(torch.int64)
+
+
 # ------------------------------------------------------------------------------------------------
 _engine_cache = {}
 

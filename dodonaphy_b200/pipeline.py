@@ -47,6 +47,27 @@ class HotPath:
         gx, gc = engine.pdm_backward(x, gpdm, self.curvature, self.lift, self.matsumoto)
         return dict(lnL=ll, grad_x=gx, grad_curvature=gc, peel=peel, blens=blens, flags=flags, grad_blens=gbl)
 
+    def blens_jacobian(self, x, peel=None, flags=None, logdet=True):
+        """d blens / d locations for every sample, (B, 2S-2, S*D), and log sqrt|det(J J^T)| -- the
+        change-of-variables term the reference obtains with ``torch.autograd.functional.jacobian``
+        and 2S-2 backward passes per sample (vi.py:376-387; ~3/4 of a reference VI sample).  Here the
+        2S-2 one-hot cotangents of all B samples go through the NJ and distance backward kernels as
+        ONE batch of B*(2S-2) replays.  (The last NJ join splits one distance into two equal halves,
+        so two rows of J coincide and the determinant is numerically ~0 in the reference as well.)"""
+        B, S, D = (int(v) for v in x.shape)
+        E = 2 * S - 2
+        if peel is None:
+            pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto)
+            peel, _, flags = engine.nj_soft(pdm, self.tau, return_flags=True)
+        cot = torch.eye(E, dtype=torch.float64, device=x.device).repeat(B, 1)
+        gpdm = engine.nj_soft_backward(peel.repeat_interleave(E, 0), flags.repeat_interleave(E, 0), cot)
+        gx, _ = engine.pdm_backward(x.repeat_interleave(E, 0), gpdm, self.curvature, self.lift, self.matsumoto)
+        J = gx.reshape(B, E, S * D)
+        if not logdet:
+            return J
+        sign, logabs = torch.linalg.slogdet(J @ J.transpose(1, 2))
+        return J, 0.5 * logabs
+
     def value(self, x):
         """Gradient-free MCMC path (Chyp_np.get_pdm -> Cpeeler.nj_np -> Cphylo.compute_LL_np)."""
         pdm = engine.pdm_forward(x, self.curvature, "numpy", "up", self.matsumoto)

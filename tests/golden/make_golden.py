@@ -232,6 +232,21 @@ def make_prune(r):
     print("prune cases:", n)
 
 
+def make_pdm_jac(r):
+    """Chyp_np.get_pdm(..., get_jacobian=True) (Chyp_np.pyx:369-410): analytic Jacobian of the pair
+    distances w.r.t. the sheet coordinates."""
+    rng = np.random.default_rng(34)
+    out = {}
+    cases = [(4, 2, -1.0), (9, 3, -0.7), (20, 5, -1.0)]
+    out["n"] = len(cases)
+    for i, (S, D, curv) in enumerate(cases):
+        x = rng.normal(0, 0.1, (S, D))
+        Dm, J = r.Chyp_np.get_pdm(x, curvature=curv, get_jacobian=True)
+        out[f"{i}_x"], out[f"{i}_curv"], out[f"{i}_pdm"], out[f"{i}_jac"] = x, curv, Dm, J
+    np.savez_compressed(os.path.join(HERE, "pdm_jac.npz"), **out)
+    print("pdm_jac cases:", len(cases))
+
+
 if __name__ == "__main__":
     r = refload.load()
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
@@ -240,3 +255,4 @@ if __name__ == "__main__":
     make_nj_hard(r)
     make_nj_soft(r)
     make_prune(r)
+    make_pdm_jac(r)

@@ -133,6 +133,12 @@ def test_numpy_path_names():
     assert Chyp_np.hyperbolic_distance(x[0], x[1]) == pytest.approx(pdm[0, 1], rel=1e-10)
     with pytest.raises(NotImplementedError):
         Chyp_np.get_pdm(x, matsumoto=True, get_jacobian=True)
+    g = load_golden("pdm_jac.npz")  # test/test_chyp_np.py:6-41: analytic pair Jacobian
+    for i in range(int(g["n"])):
+        Dm, J = Chyp_np.get_pdm(g[f"{i}_x"], curvature=float(g[f"{i}_curv"]), get_jacobian=True)
+        np.testing.assert_allclose(J, g[f"{i}_jac"], rtol=1e-9, atol=1e-12)
+        off = ~np.eye(len(Dm), dtype=bool)
+        np.testing.assert_allclose(Dm[off], g[f"{i}_pdm"][off], rtol=1e-10)
 
 
 def test_batched_model_entry_points():
@@ -182,3 +188,51 @@ def test_soft_module():
             rr, cc = nj.soft_argmin(Q, tau)
             assert r.item() == pytest.approx(rr, abs=1e-9) and c.item() == pytest.approx(cc, rel=1e-9, abs=1e-9)
     assert soft.index_to_hard_one_hot(torch.tensor(2.2), 4).tolist() == [0, 0, 1, 0]
+
+
+def test_blens_jacobian_batched_vs_autograd_oracle():
+    """vi.py:376-387: Jacobian of the decoded branch lengths w.r.t. the sampled locations."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+    from oracle import hyp, nj
+
+    S, D, B = 7, 3, 3
+    prob = synth.make_problem(S, 20, B, D=D, seed=31)
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69(), tau=1e-8, curvature=-1.0)
+    J, half_logdet = hp.blens_jacobian(torch.as_tensor(prob["xs"]).cuda())
+    assert J.shape == (B, 2 * S - 2, S * D) and half_logdet.shape == (B,)
+    for b in range(B):
+        def blens_of(flat):
+            x = flat.reshape(S, D)
+            z = torch.sqrt((x * x).sum(1) + 1)
+            H = x @ x.T - torch.outer(z, z)
+            Dm = torch.acosh(-torch.minimum(H, torch.tensor(-1.0000001, dtype=torch.float64)))
+            Dm = Dm * (1 - torch.eye(S, dtype=torch.float64))
+            return nj.nj_soft_torch(Dm, 1e-8)[1]
+
+        ref = torch.autograd.functional.jacobian(blens_of, torch.tensor(prob["xs"][b]).flatten())
+        np.testing.assert_allclose(J[b].cpu().numpy(), ref.numpy(), rtol=1e-8, atol=1e-10)
+
+
+def test_compress_alignment_on_device():
+    """phylo.compress_alignment (phylo.py:16-58) with the sort/unique on the GPU."""
+    from dodonaphy_b200 import phylo
+    from oracle import phylo as ophylo
+
+    rng = np.random.default_rng(12)
+    alphabet = np.array(list("ACGTacgtRYMWSKBDHVN?-X"))
+    probs = np.array([8, 8, 8, 8, 1, 1, 1, 1] + [0.3] * 14)
+    seqs = ["".join(rng.choice(alphabet, size=400, p=probs / probs.sum())) for _ in range(5)]
+    seqs = [q[:200] + q[:200] for q in seqs]  # duplicate columns -> weights > 1
+    masks, weights = phylo.compress_alignment_device(seqs)
+    tips, w_ref, m_ref = ophylo.compress_alignment(seqs)
+    assert np.array_equal(weights.cpu().numpy(), w_ref)
+    assert np.array_equal(masks.cpu().numpy(), m_ref)
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    eng = PruneEngine(masks, weights)
+    peel = torch.tensor([[0, 1, 5], [2, 3, 6], [5, 6, 7], [4, 7, 8]]).cuda()
+    ll, _ = eng.loglik(peel, torch.full((8,), 0.1, dtype=torch.float64).cuda(), SubstModel.jc69())
+    ref = ophylo.compute_LL_np(tips, w_ref, peel.cpu().numpy(), np.full(8, 0.1))
+    assert ll.item() == pytest.approx(ref, rel=1e-9)

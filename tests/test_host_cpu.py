@@ -183,6 +183,22 @@ def test_synthetic_generator_is_seeded_and_consistent():
     assert (a["guide_blens"] > 0).all() and a["weights"].min() >= 1
 
 
+def test_gamma_dirichlet_prior_mrbayes_known_answers():
+    """test/test_phylo.py:183-211: 17.34844 and 13.56829 (+-1e-5), and the batched form."""
+    from dodonaphy_b200 import newick, priors
+
+    labels = [str(i) for i in range(1, 7)]
+    t0 = "(6:2.000000e-02,((5:2.000000e-02,2:2.000000e-02):2.000000e-02,(4:2.000000e-02,3:2.000000e-02):2.000000e-02):2.000000e-02,1:2.000000e-02);"
+    t1 = "((2:1.179257e-01,(6:1.047047e-03,3:1.426334e-03):7.713732e-02):7.894008e-02,(4:2.848264e-03,5:2.711671e-03):1.879317e-03,1:4.419083e-03);"
+    b0 = torch.tensor(newick.newick_to_peel(t0, labels)[1])
+    b1 = torch.tensor(newick.newick_to_peel(t1, labels)[1])
+    assert priors.compute_prior_gamma_dir(b0, aT=torch.ones(1), bT=torch.full((1,), 0.1), a=torch.ones(1), c=torch.ones(1)).item() == pytest.approx(17.34844, abs=1e-5)
+    assert priors.compute_prior_gamma_dir(b1).item() == pytest.approx(13.56829, abs=1e-5)
+    both = priors.compute_prior_gamma_dir(torch.stack([b0, b1]))
+    assert both[0].item() == pytest.approx(17.34844, abs=1e-5) and both[1].item() == pytest.approx(13.56829, abs=1e-5)
+    assert priors.compute_prior_exponential(torch.full((3, 10), 0.1), rate=10.0).shape == (3,)
+
+
 # ------------------------------------------------------------------ world_size 2 over gloo
 _WORKER = r"""
 import os, sys
