@@ -25,26 +25,34 @@ from .pipeline import HotPath
 
 
 class _BatchedLogLik(torch.autograd.Function):
-    """lnL of B embeddings in one fused pass; gradients to locations and curvature."""
+    """(lnL, peel, blens) of B embeddings in one fused pass.  lnL and blens both carry gradient to the
+    locations and to the curvature leaf: the backward adds the caller's cotangent on blens (e.g. from a
+    branch-length prior) to g_lnL * d lnL/d blens and replays soft NJ and the distance kernel once."""
 
     @staticmethod
     def forward(ctx, locs, curvature_leaf, hot):
         # the leaf is log(-kappa) (base_model.py:109-124): kappa = -exp(leaf), d kappa / d leaf = kappa
         hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
-        ctx.kappa = hot.curvature
         x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
-        out = hot.value_and_grad(x)
-        ctx.save_for_backward(out["grad_x"].to(locs.device), out["grad_curvature"].to(curvature_leaf.device))
-        ctx.cshape = curvature_leaf.shape
+        out = hot.value_and_grad(x, to_locations=False)
+        ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
+        ctx.devs = (locs.device, curvature_leaf.device)
+        ctx.save_for_backward(x, out["peel"], out["flags"], out["grad_blens"])
         ctx.mark_non_differentiable(out["peel"])
         return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device)
 
     @staticmethod
     def backward(ctx, g_ll, _g_peel, g_blens):
-        gx, gc = ctx.saved_tensors
-        if g_blens is not None and bool((g_blens != 0).any()):
-            raise NotImplementedError("use connect()/compute_LL() when the loss depends on blens directly")
-        return g_ll.reshape(-1, 1, 1) * gx, ((g_ll * gc).sum() * ctx.kappa).reshape(ctx.cshape), None
+        from . import engine
+
+        x, peel, flags, dll_dblens = ctx.saved_tensors
+        hot = ctx.hot
+        gb = g_ll.to(x.device).reshape(-1, 1) * dll_dblens
+        if g_blens is not None:
+            gb = gb + g_blens.to(x.device)
+        gpdm = engine.nj_soft_backward(peel, flags, gb.contiguous())
+        gx, gc = engine.pdm_backward(x, gpdm, ctx.kappa, hot.lift, hot.matsumoto)
+        return gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]), None
 
 
 class BaseModel:

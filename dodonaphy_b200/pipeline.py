@@ -37,12 +37,15 @@ class HotPath:
         self.mix, self.tau, self.curvature, self.lift, self.matsumoto = bool(mix), tau, curvature, lift, matsumoto
         return self
 
-    def value_and_grad(self, x):
+    def value_and_grad(self, x, to_locations=True):
         """x: (B,S,D) device tensor.  Returns dict(lnL (B,), grad_x (B,S,D), grad_curvature (B,),
-        peel (B,S-1,3), blens (B,2S-2)) -- soft-NJ (VI) path."""
+        peel (B,S-1,3), blens (B,2S-2)) -- soft-NJ (VI) path.  ``to_locations=False`` stops at
+        d lnL/d blens (the caller chains NJ / distance backward itself)."""
         pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto)
         peel, blens, flags = engine.nj_soft(pdm, self.tau, return_flags=True)
         ll, gbl = self.prune.loglik(peel, blens, self.model, rates=self.rates, mix=self.mix, grad=True)
+        if not to_locations:
+            return dict(lnL=ll, peel=peel, blens=blens, flags=flags, grad_blens=gbl)
         gpdm = engine.nj_soft_backward(peel, flags, gbl)
         gx, gc = engine.pdm_backward(x, gpdm, self.curvature, self.lift, self.matsumoto)
         return dict(lnL=ll, grad_x=gx, grad_curvature=gc, peel=peel, blens=blens, flags=flags, grad_blens=gbl)
