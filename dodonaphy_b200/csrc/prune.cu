@@ -232,6 +232,12 @@ struct PruneArgs {
 };
 
 constexpr int NT = 256;  // threads per CTA = site patterns per work item
+#ifndef DODO_REG_PREFETCH
+#define DODO_REG_PREFETCH 0   // 1: operands of the next join are fetched into registers one join ahead
+#endif
+#ifndef DODO_PRUNE_CTAS
+#define DODO_PRUNE_CTAS 3
+#endif
 
 // Shared memory.  SMALL (tables and tip selectors resident): tables | gacc | fx | red | cx | ops | sel.
 // LARGE (big S: tables and masks stay in global memory, read through L1): gacc | fx | red | cx | ops.
@@ -405,7 +411,7 @@ __device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0
 
 // MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
 template <int MODE, bool SMALL, bool SCALE>
-__global__ void __launch_bounds__(NT, 3) prune_kernel(PruneArgs A, ModelDev md) {
+__global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A, ModelDev md) {
     constexpr bool GRAD = MODE == 1;
     constexpr bool GMATS = MODE == 2;
     static_assert(!(GMATS && SCALE), "GMATS is built without rescaling");
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(NT, 3) prune_kernel(PruneArgs A, ModelDev md) 
                     }
                 }
             };
+#if DODO_REG_PREFETCH
             V4 A0, B0, A1, B1;
             int A0c = 0, A1c = 0;
             {
@@ -531,6 +538,35 @@ __global__ void __launch_bounds__(NT, 3) prune_kernel(PruneArgs A, ModelDev md) 
                 step(i + 1, A1, B1, A1c, A0, B0, A0c);
             }
             if (i <= nops) step(i, A0, B0, A0c, A1, B1, A1c);
+#else
+            (void)step;
+#pragma unroll 1
+            for (int i = 1; i <= nops; ++i) {
+                const int4 o = ops_sm[i];
+                V4 Lv;
+                int cnt = 0;
+                if (o.x < 0) {
+                    Lv = tipmsg(~o.x);
+                } else {
+                    Lv = ldg256(scr + (unsigned)o.x * nthr);
+                    if (SCALE) cnt = __ldcg(cscr + (unsigned)o.x * nthr);
+                }
+                if (o.y < 0) Lv = vmul(Lv, tipmsg(~o.y));
+                else { Lv = vmul(Lv, prev); cnt += pc; }
+                if (SCALE) scale_up(Lv, cnt);
+                if (i == nops) {
+                    rootL = Lv;
+                    rootc = cnt;
+                } else {
+                    prev = matvec_t<SMALL>(tabk + (unsigned)o.z * 16u, Lv);
+                    pc = cnt;
+                    if (MODE != 0 || (o.w & 1)) {
+                        stg256(scr + (unsigned)o.z * nthr, prev);
+                        if (SCALE) __stcg(cscr + (unsigned)o.z * nthr, cnt);
+                    }
+                }
+            }
+#endif
             double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
             if (MODE != 0 || SCALE) fx[(unsigned)k * nthr + tid] = fk;
             if (SCALE) cx[(unsigned)k * nthr + tid] = rootc;
@@ -614,6 +650,7 @@ __global__ void __launch_bounds__(NT, 3) prune_kernel(PruneArgs A, ModelDev md) 
                         if (SCALE) { int neg = -we; scale_both(wprev, neg); we = -neg; }
                     }
                 };
+#if DODO_REG_PREFETCH
                 V4 A0, B0, W0, A1, B1, W1;
                 int A0c = 0, B0c = 0, W0c = 0, A1c = 0, B1c = 0, W1c = 0;
                 {
@@ -632,6 +669,55 @@ __global__ void __launch_bounds__(NT, 3) prune_kernel(PruneArgs A, ModelDev md) 
                     step(i - 1, A1, B1, W1, A1c, B1c, W1c, A0, B0, W0, A0c, B0c, W0c);
                 }
                 if (i >= 1) step(i, A0, B0, W0, A0c, B0c, W0c, A1, B1, W1, A1c, B1c, W1c);
+#else
+                (void)step;
+#pragma unroll 1
+                for (int i = nops; i >= 1; --i) {
+                    const int4 o = ops_sm[i];
+                    {
+                        // pull what the join three steps ahead needs out of HBM into L2
+                        const int4 of = ops_sm[i > 3 ? i - 3 : 0];
+                        if (of.x >= 0) prefetch_l2(scr + (unsigned)of.x * nthr);
+                        if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
+                    }
+                    V4 av, bv;
+                    int ac = 0, bc = 0;
+                    if (o.x < 0) av = tipmsg(~o.x);
+                    else { av = ldg256(scr + (unsigned)o.x * nthr); if (SCALE) ac = __ldcg(cscr + (unsigned)o.x * nthr); }
+                    if (o.y < 0) bv = tipmsg(~o.y);
+                    else { bv = ldg256(scr + (unsigned)o.y * nthr); if (SCALE) bc = __ldcg(cscr + (unsigned)o.y * nthr); }
+                    V4 w = wprev;
+                    int ew = we;
+                    if (o.w & 1) {
+                        w = ldg256(scr + (unsigned)o.z * nthr);
+                        if (SCALE) ew = __ldcg(cscr + (unsigned)o.z * nthr);
+                    }
+                    const V4 ua = vmul(w, bv), ub = vmul(w, av);
+                    double ga = rate_k * uQx(md.Q, ua, av);
+                    double gb = rate_k * uQx(md.Q, ub, bv);
+                    if (SCALE) {
+                        const double sf = pow2_256(ew - ac - bc);
+                        ga *= sf; gb *= sf;
+                    }
+                    const double g2 = warp_sum2(ga, gb, lane);
+                    if ((lane & 15u) == 0u) {
+                        const int c = lane ? o.y : o.x;
+                        gw[c < 0 ? ~c : c + S] += g2;
+                    }
+                    if (o.x >= 0) {
+                        V4 wa = matvecT_t<SMALL>(tabk + (unsigned)o.x * 16u, ua);
+                        int ea = ew - bc;
+                        if (SCALE) { int neg = -ea; scale_both(wa, neg); ea = -neg; }
+                        stg256(scr + (unsigned)o.x * nthr, wa);
+                        if (SCALE) __stcg(cscr + (unsigned)o.x * nthr, ea);
+                    }
+                    if (o.y >= 0) {
+                        wprev = matvecT_t<SMALL>(tabk + (unsigned)o.y * 16u, ub);
+                        we = ew - ac;
+                        if (SCALE) { int neg = -we; scale_both(wprev, neg); we = -neg; }
+                    }
+                }
+#endif
             }
         }
         if (GMATS) {
