@@ -410,12 +410,20 @@ __device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0
 }
 
 // MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
+//
+// Register conventions of the two sweeps (they keep the loops free of copies):
+//   forward : Bv holds "the other operand": the previous join's message when child b is internal
+//             (the schedule guarantees b is then exactly the previous join), else b's tip message.
+//   backward: Wv holds the upper message of the current join: left there by the previous join when
+//             this node is its b-child, else (a-child) fetched from scratch.
+// Latency is hidden by the 24 resident warps per SM plus an L2 prefetch three joins ahead in the
+// backward sweep; a register-level software pipeline was measured slower (more instructions).
 template <int MODE, bool SMALL, bool SCALE>
 __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A, ModelDev md) {
     constexpr bool GRAD = MODE == 1;
     constexpr bool GMATS = MODE == 2;
     static_assert(!(GMATS && SCALE), "GMATS is built without rescaling");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) double smd[];  // indexed from the symbol: keeps LDS addressing direct
     const unsigned tid = threadIdx.x;
     constexpr unsigned nthr = NT;
     const unsigned lane = tid & 31u;
@@ -423,20 +431,28 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
     constexpr unsigned nwarp = NT / 32;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
     const unsigned tabn = (unsigned)tab_doubles(S);
-    double *tab_sm = reinterpret_cast<double *>(smem_raw);       // SMALL: Pint[S-1][16] | Ttip[S][20]
-    double *gacc = tab_sm + (SMALL ? tabn : 0u);                 // [nwarp][E]
-    double *fx = gacc + nwarp * (unsigned)E;                     // [K][nthr]
-    double *red = fx + (unsigned)K * nthr;                       // [nwarp]
-    int *cx = reinterpret_cast<int *>(smem_raw + prune_smem_dbl(S, K, SMALL) * sizeof(double));  // [K][nthr]
-    int4 *ops_sm = reinterpret_cast<int4 *>(cx + (unsigned)K * nthr);                            // [S+2]
-    uint8_t *sel_sm = reinterpret_cast<uint8_t *>(ops_sm + (S + 2)) + tid;                       // SMALL: [S][nthr]
+    // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][nthr] red[nwarp] | cx | ops | sel
+    const unsigned o_gacc = SMALL ? tabn : 0u;
+    const unsigned o_fx = o_gacc + nwarp * (unsigned)E;
+    const unsigned o_red = o_fx + (unsigned)K * nthr;
+    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL);                    // int [K][nthr]
+    const unsigned o_ops = o_cx + ((unsigned)K * nthr) / 2u;                        // int4 [S+2]
+    const unsigned o_sel = o_ops + 2u * (unsigned)(S + 2);                          // u8 [S][nthr]
+    const unsigned o_T = (unsigned)(S - 1) * 16u;                                   // Ttip inside the slab
+#define GACC(i) smd[o_gacc + (i)]
+#define FX(i) smd[o_fx + (i)]
+#define RED(i) smd[o_red + (i)]
+#define CX(i) (reinterpret_cast<int *>(&smd[o_cx])[(i)])
+#define OPS(i) (reinterpret_cast<const int4 *>(&smd[o_ops])[(i)])
+#define OPSW(i) (reinterpret_cast<int4 *>(&smd[o_ops])[(i)])
+#define SEL(t) (reinterpret_cast<uint8_t *>(&smd[o_sel])[(unsigned)(t) * nthr + tid])
     if (GRAD) {
-        for (unsigned i = tid; i < nwarp * (unsigned)E; i += nthr) gacc[i] = 0.0;
+        for (unsigned i = tid; i < nwarp * (unsigned)E; i += nthr) GACC(i) = 0.0;
     }
     // scratch ring of this CTA: [k][node][thread] x 32 B (+ 4 B rescaling counters)
     V4 *scr0 = reinterpret_cast<V4 *>(A.scratch) + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid;
     int *cscr0 = SCALE ? A.cscratch + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid : nullptr;
-    double *gw = gacc + warp * (unsigned)E;
+    const unsigned gw = warp * (unsigned)E;
 
 #pragma unroll 1
     for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
@@ -449,38 +465,38 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
         const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
         __syncthreads();
         {
-            // schedule of this sample, re-encoded: child code < 0 -> tip ~code, else internal index;
-            // entries 0 and nops+1 are harmless dummies so that the one-ahead prefetch needs no bounds test
+            // schedule of this sample, re-encoded: child code < 0 -> tip ~code, else internal index
             const int4 *ops_b = A.ops + (size_t)(A.ops_batch == 1 ? 0 : b) * nops;
             for (int i = tid; i < nops + 2; i += nthr) {
-                int4 o = make_int4(~0, ~0, 0, 4);
+                int4 o = make_int4(~0, ~0, 0, 4);  // entries 0 and nops+1: harmless sentinels
                 if (i >= 1 && i <= nops) {
                     o = __ldg(ops_b + (i - 1));
                     o.x = o.x < S ? ~o.x : o.x - S;
                     o.y = o.y < S ? ~o.y : o.y - S;
                     o.z -= S;
                 }
-                ops_sm[i] = o;
+                OPSW(i) = o;
             }
-            if (SMALL) {  // tip selectors of this thread's pattern (thread-private column of sel_sm)
-                for (int t = 0; t < S; ++t) sel_sm[(unsigned)t * nthr] = (uint8_t)encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+            if (SMALL) {  // tip selectors of this thread's pattern (thread-private column)
+                for (int t = 0; t < S; ++t) SEL(t) = (uint8_t)encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
             }
         }
-        const double *tabk = tab_sm;  // tables of the current category (shared or global)
+        const double *tabg = tab_b;  // LARGE: tables of the current category in global memory
         auto stage_tables = [&](int k) {
             __syncthreads();  // everyone is done with the previous slab (and the schedule is visible)
             if (SMALL) {
                 const double2 *src = reinterpret_cast<const double2 *>(tab_b + (size_t)k * tabn);
-                double2 *dst = reinterpret_cast<double2 *>(tab_sm);
+                double2 *dst = reinterpret_cast<double2 *>(&smd[0]);
                 for (unsigned i = tid; i < tabn / 2; i += nthr) dst[i] = __ldg(src + i);
                 __syncthreads();
             } else {
-                tabk = tab_b + (size_t)k * tabn;
+                tabg = tab_b + (size_t)k * tabn;
             }
         };
+        auto tab_at = [&](unsigned off) -> const double * { return SMALL ? &smd[off] : tabg + off; };
         auto tipmsg = [&](int t) -> V4 {
-            const unsigned sel = SMALL ? (unsigned)sel_sm[(unsigned)t * nthr] : encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
-            return tip_message<SMALL>(tabk + (unsigned)(S - 1) * 16u + (unsigned)t * 20u, sel);
+            const unsigned sel = SMALL ? (unsigned)SEL(t) : encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+            return tip_message<SMALL>(tab_at(o_T + (unsigned)t * 20u), sel);
         };
 
         // ---------------- forward (post-order), one pass per rate category ----------------
@@ -490,103 +506,57 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
             stage_tables(k);
             V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
             int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * nthr : nullptr;
-            V4 prev = V4{0, 0, 0, 0};
-            V4 rootL = prev;
-            int pc = 0, rootc = 0;
-            // join i uses (Ac, Bc); the operands of join i+1 are fetched into (An, Bn) meanwhile.
-            auto step = [&](int i, const V4 &Ac, const V4 &Bc, int Acc, V4 &An, V4 &Bn, int &Anc) {
-                const int4 o = ops_sm[i];
-                const int4 on = ops_sm[i + 1];
-                Anc = 0;
-                if (on.x < 0) {
-                    An = tipmsg(~on.x);
-                } else {  // stored >= 2 joins ago (schedule_kernel)
-                    An = ldg256(scr + (unsigned)on.x * nthr);
-                    if (SCALE) Anc = __ldcg(cscr + (unsigned)on.x * nthr);
-                }
-                if (on.y < 0) Bn = tipmsg(~on.y);
-                V4 Lv;
-                int cnt = Acc;
-                if (o.y < 0) Lv = vmul(Ac, Bc);
-                else { Lv = vmul(Ac, prev); cnt += pc; }
-                if (SCALE) scale_up(Lv, cnt);
-                if (i == nops) {
-                    rootL = Lv;
-                    rootc = cnt;
-                } else {
-                    prev = matvec_t<SMALL>(tabk + (unsigned)o.z * 16u, Lv);
-                    pc = cnt;
-                    if (MODE != 0 || (o.w & 1)) {
-                        stg256(scr + (unsigned)o.z * nthr, prev);
-                        if (SCALE) __stcg(cscr + (unsigned)o.z * nthr, cnt);
-                    }
-                }
-            };
-#if DODO_REG_PREFETCH
-            V4 A0, B0, A1, B1;
-            int A0c = 0, A1c = 0;
-            {
-                const int4 o1 = ops_sm[1];
-                A0 = o1.x < 0 ? tipmsg(~o1.x) : ldg256(scr + (unsigned)o1.x * nthr);  // first join: both tips
-                B0 = tipmsg(o1.y < 0 ? ~o1.y : 0);
-                A1 = A0; B1 = B0;
-            }
-            int i = 1;
-#pragma unroll 1
-            for (; i + 1 <= nops; i += 2) {
-                step(i, A0, B0, A0c, A1, B1, A1c);
-                step(i + 1, A1, B1, A1c, A0, B0, A0c);
-            }
-            if (i <= nops) step(i, A0, B0, A0c, A1, B1, A1c);
-#else
-            (void)step;
-#pragma unroll 1
-            for (int i = 1; i <= nops; ++i) {
-                const int4 o = ops_sm[i];
-                V4 Lv;
-                int cnt = 0;
+            V4 Bv = V4{0, 0, 0, 0};
+            int bc = 0;
+            auto join = [&](const int4 &o, V4 &Lv, int &cnt) {
+                cnt = 0;
                 if (o.x < 0) {
                     Lv = tipmsg(~o.x);
                 } else {
                     Lv = ldg256(scr + (unsigned)o.x * nthr);
                     if (SCALE) cnt = __ldcg(cscr + (unsigned)o.x * nthr);
                 }
-                if (o.y < 0) Lv = vmul(Lv, tipmsg(~o.y));
-                else { Lv = vmul(Lv, prev); cnt += pc; }
+                if (o.y < 0) { Bv = tipmsg(~o.y); bc = 0; }  // both children are tips: Bv is free
+                Lv = vmul(Lv, Bv);
+                cnt += bc;
                 if (SCALE) scale_up(Lv, cnt);
-                if (i == nops) {
-                    rootL = Lv;
-                    rootc = cnt;
-                } else {
-                    prev = matvec_t<SMALL>(tabk + (unsigned)o.z * 16u, Lv);
-                    pc = cnt;
-                    if (MODE != 0 || (o.w & 1)) {
-                        stg256(scr + (unsigned)o.z * nthr, prev);
-                        if (SCALE) __stcg(cscr + (unsigned)o.z * nthr, cnt);
-                    }
+            };
+#pragma unroll 1
+            for (int i = 1; i < nops; ++i) {
+                const int4 o = OPS(i);
+                V4 Lv;
+                int cnt;
+                join(o, Lv, cnt);
+                Bv = matvec_t<SMALL>(tab_at((unsigned)o.z * 16u), Lv);
+                bc = cnt;
+                if (MODE != 0 || (o.w & 1)) {
+                    stg256(scr + (unsigned)o.z * nthr, Bv);
+                    if (SCALE) __stcg(cscr + (unsigned)o.z * nthr, cnt);
                 }
             }
-#endif
+            V4 rootL;
+            int rootc;
+            join(OPS(nops), rootL, rootc);
             double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
-            if (MODE != 0 || SCALE) fx[(unsigned)k * nthr + tid] = fk;
-            if (SCALE) cx[(unsigned)k * nthr + tid] = rootc;
+            if (MODE != 0 || SCALE) FX((unsigned)k * nthr + tid) = fk;
+            if (SCALE) CX((unsigned)k * nthr + tid) = rootc;
             fsum += fk;
             if (!A.mix) ll += SCALE ? wt * (log(fk) - (double)rootc * (256.0 * 0.6931471805599453)) : wt * log(fk);
         }
         double f = fsum / (double)K;
         int cmin = 0;
         if (SCALE) {
-            cmin = cx[tid];
-            for (int k = 1; k < K; ++k) cmin = min(cmin, cx[(unsigned)k * nthr + tid]);
+            cmin = CX(tid);
+            for (int k = 1; k < K; ++k) cmin = min(cmin, CX((unsigned)k * nthr + tid));
             if (A.mix) {
                 double s = 0.0;
-                for (int k = 0; k < K; ++k) s += fx[(unsigned)k * nthr + tid] * pow2_256(cmin - cx[(unsigned)k * nthr + tid]);
+                for (int k = 0; k < K; ++k) s += FX((unsigned)k * nthr + tid) * pow2_256(cmin - CX((unsigned)k * nthr + tid));
                 f = s / (double)K;
             }
         }
         if (A.mix) ll = SCALE ? wt * (log(f) - (double)cmin * (256.0 * 0.6931471805599453)) : wt * log(f);
         ll = warp_sum(ll);
-        if (lane == 0) red[warp] = ll;
+        if (lane == 0) RED(warp) = ll;
 
         // ---------------- backward (the same schedule reversed = pre-order) ----------------
         if (GRAD) {
@@ -596,128 +566,53 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                 V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
                 int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * nthr : nullptr;
                 const double rate_k = md.rates[k];
-                const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(unsigned)k * nthr + tid];
-                V4 wprev = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
-                // true upper message = stored * 2^(256 * we)
-                int we = SCALE ? (A.mix ? cmin : cx[(unsigned)k * nthr + tid]) : 0;
-                // join i uses (Ac, Bc, Wc); operands of join i-1 are fetched into (An, Bn, Wn) meanwhile:
-                // nothing stored by join i is read by join i-1 (its upper message, when it comes from
-                // scratch, was stored by an ancestor's join; its children are other nodes)
-                auto step = [&](int i, const V4 &Ac, const V4 &Bc, const V4 &Wc, int Acc, int Bcc, int Wcc,
-                                V4 &An, V4 &Bn, V4 &Wn, int &Anc, int &Bnc, int &Wnc) {
-                    const int4 o = ops_sm[i];
-                    const int4 on = ops_sm[i - 1];
-                    Anc = 0; Bnc = 0;
-                    if (on.x < 0) An = tipmsg(~on.x);
-                    else { An = ldg256(scr + (unsigned)on.x * nthr); if (SCALE) Anc = __ldcg(cscr + (unsigned)on.x * nthr); }
-                    if (on.y < 0) Bn = tipmsg(~on.y);
-                    else { Bn = ldg256(scr + (unsigned)on.y * nthr); if (SCALE) Bnc = __ldcg(cscr + (unsigned)on.y * nthr); }
-                    if (on.w & 1) {
-                        Wn = ldg256(scr + (unsigned)on.z * nthr);
-                        if (SCALE) Wnc = __ldcg(cscr + (unsigned)on.z * nthr);
-                    }
-                    {
-                        // pull the messages needed three joins from now out of HBM into L2
-                        const int4 of = ops_sm[i > 3 ? i - 3 : 0];
-                        if (of.x >= 0) prefetch_l2(scr + (unsigned)of.x * nthr);
-                        if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
-                    }
-                    V4 ua, ub;
-                    int ew;
-                    if (o.w & 1) { ua = vmul(Wc, Bc); ub = vmul(Wc, Ac); ew = Wcc; }
-                    else { ua = vmul(wprev, Bc); ub = vmul(wprev, Ac); ew = we; }
-                    double ga = rate_k * uQx(md.Q, ua, Ac);
-                    double gb = rate_k * uQx(md.Q, ub, Bc);
-                    if (SCALE) {
-                        const double sf = pow2_256(ew - Acc - Bcc);
-                        ga *= sf; gb *= sf;
-                    }
-                    const double g2 = warp_sum2(ga, gb, lane);
-                    if ((lane & 15u) == 0u) {
-                        const int c = lane ? o.y : o.x;
-                        gw[c < 0 ? ~c : c + S] += g2;
-                    }
-                    if (o.x >= 0) {
-                        V4 wa = matvecT_t<SMALL>(tabk + (unsigned)o.x * 16u, ua);
-                        int ea = ew - Bcc;
-                        if (SCALE) { int neg = -ea; scale_both(wa, neg); ea = -neg; }
-                        stg256(scr + (unsigned)o.x * nthr, wa);
-                        if (SCALE) __stcg(cscr + (unsigned)o.x * nthr, ea);
-                    }
-                    if (o.y >= 0) {
-                        wprev = matvecT_t<SMALL>(tabk + (unsigned)o.y * 16u, ub);
-                        we = ew - Acc;
-                        if (SCALE) { int neg = -we; scale_both(wprev, neg); we = -neg; }
-                    }
-                };
-#if DODO_REG_PREFETCH
-                V4 A0, B0, W0, A1, B1, W1;
-                int A0c = 0, B0c = 0, W0c = 0, A1c = 0, B1c = 0, W1c = 0;
-                {
-                    const int4 o1 = ops_sm[nops];
-                    if (o1.x < 0) A0 = tipmsg(~o1.x);
-                    else { A0 = ldg256(scr + (unsigned)o1.x * nthr); if (SCALE) A0c = __ldcg(cscr + (unsigned)o1.x * nthr); }
-                    if (o1.y < 0) B0 = tipmsg(~o1.y);
-                    else { B0 = ldg256(scr + (unsigned)o1.y * nthr); if (SCALE) B0c = __ldcg(cscr + (unsigned)o1.y * nthr); }
-                    W0 = wprev;
-                    A1 = A0; B1 = B0; W1 = W0;
-                }
-                int i = nops;
-#pragma unroll 1
-                for (; i - 1 >= 1; i -= 2) {
-                    step(i, A0, B0, W0, A0c, B0c, W0c, A1, B1, W1, A1c, B1c, W1c);
-                    step(i - 1, A1, B1, W1, A1c, B1c, W1c, A0, B0, W0, A0c, B0c, W0c);
-                }
-                if (i >= 1) step(i, A0, B0, W0, A0c, B0c, W0c, A1, B1, W1, A1c, B1c, W1c);
-#else
-                (void)step;
+                const double sc = A.mix ? wt / (f * (double)K) : wt / FX((unsigned)k * nthr + tid);
+                V4 Wv = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
+                int we = SCALE ? (A.mix ? cmin : CX((unsigned)k * nthr + tid)) : 0;  // true w = Wv * 2^(256 we)
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
-                    const int4 o = ops_sm[i];
+                    const int4 o = OPS(i);
                     {
                         // pull what the join three steps ahead needs out of HBM into L2
-                        const int4 of = ops_sm[i > 3 ? i - 3 : 0];
+                        const int4 of = OPS(i > 3 ? i - 3 : 0);
                         if (of.x >= 0) prefetch_l2(scr + (unsigned)of.x * nthr);
                         if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
                     }
+                    if (o.w & 1) {  // a-child: its upper message was parked in its own slot by the parent
+                        Wv = ldg256(scr + (unsigned)o.z * nthr);
+                        if (SCALE) we = __ldcg(cscr + (unsigned)o.z * nthr);
+                    }
                     V4 av, bv;
-                    int ac = 0, bc = 0;
+                    int ac = 0, bcn = 0;
                     if (o.x < 0) av = tipmsg(~o.x);
                     else { av = ldg256(scr + (unsigned)o.x * nthr); if (SCALE) ac = __ldcg(cscr + (unsigned)o.x * nthr); }
                     if (o.y < 0) bv = tipmsg(~o.y);
-                    else { bv = ldg256(scr + (unsigned)o.y * nthr); if (SCALE) bc = __ldcg(cscr + (unsigned)o.y * nthr); }
-                    V4 w = wprev;
-                    int ew = we;
-                    if (o.w & 1) {
-                        w = ldg256(scr + (unsigned)o.z * nthr);
-                        if (SCALE) ew = __ldcg(cscr + (unsigned)o.z * nthr);
-                    }
-                    const V4 ua = vmul(w, bv), ub = vmul(w, av);
+                    else { bv = ldg256(scr + (unsigned)o.y * nthr); if (SCALE) bcn = __ldcg(cscr + (unsigned)o.y * nthr); }
+                    const V4 ua = vmul(Wv, bv), ub = vmul(Wv, av);
                     double ga = rate_k * uQx(md.Q, ua, av);
                     double gb = rate_k * uQx(md.Q, ub, bv);
                     if (SCALE) {
-                        const double sf = pow2_256(ew - ac - bc);
+                        const double sf = pow2_256(we - ac - bcn);
                         ga *= sf; gb *= sf;
                     }
                     const double g2 = warp_sum2(ga, gb, lane);
                     if ((lane & 15u) == 0u) {
                         const int c = lane ? o.y : o.x;
-                        gw[c < 0 ? ~c : c + S] += g2;
+                        GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
                     }
                     if (o.x >= 0) {
-                        V4 wa = matvecT_t<SMALL>(tabk + (unsigned)o.x * 16u, ua);
-                        int ea = ew - bc;
+                        V4 wa = matvecT_t<SMALL>(tab_at((unsigned)o.x * 16u), ua);
+                        int ea = we - bcn;
                         if (SCALE) { int neg = -ea; scale_both(wa, neg); ea = -neg; }
                         stg256(scr + (unsigned)o.x * nthr, wa);
                         if (SCALE) __stcg(cscr + (unsigned)o.x * nthr, ea);
                     }
-                    if (o.y >= 0) {
-                        wprev = matvecT_t<SMALL>(tabk + (unsigned)o.y * 16u, ub);
-                        we = ew - ac;
-                        if (SCALE) { int neg = -we; scale_both(wprev, neg); we = -neg; }
+                    if (o.y >= 0) {  // the next join (in this reversed order) is exactly node b
+                        Wv = matvecT_t<SMALL>(tab_at((unsigned)o.y * 16u), ub);
+                        we -= ac;
+                        if (SCALE) { int neg = -we; scale_both(Wv, neg); we = -neg; }
                     }
                 }
-#endif
             }
         }
         if (GMATS) {
@@ -730,16 +625,16 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
             for (int k = 0; k < K; ++k) {
                 stage_tables(k);
                 V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
-                const double sc = A.mix ? wt / (f * (double)K) : wt / fx[(unsigned)k * nthr + tid];
+                const double sc = A.mix ? wt / (f * (double)K) : wt / FX((unsigned)k * nthr + tid);
                 double *gpart = A.gm_part + ((((size_t)item * K + k) * nwarp + warp) * (size_t)E) * 16;
                 V4 uprev = V4{0, 0, 0, 0};
                 auto maskvec = [&](int t) -> V4 {
-                    const unsigned m = SMALL ? (unsigned)sel_sm[(unsigned)t * nthr] : (unsigned)__ldg(tm + (size_t)t * A.ld_mask);
+                    const unsigned m = SMALL ? (unsigned)SEL(t) : (unsigned)__ldg(tm + (size_t)t * A.ld_mask);
                     return V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)};
                 };
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
-                    const int4 o = ops_sm[i];
+                    const int4 o = OPS(i);
                     const V4 av = o.x < 0 ? tipmsg(~o.x) : ldg256(scr + (unsigned)o.x * nthr);
                     const V4 bv = o.y < 0 ? tipmsg(~o.y) : ldg256(scr + (unsigned)o.y * nthr);
                     const V4 Lv = vmul(av, bv);
@@ -751,7 +646,7 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                     } else {
                         const V4 u = (o.w & 1) ? ldg256(scr + (unsigned)o.z * nthr) : uprev;
                         outer_reduce_store(u, Lv, gpart + (size_t)(o.z + S) * 16, lane);
-                        w = matvecT_t<SMALL>(tabk + (unsigned)o.z * 16u, u);
+                        w = matvecT_t<SMALL>(tab_at((unsigned)o.z * 16u), u);
                     }
                     const V4 ua = vmul(w, bv), ub = vmul(w, av);
                     if (o.x < 0) outer_reduce_store(ua, maskvec(~o.x), gpart + (size_t)(~o.x) * 16, lane);
@@ -769,7 +664,7 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
-            for (unsigned w2 = 0; w2 < nwarp; ++w2) s += red[w2];
+            for (unsigned w2 = 0; w2 < nwarp; ++w2) s += RED(w2);
             A.ll_part[item] = s;
         }
         if (GRAD) {
@@ -777,13 +672,20 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
             for (unsigned e = tid; e < (unsigned)E; e += nthr) {
                 double s = 0.0;
                 for (unsigned w2 = 0; w2 < nwarp; ++w2) {
-                    s += gacc[w2 * (unsigned)E + e];
-                    gacc[w2 * (unsigned)E + e] = 0.0;
+                    s += GACC(w2 * (unsigned)E + e);
+                    GACC(w2 * (unsigned)E + e) = 0.0;
                 }
                 gp[e] = s;
             }
         }
     }
+#undef GACC
+#undef FX
+#undef RED
+#undef CX
+#undef OPS
+#undef OPSW
+#undef SEL
 }
 
 // fixed-order reduction over the pattern tiles of every sample
