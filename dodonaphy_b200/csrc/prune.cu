@@ -269,6 +269,23 @@ __device__ __forceinline__ V4 ldg256(const V4 *p) {
     return r;
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef DODO_PF_L2_DIST
+#define DODO_PF_L2_DIST 3
+#endif
+#ifndef DODO_PF_L1
+#define DODO_PF_L1 0
+#endif
+// backward-sweep message load: through L1 when an L1 prefetch was issued one join ahead
+__device__ __forceinline__ V4 ldg256_bwd(const V4 *p) {
+#if DODO_PF_L1
+    V4 r;
+    asm volatile("ld.global.ca.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+#else
+    return ldg256(p);
+#endif
+}
 __device__ __forceinline__ void stg256(V4 *p, const V4 &v) {
     asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
@@ -573,10 +590,15 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
                     {
-                        // pull what the join three steps ahead needs out of HBM into L2
-                        const int4 of = OPS(i > 3 ? i - 3 : 0);
+                        // pull what the join a few steps ahead needs out of HBM into L2
+                        const int4 of = OPS(i > DODO_PF_L2_DIST ? i - DODO_PF_L2_DIST : 0);
                         if (of.x >= 0) prefetch_l2(scr + (unsigned)of.x * nthr);
                         if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
+#if DODO_PF_L1
+                        const int4 o1 = OPS(i - 1);
+                        if (o1.x >= 0) prefetch_l1(scr + (unsigned)o1.x * nthr);
+                        if (o1.y >= 0) prefetch_l1(scr + (unsigned)o1.y * nthr);
+#endif
                     }
                     if (o.w & 1) {  // a-child: its upper message was parked in its own slot by the parent
                         Wv = ldg256(scr + (unsigned)o.z * nthr);
@@ -585,9 +607,9 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                     V4 av, bv;
                     int ac = 0, bcn = 0;
                     if (o.x < 0) av = tipmsg(~o.x);
-                    else { av = ldg256(scr + (unsigned)o.x * nthr); if (SCALE) ac = __ldcg(cscr + (unsigned)o.x * nthr); }
+                    else { av = ldg256_bwd(scr + (unsigned)o.x * nthr); if (SCALE) ac = __ldcg(cscr + (unsigned)o.x * nthr); }
                     if (o.y < 0) bv = tipmsg(~o.y);
-                    else { bv = ldg256(scr + (unsigned)o.y * nthr); if (SCALE) bcn = __ldcg(cscr + (unsigned)o.y * nthr); }
+                    else { bv = ldg256_bwd(scr + (unsigned)o.y * nthr); if (SCALE) bcn = __ldcg(cscr + (unsigned)o.y * nthr); }
                     const V4 ua = vmul(Wv, bv), ub = vmul(Wv, av);
                     double ga = rate_k * uQx(md.Q, ua, av);
                     double gb = rate_k * uQx(md.Q, ub, bv);
