@@ -357,39 +357,46 @@ __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, doubl
     if (!ok) { __syncthreads(); return false; }
     const double NN = MODE == 0 ? (double)c.N * (double)c.N : (double)P;
     if (tid == 0) {
-        for (int i = 1; i < n; ++i) {  // order by flat index (the reference's cumsum order)
-            double ks = cand_s[i], kf = cand_f[i];
-            int j = i - 1;
-            while (j >= 0 && cand_f[j] > kf) { cand_s[j + 1] = cand_s[j]; cand_f[j + 1] = cand_f[j]; --j; }
-            cand_s[j + 1] = ks; cand_f[j + 1] = kf;
-        }
-        double Z = 0.0;
-        for (int i = 0; i < n; ++i) Z += exp_neg(fabs(cand_s[i] - m) / tau);
-        double run = 0.0, M = 0.0;
-        for (int i = 0; i < n; ++i) {
-            double e = exp_neg(fabs(cand_s[i] - m) / tau);
-            run += e;
-            M = fmax(M, (e / Z) * (run / Z));
-        }
-        const double e0 = exp_neg(M / tau);
-        double z2 = 0.0, isum = 0.0, fs = 0.0;
-        run = 0.0;
-        for (int i = 0; i < n; ++i) {
-            double e = exp_neg(fabs(cand_s[i] - m) / tau);
-            double e2 = e0;
-            if (e != 0.0) {
-                run += e;
-                e2 = exp_neg(fabs(M - (e / Z) * (run / Z)) / tau);
+        const double away = fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau;
+        if (n == 1 && cand_s[0] == m && 1.0 / tau > 750.0 && (FULL || away > 750.0)) {
+            // the usual case: one entry carries all the weight (p = c = 1, every other weight is exactly 0)
+            sh[0] = cand_f[0];
+            sh[1] = 1.0;
+        } else {
+            for (int i = 1; i < n; ++i) {  // order by flat index (the reference's cumsum order)
+                double ks = cand_s[i], kf = cand_f[i];
+                int j = i - 1;
+                while (j >= 0 && cand_f[j] > kf) { cand_s[j + 1] = cand_s[j]; cand_f[j + 1] = cand_f[j]; --j; }
+                cand_s[j + 1] = ks; cand_f[j + 1] = kf;
             }
-            z2 += e2;
-            isum = fma(e2, cand_f[i], isum);
-            fs += cand_f[i];
+            double Z = 0.0;
+            for (int i = 0; i < n; ++i) Z += exp_neg(fabs(cand_s[i] - m) / tau);
+            double run = 0.0, M = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double e = exp_neg(fabs(cand_s[i] - m) / tau);
+                run += e;
+                M = fmax(M, (e / Z) * (run / Z));
+            }
+            const double e0 = exp_neg(M / tau);
+            double z2 = 0.0, isum = 0.0, fs = 0.0;
+            run = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double e = exp_neg(fabs(cand_s[i] - m) / tau);
+                double e2 = e0;
+                if (e != 0.0) {
+                    run += e;
+                    e2 = exp_neg(fabs(M - (e / Z) * (run / Z)) / tau);
+                }
+                z2 += e2;
+                isum = fma(e2, cand_f[i], isum);
+                fs += cand_f[i];
+            }
+            z2 += (NN - (double)n) * e0;
+            isum += e0 * (NN * (NN - 1.0) * 0.5 - fs);
+            sh[0] = isum / z2;
+            double worst = FULL ? 0.0 : exp_neg(fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
+            sh[1] = (FULL || NN * worst <= 1e-18 * fmin(1.0, tau) * Z) ? 1.0 : 0.0;
         }
-        z2 += (NN - (double)n) * e0;
-        isum += e0 * (NN * (NN - 1.0) * 0.5 - fs);
-        sh[0] = isum / z2;
-        double worst = FULL ? 0.0 : exp_neg(fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
-        sh[1] = (FULL || NN * worst <= 1e-18 * fmin(1.0, tau) * Z) ? 1.0 : 0.0;
     }
     __syncthreads();
     idx_out = sh[0];
