@@ -1,0 +1,156 @@
+"""GPU edge cases: tile boundaries, tiny and ragged inputs, every IUPAC code, degenerate weights,
+limits and error paths -- each checked against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.as_tensor(a).cuda()
+
+
+def _random_tree(S, rng):
+    from oracle import hyp, nj
+
+    return nj.nj_hard(hyp.get_pdm_np(rng.normal(0, 0.1, (S, 3))))
+
+
+def _oracle(masks, weights, peel, blens, rates, model, mix, prob_rates=None, prob_freqs=None):
+    from oracle import phylo
+
+    bt = torch.tensor(blens, requires_grad=True)
+    t = bt[:, None] * torch.tensor(rates)[None, :]
+    if model == "JC69":
+        mats, fr = phylo.jc69_p_t_torch(t), torch.full([4], 0.25, dtype=torch.float64)
+    else:
+        mats, fr = phylo.gtr_p_t_torch(t, torch.tensor(prob_rates), torch.tensor(prob_freqs)), torch.tensor(prob_freqs)
+    ll = phylo.treelikelihood_torch([torch.tensor(phylo.mask_to_partial(m)) for m in masks], torch.tensor(weights), peel, mats, fr, gamma_mix=mix)
+    ll.backward()
+    return ll.item(), bt.grad.numpy()
+
+
+@pytest.mark.parametrize("L", [1, 2, 31, 32, 33, 255, 256, 257, 513])
+def test_pattern_tile_boundaries(L):
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    rng = np.random.default_rng(L)
+    S = 9
+    peel, blens = _random_tree(S, rng)
+    masks = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    weights = rng.integers(1, 5, size=L)
+    eng = PruneEngine(masks, weights)
+    ll, g = eng.loglik(_dev(peel), _dev(blens), SubstModel.jc69(), grad=True)
+    ref, gref = _oracle(masks, weights, peel, blens, np.ones(1), "JC69", False)
+    assert ll.item() == pytest.approx(ref, rel=1e-9)
+    np.testing.assert_allclose(g[0].cpu().numpy(), gref, rtol=1e-9, atol=1e-9 * np.abs(gref).max())
+
+
+def test_every_iupac_code_value_and_gradient():
+    """Masks 1..15 (two- and three-state codes take the column-summing path), GTR, K=3, both
+    category semantics, small- and large-table kernel variants."""
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    rng = np.random.default_rng(2)
+    for S in (6, 110):
+        L = 300
+        peel, blens = _random_tree(S, rng)
+        masks = rng.integers(1, 16, size=(S, L)).astype(np.uint8)
+        weights = rng.integers(0, 4, size=L)  # zero weights included
+        rates6, freqs = rng.dirichlet(np.ones(6)), rng.dirichlet(np.ones(4))
+        cat = SubstModel.discrete_gamma(0.7, 3)
+        eng = PruneEngine(masks, weights)
+        m = SubstModel.gtr(rates6, freqs)
+        for mix in (False, True):
+            ll, g = eng.loglik(_dev(peel), _dev(blens), m, rates=cat, mix=mix, grad=True)
+            ref, gref = _oracle(masks, weights, peel, blens, cat, "GTR", mix, rates6, freqs)
+            assert ll.item() == pytest.approx(ref, rel=1e-9)
+            np.testing.assert_allclose(g[0].cpu().numpy(), gref, rtol=1e-9, atol=1e-9 * np.abs(gref).max())
+
+
+def test_two_and_three_taxa_and_eight_categories():
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    rng = np.random.default_rng(3)
+    for S in (2, 3):
+        peel, blens = _random_tree(S, rng)
+        masks = (1 << rng.integers(0, 4, size=(S, 40))).astype(np.uint8)
+        weights = np.ones(40, dtype=np.int64)
+        cat = SubstModel.discrete_gamma(0.3, 8)
+        ll, g = PruneEngine(masks, weights).loglik(_dev(peel), _dev(blens), SubstModel.jc69(), rates=cat, mix=True, grad=True)
+        ref, gref = _oracle(masks, weights, peel, blens, cat, "JC69", True)
+        assert ll.item() == pytest.approx(ref, rel=1e-9)
+        np.testing.assert_allclose(g[0].cpu().numpy(), gref, rtol=1e-9, atol=1e-9 * np.abs(gref).max())
+
+
+def test_all_gap_columns_and_zero_branches():
+    """A column of N/-/? only contributes log(1) = 0; zero-length branches give P = I."""
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    rng = np.random.default_rng(4)
+    S, L = 7, 64
+    peel, blens = _random_tree(S, rng)
+    masks = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    masks[:, :5] = 15
+    weights = np.ones(L, dtype=np.int64)
+    eng = PruneEngine(masks, weights)
+    ll, _ = eng.loglik(_dev(peel), _dev(blens), SubstModel.jc69())
+    ll_without, _ = PruneEngine(masks[:, 5:], weights[5:]).loglik(_dev(peel), _dev(blens), SubstModel.jc69())
+    assert ll.item() == pytest.approx(ll_without.item(), rel=1e-12)
+    z = blens.copy()
+    z[peel[-1][1]] = 0.0  # the reference's fake-root edge of an unrooted tree (tree.py:112-121)
+    ref, _ = _oracle(masks, weights, peel, z, np.ones(1), "JC69", False)
+    got, _ = eng.loglik(_dev(peel), _dev(z), SubstModel.jc69())
+    assert got.item() == pytest.approx(ref, rel=1e-9)
+
+
+def test_limits_and_errors():
+    from dodonaphy_b200 import engine
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    eng = PruneEngine(np.ones((4, 10), dtype=np.uint8), np.ones(10))
+    peel = _dev(np.array([[0, 1, 4], [2, 3, 5], [4, 5, 6]]))
+    with pytest.raises(ValueError):
+        eng.loglik(peel, _dev(np.full(6, 0.1)), SubstModel.jc69(), rates=np.ones(9))
+    with pytest.raises(TypeError):
+        PruneEngine(np.ones((4, 10), dtype=np.float64), np.ones(10))
+    big = PruneEngine(np.ones((5000, 4), dtype=np.uint8), np.ones(4))
+    with pytest.raises(NotImplementedError):
+        big.loglik(_dev(np.zeros((4999, 3), dtype=np.int64)), _dev(np.full(9998, 0.1)), SubstModel.jc69(), grad=True)
+    with pytest.raises(ValueError):
+        engine.nj_soft(_dev(np.zeros((4, 4))), 0.0)
+    with pytest.raises(ValueError):
+        engine.nj_hard(_dev(np.zeros((1, 1))))
+    with pytest.raises(ValueError):
+        engine.pdm_forward(_dev(np.zeros((3, 16))), -1.0)
+
+
+def test_degenerate_distances_stay_memory_safe():
+    """NaN / all-equal distances must not crash the device (flags report the failure)."""
+    from dodonaphy_b200 import engine
+    from dodonaphy_b200.engine import validate_peel
+
+    d = np.full((8, 8), np.nan)
+    peel, blens = engine.nj_hard(_dev(d))
+    assert peel.shape == (7, 3)
+    p2, b2, flags = engine.nj_soft(_dev(d), 1e-8, return_flags=True)
+    assert int((flags & 8).sum().item()) > 0
+    same = np.ones((40, 40)) - np.eye(40)
+    p3, b3, f3 = engine.nj_soft(_dev(same), 1e-8, return_flags=True)  # 780 exact ties -> general path
+    validate_peel(p3.cpu().numpy(), 40)
+    from oracle import nj
+
+    p_ref, b_ref = nj.nj_soft(same, 1e-8)
+    assert np.array_equal(p3.cpu().numpy(), p_ref)
+    torch.cuda.synchronize()
+
+
+def test_pdm_shapes():
+    from dodonaphy_b200 import engine
+    from oracle import hyp
+
+    rng = np.random.default_rng(6)
+    for S, D in ((1, 3), (2, 1), (5, 15), (33, 2)):
+        x = rng.normal(0, 0.2, (S, D))
+        np.testing.assert_allclose(engine.pdm_forward(_dev(x), -1.0).cpu().numpy(), hyp.get_pdm_torch(x), rtol=1e-10, atol=1e-13)
