@@ -241,14 +241,14 @@ constexpr int NT = 256;  // threads per CTA = site patterns per work item
 
 // Shared memory.  SMALL (tables and tip selectors resident): tables | gacc | fx | red | cx | ops | sel.
 // LARGE (big S: tables and masks stay in global memory, read through L1): gacc | fx | red | cx | ops.
-__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small) {
+__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np) {
     const size_t nwarp = NT / 32, E = 2 * (size_t)S - 2;
-    size_t dbl = nwarp * E + (size_t)K * NT + nwarp + (small ? tab_doubles(S) : 0);
+    size_t dbl = nwarp * E + (size_t)K * NT * np + nwarp + (small ? tab_doubles(S) : 0);
     return (dbl + 1) & ~(size_t)1;  // keep what follows 16-byte aligned
 }
-__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small) {
-    return prune_smem_dbl(S, K, small) * sizeof(double) + (size_t)K * NT * sizeof(int) +
-           (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT : 0);
+__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np) {
+    return prune_smem_dbl(S, K, small, np) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
+           (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT * np : 0);
 }
 
 __device__ __forceinline__ V4 lds4(const double *p) {
@@ -426,60 +426,110 @@ __device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0
     return scalbn(1.0, 256 * d);
 }
 
+// P x / P^T x for NP patterns at once: every row of P is loaded once and applied to all of them
+template <bool SMALL, int NP>
+__device__ __forceinline__ void matvec_n(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    const V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL>(P + 4), r2 = ld4t<SMALL>(P + 8), r3 = ld4t<SMALL>(P + 12);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const V4 v = x[q];
+        y[q].a = fma(r0.d, v.d, fma(r0.c, v.c, fma(r0.b, v.b, r0.a * v.a)));
+        y[q].b = fma(r1.d, v.d, fma(r1.c, v.c, fma(r1.b, v.b, r1.a * v.a)));
+        y[q].c = fma(r2.d, v.d, fma(r2.c, v.c, fma(r2.b, v.b, r2.a * v.a)));
+        y[q].d = fma(r3.d, v.d, fma(r3.c, v.c, fma(r3.b, v.b, r3.a * v.a)));
+    }
+}
+template <bool SMALL, int NP>
+__device__ __forceinline__ void matvecT_n(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    V4 r = ld4t<SMALL>(P);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) y[q] = V4{r.a * x[q].a, r.b * x[q].a, r.c * x[q].a, r.d * x[q].a};
+    r = ld4t<SMALL>(P + 4);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        y[q].a = fma(r.a, x[q].b, y[q].a), y[q].b = fma(r.b, x[q].b, y[q].b);
+        y[q].c = fma(r.c, x[q].b, y[q].c), y[q].d = fma(r.d, x[q].b, y[q].d);
+    }
+    r = ld4t<SMALL>(P + 8);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        y[q].a = fma(r.a, x[q].c, y[q].a), y[q].b = fma(r.b, x[q].c, y[q].b);
+        y[q].c = fma(r.c, x[q].c, y[q].c), y[q].d = fma(r.d, x[q].c, y[q].d);
+    }
+    r = ld4t<SMALL>(P + 12);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        y[q].a = fma(r.a, x[q].d, y[q].a), y[q].b = fma(r.b, x[q].d, y[q].b);
+        y[q].c = fma(r.c, x[q].d, y[q].c), y[q].d = fma(r.d, x[q].d, y[q].d);
+    }
+}
+
 // MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
+// NP: site patterns per thread (1 or 2).  With NP = 2 the schedule decode, the branches, the address
+// arithmetic and -- above all -- the warp-wide fills of registers with the (warp-uniform) entries of P
+// are shared by two independent patterns, which also doubles the instruction-level parallelism.
 //
 // Register conventions of the two sweeps (they keep the loops free of copies):
 //   forward : Bv holds "the other operand": the previous join's message when child b is internal
 //             (the schedule guarantees b is then exactly the previous join), else b's tip message.
 //   backward: Wv holds the upper message of the current join: left there by the previous join when
 //             this node is its b-child, else (a-child) fetched from scratch.
-// Latency is hidden by the 24 resident warps per SM plus an L2 prefetch three joins ahead in the
-// backward sweep; a register-level software pipeline was measured slower (more instructions).
-template <int MODE, bool SMALL, bool SCALE>
-__global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A, ModelDev md) {
+// Latency is hidden by the resident warps plus an L2 prefetch three joins ahead in the backward
+// sweep; a register-level software pipeline was measured slower (more instructions).
+template <int MODE, bool SMALL, bool SCALE, int NP>
+__global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kernel(PruneArgs A, ModelDev md) {
     constexpr bool GRAD = MODE == 1;
     constexpr bool GMATS = MODE == 2;
     static_assert(!(GMATS && SCALE), "GMATS is built without rescaling");
+    static_assert(!(GMATS && NP != 1), "GMATS handles one pattern per thread");
     extern __shared__ __align__(16) double smd[];  // indexed from the symbol: keeps LDS addressing direct
     const unsigned tid = threadIdx.x;
     constexpr unsigned nthr = NT;
+    constexpr unsigned npt = NT * NP;  // patterns per work item
     const unsigned lane = tid & 31u;
     const unsigned warp = tid >> 5;
     constexpr unsigned nwarp = NT / 32;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
     const unsigned tabn = (unsigned)tab_doubles(S);
-    // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][nthr] red[nwarp] | cx | ops | sel
+    // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] | cx | ops | sel
     const unsigned o_gacc = SMALL ? tabn : 0u;
     const unsigned o_fx = o_gacc + nwarp * (unsigned)E;
-    const unsigned o_red = o_fx + (unsigned)K * nthr;
-    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL);                    // int [K][nthr]
-    const unsigned o_ops = o_cx + ((unsigned)K * nthr) / 2u;                        // int4 [S+2]
-    const unsigned o_sel = o_ops + 2u * (unsigned)(S + 2);                          // u8 [S][nthr]
+    const unsigned o_red = o_fx + (unsigned)K * npt;
+    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP);                // int [K][npt]
+    const unsigned o_ops = o_cx + ((unsigned)K * npt) / 2u;                         // int4 [S+2]
+    const unsigned o_sel = o_ops + 2u * (unsigned)(S + 2);                          // u8 [S][npt]
     const unsigned o_T = (unsigned)(S - 1) * 16u;                                   // Ttip inside the slab
 #define GACC(i) smd[o_gacc + (i)]
-#define FX(i) smd[o_fx + (i)]
+#define FX(k, q) smd[o_fx + ((unsigned)(k) * NP + (q)) * nthr + tid]
 #define RED(i) smd[o_red + (i)]
-#define CX(i) (reinterpret_cast<int *>(&smd[o_cx])[(i)])
+#define CX(k, q) (reinterpret_cast<int *>(&smd[o_cx])[((unsigned)(k) * NP + (q)) * nthr + tid])
 #define OPS(i) (reinterpret_cast<const int4 *>(&smd[o_ops])[(i)])
 #define OPSW(i) (reinterpret_cast<int4 *>(&smd[o_ops])[(i)])
-#define SEL(t) (reinterpret_cast<uint8_t *>(&smd[o_sel])[(unsigned)(t) * nthr + tid])
+#define SEL(t, q) (reinterpret_cast<uint8_t *>(&smd[o_sel])[((unsigned)(t) * NP + (q)) * nthr + tid])
+#define SCR(node, q) (scr + ((unsigned)(node) * NP + (q)) * nthr)
+#define CSCR(node, q) (cscr + ((unsigned)(node) * NP + (q)) * nthr)
     if (GRAD) {
         for (unsigned i = tid; i < nwarp * (unsigned)E; i += nthr) GACC(i) = 0.0;
     }
-    // scratch ring of this CTA: [k][node][thread] x 32 B (+ 4 B rescaling counters)
-    V4 *scr0 = reinterpret_cast<V4 *>(A.scratch) + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid;
-    int *cscr0 = SCALE ? A.cscratch + (size_t)blockIdx.x * (size_t)K * (S - 1) * nthr + tid : nullptr;
+    // scratch ring of this CTA: [k][node][pattern] x 32 B (+ 4 B rescaling counters)
+    V4 *scr0 = reinterpret_cast<V4 *>(A.scratch) + (size_t)blockIdx.x * (size_t)K * (S - 1) * npt + tid;
+    int *cscr0 = SCALE ? A.cscratch + (size_t)blockIdx.x * (size_t)K * (S - 1) * npt + tid : nullptr;
     const unsigned gw = warp * (unsigned)E;
 
 #pragma unroll 1
     for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int b = item / A.n_tiles;
         const int tile = item - b * A.n_tiles;
-        const int p = tile * NT + (int)tid;
-        const bool valid = p < A.L;
-        const double wt = valid ? __ldg(A.weights + p) : 0.0;
+        double wt[NP];
+        const uint8_t *tm[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int p = tile * (int)npt + q * (int)nthr + (int)tid;
+            const bool valid = p < A.L;
+            wt[q] = valid ? __ldg(A.weights + p) : 0.0;
+            tm[q] = A.tipmask + (valid ? p : A.L - 1);
+        }
         const double *tab_b = A.tab + (size_t)b * K * tabn;
-        const uint8_t *tm = A.tipmask + (valid ? p : A.L - 1);
         __syncthreads();
         {
             // schedule of this sample, re-encoded: child code < 0 -> tip ~code, else internal index
@@ -494,8 +544,10 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                 }
                 OPSW(i) = o;
             }
-            if (SMALL) {  // tip selectors of this thread's pattern (thread-private column)
-                for (int t = 0; t < S; ++t) SEL(t) = (uint8_t)encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+            if (SMALL) {  // tip selectors of this thread's patterns (thread-private columns)
+                for (int t = 0; t < S; ++t)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) SEL(t, q) = (uint8_t)encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
             }
         }
         const double *tabg = tab_b;  // LARGE: tables of the current category in global memory
@@ -511,67 +563,93 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
             }
         };
         auto tab_at = [&](unsigned off) -> const double * { return SMALL ? &smd[off] : tabg + off; };
-        auto tipmsg = [&](int t) -> V4 {
-            const unsigned sel = SMALL ? (unsigned)SEL(t) : encode_sel(__ldg(tm + (size_t)t * A.ld_mask));
+        auto tipmsg = [&](int t, int q) -> V4 {
+            const unsigned sel = SMALL ? (unsigned)SEL(t, q) : encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
             return tip_message<SMALL>(tab_at(o_T + (unsigned)t * 20u), sel);
         };
 
         // ---------------- forward (post-order), one pass per rate category ----------------
-        double fsum = 0.0, ll = 0.0;
+        double fsum[NP], ll = 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) fsum[q] = 0.0;
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
             stage_tables(k);
-            V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
-            int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * nthr : nullptr;
-            V4 Bv = V4{0, 0, 0, 0};
-            int bc = 0;
-            auto join = [&](const int4 &o, V4 &Lv, int &cnt) {
-                cnt = 0;
-                if (o.x < 0) {
-                    Lv = tipmsg(~o.x);
-                } else {
-                    Lv = ldg256(scr + (unsigned)o.x * nthr);
-                    if (SCALE) cnt = __ldcg(cscr + (unsigned)o.x * nthr);
+            V4 *scr = scr0 + (size_t)k * (S - 1) * npt;
+            int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * npt : nullptr;
+            V4 Bv[NP];
+            int bc[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) { Bv[q] = V4{0, 0, 0, 0}; bc[q] = 0; }
+            auto join = [&](const int4 &o, V4 (&Lv)[NP], int (&cnt)[NP]) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    cnt[q] = 0;
+                    if (o.x < 0) {
+                        Lv[q] = tipmsg(~o.x, q);
+                    } else {
+                        Lv[q] = ldg256(SCR(o.x, q));
+                        if (SCALE) cnt[q] = __ldcg(CSCR(o.x, q));
+                    }
                 }
-                if (o.y < 0) { Bv = tipmsg(~o.y); bc = 0; }  // both children are tips: Bv is free
-                Lv = vmul(Lv, Bv);
-                cnt += bc;
-                if (SCALE) scale_up(Lv, cnt);
+                if (o.y < 0) {  // both children are tips: Bv is free
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) { Bv[q] = tipmsg(~o.y, q); bc[q] = 0; }
+                }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    Lv[q] = vmul(Lv[q], Bv[q]);
+                    cnt[q] += bc[q];
+                    if (SCALE) scale_up(Lv[q], cnt[q]);
+                }
             };
 #pragma unroll 1
             for (int i = 1; i < nops; ++i) {
                 const int4 o = OPS(i);
-                V4 Lv;
-                int cnt;
+                V4 Lv[NP];
+                int cnt[NP];
                 join(o, Lv, cnt);
-                Bv = matvec_t<SMALL>(tab_at((unsigned)o.z * 16u), Lv);
-                bc = cnt;
+                matvec_n<SMALL, NP>(tab_at((unsigned)o.z * 16u), Lv, Bv);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) bc[q] = cnt[q];
                 if (MODE != 0 || (o.w & 1)) {
-                    stg256(scr + (unsigned)o.z * nthr, Bv);
-                    if (SCALE) __stcg(cscr + (unsigned)o.z * nthr, cnt);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        stg256(SCR(o.z, q), Bv[q]);
+                        if (SCALE) __stcg(CSCR(o.z, q), cnt[q]);
+                    }
                 }
             }
-            V4 rootL;
-            int rootc;
+            V4 rootL[NP];
+            int rootc[NP];
             join(OPS(nops), rootL, rootc);
-            double fk = fma(md.pi[3], rootL.d, fma(md.pi[2], rootL.c, fma(md.pi[1], rootL.b, md.pi[0] * rootL.a)));
-            if (MODE != 0 || SCALE) FX((unsigned)k * nthr + tid) = fk;
-            if (SCALE) CX((unsigned)k * nthr + tid) = rootc;
-            fsum += fk;
-            if (!A.mix) ll += SCALE ? wt * (log(fk) - (double)rootc * (256.0 * 0.6931471805599453)) : wt * log(fk);
-        }
-        double f = fsum / (double)K;
-        int cmin = 0;
-        if (SCALE) {
-            cmin = CX(tid);
-            for (int k = 1; k < K; ++k) cmin = min(cmin, CX((unsigned)k * nthr + tid));
-            if (A.mix) {
-                double s = 0.0;
-                for (int k = 0; k < K; ++k) s += FX((unsigned)k * nthr + tid) * pow2_256(cmin - CX((unsigned)k * nthr + tid));
-                f = s / (double)K;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const V4 r = rootL[q];
+                const double fk = fma(md.pi[3], r.d, fma(md.pi[2], r.c, fma(md.pi[1], r.b, md.pi[0] * r.a)));
+                if (MODE != 0 || SCALE) FX(k, q) = fk;
+                if (SCALE) CX(k, q) = rootc[q];
+                fsum[q] += fk;
+                if (!A.mix) ll += SCALE ? wt[q] * (log(fk) - (double)rootc[q] * (256.0 * 0.6931471805599453)) : wt[q] * log(fk);
             }
         }
-        if (A.mix) ll = SCALE ? wt * (log(f) - (double)cmin * (256.0 * 0.6931471805599453)) : wt * log(f);
+        double f[NP];
+        int cmin[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            f[q] = fsum[q] / (double)K;
+            cmin[q] = 0;
+            if (SCALE) {
+                cmin[q] = CX(0, q);
+                for (int k = 1; k < K; ++k) cmin[q] = min(cmin[q], CX(k, q));
+                if (A.mix) {
+                    double s = 0.0;
+                    for (int k = 0; k < K; ++k) s += FX(k, q) * pow2_256(cmin[q] - CX(k, q));
+                    f[q] = s / (double)K;
+                }
+            }
+            if (A.mix) ll += SCALE ? wt[q] * (log(f[q]) - (double)cmin[q] * (256.0 * 0.6931471805599453)) : wt[q] * log(f[q]);
+        }
         ll = warp_sum(ll);
         if (lane == 0) RED(warp) = ll;
 
@@ -580,42 +658,55 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
                 stage_tables(k);
-                V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
-                int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * nthr : nullptr;
+                V4 *scr = scr0 + (size_t)k * (S - 1) * npt;
+                int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * npt : nullptr;
                 const double rate_k = md.rates[k];
-                const double sc = A.mix ? wt / (f * (double)K) : wt / FX((unsigned)k * nthr + tid);
-                V4 Wv = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
-                int we = SCALE ? (A.mix ? cmin : CX((unsigned)k * nthr + tid)) : 0;  // true w = Wv * 2^(256 we)
+                V4 Wv[NP];
+                int we[NP];  // true w = Wv * 2^(256 we)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const double sc = A.mix ? wt[q] / (f[q] * (double)K) : wt[q] / FX(k, q);
+                    Wv[q] = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
+                    we[q] = SCALE ? (A.mix ? cmin[q] : CX(k, q)) : 0;
+                }
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
                     {
                         // pull what the join a few steps ahead needs out of HBM into L2
                         const int4 of = OPS(i > DODO_PF_L2_DIST ? i - DODO_PF_L2_DIST : 0);
-                        if (of.x >= 0) prefetch_l2(scr + (unsigned)of.x * nthr);
-                        if (of.y >= 0) prefetch_l2(scr + (unsigned)of.y * nthr);
-#if DODO_PF_L1
-                        const int4 o1 = OPS(i - 1);
-                        if (o1.x >= 0) prefetch_l1(scr + (unsigned)o1.x * nthr);
-                        if (o1.y >= 0) prefetch_l1(scr + (unsigned)o1.y * nthr);
-#endif
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            if (of.x >= 0) prefetch_l2(SCR(of.x, q));
+                            if (of.y >= 0) prefetch_l2(SCR(of.y, q));
+                        }
                     }
                     if (o.w & 1) {  // a-child: its upper message was parked in its own slot by the parent
-                        Wv = ldg256(scr + (unsigned)o.z * nthr);
-                        if (SCALE) we = __ldcg(cscr + (unsigned)o.z * nthr);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            Wv[q] = ldg256(SCR(o.z, q));
+                            if (SCALE) we[q] = __ldcg(CSCR(o.z, q));
+                        }
                     }
-                    V4 av, bv;
-                    int ac = 0, bcn = 0;
-                    if (o.x < 0) av = tipmsg(~o.x);
-                    else { av = ldg256_bwd(scr + (unsigned)o.x * nthr); if (SCALE) ac = __ldcg(cscr + (unsigned)o.x * nthr); }
-                    if (o.y < 0) bv = tipmsg(~o.y);
-                    else { bv = ldg256_bwd(scr + (unsigned)o.y * nthr); if (SCALE) bcn = __ldcg(cscr + (unsigned)o.y * nthr); }
-                    const V4 ua = vmul(Wv, bv), ub = vmul(Wv, av);
-                    double ga = rate_k * uQx(md.Q, ua, av);
-                    double gb = rate_k * uQx(md.Q, ub, bv);
-                    if (SCALE) {
-                        const double sf = pow2_256(we - ac - bcn);
-                        ga *= sf; gb *= sf;
+                    V4 av[NP], bv[NP], ua[NP], ub[NP];
+                    int ac[NP], bcn[NP];
+                    double ga = 0.0, gb = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        ac[q] = 0; bcn[q] = 0;
+                        if (o.x < 0) av[q] = tipmsg(~o.x, q);
+                        else { av[q] = ldg256_bwd(SCR(o.x, q)); if (SCALE) ac[q] = __ldcg(CSCR(o.x, q)); }
+                        if (o.y < 0) bv[q] = tipmsg(~o.y, q);
+                        else { bv[q] = ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
+                        ua[q] = vmul(Wv[q], bv[q]);
+                        ub[q] = vmul(Wv[q], av[q]);
+                        double gaq = rate_k * uQx(md.Q, ua[q], av[q]);
+                        double gbq = rate_k * uQx(md.Q, ub[q], bv[q]);
+                        if (SCALE) {
+                            const double sf = pow2_256(we[q] - ac[q] - bcn[q]);
+                            gaq *= sf; gbq *= sf;
+                        }
+                        ga += gaq; gb += gbq;
                     }
                     const double g2 = warp_sum2(ga, gb, lane);
                     if ((lane & 15u) == 0u) {
@@ -623,16 +714,23 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                         GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
                     }
                     if (o.x >= 0) {
-                        V4 wa = matvecT_t<SMALL>(tab_at((unsigned)o.x * 16u), ua);
-                        int ea = we - bcn;
-                        if (SCALE) { int neg = -ea; scale_both(wa, neg); ea = -neg; }
-                        stg256(scr + (unsigned)o.x * nthr, wa);
-                        if (SCALE) __stcg(cscr + (unsigned)o.x * nthr, ea);
+                        V4 wa[NP];
+                        matvecT_n<SMALL, NP>(tab_at((unsigned)o.x * 16u), ua, wa);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            int ea = we[q] - bcn[q];
+                            if (SCALE) { int neg = -ea; scale_both(wa[q], neg); ea = -neg; }
+                            stg256(SCR(o.x, q), wa[q]);
+                            if (SCALE) __stcg(CSCR(o.x, q), ea);
+                        }
                     }
                     if (o.y >= 0) {  // the next join (in this reversed order) is exactly node b
-                        Wv = matvecT_t<SMALL>(tab_at((unsigned)o.y * 16u), ub);
-                        we -= ac;
-                        if (SCALE) { int neg = -we; scale_both(Wv, neg); we = -neg; }
+                        matvecT_n<SMALL, NP>(tab_at((unsigned)o.y * 16u), ub, Wv);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            we[q] -= ac[q];
+                            if (SCALE) { int neg = -we[q]; scale_both(Wv[q], neg); we[q] = -neg; }
+                        }
                     }
                 }
             }
@@ -646,19 +744,19 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
                 stage_tables(k);
-                V4 *scr = scr0 + (size_t)k * (S - 1) * nthr;
-                const double sc = A.mix ? wt / (f * (double)K) : wt / FX((unsigned)k * nthr + tid);
+                V4 *scr = scr0 + (size_t)k * (S - 1) * npt;
+                const double sc = A.mix ? wt[0] / (f[0] * (double)K) : wt[0] / FX(k, 0);
                 double *gpart = A.gm_part + ((((size_t)item * K + k) * nwarp + warp) * (size_t)E) * 16;
                 V4 uprev = V4{0, 0, 0, 0};
                 auto maskvec = [&](int t) -> V4 {
-                    const unsigned m = SMALL ? (unsigned)SEL(t) : (unsigned)__ldg(tm + (size_t)t * A.ld_mask);
+                    const unsigned m = SMALL ? (unsigned)SEL(t, 0) : (unsigned)__ldg(tm[0] + (size_t)t * A.ld_mask);
                     return V4{(double)(m & 1u), (double)((m >> 1) & 1u), (double)((m >> 2) & 1u), (double)((m >> 3) & 1u)};
                 };
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
-                    const V4 av = o.x < 0 ? tipmsg(~o.x) : ldg256(scr + (unsigned)o.x * nthr);
-                    const V4 bv = o.y < 0 ? tipmsg(~o.y) : ldg256(scr + (unsigned)o.y * nthr);
+                    const V4 av = o.x < 0 ? tipmsg(~o.x, 0) : ldg256(SCR(o.x, 0));
+                    const V4 bv = o.y < 0 ? tipmsg(~o.y, 0) : ldg256(SCR(o.y, 0));
                     const V4 Lv = vmul(av, bv);
                     V4 w;
                     if (i == nops) {
@@ -666,13 +764,13 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
                         gpi0 = fma(sc, Lv.a, gpi0); gpi1 = fma(sc, Lv.b, gpi1);
                         gpi2 = fma(sc, Lv.c, gpi2); gpi3 = fma(sc, Lv.d, gpi3);
                     } else {
-                        const V4 u = (o.w & 1) ? ldg256(scr + (unsigned)o.z * nthr) : uprev;
+                        const V4 u = (o.w & 1) ? ldg256(SCR(o.z, 0)) : uprev;
                         outer_reduce_store(u, Lv, gpart + (size_t)(o.z + S) * 16, lane);
                         w = matvecT_t<SMALL>(tab_at((unsigned)o.z * 16u), u);
                     }
                     const V4 ua = vmul(w, bv), ub = vmul(w, av);
                     if (o.x < 0) outer_reduce_store(ua, maskvec(~o.x), gpart + (size_t)(~o.x) * 16, lane);
-                    else stg256(scr + (unsigned)o.x * nthr, ua);
+                    else stg256(SCR(o.x, 0), ua);
                     if (o.y < 0) outer_reduce_store(ub, maskvec(~o.y), gpart + (size_t)(~o.y) * 16, lane);
                     else uprev = ub;
                 }
@@ -708,6 +806,8 @@ __global__ void __launch_bounds__(NT, DODO_PRUNE_CTAS) prune_kernel(PruneArgs A,
 #undef OPS
 #undef OPSW
 #undef SEL
+#undef SCR
+#undef CSCR
 }
 
 // fixed-order reduction over the pattern tiles of every sample
@@ -755,17 +855,30 @@ __global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, co
 }
 
 typedef void (*prune_fn_t)(PruneArgs, ModelDev);
-static prune_fn_t prune_entry(int mode, bool small, bool scale) {
-    if (mode == 2) return small ? prune_kernel<2, true, false> : prune_kernel<2, false, false>;
-    if (mode == 1) {
-        if (small) return scale ? prune_kernel<1, true, true> : prune_kernel<1, true, false>;
-        return scale ? prune_kernel<1, false, true> : prune_kernel<1, false, false>;
-    }
-    if (small) return scale ? prune_kernel<0, true, true> : prune_kernel<0, true, false>;
-    return scale ? prune_kernel<0, false, true> : prune_kernel<0, false, false>;
+template <int MODE, int NP>
+static prune_fn_t prune_pick(bool small, bool scale) {
+    if (small) return scale ? prune_kernel<MODE, true, true, NP> : prune_kernel<MODE, true, false, NP>;
+    return scale ? prune_kernel<MODE, false, true, NP> : prune_kernel<MODE, false, false, NP>;
 }
-// tables + selectors live in shared memory when that still leaves room for 3 CTAs per SM
-static bool prune_small(int S, int K) { return prune_smem_bytes(S, K, true) <= 74 * 1024; }
+static prune_fn_t prune_entry(int mode, bool small, bool scale, int np) {
+    if (mode == 2) return small ? prune_kernel<2, true, false, 1> : prune_kernel<2, false, false, 1>;
+    if (mode == 1) return np == 2 ? prune_pick<1, 2>(small, scale) : prune_pick<1, 1>(small, scale);
+    return np == 2 ? prune_pick<0, 2>(small, scale) : prune_pick<0, 1>(small, scale);
+}
+// tables + selectors live in shared memory when that still leaves room for several CTAs per SM
+static bool prune_small(int S, int K, int np) { return prune_smem_bytes(S, K, true, np) <= (np == 2 ? 110 : 74) * 1024; }
+// patterns per thread.  Two per thread halve the warp-uniform work (schedule decode, P fills) per
+// pattern but cost registers (116 vs 78 -> 2 instead of 3 CTAs per SM): measured 5.1 ms against
+// 4.75 ms at 64 taxa x 10k patterns x 128 samples x 4 categories, so one per thread is the default.
+static int prune_np(int B, int L, uint32_t flags) {
+    (void)B; (void)L;
+    if (flags & DODO_PRUNE_GMATS) return 1;
+#ifdef DODO_PRUNE_NP
+    return DODO_PRUNE_NP;
+#else
+    return 1;
+#endif
+}
 static int prune_mode(uint32_t flags) { return (flags & DODO_PRUNE_GMATS) ? 2 : ((flags & DODO_PRUNE_GRAD) ? 1 : 0); }
 
 }  // namespace dodo
@@ -785,15 +898,16 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     plan->B = B; plan->S = S; plan->L = L; plan->K = K; plan->flags = flags;
     (void)threads_hint;
     const int threads = NT;
-    const bool small = prune_small(S, K);
+    const int np = prune_np(B, L, flags);
+    const bool small = prune_small(S, K, np);
     const bool scale = (flags & DODO_PRUNE_SCALE) != 0;
-    const size_t smem = prune_smem_bytes(S, K, small);
+    const size_t smem = prune_smem_bytes(S, K, small, np);
     if (smem > 227 * 1024) {
         set_error("dodo_prune_plan: %d taxa need %zu bytes of shared memory per CTA (limit 227 KB)", S, smem);
         return DODO_ENOTIMPL;
     }
     plan->threads = threads;
-    plan->tile_patterns = threads;
+    plan->tile_patterns = threads * np;
     plan->n_tiles = (L + plan->tile_patterns - 1) / plan->tile_patterns;
     long long items = (long long)B * plan->n_tiles;
     DODO_CHECK_ARG(items < (1ll << 31), "dodo_prune_plan: too many work items");
@@ -801,7 +915,7 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     int grid = grid_hint;
     if (grid <= 0) {
         // persistent grid: every CTA the SMs can hold at once (a multiple of the SM count)
-        prune_fn_t fn = prune_entry(prune_mode(flags), small, scale);
+        prune_fn_t fn = prune_entry(prune_mode(flags), small, scale, np);
         if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
@@ -818,9 +932,9 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     plan->off_ops = off;     off = align_up(off + (uint64_t)B * nI * sizeof(int4), 256);
     plan->off_sched = off;   off = align_up(off + (uint64_t)B * 6 * S * sizeof(int), 256);
     plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S) * sizeof(double), 256);
-    plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * threads * 32, 256);
+    plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * threads * np * 32, 256);
     plan->off_tiptab = off;  // rescaling counters (int32 per stored message)
-    if (scale) off = align_up(off + (uint64_t)grid * K * nI * threads * sizeof(int), 256);
+    if (scale) off = align_up(off + (uint64_t)grid * K * nI * threads * np * sizeof(int), 256);
     plan->off_ll_part = off; off = align_up(off + (uint64_t)plan->n_items * sizeof(double), 256);
     plan->off_g_part = off;
     if (flags & DODO_PRUNE_GRAD) off = align_up(off + (uint64_t)plan->n_items * E * sizeof(double), 256);
@@ -891,13 +1005,14 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.B = B; A.S = S; A.L = L; A.K = K;
     A.n_tiles = plan->n_tiles; A.n_items = plan->n_items; A.tile_patterns = plan->tile_patterns;
     A.mix = ((plan->flags & DODO_PRUNE_MIX) && K > 1) ? 1 : 0;
-    const bool small = prune_small(S, K);
-    size_t smem = prune_smem_bytes(S, K, small);
+    const int np = plan->tile_patterns / plan->threads;
+    const bool small = prune_small(S, K, np);
+    size_t smem = prune_smem_bytes(S, K, small, np);
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
     {
-        prune_fn_t fn = prune_entry(prune_mode(plan->flags), small, (plan->flags & DODO_PRUNE_SCALE) != 0);
+        prune_fn_t fn = prune_entry(prune_mode(plan->flags), small, (plan->flags & DODO_PRUNE_SCALE) != 0, np);
         if (smem > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<plan->grid, plan->threads, smem, stream>>>(A, md);
     }
