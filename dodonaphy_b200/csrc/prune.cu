@@ -700,13 +700,15 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         else { bv[q] = ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
                         ua[q] = vmul(Wv[q], bv[q]);
                         ub[q] = vmul(Wv[q], av[q]);
-                        double gaq = rate_k * uQx(md.Q, ua[q], av[q]);
-                        double gbq = rate_k * uQx(md.Q, ub[q], bv[q]);
+                        // explicitly rounded: the result must not depend on whether the (exact)
+                        // rescaling factor sits between the product and the accumulation
+                        double gaq = __dmul_rn(rate_k, uQx(md.Q, ua[q], av[q]));
+                        double gbq = __dmul_rn(rate_k, uQx(md.Q, ub[q], bv[q]));
                         if (SCALE) {
                             const double sf = pow2_256(we[q] - ac[q] - bcn[q]);
-                            gaq *= sf; gbq *= sf;
+                            gaq = __dmul_rn(gaq, sf); gbq = __dmul_rn(gbq, sf);
                         }
-                        ga += gaq; gb += gbq;
+                        ga = __dadd_rn(ga, gaq); gb = __dadd_rn(gb, gbq);
                     }
                     const double g2 = warp_sum2(ga, gb, lane);
                     if ((lane & 15u) == 0u) {
