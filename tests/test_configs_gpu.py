@@ -111,3 +111,54 @@ def test_c5_shape_long_alignment_site_blocks():
     ref.backward()
     assert ll.item() == pytest.approx(ref.item(), rel=1e-9)
     np.testing.assert_allclose(g[0].cpu().numpy(), bt.grad.numpy(), rtol=1e-9, atol=1e-9 * np.abs(bt.grad.numpy()).max())
+
+
+def test_c2_full_size_headline_workload():
+    """configs[1] at full size (64 taxa x 10 000 patterns x 128 samples, GTR+G4, soft NJ): two samples
+    against the oracle end to end, plus size-independent properties for the whole batch: lnL additive
+    over site blocks, forward-only == forward of the gradient kernel, directional finite difference
+    of lnL along the gradient w.r.t. the locations."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+    from oracle import hyp, nj, phylo
+
+    S, L, B, D, K = 64, 10000, 128, 5, 4
+    prob = synth.make_problem(S, L, B, D=D, seed=1002)
+    model = SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(0.5, K)
+    hp = HotPath(prob["masks"], prob["weights"], model, rates=rates, mix=True, tau=1e-8)
+    x = _dev(prob["xs"])
+    out = hp.value_and_grad(x)
+    assert torch.isfinite(out["lnL"]).all() and int((out["flags"] & 12).sum().item()) == 0
+    tips = [torch.tensor(phylo.mask_to_partial(m)) for m in prob["masks"]]
+    for b in (0, 77):
+        peel, blens = nj.nj_soft(hyp.get_pdm_torch(prob["xs"][b]), 1e-8)
+        assert np.array_equal(out["peel"][b].cpu().numpy(), peel)
+        bt = torch.tensor(blens, requires_grad=True)
+        mats = phylo.gtr_p_t_torch(bt[:, None] * torch.tensor(rates)[None, :], torch.tensor(prob["rates"]), torch.tensor(prob["freqs"]))
+        ref = phylo.treelikelihood_torch(tips, torch.tensor(prob["weights"]), peel, mats, torch.tensor(prob["freqs"]), gamma_mix=True)
+        ref.backward()
+        assert out["lnL"][b].item() == pytest.approx(ref.item(), rel=1e-9)
+        g = out["grad_blens"][b].cpu().numpy()
+        np.testing.assert_allclose(g, bt.grad.numpy(), rtol=1e-9, atol=1e-9 * np.abs(g).max())
+    # additivity over site blocks (what site sharding relies on)
+    halves = 0.0
+    for lo, hi in ((0, 4321), (4321, L)):
+        eng = PruneEngine(np.ascontiguousarray(prob["masks"][:, lo:hi]), prob["weights"][lo:hi])
+        halves = halves + eng.loglik(out["peel"], out["blens"], model, rates=rates, mix=True)[0]
+    np.testing.assert_allclose(halves.cpu().numpy(), out["lnL"].cpu().numpy(), rtol=1e-12)
+    # forward-only kernel agrees with the gradient kernel's value bit for bit
+    fwd, _ = hp.prune.loglik(out["peel"], out["blens"], model, rates=rates, mix=True, grad=False)
+    assert torch.equal(fwd, out["lnL"])
+    # directional derivative w.r.t. the locations (through soft NJ and the distance kernel)
+    d = out["grad_x"] / out["grad_x"].abs().amax(dim=(1, 2), keepdim=True)
+    h = 1e-7
+    plus = hp.value_and_grad(x + h * d)
+    minus = hp.value_and_grad(x - h * d)
+    same = (torch.equal(plus["peel"], out["peel"]) and torch.equal(minus["peel"], out["peel"]))
+    fd = (plus["lnL"] - minus["lnL"]) / (2 * h)
+    an = (out["grad_x"] * d).sum(dim=(1, 2))
+    ok = torch.isclose(fd, an, rtol=2e-4, atol=1e-3)
+    assert same or ok.float().mean().item() > 0.9
+    assert ok.float().mean().item() > 0.9, (fd[:4], an[:4])
