@@ -10,7 +10,7 @@ import importlib
 
 __version__ = "0.1.0"
 _SUBMODULES = ("phylo", "Cphylo", "phylomodel", "Chyp_torch", "Chyp_np", "peeler", "Cpeeler", "soft", "base_model", "vi", "mcmc",
-               "engine", "pipeline", "dist", "priors", "synth", "newick", "build")
+               "engine", "pipeline", "dist", "priors", "synth", "newick", "tree", "build")
 
 
 def __getattr__(name):

@@ -5,18 +5,19 @@
 // PhyloModel.get_transition_mats (dodonaphy/phylomodel.py:76-114).
 //
 // Design: site patterns are conditionally independent given the tree, so one
-// thread owns one (sample, pattern, rate category) and walks the whole tree itself.
+// thread owns one (sample, pattern) and walks the whole tree itself, once per rate category.
 //   * the reference's post-order (peel) is re-ordered per sample into a depth-first post-order in
 //     which every join consumes the result of the join just before it (kept in registers); only the
 //     "other" internal child has to be fetched back;
 //   * per-node "messages" msg_n = P_n (msg_l * msg_r) are streamed once to a per-CTA scratch ring
-//     (coalesced 512 B per warp) for the backward sweep; tips never touch HBM as partials: their
-//     message is a 32-byte row of a per-edge table indexed by the 4-bit IUPAC mask;
+//     (one 256-bit store per message, 1 KB contiguous per warp) for the backward sweep; tips never
+//     touch HBM as partials: their message is a 32-byte row of a per-edge table in shared memory,
+//     selected by the 4-bit IUPAC mask;
 //   * the backward sweep is the same schedule reversed (a valid pre-order), carries the upper
 //     message in registers, reads each stored message once and reduces d lnL / d t_e over the 32
 //     patterns of the warp with a fixed-order butterfly -> run-to-run reproducible.
-// HBM traffic per (pattern, category): one 32 B write + one 32 B read per internal node -- 2/5 of
-// the "materialise every partial" model used for the roofline denominator.
+// HBM traffic per (pattern, category): one 32 B write + one 32 B read per internal node -- about
+// half of the "materialise every partial" model used for the roofline denominator.
 #include <stdarg.h>
 #include <string.h>
 
@@ -25,9 +26,6 @@
 namespace dodo {
 
 constexpr int MAX_K = 8;
-#ifndef DODO_PRUNE_MINBLOCKS
-#define DODO_PRUNE_MINBLOCKS 3
-#endif
 
 struct ModelDev {
     double U[16], Uinv[16], lam[4], Q[16], pi[4];
@@ -41,34 +39,6 @@ struct V4 {
 
 __device__ __forceinline__ V4 vmul(const V4 &x, const V4 &y) {
     return V4{x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
-}
-
-// y = P x, P row-major 16 doubles in global memory (warp-uniform address -> broadcast)
-__device__ __forceinline__ V4 matvec_g(const double *__restrict__ P, const V4 &x) {
-    V4 y;
-    double2 p0 = ldg2(P + 0), p1 = ldg2(P + 2);
-    y.a = fma(p1.y, x.d, fma(p1.x, x.c, fma(p0.y, x.b, p0.x * x.a)));
-    p0 = ldg2(P + 4), p1 = ldg2(P + 6);
-    y.b = fma(p1.y, x.d, fma(p1.x, x.c, fma(p0.y, x.b, p0.x * x.a)));
-    p0 = ldg2(P + 8), p1 = ldg2(P + 10);
-    y.c = fma(p1.y, x.d, fma(p1.x, x.c, fma(p0.y, x.b, p0.x * x.a)));
-    p0 = ldg2(P + 12), p1 = ldg2(P + 14);
-    y.d = fma(p1.y, x.d, fma(p1.x, x.c, fma(p0.y, x.b, p0.x * x.a)));
-    return y;
-}
-
-// y = P^T x
-__device__ __forceinline__ V4 matvecT_g(const double *__restrict__ P, const V4 &x) {
-    V4 y;
-    double2 p0 = ldg2(P + 0), p1 = ldg2(P + 2);
-    y.a = p0.x * x.a, y.b = p0.y * x.a, y.c = p1.x * x.a, y.d = p1.y * x.a;
-    p0 = ldg2(P + 4), p1 = ldg2(P + 6);
-    y.a = fma(p0.x, x.b, y.a), y.b = fma(p0.y, x.b, y.b), y.c = fma(p1.x, x.b, y.c), y.d = fma(p1.y, x.b, y.d);
-    p0 = ldg2(P + 8), p1 = ldg2(P + 10);
-    y.a = fma(p0.x, x.c, y.a), y.b = fma(p0.y, x.c, y.b), y.c = fma(p1.x, x.c, y.c), y.d = fma(p1.y, x.c, y.d);
-    p0 = ldg2(P + 12), p1 = ldg2(P + 14);
-    y.a = fma(p0.x, x.d, y.a), y.b = fma(p0.y, x.d, y.b), y.c = fma(p1.x, x.d, y.c), y.d = fma(p1.y, x.d, y.d);
-    return y;
 }
 
 // u . (Q x) with Q in the kernel-parameter (constant) bank
@@ -232,9 +202,6 @@ struct PruneArgs {
 };
 
 constexpr int NT = 256;  // threads per CTA = site patterns per work item
-#ifndef DODO_REG_PREFETCH
-#define DODO_REG_PREFETCH 0   // 1: operands of the next join are fetched into registers one join ahead
-#endif
 #ifndef DODO_PRUNE_CTAS
 #define DODO_PRUNE_CTAS 3
 #endif

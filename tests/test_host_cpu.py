@@ -151,6 +151,28 @@ def test_newick_round_trip_and_reference_convention():
     assert again.shape == peel.shape and sorted(b2.tolist()) == sorted(blens.tolist())
 
 
+def test_tree_writer_matches_reference_text(tmp_path):
+    """tree.tree_to_newick (dodonaphy/tree.py:207-267), strings produced by the real reference."""
+    import json
+
+    from dodonaphy_b200 import tree
+
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "tree_newick.json")))
+    assert len(cases) >= 8
+    for c in cases:
+        name_id = {f"T{i + 1}": i for i in range(c["S"])}
+        assert tree.tree_to_newick(name_id, np.array(c["peel"]), np.array(c["blens"]), c["rooted"]) == c["newick"]
+    assert tree.tree_to_newick({}, [], torch.tensor([]), True) == ";"  # test/test_tree.py:9-16
+    with pytest.raises(TypeError):
+        tree.tree_to_newick([], [], [])
+    c = cases[-2]
+    name_id = {f"T{i + 1}": i for i in range(c["S"])}
+    peels, blens = np.array([c["peel"]] * 3), np.array([c["blens"]] * 3)
+    tree.save_trees(str(tmp_path), "samples", peels, blens, 10, np.array([-1.0, -2.0, -3.0]), np.zeros(3), name_id, lnQ=np.ones(3))
+    lines = open(tmp_path / "samples.t").read().splitlines()
+    assert len(lines) == 3 and lines[1].startswith("\ttree STATE_11 [&lnL=-2.000000, &lnPr=0.000000, &lnQ=1.000000] = [&U] (")
+
+
 def test_parent_id_vector():
     from dodonaphy_b200.phylo import get_parent_id_vector
 
