@@ -64,22 +64,32 @@ def compress_alignment_device(sequences, device="cuda"):
 
 
 # ------------------------------------------------------------------------------------------------
-_engine_cache = {}
+_engine_cache = []  # [(weakrefs of the tip objects + weights, versions, engine)]
+
+
+def _versions(objs):
+    return tuple(int(o._version) if isinstance(o, torch.Tensor) else 0 for o in objs)
 
 
 def _engine_for(partials, weights, n_tips):
     """PruneEngine for this alignment; tips are uploaded once and reused (the reference's partial
-    list is owned by the model and re-passed on every call, base_model.py:54)."""
-    tips = partials[:n_tips]
-    key = (n_tips, tuple(int(t.data_ptr()) if isinstance(t, torch.Tensor) else id(t) for t in tips),
-           int(weights.data_ptr()) if isinstance(weights, torch.Tensor) else id(weights))
-    eng = _engine_cache.get(key)
-    if eng is None:
-        if len(_engine_cache) > 8:
-            _engine_cache.clear()
-        w = weights.detach().cpu().numpy() if isinstance(weights, torch.Tensor) else np.asarray(weights)
-        eng = _engine.PruneEngine(_engine.pack_tip_partials(tips), w)
-        _engine_cache[key] = eng
+    list is owned by the model and re-passed on every call, base_model.py:54).  An entry is reused
+    only for the very same tip / weight objects, unmodified since (weak references + tensor
+    versions), so recycled memory can never alias a stale upload."""
+    import weakref
+
+    objs = list(partials[:n_tips]) + [weights]
+    for refs, vers, eng in _engine_cache:
+        if len(refs) == len(objs) and all(r() is o for r, o in zip(refs, objs)) and vers == _versions(objs):
+            return eng
+    w = weights.detach().cpu().numpy() if isinstance(weights, torch.Tensor) else np.asarray(weights)
+    eng = _engine.PruneEngine(_engine.pack_tip_partials(objs[:-1]), w)
+    try:
+        refs = tuple(weakref.ref(o) for o in objs)
+    except TypeError:  # not weak-referenceable (e.g. a list): do not cache
+        return eng
+    _engine_cache[:] = [e for e in _engine_cache if all(r() is not None for r in e[0])][-7:]
+    _engine_cache.append((refs, _versions(objs), eng))
     return eng
 
 
