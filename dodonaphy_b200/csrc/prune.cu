@@ -199,6 +199,7 @@ struct PruneArgs {
     int B, S, L, K;
     int n_tiles, n_items, tile_patterns;
     int mix;
+    int jc;  // transition matrices have the JC69 structure (two distinct entries)
 };
 
 constexpr int NT = 256;  // threads per CTA = site patterns per work item
@@ -394,6 +395,20 @@ __device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0
 }
 
 // P x / P^T x for NP patterns at once: every row of P is loaded once and applied to all of them
+// JC69: P = (a-b) I + b J is symmetric with two distinct entries, so P x = (a-b) x + b sum(x): one
+// 16-byte load and 8 flops instead of eight loads and 16 flops (warp-uniform runtime switch).
+template <bool SMALL, int NP>
+__device__ __forceinline__ void matvec_jc(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    const double2 ab = SMALL ? *reinterpret_cast<const double2 *>(P) : ldg2(P);
+    const double amb = ab.x - ab.y;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const V4 v = x[q];
+        const double bs = ab.y * ((v.a + v.b) + (v.c + v.d));
+        y[q] = V4{fma(amb, v.a, bs), fma(amb, v.b, bs), fma(amb, v.c, bs), fma(amb, v.d, bs)};
+    }
+}
+
 template <bool SMALL, int NP>
 __device__ __forceinline__ void matvec_n(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
     const V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL>(P + 4), r2 = ld4t<SMALL>(P + 8), r3 = ld4t<SMALL>(P + 12);
@@ -457,6 +472,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
     const unsigned warp = tid >> 5;
     constexpr unsigned nwarp = NT / 32;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
+    const bool jc = A.jc != 0;
     const unsigned tabn = (unsigned)tab_doubles(S);
     // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] | cx | ops | sel
     const unsigned o_gacc = SMALL ? tabn : 0u;
@@ -576,7 +592,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 V4 Lv[NP];
                 int cnt[NP];
                 join(o, Lv, cnt);
-                matvec_n<SMALL, NP>(tab_at((unsigned)o.z * 16u), Lv, Bv);
+                if (jc) matvec_jc<SMALL, NP>(tab_at((unsigned)o.z * 16u), Lv, Bv);
+                else matvec_n<SMALL, NP>(tab_at((unsigned)o.z * 16u), Lv, Bv);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) bc[q] = cnt[q];
                 if (MODE != 0 || (o.w & 1)) {
@@ -684,7 +701,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     }
                     if (o.x >= 0) {
                         V4 wa[NP];
-                        matvecT_n<SMALL, NP>(tab_at((unsigned)o.x * 16u), ua, wa);
+                        if (jc) matvec_jc<SMALL, NP>(tab_at((unsigned)o.x * 16u), ua, wa);
+                        else matvecT_n<SMALL, NP>(tab_at((unsigned)o.x * 16u), ua, wa);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             int ea = we[q] - bcn[q];
@@ -694,7 +712,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         }
                     }
                     if (o.y >= 0) {  // the next join (in this reversed order) is exactly node b
-                        matvecT_n<SMALL, NP>(tab_at((unsigned)o.y * 16u), ub, Wv);
+                        if (jc) matvec_jc<SMALL, NP>(tab_at((unsigned)o.y * 16u), ub, Wv);
+                        else matvecT_n<SMALL, NP>(tab_at((unsigned)o.y * 16u), ub, Wv);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             we[q] -= ac[q];
@@ -974,6 +993,7 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.B = B; A.S = S; A.L = L; A.K = K;
     A.n_tiles = plan->n_tiles; A.n_items = plan->n_items; A.tile_patterns = plan->tile_patterns;
     A.mix = ((plan->flags & DODO_PRUNE_MIX) && K > 1) ? 1 : 0;
+    A.jc = (model->kind == DODO_MODEL_JC69 && d_P_in == nullptr) ? 1 : 0;
     const int np = plan->tile_patterns / plan->threads;
     const bool small = prune_small(S, K, np);
     size_t smem = prune_smem_bytes(S, K, small, np);
