@@ -9,7 +9,7 @@ into it does (there is no CPU fallback).
 import importlib
 
 __version__ = "0.1.0"
-_SUBMODULES = ("phylo", "Cphylo", "phylomodel", "Chyp_torch", "Chyp_np", "peeler", "Cpeeler", "soft", "base_model", "vi", "mcmc",
+_SUBMODULES = ("phylo", "Cphylo", "phylomodel", "Chyp_torch", "Chyp_np", "peeler", "Cpeeler", "soft", "base_model", "vi", "mcmc", "hmap", "laplace",
                "engine", "pipeline", "dist", "priors", "synth", "newick", "tree", "build")
 
 

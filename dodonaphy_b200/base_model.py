@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import Chyp_np, Chyp_torch, Cpeeler, peeler
-from .phylo import LikelihoodInstance, TreeLikelihood
+from .phylo import LikelihoodInstance, TreeLikelihood, calculate_treelikelihood
 from .phylomodel import PhyloModel
 from .pipeline import HotPath
 
@@ -102,8 +102,15 @@ class BaseModel:
 
     # -- one tree -------------------------------------------------------------------------------
     def compute_LL(self, peel, blen):
-        """lnL of one tree; ``blen`` a torch tensor (gradient flows) or an ndarray (MCMC)."""
-        self._inst.model = self.phylomodel.device_model()
+        """lnL of one tree; ``blen`` a torch tensor (gradient flows) or an ndarray (MCMC).
+
+        With learnable model parameters (GTR) the likelihood is taken through explicit transition
+        matrices, exactly the reference's non-bito branch (base_model.py:239-247), so the rates and
+        frequencies receive gradient; otherwise value and d lnL/d blens come from one fused call."""
+        pm = self.phylomodel
+        if isinstance(blen, torch.Tensor) and not (pm.fix_sub_rates and pm.fix_freqs) and self.rates is None:
+            return calculate_treelikelihood(self.partials, self.weights, peel, pm.get_transition_mats(blen), pm.freqs)
+        self._inst.model = pm.device_model()
         if isinstance(blen, torch.Tensor):
             return TreeLikelihood.apply(blen, peel, self._inst)
         out = TreeLikelihood.apply(torch.as_tensor(np.asarray(blen, dtype=np.float64)), peel, self._inst)

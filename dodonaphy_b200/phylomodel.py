@@ -85,6 +85,21 @@ class PhyloModel:
         if self.name != "JC69":
             self._freqs_leaf = _SimplexLeaf(value, not self.fix_freqs)
 
+    # Dirichlet(1) priors on the GTR exchangeabilities and frequencies (phylomodel.py:48-54,140-154)
+    def compute_ln_prior_sub_rates(self):
+        if self.name == "JC69":
+            return torch.zeros(1, dtype=torch.float64)
+        if self.name == "GTR":
+            return torch.distributions.Dirichlet(torch.ones(6, dtype=torch.float64)).log_prob(self.sub_rates)
+        raise RuntimeError(f"Model {self.name} has no prior on rates available.")
+
+    def compute_ln_prior_freqs(self):
+        if self.name == "JC69":
+            return torch.zeros(1, dtype=torch.float64)
+        if self.name == "GTR":
+            return torch.distributions.Dirichlet(torch.ones(4, dtype=torch.float64)).log_prob(self.freqs)
+        raise RuntimeError(f"Model {self.name} has no prior on freqs available.")
+
     # ------------------------------------------------------------------ P(t) as tensors
     def get_transition_mats(self, blens):
         if self.name == "JC69":
