@@ -81,3 +81,75 @@ def poincare_to_hyper_2d(location):
     location = np.asarray(location, dtype=np.float64)
     a = np.sum(location * location, axis=-1, keepdims=True)
     return np.concatenate(((1 + a) / (1 - a), 2 * location / (1 - a + eps)), axis=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# NumPy chart changes of the MCMC side (Chyp_np.pyx:41-229), row-vectorised; same names.
+def _lorentz_rows(x, y):
+    return -x[..., 0] * y[..., 0] + np.sum(x[..., 1:] * y[..., 1:], axis=-1)
+
+
+def parallel_transport(xi, x, y):
+    alpha = -_lorentz_rows(x, y)
+    coef = _lorentz_rows(y, xi) / (alpha + 1)
+    return xi + np.expand_dims(coef, -1) * (x + y)
+
+
+def exponential_map(x, v):
+    vnorm = np.expand_dims(np.sqrt(np.maximum(_lorentz_rows(v, v), eps)), -1)
+    return np.cosh(vnorm) * x + np.sinh(vnorm) * v / vnorm
+
+
+def exp_map_inverse(z, mu):
+    alpha = np.expand_dims(-_lorentz_rows(mu, z), -1)
+    return np.arccosh(alpha) / np.sqrt(alpha**2 - 1) * (z - alpha * mu)
+
+
+def unwrap(z, dim=None):
+    """Sheet point(s) -> spatial part of the tangent vector at the origin pointing to them."""
+    z = np.asarray(z, dtype=np.float64)
+    mu0 = np.zeros_like(z)
+    mu0[..., 0] = 1.0
+    return exp_map_inverse(z, mu0)[..., 1:]
+
+
+unwrap_2d = unwrap
+
+
+def tangent_to_hyper(mu, v_tilde, dim=None):
+    """Carry v_tilde from T_0 to T_mu and shoot onto the sheet.  Unlike the torch twin, the lifted
+    vector's time coordinate is zero here (Chyp_np.pyx:161 vs Chyp_torch.pyx:343)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    v_tilde = np.asarray(v_tilde, dtype=np.float64).reshape(mu.shape[:-1] + (mu.shape[-1] - 1,))
+    one = np.ones(v_tilde.shape[:-1] + (1,))
+    mu0 = np.concatenate((one, np.zeros_like(v_tilde)), -1)
+    return exponential_map(mu, parallel_transport(np.concatenate((0.0 * one, v_tilde), -1), mu0, mu))
+
+
+def tangent_to_hyper_jacobian(mu, v_tilde, dim):
+    r = np.linalg.norm(v_tilde, axis=-1)
+    return (dim - 1) * np.log(np.sinh(r) / r)
+
+
+def hyper_to_poincare(location):
+    location = np.asarray(location, dtype=np.float64)
+    return location[..., 1:] / (1 + location[..., :1])
+
+
+def hyper_to_poincare_jacobian(location):
+    location = np.asarray(location, dtype=np.float64)
+    n = location.shape[-1]
+    a = 1 + location[..., 0]
+    return np.log(np.abs((a**2 + np.sum(location[..., 1:] ** 2, axis=-1)) / a ** (2 * (n + 1))))
+
+
+def project_up_jacobian(loc):
+    """d sheet / d loc for all points: block diagonal of [(x/z)^T ; I_D] blocks, (n(D+1), nD)."""
+    loc = np.asarray(loc, dtype=np.float64)
+    n, D = loc.shape
+    col = loc / np.sqrt(np.sum(loc**2, axis=1, keepdims=True) + 1)
+    out = np.zeros((n * (D + 1), n * D))
+    for i in range(n):
+        out[i * (D + 1), i * D:(i + 1) * D] = col[i]
+        out[i * (D + 1) + 1:(i + 1) * (D + 1), i * D:(i + 1) * D] = np.eye(D)
+    return out

@@ -13,6 +13,8 @@ Outputs (committed; small):
   nj_hard.npz    Cpeeler.nj_np outputs.
   nj_soft.npz    peeler.nj_torch outputs + autograd gradient of a random linear functional of blens.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
+  pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
+  charts.npz     tangent-space / sheet / ball chart changes of Chyp_torch (t02p, p2t0, ...).
 
 The tests never read /root/reference; they read these files.
 """
@@ -247,12 +249,46 @@ def make_pdm_jac(r):
     print("pdm_jac cases:", len(cases))
 
 
+def make_charts(r):
+    """Chart changes around the wrap embedding (Chyp_torch.pyx:39-117,212-362,425-457) on seeded rows."""
+    C = r.Chyp_torch
+    g = torch.Generator().manual_seed(5)
+    x = 0.3 * torch.randn(6, 3, dtype=torch.float64, generator=g)
+    mu = 0.2 * torch.randn(6, 3, dtype=torch.float64, generator=g)
+    out = {"x": x.numpy(), "mu": mu.numpy()}
+    out["t02p"] = C.t02p(x).numpy()
+    p, jac = C.t02p(x, mu, get_jacobian=True)
+    out["t02p_mu"], out["t02p_mu_jac"] = p.numpy(), jac.numpy()
+    q, qjac = C.p2t0(p, mu, get_jacobian=True)
+    out["p2t0_mu"], out["p2t0_mu_jac"] = q.numpy(), qjac.numpy()
+    out["p2t0"] = C.p2t0(p).numpy()
+    out["real2ball"], out["ball2real"] = C.real2ball(x, 2.0).numpy(), C.ball2real(p).numpy()
+    out["ladj"] = C.real2ball_LADJ(x, 2.0).numpy()
+    muh, xh = C.project_up_2d(mu), C.project_up_2d(x)
+    out["tangent_to_hyper"] = np.stack([C.tangent_to_hyper(muh[i], x[i], 3).numpy() for i in range(6)])
+    out["transport"] = np.stack([C.parallel_transport(xh[i] - muh[i], muh[i], xh[(i + 1) % 6]).numpy() for i in range(6)])
+    out["exp_inverse"] = np.stack([C.exp_map_inverse(xh[i], muh[i]).numpy() for i in range(6)])
+    out["exp_map"] = np.stack([C.exponential_map(muh[i], C.exp_map_inverse(xh[i], muh[i])).numpy() for i in range(6)])
+    out["h2p_jac"] = np.array([float(C.hyper_to_poincare_jacobian(xh[i])) for i in range(6)])
+    # NumPy twins (Chyp_np.pyx:41-229)
+    N = r.Chyp_np
+    xn, mun = x.numpy(), mu.numpy()
+    xhn, muhn = np.stack([N.project_up(v) for v in xn]), np.stack([N.project_up(v) for v in mun])
+    out["np_tangent_to_hyper"] = np.stack([N.tangent_to_hyper(muhn[i], xn[i], 3) for i in range(6)])
+    out["np_unwrap"] = N.unwrap_2d(xhn)
+    out["np_exp_inverse"] = np.stack([N.exp_map_inverse(xhn[i], muhn[i]) for i in range(6)])
+    out["np_transport"] = np.stack([N.parallel_transport(xhn[i] - muhn[i], muhn[i], xhn[(i + 1) % 6]) for i in range(6)])
+    out["np_h2p"] = np.stack([N.hyper_to_poincare(xhn[i]) for i in range(6)])
+    out["np_h2p_jac"] = np.array([N.hyper_to_poincare_jacobian(xhn[i]) for i in range(6)])
+    out["np_project_up_jacobian"] = N.project_up_jacobian(xn)
+    np.savez_compressed(os.path.join(HERE, "charts.npz"), **out)
+    print("charts: ok")
+
+
 if __name__ == "__main__":
     r = refload.load()
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
-    make_ds1(r)
-    make_pdm(r)
-    make_nj_hard(r)
-    make_nj_soft(r)
-    make_prune(r)
-    make_pdm_jac(r)
+    makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
+                  pdm_jac=make_pdm_jac, charts=make_charts)
+    for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
+        makers[name](r)

@@ -270,3 +270,48 @@ def test_sharding_world_size_2_gloo(tmp_path):
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{out}"
         assert f"rank {r} ok" in out
+
+
+def test_chart_changes_against_reference_fixture():
+    """Chyp_torch chart changes (Chyp_torch.pyx:39-117,212-362,425-457) vs outputs of the reference.
+    The reference accumulates the two log-Jacobians, real2ball_LADJ and hyper_to_poincare in float32
+    buffers (``torch.zeros(1)`` / ``torch.zeros(dim)``), hence the looser tolerance on those."""
+    import torch
+
+    from conftest import load_golden
+    from dodonaphy_b200 import Chyp_torch as C
+
+    g = load_golden("charts.npz")
+    x, mu = torch.tensor(g["x"]), torch.tensor(g["mu"])
+    np.testing.assert_allclose(C.t02p(x).numpy(), g["t02p"], rtol=0, atol=5e-8)
+    p, jac = C.t02p(x, mu, get_jacobian=True)
+    np.testing.assert_allclose(p.numpy(), g["t02p_mu"], rtol=0, atol=5e-8)
+    np.testing.assert_allclose(jac.numpy(), g["t02p_mu_jac"], rtol=1e-5)
+    pr = torch.tensor(g["t02p_mu"])
+    q, qjac = C.p2t0(pr, mu, get_jacobian=True)
+    np.testing.assert_allclose(q.numpy(), g["p2t0_mu"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(qjac.numpy(), g["p2t0_mu_jac"], rtol=1e-5)
+    np.testing.assert_allclose(C.p2t0(pr).numpy(), g["p2t0"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(C.p2t0(C.t02p(x)).numpy(), g["x"], rtol=0, atol=1e-12)  # inverse charts at the origin
+    np.testing.assert_allclose(C.real2ball(x, 2.0).numpy(), g["real2ball"], rtol=1e-14)
+    np.testing.assert_allclose(C.ball2real(pr).numpy(), g["ball2real"], rtol=1e-14)
+    np.testing.assert_allclose(C.real2ball_LADJ(x, 2.0).numpy(), g["ladj"], rtol=1e-6)
+    muh, xh = C.project_up(mu), C.project_up(x)
+    np.testing.assert_allclose(C.tangent_to_hyper(muh, x).numpy(), g["tangent_to_hyper"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(C.parallel_transport(xh - muh, muh, xh.roll(-1, 0)).numpy(), g["transport"], rtol=1e-13, atol=1e-15)
+    v = C.exp_map_inverse(xh, muh)
+    np.testing.assert_allclose(v.numpy(), g["exp_inverse"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(C.exponential_map(muh, v).numpy(), g["exp_map"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(C.hyper_to_poincare_jacobian(xh).numpy(), g["h2p_jac"], rtol=1e-13)
+    # NumPy twins
+    from dodonaphy_b200 import Chyp_np as N
+
+    xn, mun = g["x"], g["mu"]
+    xhn, muhn = N.project_up_2d(xn), N.project_up_2d(mun)
+    np.testing.assert_allclose(N.tangent_to_hyper(muhn, xn), g["np_tangent_to_hyper"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(N.unwrap_2d(xhn), g["np_unwrap"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(N.exp_map_inverse(xhn, muhn), g["np_exp_inverse"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(N.parallel_transport(xhn - muhn, muhn, np.roll(xhn, -1, 0)), g["np_transport"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(N.hyper_to_poincare(xhn), g["np_h2p"], rtol=1e-14)
+    np.testing.assert_allclose(N.hyper_to_poincare_jacobian(xhn), g["np_h2p_jac"], rtol=1e-13)
+    np.testing.assert_array_equal(N.project_up_jacobian(xn), g["np_project_up_jacobian"])
