@@ -55,6 +55,50 @@ class _BatchedLogLik(torch.autograd.Function):
         return gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]), None
 
 
+class _BatchedLogLikModel(torch.autograd.Function):
+    """As ``_BatchedLogLik`` with a learnable GTR model: gradient also reaches the unconstrained
+    rate / frequency leaves (phylomodel.py:19-45).  P(t) of the whole batch is formed as a (B,E,K,4,4)
+    device tensor, the pruning kernel returns d lnL/d P and d lnL/d pi (DODO_PRUNE_GMATS), and the
+    chain rule to branch lengths and model leaves is one autograd pass over that small tensor --
+    the batched form of the reference's non-bito branch (base_model.py:239-247)."""
+
+    @staticmethod
+    def forward(ctx, locs, curvature_leaf, raw_rates, raw_freqs, hot):
+        from . import engine
+
+        hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
+        x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
+        pdm = engine.pdm_forward(x, hot.curvature, "torch", hot.lift, hot.matsumoto)
+        peel, blens, flags = engine.nj_soft(pdm, hot.tau, return_flags=True)
+        P, pi = PhyloModel.transition_mats_from_raw(raw_rates.detach(), raw_freqs.detach(), blens, hot.rates)
+        out = hot.prune.loglik_mats(peel, P, pi.numpy(), grad=True, mix=hot.mix)
+        ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
+        ctx.devs = (locs.device, curvature_leaf.device)
+        ctx.save_for_backward(x, peel, flags, blens, out["grad_mats"], out["grad_pi"], raw_rates.detach(), raw_freqs.detach())
+        ctx.mark_non_differentiable(peel)
+        return out["lnL"].to(locs.device), peel, blens.to(locs.device)
+
+    @staticmethod
+    def backward(ctx, g_ll, _g_peel, g_blens):
+        from . import engine
+
+        x, peel, flags, blens, gP, gpi, raw_rates, raw_freqs = ctx.saved_tensors
+        hot = ctx.hot
+        w = g_ll.to(x.device).reshape(-1)
+        with torch.enable_grad():
+            bl = blens.detach().requires_grad_(True)
+            rr, rf = raw_rates.clone().requires_grad_(True), raw_freqs.clone().requires_grad_(True)
+            P, pi = PhyloModel.transition_mats_from_raw(rr, rf, bl, hot.rates)
+            obj = (P * (gP * w.reshape(-1, 1, 1, 1, 1))).sum() + (pi * (gpi * w.reshape(-1, 1)).sum(0).cpu()).sum()
+            gb, g_rates, g_freqs = torch.autograd.grad(obj, (bl, rr, rf))
+        if g_blens is not None:
+            gb = gb + g_blens.to(x.device)
+        gpdm = engine.nj_soft_backward(peel, flags, gb.contiguous())
+        gx, gc = engine.pdm_backward(x, gpdm, ctx.kappa, hot.lift, hot.matsumoto)
+        return (gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]),
+                g_rates, g_freqs, None)
+
+
 class BaseModel:
     def __init__(self, inference_name, partials, weights, dim, soft_temp, curvature=-1.0, embedder="up",
                  connector="nj", normalise_leaf=False, loss_fn="likelihood", require_grad=True, matsumoto=False,
@@ -140,7 +184,11 @@ class BaseModel:
 
     def log_likelihood_batch(self, locs):
         """VI: (B,S,D) sampled locations -> (lnL (B,), peel (B,S-1,3), blens (B,2S-2)); lnL carries
-        gradient to ``locs`` and to the curvature leaf."""
+        gradient to ``locs``, to the curvature leaf and -- for a learnable GTR model -- to the
+        unconstrained rate and frequency leaves."""
+        pm = self.phylomodel
+        if not (pm.fix_sub_rates and pm.fix_freqs):
+            return _BatchedLogLikModel.apply(locs, self._curvature, pm._sub_rates, pm._freqs, self._hotpath())
         return _BatchedLogLik.apply(locs, self._curvature, self._hotpath())
 
     def log_likelihood_batch_np(self, locs):

@@ -9,8 +9,8 @@ Hydra+, logging, plots and checkpoints are host code outside the path (SURVEY.md
 One evaluation of the loss is one pass of the fused pipeline with a batch of one:
 locations -> distances -> soft NJ -> pruning value + d lnL/d blens -> NJ / distance backward, i.e.
 ten kernel launches instead of ~(S-1) x (soft-sort + three torch ops) autograd nodes.  With a
-learnable GTR model the likelihood goes through explicit transition matrices instead
-(``BaseModel.compute_LL``'s reference branch) so that the rates and frequencies receive gradient.
+learnable GTR model the pruning kernel additionally returns d lnL/d P and d lnL/d pi, from which the
+rate and frequency leaves receive gradient (``base_model._BatchedLogLikModel``).
 """
 import numpy as np
 import torch
@@ -76,13 +76,12 @@ class HMAP(BaseModel):
         peel, blens, pdm = super().connect(self.get_locs())
         return (peel, blens, pdm) if get_pdm else (peel, blens)
 
-    def _fused(self):
-        return self.phylomodel.fix_sub_rates and self.phylomodel.fix_freqs
-
-    def compute_loss(self):
+    def compute_loss(self, fused=True):
+        """-(ln prior + lnL) of the current embedding.  ``fused=False`` takes the reference's
+        call-by-call route (connect -> compute_LL) instead of the single batched pass."""
         if self.connector != "nj":
             self.connect()
-        if self._fused():
+        if fused:
             ll, peel, blens = self.log_likelihood_batch(self.get_locs().unsqueeze(0))
             self.peel, self.blens, self.ln_p = peel[0].cpu().numpy(), blens[0], ll[0]
         else:
@@ -144,7 +143,7 @@ class HMAP(BaseModel):
         """Adam with the reference's 1/(epoch+1)^(1/4) learning-rate decay; returns the history of
         log posteriors (one entry before the first step, one after every step)."""
         self.loss = self.compute_loss()
-        history = [float(self.ln_p) + float(self.ln_prior)]
+        history = [float(self.ln_p.detach()) + float(self.ln_prior.detach())]
         self.record_if_best()
         optimizer = torch.optim.Adam(params=list(self.params_optim.values()), lr=learn_rate)
         scheduler = torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda epoch: 1.0 / (epoch + 1.0) ** 0.25)
@@ -160,5 +159,5 @@ class HMAP(BaseModel):
             optimizer.step(closure)
             scheduler.step()
             self.record_if_best()
-            history.append(float(self.ln_p) + float(self.ln_prior))
+            history.append(float(self.ln_p.detach()) + float(self.ln_prior.detach()))
         return history

@@ -137,6 +137,25 @@ class PhyloModel:
         lam, V = torch.linalg.eigh(root @ self.compute_Q_martix() @ inv_root)
         return inv_root @ V, lam, torch.linalg.inv(V) @ root
 
+    @staticmethod
+    def transition_mats_from_raw(raw_rates, raw_freqs, blens, cat_rates=None):
+        """Differentiable P(t) for a batch: unconstrained leaves (5), (3) on the host, blens (B,E) on
+        any device, K category rates -> (B,E,K,4,4) on blens' device, and pi (4,) on the host.
+        The 4x4 eigen-system is host arithmetic; the (B,E,K,4,4) tensor is formed where blens live."""
+        r, pi = _SIMPLEX(raw_rates), _SIMPLEX(raw_freqs)
+        iu = torch.triu_indices(4, 4, 1)
+        R = torch.zeros((4, 4), dtype=torch.float64).index_put((iu[0], iu[1]), r)
+        Q = (R + R.T) * pi
+        Q = Q - torch.diag(Q.sum(dim=1))
+        Q = Q / -(torch.diagonal(Q) * pi).sum()
+        root, inv_root = torch.diag(pi.sqrt()), torch.diag(pi.rsqrt())
+        lam, V = torch.linalg.eigh(root @ Q @ inv_root)
+        dev = blens.device
+        U, Uinv, lam = (inv_root @ V).to(dev), (torch.linalg.inv(V) @ root).to(dev), lam.to(dev)
+        cat = torch.ones(1, dtype=torch.float64, device=dev) if cat_rates is None else torch.as_tensor(cat_rates, dtype=torch.float64, device=dev)
+        t = blens.unsqueeze(-1) * cat  # (B,E,K)
+        return (U * torch.exp(t.unsqueeze(-1) * lam).unsqueeze(-2)) @ Uinv, pi
+
     def GTR_p_t(self, branch_lengths):
         """(E,) -> (E,4,4); (E,K) -> (E,K,4,4):  U diag(exp(lam t)) U^-1."""
         U, lam, Uinv = self._eigensystem()

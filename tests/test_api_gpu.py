@@ -348,28 +348,67 @@ def test_hmap_loss_gradient_and_learn():
 
 
 def test_hmap_gtr_parameters_receive_gradient():
-    """With a learnable GTR model the likelihood goes through explicit matrices (base_model.py:239-247)."""
+    """Learnable GTR: the fused batched pass (d lnL/d P, d lnL/d pi from the kernel, chain rule to the
+    unconstrained leaves) and the reference's call-by-call route (base_model.py:239-247) give the same
+    loss and gradients, and both equal the oracle's autograd."""
+    from torch.distributions.transforms import StickBreakingTransform
+
     from dodonaphy_b200 import synth
     from dodonaphy_b200.hmap import HMAP
-    from oracle import nj
     from oracle.phylo import gtr_p_t_torch, mask_to_partial, treelikelihood_torch
 
     S, D, L = 6, 2, 40
     prob = synth.make_problem(S, L, 1, D=D, seed=78)
-    m = HMAP(_partials(prob["masks"])[:S], torch.tensor(prob["weights"]), dim=D, soft_temp=1e-8, prior="None", model_name="GTR")
+    m = HMAP(_partials(prob["masks"])[:S], torch.tensor(prob["weights"]), dim=D, soft_temp=1e-8, prior="gammadir", model_name="GTR")
     m.init_embedding_params(prob["xs"][0])
     assert {"sub_rates", "freqs", "curvature", "leaf_loc"} <= set(m.params_optim)
-    loss = m.compute_loss()
-    loss.sum().backward()
-    for name in ("sub_rates", "freqs", "leaf_loc"):
-        g = m.params_optim[name].grad
-        assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
-    # value against the oracle on the same tree and parameters
+    grads = {}
+    for fused in (True, False):
+        for p in m.params_optim.values():
+            p.grad = None
+        loss = m.compute_loss(fused=fused)
+        loss.sum().backward()
+        grads[fused] = (float(loss.detach()), {k: v.grad.clone() for k, v in m.params_optim.items() if v.grad is not None})
+    assert set(grads[True][1]) == set(grads[False][1]) >= {"sub_rates", "freqs", "leaf_loc", "curvature"}
+    np.testing.assert_allclose(grads[True][0], grads[False][0], rtol=1e-11)
+    for k in grads[True][1]:
+        np.testing.assert_allclose(grads[True][1][k].numpy(), grads[False][1][k].numpy(), rtol=1e-8, atol=1e-9, err_msg=k)
+    # oracle: same tree, autograd through the reference's eigen-decomposition P(t)
     tips = [torch.tensor(mask_to_partial(x)) for x in prob["masks"]]
-    mats = gtr_p_t_torch(m.blens.detach(), m.phylomodel.sub_rates.detach(), m.phylomodel.freqs.detach())
-    ref = treelikelihood_torch(tips, torch.tensor(prob["weights"], dtype=torch.float64), m.peel, mats,
-                               m.phylomodel.freqs.detach())
-    np.testing.assert_allclose(float(m.ln_p), float(ref), rtol=1e-10)
+    rr = m.phylomodel._sub_rates.detach().clone().requires_grad_(True)
+    rf = m.phylomodel._freqs.detach().clone().requires_grad_(True)
+    sb = StickBreakingTransform()
+    mats = gtr_p_t_torch(m.blens.detach(), sb(rr), sb(rf))
+    ref = treelikelihood_torch(tips, torch.tensor(prob["weights"], dtype=torch.float64), m.peel, mats, sb(rf))
+    np.testing.assert_allclose(float(m.ln_p.detach()), float(ref.detach()), rtol=1e-10)
+    g_rr, g_rf = torch.autograd.grad(ref + m.phylomodel.compute_ln_prior_sub_rates() * 0, (rr, rf))
+    prior_r = torch.autograd.grad(torch.distributions.Dirichlet(torch.ones(6, dtype=torch.float64)).log_prob(sb(rr)), rr)[0]
+    prior_f = torch.autograd.grad(torch.distributions.Dirichlet(torch.ones(4, dtype=torch.float64)).log_prob(sb(rf)), rf)[0]
+    np.testing.assert_allclose(-grads[True][1]["sub_rates"].numpy(), (g_rr + prior_r).numpy(), rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(-grads[True][1]["freqs"].numpy(), (g_rf + prior_f).numpy(), rtol=1e-8, atol=1e-9)
+
+
+def test_vi_learns_gtr_parameters_in_the_batched_step():
+    """vi.py:228-249 with model_name='GTR' and gamma rate categories: one batched ELBO step puts
+    gradient on the rate / frequency leaves."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.vi import DodonaphyVI
+
+    S, D, L = 8, 3, 64
+    prob = synth.make_problem(S, L, 1, D=D, seed=80)
+    torch.manual_seed(3)
+    vi = DodonaphyVI(_partials(prob["masks"])[:S], torch.tensor(prob["weights"]), dim=D, model_name="GTR",
+                     n_rate_categories=4, gamma_shape=0.5)
+    vi.set_params_optim(prob["xs"][0], torch.full((S, D), -8.0, dtype=torch.float64))
+    elbo = vi.elbo_siwae(importance=4)
+    (-elbo).backward()
+    for k in ("leaf_mu", "leaf_sigma", "sub_rates", "freqs", "curvature"):
+        g = vi.params_optim[k].grad
+        assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0, k
+    before = vi.phylomodel.sub_rates.detach().clone()
+    trace = vi.learn(epochs=3, importance_samples=2, lr=0.05)
+    assert len(trace) == 3 and np.isfinite(trace).all()
+    assert not torch.allclose(before, vi.phylomodel.sub_rates.detach())
 
 
 def test_laplace_hessian_matches_double_backward_oracle():
