@@ -54,6 +54,10 @@ _SIGNATURES = {
     "dodo_soft_argmin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "dodo_nj_soft_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "dodo_geo_workspace_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
+    "dodo_geo_soft": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 8),
+    "dodo_geo_soft_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dodo_geo_hard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

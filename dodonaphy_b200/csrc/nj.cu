@@ -671,6 +671,346 @@ __global__ void __launch_bounds__(256) soft_argmin_kernel(const double *__restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ geodesic
+// The "geodesics" connector: repeatedly join the two live points whose LCA -- the point of their
+// geodesic nearest the origin of the Poincare ball -- is deepest.
+//   geo_soft_kernel      peeler.make_soft_peel_tips    (dodonaphy/peeler.py:14-70)
+//   geo_soft_bwd_kernel  the VJP torch autograd takes through it (locations carry gradient, the
+//                        one-hot selections do not, soft.py:56-61)
+//   geo_hard_kernel      peeler.make_hard_peel_geodesic (dodonaphy/peeler.py:73-152)
+// LCA arithmetic: poincare.hyp_lca (dodonaphy/poincare.py:6-115) -- invert the ball in the circle
+// centred at a/|a|^2, mirror the image of the origin in the line through the image of b, invert
+// back, halve the hyperbolic distance from the origin.
+constexpr int GEO_MAX_D = 16;
+constexpr double GEO_MIN_NORM = 1e-15;  // poincare.py:34
+
+__host__ __device__ inline size_t geo_ws_doubles(int S, int D) {
+    return 2 * (size_t)S * S + (size_t)(2 * S) * (size_t)(D + 2);
+}
+
+__device__ void lca_point(const double *a, const double *b, int D, double *proj) {
+    double r[GEO_MAX_D], v[GEO_MAX_D];
+    double na2 = 0.0;
+    for (int d = 0; d < D; ++d) na2 += a[d] * a[d];
+    double rr = 0.0;
+    for (int d = 0; d < D; ++d) { r[d] = a[d] / na2; rr += r[d] * r[d]; }
+    const double r2 = rr - 1.0;
+    double s1 = 0.0;
+    for (int d = 0; d < D; ++d) { v[d] = b[d] - r[d]; s1 += v[d] * v[d]; }
+    const double c1 = r2 / s1;
+    double dot = 0.0, nv = 0.0;
+    for (int d = 0; d < D; ++d) { v[d] = c1 * v[d] + r[d]; dot += a[d] * v[d]; nv += v[d] * v[d]; }
+    nv = fmax(nv, GEO_MIN_NORM);
+    double s2 = 0.0;
+    for (int d = 0; d < D; ++d) { v[d] = (2.0 * (dot * v[d] / nv) - a[d]) - r[d]; s2 += v[d] * v[d]; }
+    const double c2 = r2 / s2;
+    double no = 0.0;
+    for (int d = 0; d < D; ++d) { v[d] = c2 * v[d] + r[d]; no += v[d] * v[d]; }
+    const double h = 1.0 + sqrt(1.0 - no);
+    for (int d = 0; d < D; ++d) proj[d] = v[d] / h;
+}
+
+__device__ __forceinline__ double depth_of(const double *p, int D) {  // poincare.hyp_dist_o
+    double n2 = 0.0;
+    for (int d = 0; d < D; ++d) n2 += p[d] * p[d];
+    return 2.0 * atanh(sqrt(n2));
+}
+
+__device__ double lca_depth(const double *a, const double *b, int D) {
+    double p[GEO_MAX_D];
+    lca_point(a, b, D, p);
+    return depth_of(p, D);
+}
+
+// adjoint of y = (r2 / |x - r|^2) (x - r) + r with r2 = |r|^2 - 1; accumulates into gx, gr
+__device__ void invert_vjp(const double *r, double r2, const double *x, const double *gy, int D, double *gx, double *gr) {
+    double u[GEO_MAX_D];
+    double s = 0.0, gu_dot = 0.0;
+    for (int d = 0; d < D; ++d) { u[d] = x[d] - r[d]; s += u[d] * u[d]; gu_dot += gy[d] * u[d]; }
+    const double c = r2 / s;
+    const double g_r2 = gu_dot / s, g_s = -gu_dot * r2 / (s * s);
+    for (int d = 0; d < D; ++d) {
+        const double gu = c * gy[d] + 2.0 * g_s * u[d];
+        gx[d] += gu;
+        gr[d] += gy[d] - gu + 2.0 * g_r2 * r[d];
+    }
+}
+
+// adjoint of proj = lca_point(a, b): ga += J_a^T gproj, gb += J_b^T gproj
+__device__ void lca_point_vjp(const double *a, const double *b, int D, const double *gproj, double *ga, double *gb) {
+    double r[GEO_MAX_D], binv[GEO_MAX_D], m[GEO_MAX_D], o[GEO_MAX_D];
+    double na2 = 0.0;
+    for (int d = 0; d < D; ++d) na2 += a[d] * a[d];
+    double rr = 0.0;
+    for (int d = 0; d < D; ++d) { r[d] = a[d] / na2; rr += r[d] * r[d]; }
+    const double r2 = rr - 1.0;
+    double s1 = 0.0;
+    for (int d = 0; d < D; ++d) { binv[d] = b[d] - r[d]; s1 += binv[d] * binv[d]; }
+    const double c1 = r2 / s1;
+    double dot = 0.0, nv_raw = 0.0;
+    for (int d = 0; d < D; ++d) { binv[d] = c1 * binv[d] + r[d]; dot += a[d] * binv[d]; nv_raw += binv[d] * binv[d]; }
+    const double nv = fmax(nv_raw, GEO_MIN_NORM);
+    double s2 = 0.0;
+    for (int d = 0; d < D; ++d) { m[d] = 2.0 * (dot * binv[d] / nv) - a[d]; const double u = m[d] - r[d]; s2 += u * u; }
+    const double c2 = r2 / s2;
+    double no = 0.0;
+    for (int d = 0; d < D; ++d) { o[d] = c2 * (m[d] - r[d]) + r[d]; no += o[d] * o[d]; }
+    const double q = sqrt(1.0 - no), h = 1.0 + q;
+    // halve
+    double go[GEO_MAX_D], gr[GEO_MAX_D], gm[GEO_MAX_D], gbinv[GEO_MAX_D];
+    double gp_dot_o = 0.0;
+    for (int d = 0; d < D; ++d) gp_dot_o += gproj[d] * o[d];
+    const double gq = -gp_dot_o / (h * h);
+    for (int d = 0; d < D; ++d) { go[d] = gproj[d] / h - (gq / q) * o[d]; gr[d] = 0.0; gm[d] = 0.0; gbinv[d] = 0.0; }
+    // second inversion: o = invert(r, m)
+    invert_vjp(r, r2, m, go, D, gm, gr);
+    // mirror: m = 2 (dot/nv) binv - a ; dot = a . binv ; nv = max(|binv|^2, MIN)
+    double gm_dot_binv = 0.0;
+    for (int d = 0; d < D; ++d) gm_dot_binv += gm[d] * binv[d];
+    const double k = dot / nv;
+    const double g_k = 2.0 * gm_dot_binv;
+    const double g_dot = g_k / nv;
+    const double g_nv = nv_raw > GEO_MIN_NORM ? -g_k * dot / (nv * nv) : 0.0;
+    for (int d = 0; d < D; ++d) {
+        ga[d] += -gm[d] + g_dot * binv[d];
+        gbinv[d] += 2.0 * k * gm[d] + g_dot * a[d] + 2.0 * g_nv * binv[d];
+    }
+    // first inversion: binv = invert(r, b)
+    invert_vjp(r, r2, b, gbinv, D, gb, gr);
+    // centre: r = a / |a|^2
+    double gr_dot_a = 0.0;
+    for (int d = 0; d < D; ++d) gr_dot_a += gr[d] * a[d];
+    for (int d = 0; d < D; ++d) ga[d] += gr[d] / na2 - 2.0 * gr_dot_a / (na2 * na2) * a[d];
+}
+
+// adjoint of t = depth_of(lca_point(a, b))
+__device__ void lca_depth_vjp(const double *a, const double *b, int D, double gt, double *ga, double *gb) {
+    double p[GEO_MAX_D], gp[GEO_MAX_D];
+    lca_point(a, b, D, p);
+    double n2 = 0.0;
+    for (int d = 0; d < D; ++d) n2 += p[d] * p[d];
+    const double n = sqrt(n2);
+    const double gn = n > 0.0 ? gt * 2.0 / (1.0 - n2) / n : 0.0;
+    for (int d = 0; d < D; ++d) gp[d] = gn * p[d];
+    lca_point_vjp(a, b, D, gp, ga, gb);
+}
+
+__global__ void __launch_bounds__(1024) geo_soft_kernel(const double *__restrict__ x, int S, int D, double tau,
+                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
+                                                        double *__restrict__ int_locs, double *__restrict__ blens,
+                                                        int32_t *__restrict__ slots, double *__restrict__ tape,
+                                                        int32_t *__restrict__ flags) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    double *M = ws + (size_t)b * geo_ws_doubles(S, D);  // depth of lca(locs[i], locs[j]), symmetric store
+    double *A = M + (size_t)S * S;                      // scores handed to the soft argmin
+    double *locs = A + (size_t)S * S;                   // [S][D] current locations
+    double *sh = reinterpret_cast<double *>(smem_raw);  // [32]
+    double *newp = sh + 32;                             // [GEO_MAX_D]
+    int *live = reinterpret_cast<int *>(newp + GEO_MAX_D);  // [S]
+    int *node_of = live + S;                                // [S]
+    int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    double *il = int_locs + (size_t)b * (S - 1) * D;
+    double *bl = blens + (size_t)b * (2 * S - 2);
+    int32_t *sl = slots + (size_t)b * (S - 1) * 2;
+    double *tp = tape + (size_t)b * (S - 1) * 2 * D;
+    int32_t *fl = flags + (size_t)b * (S - 1);
+
+    for (int i = tid; i < S * D; i += T) locs[i] = x[(size_t)b * S * D + i];
+    for (int i = tid; i < S; i += T) { live[i] = 1; node_of[i] = i; }
+    __syncthreads();
+    for (long long l = tid; l < (long long)S * S; l += T) {
+        const int i = (int)(l / S), j = (int)(l - (long long)i * S);
+        if (i == j) M[l] = 0.0;
+        else if (i > j) {
+            const double t = lca_depth(locs + (size_t)i * D, locs + (size_t)j * D, D);  // utils.get_plca: row = first argument
+            M[l] = t;
+            M[(size_t)j * S + i] = t;
+        }
+    }
+    __syncthreads();
+
+    for (int step = 0; step < S - 1; ++step) {
+        double mx = 0.0;  // the masked matrix always contains zeros (diagonal, retired rows)
+        for (long long l = tid; l < (long long)S * S; l += T) {
+            const int i = (int)(l / S), j = (int)(l - (long long)i * S);
+            if (i > j && live[i] && live[j]) mx = fmax(mx, M[l]);
+        }
+        const double big = block_reduce(mx, sh, 2) + 1.0;
+        for (long long l = tid; l < (long long)S * S; l += T) {
+            const int i = (int)(l / S), j = (int)(l - (long long)i * S);
+            const double t = M[l];
+            A[l] = (i > j && live[i] && live[j] && t != 0.0) ? -t : big;  // -where(tril != 0, tril, -big)
+        }
+        __syncthreads();
+        SoftCtx c{A, nullptr, nullptr, nullptr, nullptr, 0, S, 0, 0.0, (long long)S * S, 0};
+        double idx;
+        bool ok;
+        soft_argmin_block<2>(c, tau, sh, idx, ok);
+        const double rowf = trunc(idx / (double)S), colf = fmod(idx, (double)S);
+        const int f = (int)rint(rowf), g = (int)rint(colf);
+        const bool bad = !(idx == idx) || f < 0 || f >= S || g < 0 || g >= S || f == g || !live[f] || !live[g];
+        if (bad) {
+            if (tid == 0)
+                for (int t = step; t < S - 1; ++t) fl[t] = 8;
+            return;
+        }
+        __syncthreads();  // everyone has read live[] before it changes
+        if (tid == 0) {
+            const double *pf = locs + (size_t)f * D, *pg = locs + (size_t)g * D;
+            double np_[GEO_MAX_D];
+            lca_point(pf, pg, D, np_);
+            const int parent = S + step;
+            pl[step * 3 + 0] = node_of[f];
+            pl[step * 3 + 1] = node_of[g];
+            pl[step * 3 + 2] = parent;
+            bl[node_of[f]] = lca_depth(pf, np_, D);
+            bl[node_of[g]] = lca_depth(pg, np_, D);
+            sl[step * 2 + 0] = f;
+            sl[step * 2 + 1] = g;
+            for (int d = 0; d < D; ++d) {
+                tp[(size_t)(step * 2 + 0) * D + d] = pf[d];
+                tp[(size_t)(step * 2 + 1) * D + d] = pg[d];
+                il[(size_t)step * D + d] = np_[d];
+                newp[d] = np_[d];
+            }
+            fl[step] = ok ? 0 : 4;
+            node_of[g] = parent;
+            live[f] = 0;
+        }
+        __syncthreads();
+        for (int d = tid; d < D; d += T) locs[(size_t)g * D + d] = newp[d];
+        __syncthreads();
+        for (int i = tid; i < S; i += T) {
+            if (i == g || !live[i]) continue;
+            const double t = i > g ? lca_depth(locs + (size_t)i * D, locs + (size_t)g * D, D)
+                                   : lca_depth(locs + (size_t)g * D, locs + (size_t)i * D, D);
+            M[(size_t)i * S + g] = t;
+            M[(size_t)g * S + i] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// one thread per tree: reverse replay of the joins with the adjoint of every slot's location
+__global__ void geo_soft_bwd_kernel(const int64_t *__restrict__ peel, const int32_t *__restrict__ slots,
+                                    const double *__restrict__ tape, const double *__restrict__ gblens,
+                                    const double *__restrict__ gint, int B, int S, int D, double *__restrict__ gx) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    const int32_t *sl = slots + (size_t)b * (S - 1) * 2;
+    const double *tp = tape + (size_t)b * (S - 1) * 2 * D;
+    const double *gb_ = gblens + (size_t)b * (2 * S - 2);
+    double *adj = gx + (size_t)b * S * D;  // adjoint of the CURRENT content of every slot
+    for (int i = 0; i < S * D; ++i) adj[i] = 0.0;
+    for (int step = S - 2; step >= 0; --step) {
+        const int f = sl[step * 2 + 0], g = sl[step * 2 + 1];
+        if (f < 0 || g < 0 || f >= S || g >= S) continue;  // tree stopped early (flag 8)
+        const double *pf = tp + (size_t)(step * 2 + 0) * D, *pg = tp + (size_t)(step * 2 + 1) * D;
+        double np_[GEO_MAX_D], gnew[GEO_MAX_D], gf[GEO_MAX_D], gg[GEO_MAX_D];
+        lca_point(pf, pg, D, np_);
+        for (int d = 0; d < D; ++d) {
+            gnew[d] = adj[(size_t)g * D + d] + (gint ? gint[((size_t)b * (S - 1) + step) * D + d] : 0.0);
+            gf[d] = 0.0;
+            gg[d] = 0.0;
+        }
+        lca_depth_vjp(pf, np_, D, gb_[pl[step * 3 + 0]], gf, gnew);
+        lca_depth_vjp(pg, np_, D, gb_[pl[step * 3 + 1]], gg, gnew);
+        lca_point_vjp(pf, pg, D, gnew, gf, gg);
+        for (int d = 0; d < D; ++d) {
+            adj[(size_t)g * D + d] = gg[d];
+            adj[(size_t)f * D + d] += gf[d];
+        }
+    }
+}
+
+// hard variant on hyperboloid points.  Node n's sheet coordinates live in pts[n], its ball
+// coordinates in ball[n]; the depth matrix is indexed by storage slot (a new node takes the slot of
+// its first child).  The reference pops a binary heap keyed by -depth; away from exact ties that is
+// the deepest live pair, which is what is selected here (lowest slot pair on ties).
+__global__ void __launch_bounds__(1024) geo_hard_kernel(const double *__restrict__ sheet, int S, int D1,
+                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
+                                                        double *__restrict__ int_locs) {
+    extern __shared__ unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int D = D1 - 1;
+    double *M = ws + (size_t)b * geo_ws_doubles(S, D);
+    double *ball = M + 2 * (size_t)S * S;              // [S][D] ball coordinates by slot
+    double *sh = reinterpret_cast<double *>(smem_raw);  // [32]
+    unsigned long long *shk = reinterpret_cast<unsigned long long *>(sh + 32);  // [32]
+    int *live = reinterpret_cast<int *>(shk + 32);      // [S]
+    int *node_of = live + S;                            // [S]
+    int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    double *il = int_locs + (size_t)b * (S - 1) * D1;
+    const double *z = sheet + (size_t)b * S * D1;
+
+    for (int i = tid; i < S; i += T) {
+        live[i] = 1;
+        node_of[i] = i;
+        for (int d = 0; d < D; ++d) ball[(size_t)i * D + d] = z[(size_t)i * D1 + 1 + d] / (1.0 + z[(size_t)i * D1]);
+    }
+    __syncthreads();
+    for (long long l = tid; l < (long long)S * S; l += T) {
+        const int i = (int)(l / S), j = (int)(l - (long long)i * S);
+        if (i > j) M[l] = lca_depth(ball + (size_t)i * D, ball + (size_t)j * D, D);  // utils.get_plca_np order
+    }
+    __syncthreads();
+    for (int step = 0; step < S - 1; ++step) {
+        // deepest live pair; key = flat slot index, smallest wins ties
+        QKey best{DBL_MAX, ~0ull};
+        for (long long l = tid; l < (long long)S * S; l += T) {
+            const int i = (int)(l / S), j = (int)(l - (long long)i * S);
+            if (i > j && live[i] && live[j]) best = qmin(best, QKey{-M[l], (unsigned long long)l});
+        }
+        best = warp_qmin(best);
+        __syncthreads();
+        if (lane == 0) { sh[warp] = best.q; shk[warp] = best.key; }
+        __syncthreads();
+        best = QKey{sh[0], shk[0]};
+        for (int w = 1; w < nwarp; ++w) best = qmin(best, QKey{sh[w], shk[w]});
+        if (best.key == ~0ull) return;  // NaN input: nothing comparable
+        const int si = (int)(best.key / S), sj = (int)(best.key - (unsigned long long)si * S);
+        const int ni = node_of[si], nj_ = node_of[sj];
+        // Edge(from_, to_): initial pairs are (larger, smaller) tip id; later pairs (older node, newer node)
+        const bool both_tips = ni < S && nj_ < S;
+        const int a_slot = both_tips ? (ni > nj_ ? si : sj) : (ni < nj_ ? si : sj);
+        const int b_slot = a_slot == si ? sj : si;
+        const int parent = S + step;
+        __syncthreads();
+        if (tid == 0) {
+            double p[GEO_MAX_D];
+            lca_point(ball + (size_t)a_slot * D, ball + (size_t)b_slot * D, D, p);
+            double n2 = 0.0;
+            for (int d = 0; d < D; ++d) n2 += p[d] * p[d];
+            // Chyp_np.poincare_to_hyper, then back to the ball as the reference does on every later use
+            const double z0 = (1.0 + n2) / (1.0 - n2);
+            il[(size_t)step * D1] = z0;
+            for (int d = 0; d < D; ++d) {
+                const double zd = 2.0 * p[d] / (1.0 - n2 + DBL_EPSILON);
+                il[(size_t)step * D1 + 1 + d] = zd;
+                ball[(size_t)a_slot * D + d] = zd / (1.0 + z0);
+            }
+            pl[step * 3 + 0] = node_of[a_slot];
+            pl[step * 3 + 1] = node_of[b_slot];
+            pl[step * 3 + 2] = parent;
+            node_of[a_slot] = parent;
+            live[b_slot] = 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < S; i += T) {
+            if (i == a_slot || !live[i]) continue;
+            // new edges are Edge(dist(old, new), old, new): the older node is the first argument
+            const double t = lca_depth(ball + (size_t)i * D, ball + (size_t)a_slot * D, D);
+            if (i > a_slot) M[(size_t)i * S + a_slot] = t;
+            else M[(size_t)a_slot * S + i] = t;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace dodo
 
 using namespace dodo;
@@ -728,6 +1068,56 @@ extern "C" int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, c
     if (smem > 48 * 1024)
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_soft_bwd_kernel<<<B, nj_threads(S), smem, stream>>>(d_peel, d_flags, d_grad_blens, S, (double *)d_ws, d_grad_pdm);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+// ---- geodesic connector
+extern "C" uint64_t dodo_geo_workspace_bytes(int B, int S, int D) {
+    return (uint64_t)B * geo_ws_doubles(S, D) * sizeof(double);
+}
+
+extern "C" int dodo_geo_soft(const double *d_x, int B, int S, int D, double tau, void *d_ws, int64_t *d_peel,
+                             double *d_int_locs, double *d_blens, int32_t *d_slots, double *d_tape,
+                             int32_t *d_flags, void *stream_) {
+    DODO_CHECK_ARG(d_x && d_ws && d_peel && d_int_locs && d_blens && d_slots && d_tape && d_flags,
+                   "dodo_geo_soft: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_geo_soft: need B>=1, S>=2");
+    DODO_CHECK_ARG(D >= 1 && D < GEO_MAX_D, "dodo_geo_soft: embedding dimension must be 1..15");
+    DODO_CHECK_ARG(tau > 0.0, "dodo_geo_soft: tau must be positive");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DODO_CUDA(cudaMemsetAsync(d_slots, 0xff, (size_t)B * (S - 1) * 2 * sizeof(int32_t), stream));
+    size_t smem = (32 + GEO_MAX_D) * sizeof(double) + 2 * (size_t)S * sizeof(int);
+    if (smem > 48 * 1024)
+        DODO_CUDA(cudaFuncSetAttribute(geo_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    geo_soft_kernel<<<B, nj_threads(S), smem, stream>>>(d_x, S, D, tau, (double *)d_ws, d_peel, d_int_locs, d_blens,
+                                                        d_slots, d_tape, d_flags);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+extern "C" int dodo_geo_soft_bwd(const int64_t *d_peel, const int32_t *d_slots, const double *d_tape,
+                                 const double *d_grad_blens, const double *d_grad_int_locs, int B, int S, int D,
+                                 double *d_grad_x, void *stream_) {
+    DODO_CHECK_ARG(d_peel && d_slots && d_tape && d_grad_blens && d_grad_x, "dodo_geo_soft_bwd: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_geo_soft_bwd: need B>=1, S>=2");
+    DODO_CHECK_ARG(D >= 1 && D < GEO_MAX_D, "dodo_geo_soft_bwd: embedding dimension must be 1..15");
+    geo_soft_bwd_kernel<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream_>>>(d_peel, d_slots, d_tape, d_grad_blens,
+                                                                        d_grad_int_locs, B, S, D, d_grad_x);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+extern "C" int dodo_geo_hard(const double *d_sheet, int B, int S, int D1, void *d_ws, int64_t *d_peel,
+                             double *d_int_locs, void *stream_) {
+    DODO_CHECK_ARG(d_sheet && d_ws && d_peel && d_int_locs, "dodo_geo_hard: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_geo_hard: need B>=1, S>=2");
+    DODO_CHECK_ARG(D1 >= 2 && D1 <= GEO_MAX_D, "dodo_geo_hard: sheet points need 2..16 coordinates");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t smem = 32 * sizeof(double) + 32 * sizeof(unsigned long long) + 2 * (size_t)S * sizeof(int);
+    if (smem > 48 * 1024)
+        DODO_CUDA(cudaFuncSetAttribute(geo_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    geo_hard_kernel<<<B, nj_threads(S), smem, stream>>>(d_sheet, S, D1, (double *)d_ws, d_peel, d_int_locs);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

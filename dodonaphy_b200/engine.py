@@ -368,3 +368,64 @@ def nj_soft_backward(peel, flags, grad_blens):
         ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), g.device)
         _lib.check(lib.dodo_nj_soft_bwd(_ptr(peel), _ptr(flags), _ptr(g), B, S, _ptr(ws), _ptr(out), _stream()))
     return out[0] if squeeze else out
+
+
+# --------------------------------------------------------------------------------------------
+# geodesic connector (K2g)
+# --------------------------------------------------------------------------------------------
+def geo_soft(x, tau=1e-8):
+    """Batched peeler.make_soft_peel_tips: ball locations (B,S,D) or (S,D) ->
+    dict(peel, int_locs, blens, flags, slots, tape); slots/tape feed ``geo_soft_backward``."""
+    lib = _lib.load()
+    x, squeeze = _as_batch(x, 3)
+    B, S, D = (int(v) for v in x.shape)
+    if S < 2:
+        raise ValueError("need at least 2 taxa")
+    with torch.cuda.device(x.device):
+        dev = x.device
+        out = dict(peel=torch.zeros((B, S - 1, 3), dtype=torch.int64, device=dev),
+                   int_locs=torch.zeros((B, S - 1, D), dtype=torch.float64, device=dev),
+                   blens=torch.zeros((B, 2 * S - 2), dtype=torch.float64, device=dev),
+                   flags=torch.zeros((B, S - 1), dtype=torch.int32, device=dev),
+                   slots=torch.empty((B, S - 1, 2), dtype=torch.int32, device=dev),
+                   tape=torch.zeros((B, S - 1, 2, D), dtype=torch.float64, device=dev))
+        ws = _workspace("geo", lib.dodo_geo_workspace_bytes(B, S, D), dev)
+        _lib.check(lib.dodo_geo_soft(_ptr(x), B, S, D, float(tau), _ptr(ws), _ptr(out["peel"]), _ptr(out["int_locs"]),
+                                     _ptr(out["blens"]), _ptr(out["slots"]), _ptr(out["tape"]), _ptr(out["flags"]),
+                                     _stream()))
+    if squeeze:
+        out = {k: v[0] for k, v in out.items()}
+    return out
+
+
+def geo_soft_backward(peel, slots, tape, grad_blens, grad_int_locs=None):
+    """VJP of (blens, int_locs) w.r.t. the ball locations: returns (B,S,D)."""
+    lib = _lib.load()
+    g, squeeze = _as_batch(grad_blens, 2)
+    B, S = int(g.shape[0]), int(g.shape[1]) // 2 + 1
+    D = int(tape.shape[-1])
+    dev = g.device
+    peel = peel.reshape(B, S - 1, 3).to(device=dev, dtype=torch.int64).contiguous()
+    slots = slots.reshape(B, S - 1, 2).to(device=dev, dtype=torch.int32).contiguous()
+    tape = tape.reshape(B, S - 1, 2, D).to(device=dev, dtype=torch.float64).contiguous()
+    gi = None if grad_int_locs is None else grad_int_locs.reshape(B, S - 1, D).to(device=dev, dtype=torch.float64).contiguous()
+    with torch.cuda.device(dev):
+        gx = torch.empty((B, S, D), dtype=torch.float64, device=dev)
+        _lib.check(lib.dodo_geo_soft_bwd(_ptr(peel), _ptr(slots), _ptr(tape), _ptr(g), _ptr(gi), B, S, D, _ptr(gx), _stream()))
+    return gx[0] if squeeze else gx
+
+
+def geo_hard(sheet):
+    """Batched peeler.make_hard_peel_geodesic: hyperboloid points (B,S,D+1) or (S,D+1) ->
+    (peel (B,S-1,3), int_locs (B,S-1,D+1))."""
+    lib = _lib.load()
+    z, squeeze = _as_batch(sheet, 3)
+    B, S, D1 = (int(v) for v in z.shape)
+    if S < 2:
+        raise ValueError("need at least 2 taxa")
+    with torch.cuda.device(z.device):
+        peel = torch.zeros((B, S - 1, 3), dtype=torch.int64, device=z.device)
+        il = torch.zeros((B, S - 1, D1), dtype=torch.float64, device=z.device)
+        ws = _workspace("geo", lib.dodo_geo_workspace_bytes(B, S, D1 - 1), z.device)
+        _lib.check(lib.dodo_geo_hard(_ptr(z), B, S, D1, _ptr(ws), _ptr(peel), _ptr(il), _stream()))
+    return (peel[0], il[0]) if squeeze else (peel, il)

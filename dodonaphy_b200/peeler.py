@@ -60,3 +60,45 @@ def compute_Q(pdm, mask=False, fill_value=None):
     Q = torch.where(both, Q, torch.full_like(Q, fill))
     Q.fill_diagonal_(fill)
     return 0.5 * (Q + Q.T)
+
+
+# ------------------------------------------------------------------------------------------------
+# geodesic connector (peeler.py:14-152)
+class _SoftGeodesic(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, leaf_locs, tau):
+        out = _engine.geo_soft(leaf_locs.detach(), tau)
+        if int((out["flags"] & 8).max().item()):
+            raise RuntimeError("geodesic connector: the soft argmin selected a retired point (near-tied LCA depths)")
+        ctx.save_for_backward(out["peel"], out["slots"], out["tape"])
+        ctx.dev = leaf_locs.device
+        ctx.mark_non_differentiable(out["peel"])
+        return out["peel"], out["int_locs"].to(leaf_locs.device), out["blens"].to(leaf_locs.device)
+
+    @staticmethod
+    def backward(ctx, _gpeel, g_int, g_blens):
+        peel, slots, tape = ctx.saved_tensors
+        gx = _engine.geo_soft_backward(peel, slots, tape, g_blens.contiguous(), None if g_int is None else g_int.contiguous())
+        return gx.to(ctx.dev), None
+
+
+def make_soft_peel_tips(leaf_locs, connector="geodesics", curvature=-torch.ones(1)):
+    """(S,D) [or (B,S,D)] Poincare-ball locations -> (peel ndarray int, int_locs, blens); the internal
+    locations and branch lengths carry gradient to ``leaf_locs`` (peeler.py:14-70)."""
+    if connector != "geodesics":
+        raise NotImplementedError(f"Connector must be geodesics, got {connector}")
+    if not torch.isclose(torch.as_tensor(curvature, dtype=torch.float64), -torch.ones(1, dtype=torch.float64)).all():
+        raise NotImplementedError(f"Curvature must be -1, got {curvature}")
+    leaf_locs = torch.as_tensor(leaf_locs, dtype=torch.float64)
+    peel, int_locs, blens = _SoftGeodesic.apply(leaf_locs, 1e-8)
+    return peel.cpu().numpy().astype(int), int_locs, blens
+
+
+def make_hard_peel_geodesic(leaf_locs, matsumoto=False):
+    """(S,D+1) hyperboloid points -> (peel ndarray int (S-1,3), int_locs ndarray (S-1,D+1))
+    (peeler.py:73-152).  NumPy in, NumPy out, as the MCMC side calls it."""
+    if matsumoto:
+        raise NotImplementedError("the Matsumoto adjustment of the heap keys is not on the path")
+    z = np.ascontiguousarray(leaf_locs, dtype=np.float64)
+    peel, int_locs = _engine.geo_hard(torch.from_numpy(z))
+    return peel.cpu().numpy().astype(int), int_locs.cpu().numpy()

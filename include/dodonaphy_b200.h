@@ -151,6 +151,31 @@ int dodo_soft_argmin(const double *d_Q, int B, int rows, int cols, double tau, d
 int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, const double *d_grad_blens,
                      int B, int S, void *d_ws, double *d_grad_pdm, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K2g: the "geodesics" tree connector (the reference's other --connect mode with gradients):
+ * repeatedly join the two live points of the Poincare ball whose geodesic passes furthest from the
+ * origin, the joined node sitting at that geodesic's point nearest the origin.
+ *   dodo_geo_soft      replaces peeler.make_soft_peel_tips     dodonaphy/peeler.py:14-70
+ *                      (poincare.hyp_lca dodonaphy/poincare.py:62-80, utils.get_plca utils.py:141-171,
+ *                       selection by soft.argmin at temperature tau; the reference fixes tau = 1e-8)
+ *   dodo_geo_soft_bwd  the vector-Jacobian product torch autograd takes through it
+ *   dodo_geo_hard      replaces peeler.make_hard_peel_geodesic dodonaphy/peeler.py:73-152
+ * d_x [B][S][D] ball coordinates, D <= 15; d_sheet [B][S][D+1] hyperboloid coordinates.
+ * Outputs: d_peel int64 [B][S-1][3]; d_int_locs [B][S-1][D] (soft, ball) or [B][S-1][D+1] (hard,
+ * sheet); d_blens [B][2S-2]; d_flags int32 [B][S-1] (bit2 exactness guard, bit3 invalid selection,
+ * as dodo_nj_soft).  d_slots int32 [B][S-1][2] and d_tape [B][S-1][2][D] record each join for the
+ * backward call.  d_grad_int_locs may be NULL.  Workspace: dodo_geo_workspace_bytes(B, S, D).
+ * --------------------------------------------------------------------------------------------- */
+uint64_t dodo_geo_workspace_bytes(int B, int S, int D);
+int dodo_geo_soft(const double *d_x, int B, int S, int D, double tau, void *d_ws, int64_t *d_peel,
+                  double *d_int_locs, double *d_blens, int32_t *d_slots, double *d_tape,
+                  int32_t *d_flags, void *stream);
+int dodo_geo_soft_bwd(const int64_t *d_peel, const int32_t *d_slots, const double *d_tape,
+                      const double *d_grad_blens, const double *d_grad_int_locs, int B, int S, int D,
+                      double *d_grad_x, void *stream);
+int dodo_geo_hard(const double *d_sheet, int B, int S, int D1, void *d_ws, int64_t *d_peel,
+                  double *d_int_locs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ Outputs (committed; small):
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
   charts.npz     tangent-space / sheet / ball chart changes of Chyp_torch (t02p, p2t0, ...).
+  geodesic.npz   peeler.make_soft_peel_tips (+ autograd gradient) and peeler.make_hard_peel_geodesic.
 
 The tests never read /root/reference; they read these files.
 """
@@ -285,10 +286,41 @@ def make_charts(r):
     print("charts: ok")
 
 
+def make_geodesic(r):
+    """peeler.make_soft_peel_tips (+ autograd of a random linear functional of blens and int_locs) and
+    peeler.make_hard_peel_geodesic (peeler.py:14-152), incl. the inputs of test/test_peeler.py:22-85,401-470."""
+    rng = np.random.default_rng(35)
+    soft = [rng.normal(0, 0.2, (6, 3)), rng.normal(0, 0.1, (12, 2)), rng.normal(0, 0.15, (27, 3)), rng.normal(0, 0.05, (40, 5)),
+            0.9 * np.array([[np.cos(np.pi), np.sin(np.pi)], [np.cos(0.9 * np.pi), np.sin(0.9 * np.pi)],
+                            [np.cos(-0.5 * np.pi), np.sin(-0.5 * np.pi)]]),
+            np.stack([rr * np.array([np.cos(t), np.sin(t)]) for rr, t in
+                      zip([0.6, 0.6, 0.5, 0.5], [np.pi * 0.2, 0, np.pi, -np.pi * 0.9])])]
+    out = {"n_soft": len(soft)}
+    for i, x in enumerate(soft):
+        xt = torch.tensor(x, requires_grad=True)
+        peel, il, bl = r.peeler.make_soft_peel_tips(xt, connector="geodesics", curvature=-torch.ones(1))
+        wb, wi = rng.normal(size=bl.shape), rng.normal(size=il.shape)
+        (g,) = torch.autograd.grad((bl * torch.tensor(wb)).sum() + (il * torch.tensor(wi)).sum(), xt)
+        out[f"s{i}_x"], out[f"s{i}_peel"], out[f"s{i}_int"], out[f"s{i}_blens"] = x, np.asarray(peel, dtype=np.int64), il.detach().numpy(), bl.detach().numpy()
+        out[f"s{i}_wb"], out[f"s{i}_wi"], out[f"s{i}_grad"] = wb, wi, g.numpy()
+    dog = np.stack([0.5 * np.array([np.cos(t), np.sin(t)]) for t in (np.pi / 10, -np.pi / 10, np.pi * 6 / 8, -np.pi * 6 / 8)])
+    hard = [dog, np.array([(0.05909264, 0.16842421, -0.03628194), (0.08532969, -0.07187002, 0.17884444),
+                           (-0.11422830, 0.01955054, 0.14127290), (-0.06550432, 0.07029946, -0.14566249),
+                           (-0.07060744, -0.12278600, -0.17569585), (0.11386343, -0.03121063, -0.18112418)]),
+            rng.normal(0, 0.2, (6, 3)), rng.normal(0, 0.1, (30, 2)), rng.normal(0, 0.05, (64, 5))]
+    out["n_hard"] = len(hard)
+    for i, x in enumerate(hard):
+        sheet = r.Chyp_np.poincare_to_hyper_2d(x)
+        peel, il = r.peeler.make_hard_peel_geodesic(sheet)
+        out[f"h{i}_sheet"], out[f"h{i}_peel"], out[f"h{i}_int"] = sheet, np.asarray(peel, dtype=np.int64), il
+    np.savez_compressed(os.path.join(HERE, "geodesic.npz"), **out)
+    print("geodesic: soft", len(soft), "hard", len(hard), "dogbone peel", out["h0_peel"].tolist())
+
+
 if __name__ == "__main__":
     r = refload.load()
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
-                  pdm_jac=make_pdm_jac, charts=make_charts)
+                  pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         makers[name](r)

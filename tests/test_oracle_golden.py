@@ -236,3 +236,29 @@ def test_soft_argmin_closed_form_matches_dense():
             Q = np.tril(rng.normal(size=(n, n)))
             Q[rng.integers(1, n), 0] = Q.min()  # inject an exact tie
             assert nj.soft_argmin(Q, tau) == pytest.approx(nj.soft_argmin_dense(Q, tau), rel=1e-12, abs=1e-12)
+
+
+def test_geodesic_oracle_against_reference_outputs():
+    """oracle/geodesic.py vs peeler.make_soft_peel_tips / make_hard_peel_geodesic run on the reference."""
+    import torch
+
+    from oracle import geodesic as G
+
+    g = load_golden("geodesic.npz")
+    for i in range(int(g["n_soft"])):
+        x = g[f"s{i}_x"]
+        peel, il, bl = G.soft_peel_tips(x)
+        np.testing.assert_array_equal(peel, g[f"s{i}_peel"])
+        np.testing.assert_allclose(il, g[f"s{i}_int"], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(bl, g[f"s{i}_blens"], rtol=1e-11, atol=1e-13)
+        if x.shape[0] <= 12:
+            xt = torch.tensor(x, requires_grad=True)
+            _, il2, bl2 = G.soft_peel_tips_torch(xt)
+            (gr,) = torch.autograd.grad((bl2 * torch.tensor(g[f"s{i}_wb"])).sum() + (il2 * torch.tensor(g[f"s{i}_wi"])).sum(), xt)
+            np.testing.assert_allclose(gr.numpy(), g[f"s{i}_grad"], rtol=1e-9, atol=1e-11 * np.abs(g[f"s{i}_grad"]).max())
+    for i in range(int(g["n_hard"])):
+        if g[f"h{i}_sheet"].shape[0] > 30:
+            continue
+        peel, il = G.hard_peel_geodesic(g[f"h{i}_sheet"])
+        np.testing.assert_array_equal(peel, g[f"h{i}_peel"])
+        np.testing.assert_allclose(il, g[f"h{i}_int"], rtol=1e-12, atol=1e-14)
