@@ -37,3 +37,28 @@ def calculate_treelikelihood(partials, weights, post_indexing, mats, freqs):
         raise ValueError(f"mats must have shape ({eng.E}, [K,] 4, 4)")
     out = eng.loglik_mats(peel_t, m.reshape(1, eng.E, -1, 4, 4).to(eng.device), np.asarray(freqs, dtype=np.float64))
     return np.float64(out["lnL"].item())
+
+
+def compute_branch_lengths_np(S, peel, leaf_x, int_x, curvature=-1.0, matsumoto=False):
+    """Branch lengths of a geodesic-connected tree from node locations (Cphylo.pyx:116-160): the
+    hyperbolic distance from each child to its parent, floored at machine epsilon.
+
+    Kept exactly as the reference evaluates it, including two quirks parity depends on: the parent
+    (and internal child) row is ``int_x[node - S - 1]`` -- one row before the node's own, wrapping to
+    the last row for the first internal node -- and both end points are lifted to the sheet twice
+    (once here, once inside ``Chyp_np.hyperbolic_distance``)."""
+    from . import Chyp_np
+
+    leaf_x = np.asarray(leaf_x, dtype=np.float64)
+    int_x = np.asarray(int_x, dtype=np.float64)
+    blens = np.zeros(2 * S - 2, dtype=np.float64)
+    tiny = np.finfo(np.double).eps
+    for left, right, parent in np.asarray(peel)[: S - 1]:
+        up = Chyp_np.project_up(int_x[int(parent) - S - 1])
+        for child in (int(left), int(right)):
+            here = leaf_x[child] if child < S else int_x[child - S - 1]
+            hd = Chyp_np.hyperbolic_distance(Chyp_np.project_up(here), up, curvature)
+            if matsumoto:
+                hd = np.log(np.cosh(hd))
+            blens[child] = np.maximum(hd, tiny)
+    return blens

@@ -37,21 +37,18 @@ class _BatchedLogLik(torch.autograd.Function):
         out = hot.value_and_grad(x, to_locations=False)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
-        ctx.save_for_backward(x, out["peel"], out["flags"], out["grad_blens"])
+        ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens") if k in out}
         ctx.mark_non_differentiable(out["peel"])
         return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device)
 
     @staticmethod
     def backward(ctx, g_ll, _g_peel, g_blens):
-        from . import engine
-
-        x, peel, flags, dll_dblens = ctx.saved_tensors
-        hot = ctx.hot
-        gb = g_ll.to(x.device).reshape(-1, 1) * dll_dblens
+        x, hot = ctx.x, ctx.hot
+        gb = g_ll.to(x.device).reshape(-1, 1) * ctx.dec["grad_blens"]
         if g_blens is not None:
             gb = gb + g_blens.to(x.device)
-        gpdm = engine.nj_soft_backward(peel, flags, gb.contiguous())
-        gx, gc = engine.pdm_backward(x, gpdm, ctx.kappa, hot.lift, hot.matsumoto)
+        hot.curvature = ctx.kappa
+        gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())
         return gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]), None
 
 
@@ -64,26 +61,23 @@ class _BatchedLogLikModel(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, locs, curvature_leaf, raw_rates, raw_freqs, hot):
-        from . import engine
-
         hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
         x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
-        pdm = engine.pdm_forward(x, hot.curvature, "torch", hot.lift, hot.matsumoto)
-        peel, blens, flags = engine.nj_soft(pdm, hot.tau, return_flags=True)
+        dec = hot.decode(x)
+        peel, blens = dec["peel"], dec["blens"]
         P, pi = PhyloModel.transition_mats_from_raw(raw_rates.detach(), raw_freqs.detach(), blens, hot.rates)
         out = hot.prune.loglik_mats(peel, P, pi.numpy(), grad=True, mix=hot.mix)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
-        ctx.save_for_backward(x, peel, flags, blens, out["grad_mats"], out["grad_pi"], raw_rates.detach(), raw_freqs.detach())
+        ctx.x, ctx.dec = x, dec
+        ctx.save_for_backward(blens, out["grad_mats"], out["grad_pi"], raw_rates.detach(), raw_freqs.detach())
         ctx.mark_non_differentiable(peel)
         return out["lnL"].to(locs.device), peel, blens.to(locs.device)
 
     @staticmethod
     def backward(ctx, g_ll, _g_peel, g_blens):
-        from . import engine
-
-        x, peel, flags, blens, gP, gpi, raw_rates, raw_freqs = ctx.saved_tensors
-        hot = ctx.hot
+        blens, gP, gpi, raw_rates, raw_freqs = ctx.saved_tensors
+        x, hot = ctx.x, ctx.hot
         w = g_ll.to(x.device).reshape(-1)
         with torch.enable_grad():
             bl = blens.detach().requires_grad_(True)
@@ -93,8 +87,8 @@ class _BatchedLogLikModel(torch.autograd.Function):
             gb, g_rates, g_freqs = torch.autograd.grad(obj, (bl, rr, rf))
         if g_blens is not None:
             gb = gb + g_blens.to(x.device)
-        gpdm = engine.nj_soft_backward(peel, flags, gb.contiguous())
-        gx, gc = engine.pdm_backward(x, gpdm, ctx.kappa, hot.lift, hot.matsumoto)
+        hot.curvature = ctx.kappa
+        gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())
         return (gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]),
                 g_rates, g_freqs, None)
 
@@ -161,15 +155,27 @@ class BaseModel:
         return np.float64(out.item())
 
     def connect(self, locs):
-        """Decode one embedding into (peel, blens, pdm) by neighbour joining."""
-        if self.connector not in ("nj",):
-            raise NotImplementedError(f"connector {self.connector!r} is outside the NJ hot path")
+        """Decode one embedding into (peel, blens, pdm): neighbour joining on the pairwise distances
+        or the geodesic connector (vi.py:467-491; chain.py:171-221, where the third item is the
+        internal-node locations for 'geodesics')."""
+        if self.connector not in ("nj", "geodesics"):
+            raise NotImplementedError(f"connector {self.connector!r} is outside the hot path")
         if self.require_grad:
             pdm = Chyp_torch.get_pdm(locs, curvature=self.curvature, matsumoto=self.matsumoto, projection=self.embedder)
-            peel, blens = peeler.nj_torch(pdm, tau=self.soft_temp)
-        else:
-            pdm = Chyp_np.get_pdm(locs, curvature=float(self.curvature), matsumoto=self.matsumoto)
-            peel, blens = Cpeeler.nj_np(pdm)
+            if self.connector == "geodesics":
+                peel, _, blens = peeler.make_soft_peel_tips(locs, connector="geodesics", curvature=self.curvature.detach())
+            else:
+                peel, blens = peeler.nj_torch(pdm, tau=self.soft_temp)
+            return peel, blens, pdm
+        if self.connector == "geodesics":
+            from . import Cphylo
+
+            peel, int_x = peeler.make_hard_peel_geodesic(locs)
+            blens = Cphylo.compute_branch_lengths_np(self.S, peel, locs, int_x, curvature=float(self.curvature),
+                                                     matsumoto=self.matsumoto)
+            return peel, blens, int_x
+        pdm = Chyp_np.get_pdm(locs, curvature=float(self.curvature), matsumoto=self.matsumoto)
+        peel, blens = Cpeeler.nj_np(pdm)
         return peel, blens, pdm
 
     # -- a batch of trees -------------------------------------------------------------------------
@@ -177,7 +183,8 @@ class BaseModel:
         model = self.phylomodel.device_model()
         if self._hot is None:
             self._hot = HotPath.from_engine(self._inst.engine, model, rates=self.rates, mix=self.rates is not None,
-                                            tau=self.soft_temp, lift=self.embedder, matsumoto=self.matsumoto)
+                                            tau=self.soft_temp, lift=self.embedder, matsumoto=self.matsumoto,
+                                            connector="geodesics" if self.connector == "geodesics" else "nj")
         self._hot.model = model
         self._hot.tau = self.soft_temp
         return self._hot

@@ -69,9 +69,9 @@ class HMAP(BaseModel):
     # ------------------------------------------------------------------ one evaluation
     def connect(self, get_pdm=False):
         """Decode the current locations into a tree (one-tree interface of hmap.py:310-334)."""
-        if self.connector != "nj":
-            if self.connector in ("geodesics", "fix"):
-                raise NotImplementedError(f"connector {self.connector!r} embeds internal nodes; only 'nj' is on the path")
+        if self.connector not in ("nj", "geodesics"):
+            if self.connector == "fix":
+                raise NotImplementedError("connector 'fix' embeds internal nodes; only 'nj' and 'geodesics' are on the path")
             raise ValueError(f"Connection must be one of 'nj', 'geodesics', 'fix'. Got {self.connector}")
         peel, blens, pdm = super().connect(self.get_locs())
         return (peel, blens, pdm) if get_pdm else (peel, blens)
@@ -79,7 +79,7 @@ class HMAP(BaseModel):
     def compute_loss(self, fused=True):
         """-(ln prior + lnL) of the current embedding.  ``fused=False`` takes the reference's
         call-by-call route (connect -> compute_LL) instead of the single batched pass."""
-        if self.connector != "nj":
+        if self.connector not in ("nj", "geodesics"):
             self.connect()
         if fused:
             ll, peel, blens = self.log_likelihood_batch(self.get_locs().unsqueeze(0))

@@ -15,7 +15,8 @@ from . import engine
 
 class HotPath:
     def __init__(self, tipmask, weights, model, rates=None, mix=False, tau=1e-8, curvature=-1.0,
-                 lift="up", matsumoto=False, device=None):
+                 lift="up", matsumoto=False, device=None, connector="nj"):
+        self.connector = connector
         self.prune = engine.PruneEngine(tipmask, weights, device=device)
         self.device = self.prune.device
         self.model = model
@@ -27,9 +28,11 @@ class HotPath:
         self.matsumoto = matsumoto
 
     @classmethod
-    def from_engine(cls, prune_engine, model, rates=None, mix=False, tau=1e-8, curvature=-1.0, lift="up", matsumoto=False):
+    def from_engine(cls, prune_engine, model, rates=None, mix=False, tau=1e-8, curvature=-1.0, lift="up", matsumoto=False,
+                    connector="nj"):
         """Share an existing PruneEngine (tips already resident on the device)."""
         self = cls.__new__(cls)
+        self.connector = connector
         self.prune = prune_engine
         self.device = prune_engine.device
         self.model = model
@@ -37,18 +40,41 @@ class HotPath:
         self.mix, self.tau, self.curvature, self.lift, self.matsumoto = bool(mix), tau, curvature, lift, matsumoto
         return self
 
-    def value_and_grad(self, x, to_locations=True):
-        """x: (B,S,D) device tensor.  Returns dict(lnL (B,), grad_x (B,S,D), grad_curvature (B,),
-        peel (B,S-1,3), blens (B,2S-2)) -- soft-NJ (VI) path.  ``to_locations=False`` stops at
-        d lnL/d blens (the caller chains NJ / distance backward itself)."""
+    # -- tree decoding: the differentiable connector and its reverse ------------------------------
+    def decode(self, x):
+        """x (B,S,D) -> dict(peel, blens, + what ``decode_backward`` needs).  'nj': distance kernel +
+        soft NJ (vi.py:476-484); 'geodesics': the LCA connector on x taken as ball coordinates
+        (vi.py:479-482; curvature -1 only, as in the reference)."""
+        if self.connector == "geodesics":
+            if abs(float(self.curvature) + 1.0) > 1e-8:
+                raise NotImplementedError(f"Curvature must be -1, got {self.curvature}")
+            out = engine.geo_soft(x, 1e-8)
+            out["flags"] = out["flags"] & 8  # only an invalid selection matters downstream
+            return out
+        if self.connector != "nj":
+            raise NotImplementedError(f"connector {self.connector!r} has no differentiable device path")
         pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto)
         peel, blens, flags = engine.nj_soft(pdm, self.tau, return_flags=True)
-        ll, gbl = self.prune.loglik(peel, blens, self.model, rates=self.rates, mix=self.mix, grad=True)
-        if not to_locations:
-            return dict(lnL=ll, peel=peel, blens=blens, flags=flags, grad_blens=gbl)
-        gpdm = engine.nj_soft_backward(peel, flags, gbl)
-        gx, gc = engine.pdm_backward(x, gpdm, self.curvature, self.lift, self.matsumoto)
-        return dict(lnL=ll, grad_x=gx, grad_curvature=gc, peel=peel, blens=blens, flags=flags, grad_blens=gbl)
+        return dict(peel=peel, blens=blens, flags=flags)
+
+    def decode_backward(self, x, dec, grad_blens):
+        """VJP of ``decode``: d/d x (B,S,D) and d/d curvature (B,) of sum(grad_blens * blens)."""
+        if self.connector == "geodesics":
+            gx = engine.geo_soft_backward(dec["peel"], dec["slots"], dec["tape"], grad_blens)
+            return gx, torch.zeros(gx.shape[0], dtype=torch.float64, device=gx.device)
+        gpdm = engine.nj_soft_backward(dec["peel"], dec["flags"], grad_blens)
+        return engine.pdm_backward(x, gpdm, self.curvature, self.lift, self.matsumoto)
+
+    def value_and_grad(self, x, to_locations=True):
+        """x: (B,S,D) device tensor.  Returns dict(lnL (B,), grad_x (B,S,D), grad_curvature (B,),
+        peel (B,S-1,3), blens (B,2S-2)) -- the differentiable (VI) path.  ``to_locations=False`` stops
+        at d lnL/d blens (the caller chains ``decode_backward`` itself)."""
+        dec = self.decode(x)
+        ll, gbl = self.prune.loglik(dec["peel"], dec["blens"], self.model, rates=self.rates, mix=self.mix, grad=True)
+        dec.update(lnL=ll, grad_blens=gbl)
+        if to_locations:
+            dec["grad_x"], dec["grad_curvature"] = self.decode_backward(x, dec, gbl)
+        return dec
 
     def blens_jacobian(self, x, peel=None, flags=None, logdet=True):
         """d blens / d locations for every sample, (B, 2S-2, S*D), and log sqrt|det(J J^T)| -- the
@@ -59,12 +85,17 @@ class HotPath:
         so two rows of J coincide and the determinant is numerically ~0 in the reference as well.)"""
         B, S, D = (int(v) for v in x.shape)
         E = 2 * S - 2
-        if peel is None:
-            pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto)
-            peel, _, flags = engine.nj_soft(pdm, self.tau, return_flags=True)
         cot = torch.eye(E, dtype=torch.float64, device=x.device).repeat(B, 1)
-        gpdm = engine.nj_soft_backward(peel.repeat_interleave(E, 0), flags.repeat_interleave(E, 0), cot)
-        gx, _ = engine.pdm_backward(x.repeat_interleave(E, 0), gpdm, self.curvature, self.lift, self.matsumoto)
+        if self.connector == "geodesics":
+            dec = self.decode(x)
+            rep = {k: dec[k].repeat_interleave(E, 0) for k in ("peel", "slots", "tape")}
+            gx, _ = self.decode_backward(None, rep, cot)
+        else:
+            if peel is None:
+                dec = self.decode(x)
+                peel, flags = dec["peel"], dec["flags"]
+            rep = dict(peel=peel.repeat_interleave(E, 0), flags=flags.repeat_interleave(E, 0))
+            gx, _ = self.decode_backward(x.repeat_interleave(E, 0), rep, cot)
         J = gx.reshape(B, E, S * D)
         if not logdet:
             return J
@@ -73,6 +104,8 @@ class HotPath:
 
     def value(self, x):
         """Gradient-free MCMC path (Chyp_np.get_pdm -> Cpeeler.nj_np -> Cphylo.compute_LL_np)."""
+        if self.connector != "nj":
+            raise NotImplementedError("the batched gradient-free path decodes with hard NJ only")
         pdm = engine.pdm_forward(x, self.curvature, "numpy", "up", self.matsumoto)
         peel, blens = engine.nj_hard(pdm)
         ll, _ = self.prune.loglik(peel, blens, self.model, rates=self.rates, mix=self.mix, grad=False)

@@ -313,6 +313,11 @@ def make_geodesic(r):
         sheet = r.Chyp_np.poincare_to_hyper_2d(x)
         peel, il = r.peeler.make_hard_peel_geodesic(sheet)
         out[f"h{i}_sheet"], out[f"h{i}_peel"], out[f"h{i}_int"] = sheet, np.asarray(peel, dtype=np.int64), il
+    # the MCMC route (chain.py:176-185): raw (S, D) locations go in as they are
+    leaf_x = rng.normal(0, 0.1, (9, 3))
+    peel, int_x = r.peeler.make_hard_peel_geodesic(leaf_x)
+    out["chain_x"], out["chain_peel"], out["chain_int"] = leaf_x, np.asarray(peel, dtype=np.int64), int_x
+    out["chain_blens"] = r.Cphylo.compute_branch_lengths_np(9, np.asarray(peel, dtype=np.int64), leaf_x, int_x)
     np.savez_compressed(os.path.join(HERE, "geodesic.npz"), **out)
     print("geodesic: soft", len(soft), "hard", len(hard), "dogbone peel", out["h0_peel"].tolist())
 
