@@ -41,28 +41,50 @@ __device__ __forceinline__ QKey warp_qmin(QKey v) {
     return v;
 }
 
-// workspace per tree (doubles): Dm[S*S] | Ab[S*S] ; ints are in shared memory
-__host__ __device__ inline size_t nj_ws_doubles(int S) { return 2 * (size_t)S * S + 4 * (size_t)S; }
+// Storage scheme of the NJ kernels.  A new node always takes a FRESH slot at the end of the matrix, so
+// slot order == pool order (survivors in their order, then new nodes in creation order) and a row scan
+// in pool order walks memory monotonically.  Every join retires two slots; once the spare slots are
+// used up the live rows/columns are repacked densely into the other half of the workspace.  With
+// `spare` free slots after a repack the dead-slot overhead of the scans is ~spare/n and the repacking
+// overhead ~4/spare of the scan traffic, hence spare = 2 sqrt(n).
+__host__ __device__ inline int nj_spare(int n) {
+    const int s = (int)(2.0 * sqrt((double)n));
+    return s < 16 ? 16 : s;
+}
+// row stride for n live rows: spare slots, rounded so that every row starts on a 128-byte line
+__host__ __device__ inline int nj_ld(int n) { return (n + nj_spare(n) + 15) & ~15; }
+// workspace per tree (doubles): two ld x ld matrices (the backward kernel uses the second half as its
+// S x S adjoint matrix); ints are in shared memory
+__host__ __device__ inline size_t nj_ws_doubles(int S) {
+    return 2 * (size_t)nj_ld(S) * nj_ld(S) + ((4 * (size_t)S + 15) & ~(size_t)15);
+}
 
 // ------------------------------------------------------------------------------------------ hard
-__global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
+__global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
                                                        int64_t *__restrict__ peel, double *__restrict__ blens) {
     extern __shared__ unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     double *Dm = ws + (size_t)b * nj_ws_doubles(S);
+    const int LD = nj_ld(S);
+    double *Dalt = Dm + (size_t)LD * LD;  // second matrix of the workspace: target of the next repack
+    int ld = LD;                          // row stride of the current matrix
+    int used = S;                         // slots handed out so far
     const double *P = pdm + (size_t)b * S * S;
-    double *xs = reinterpret_cast<double *>(smem_raw);  // [S] by storage slot
-    double *newd = xs + S;                              // [S]
-    int *act = reinterpret_cast<int *>(newd + S);       // [S] pool position -> storage slot
-    int *act2 = act + S;                                // [S]
-    int *id_of = act2 + S;                              // [S] storage slot -> node id
+    double *xs = reinterpret_cast<double *>(smem_raw);  // [LD] by storage slot
+    double *newd = xs + LD;                             // [LD]
+    int *act = reinterpret_cast<int *>(newd + LD);      // [LD] pool position -> storage slot
+    int *act2 = act + LD;                               // [LD]
+    int *id_of = act2 + LD;                             // [LD] storage slot -> node id
     __shared__ QKey wbest[32];
     __shared__ int sh_pa, sh_pb;
     int64_t *pl = peel + (size_t)b * (S - 1) * 3;
     double *bl = blens + (size_t)b * (2 * S - 2);
 
-    for (size_t i = tid; i < (size_t)S * S; i += T) Dm[i] = P[i];
+    for (size_t i = tid; i < (size_t)S * S; i += T) {
+        const int r = (int)(i / S), c = (int)(i - (size_t)r * S);
+        Dm[(size_t)r * ld + c] = P[i];
+    }
     for (int s = tid; s < S; s += T) {
         act[s] = s;
         id_of[s] = s;
@@ -76,6 +98,20 @@ __global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict_
     __syncthreads();
 
     for (int n = S; n > 1; --n) {
+        if (used == ld) {  // no free slot left: repack the live rows/columns densely in pool order
+            const int nld = nj_ld(n);
+            for (size_t i = tid; i < (size_t)n * n; i += T) {
+                const int p = (int)(i / n), q = (int)(i - (size_t)p * n);
+                Dalt[(size_t)p * nld + q] = Dm[(size_t)act[p] * ld + act[q]];
+            }
+            for (int p = tid; p < n; p += T) { newd[p] = xs[act[p]]; act2[p] = id_of[act[p]]; }
+            __syncthreads();
+            for (int p = tid; p < n; p += T) { xs[p] = newd[p]; id_of[p] = act2[p]; act[p] = p; }
+            double *t = Dm; Dm = Dalt; Dalt = t;
+            ld = nld;
+            used = n;
+            __syncthreads();
+        }
         const double nm2 = (double)n - 2.0;
         // ---- first strict minimum of q over pairs (pa < pb) in pool order (Cpeeler.pyx:58-66)
         QKey best;
@@ -84,7 +120,7 @@ __global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict_
         for (int pa = warp; pa < n - 1; pa += nwarp) {
             const int sa = act[pa];
             const double xa = xs[sa];
-            const double *row = Dm + (size_t)sa * S;
+            const double *row = Dm + (size_t)sa * ld;
             for (int pb = pa + 1 + lane; pb < n; pb += 32) {
                 const int sb = act[pb];
                 double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, row[sb]), xa), xs[sb]);
@@ -111,18 +147,19 @@ __global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict_
         const int sa = act[pa], sb = act[pb];
         const int n1 = id_of[sa], n2 = id_of[sb];
         const int parent = S + (S - n);
-        const double d12 = Dm[(size_t)sa * S + sb];
+        const int ns = used++;  // the new node's slot
+        const double d12 = Dm[(size_t)sa * ld + sb];
         // ---- distances of the new node, running row sums (Cpeeler.pyx:81-95)
         for (int p = tid; p < n; p += T) {
             if (p == pa || p == pb) continue;
             const int sx = act[p];
-            const double *rx = Dm + (size_t)sx * S;
+            const double *rx = Dm + (size_t)sx * ld;
             double v1 = __dadd_rn(__dadd_rn(0.0, rx[sa]), rx[sb]);
             double dist = __dmul_rn(0.5, __dsub_rn(v1, d12));
             newd[sx] = dist;
             double x = __dadd_rn(xs[sx], dist);
-            x = __dsub_rn(x, Dm[(size_t)sa * S + sx]);
-            x = __dsub_rn(x, Dm[(size_t)sb * S + sx]);
+            x = __dsub_rn(x, Dm[(size_t)sa * ld + sx]);
+            x = __dsub_rn(x, Dm[(size_t)sb * ld + sx]);
             xs[sx] = x;
         }
         __syncthreads();
@@ -149,19 +186,19 @@ __global__ void __launch_bounds__(1024) nj_hard_kernel(const double *__restrict_
                 if (p == pa || p == pb) continue;
                 acc = __dadd_rn(acc, newd[act[p]]);
             }
-            xs[sa] = acc;
-            id_of[sa] = parent;
+            xs[ns] = acc;
+            id_of[ns] = parent;
         }
-        // new node takes the storage slot of n1; pool = survivors in order, then the new node
+        // pool = survivors in order, then the new node
         for (int p = tid; p < n; p += T) {
             if (p == pa || p == pb) continue;
             const int sx = act[p];
             const double dist = newd[sx];
-            Dm[(size_t)sa * S + sx] = dist;
-            Dm[(size_t)sx * S + sa] = dist;
+            Dm[(size_t)ns * ld + sx] = dist;
+            Dm[(size_t)sx * ld + ns] = dist;
             act2[p - (p > pa) - (p > pb)] = sx;
         }
-        if (tid == 0) act2[n - 2] = sa;
+        if (tid == 0) act2[n - 2] = ns;
         __syncthreads();
         for (int p = tid; p < n - 1; p += T) act[p] = act2[p];
         __syncthreads();
@@ -480,7 +517,7 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     idx_out = isum / z2;
 }
 
-__global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
+__global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
                                                        double *__restrict__ blens, int32_t *__restrict__ flags) {
     extern __shared__ unsigned char smem_raw[];
@@ -488,14 +525,17 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     const int N = 2 * S - 1;
     double *Dm = ws + (size_t)b * nj_ws_doubles(S);
+    const int LD = nj_ld(S);
+    double *Dalt = Dm + (size_t)LD * LD;  // repack target (storage scheme: see nj_ws_doubles)
+    int ld = LD, used = S;
     const double *P = pdm + (size_t)b * S * S;
-    double *rs = reinterpret_cast<double *>(smem_raw);  // [S]
-    double *newd = rs + S;                              // [S]
-    double *sh = newd + S;                              // [32]
-    int *act = reinterpret_cast<int *>(sh + 32);        // [S]
-    int *act2 = act + S;                                // [S]
-    int *id_of = act2 + S;                              // [S]
-    int *pos_of = id_of + S;                            // [N]
+    double *rs = reinterpret_cast<double *>(smem_raw);  // [LD] by storage slot
+    double *newd = rs + LD;                             // [LD]
+    double *sh = newd + LD;                             // [32]
+    int *act = reinterpret_cast<int *>(sh + 32);        // [LD]
+    int *act2 = act + LD;                               // [LD]
+    int *id_of = act2 + LD;                             // [LD]
+    int *pos_of = id_of + LD;                           // [N]
     int64_t *pl = peel + (size_t)b * (S - 1) * 3;
     double *bl = blens + (size_t)b * (2 * S - 2);
     int32_t *fl = flags + (size_t)b * (S - 1);
@@ -504,7 +544,7 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
     for (size_t i = tid; i < (size_t)S * S; i += T) {
         int r = (int)(i / S), cc = (int)(i - (size_t)r * S);
         const double v = P[i];
-        Dm[i] = (r == cc) ? 0.0 : v;  // dists.fill_diagonal_(0.0), peeler.py:178
+        Dm[(size_t)r * ld + cc] = (r == cc) ? 0.0 : v;  // dists.fill_diagonal_(0.0), peeler.py:178
         if (r != cc && v != P[(size_t)cc * S + r]) asym = 1;
     }
     const int symmetric = __syncthreads_or(asym) ? 0 : 1;  // new rows/columns are written symmetrically
@@ -513,10 +553,24 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
     __syncthreads();
 
     for (int n = S; n > 1; --n) {
+        if (used == ld) {  // no free slot left: repack live rows/columns densely in pool order
+            const int nld = nj_ld(n);
+            for (size_t i = tid; i < (size_t)n * n; i += T) {
+                const int p = (int)(i / n), q = (int)(i - (size_t)p * n);
+                Dalt[(size_t)p * nld + q] = Dm[(size_t)act[p] * ld + act[q]];
+            }
+            for (int p = tid; p < n; p += T) act2[p] = id_of[act[p]];
+            __syncthreads();
+            for (int p = tid; p < n; p += T) { id_of[p] = act2[p]; act[p] = p; }
+            double *t = Dm; Dm = Dalt; Dalt = t;
+            ld = nld;
+            used = n;
+            __syncthreads();
+        }
         // fresh row sums over the active set (peeler.py:240, :261)
         for (int p = warp; p < n; p += nwarp) {
             const int sx = act[p];
-            const double *row = Dm + (size_t)sx * S;
+            const double *row = Dm + (size_t)sx * ld;
             double acc = 0.0;
             for (int q = lane; q < n; q += 32) {
                 int sy = act[q];
@@ -526,7 +580,7 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
             if (lane == 0) rs[sx] = acc;
         }
         __syncthreads();
-        SoftCtx c{Dm, rs, act, id_of, pos_of, S, N, n, (double)(n - 2), 0, symmetric};
+        SoftCtx c{Dm, rs, act, id_of, pos_of, ld, N, n, (double)(n - 2), 0, symmetric};
         double idx;
         bool ok;
         if (full) soft_argmin_block<1>(c, tau, sh, idx, ok);
@@ -546,7 +600,8 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
         }
         const int sl = act[pc], sr = act[pr];
         const int parent = S + (S - n);
-        const double d_lr = Dm[(size_t)sl * S + sr];
+        const int ns = used++;  // the new node's slot
+        const double d_lr = Dm[(size_t)sl * ld + sr];
         const double nact = fmax((double)n, 3.0);
         double d_pl = 0.5 * d_lr + (rs[sl] - rs[sr]) / (2.0 * (nact - 2.0));
         if (!(d_pl > DBL_EPSILON)) { fbits |= (d_pl == DBL_EPSILON) ? 0 : 1; d_pl = DBL_EPSILON; }
@@ -555,7 +610,7 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
         for (int p = tid; p < n; p += T) {
             if (p == pc || p == pr) continue;
             const int sx = act[p];
-            newd[sx] = 0.5 * ((Dm[(size_t)sl * S + sx] + Dm[(size_t)sr * S + sx]) - d_lr);
+            newd[sx] = 0.5 * ((Dm[(size_t)sl * ld + sx] + Dm[(size_t)sr * ld + sx]) - d_lr);
         }
         __syncthreads();
         if (tid == 0) {
@@ -565,7 +620,7 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
             bl[left] = d_pl;
             bl[right] = d_pr;
             fl[S - n] = fbits;
-            id_of[sl] = parent;
+            id_of[ns] = parent;
             pos_of[left] = -1;
             pos_of[right] = -1;
         }
@@ -574,11 +629,11 @@ __global__ void __launch_bounds__(1024) nj_soft_kernel(const double *__restrict_
             if (p == pc || p == pr) continue;
             const int sx = act[p];
             const double u = newd[sx];
-            Dm[(size_t)sl * S + sx] = u;
-            Dm[(size_t)sx * S + sl] = u;
+            Dm[(size_t)ns * ld + sx] = u;
+            Dm[(size_t)sx * ld + ns] = u;
             act2[p - (p > plo) - (p > phi)] = sx;
         }
-        if (tid == 0) act2[n - 2] = sl;
+        if (tid == 0) act2[n - 2] = ns;
         __syncthreads();
         for (int p = tid; p < n - 1; p += T) {
             act[p] = act2[p];
@@ -1035,7 +1090,7 @@ extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64
     DODO_CHECK_ARG(d_pdm && d_ws && d_peel && d_blens, "dodo_nj_hard: NULL argument");
     DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_hard: need B>=1, S>=2");
     cudaStream_t stream = (cudaStream_t)stream_;
-    size_t smem = 2 * (size_t)S * sizeof(double) + 3 * (size_t)S * sizeof(int);
+    size_t smem = 2 * (size_t)nj_ld(S) * sizeof(double) + 3 * (size_t)nj_ld(S) * sizeof(int);
     if (smem > 48 * 1024)
         DODO_CUDA(cudaFuncSetAttribute(nj_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_hard_kernel<<<B, nj_threads(S), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens);
@@ -1051,7 +1106,7 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
     cudaStream_t stream = (cudaStream_t)stream_;
     const int full = tau < 0.0 ? 1 : 0;  // negative tau selects the exhaustive N^2 enumeration
     const double t = fabs(tau);
-    size_t smem = (2 * (size_t)S + 32) * sizeof(double) + (3 * (size_t)S + 2 * (size_t)S) * sizeof(int);
+    size_t smem = (2 * (size_t)nj_ld(S) + 32) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
     if (smem > 48 * 1024)
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_soft_kernel<<<B, nj_threads(S), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);

@@ -43,7 +43,7 @@ def test_plan_and_argument_validation_without_gpu():
     assert lib.dodo_prune_plan(1, 8, 10, 9, 0, 1, 0, ctypes.byref(plan)) == _lib.DODO_EINVAL
     with pytest.raises(ValueError):
         _lib.check(lib.dodo_prune_plan(1, 8, 10, 1, _lib.PRUNE_GRAD | _lib.PRUNE_GMATS, 1, 0, ctypes.byref(plan)))
-    assert lib.dodo_nj_workspace_bytes(3, 10) == 3 * (2 * 100 + 40) * 8
+    assert lib.dodo_nj_workspace_bytes(3, 10) == 3 * (2 * 32 * 32 + 48) * 8  # stride 10 + 16 spare slots -> 32
     assert lib.dodo_pdm_workspace_bytes(2, 5, 3) == 2 * 5 * 5 * 8
 
 
