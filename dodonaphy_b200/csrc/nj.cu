@@ -1083,7 +1083,9 @@ extern "C" uint64_t dodo_nj_workspace_bytes(int B, int S) {
     return (uint64_t)B * nj_ws_doubles(S) * sizeof(double);
 }
 
-static int nj_threads(int S) { return S <= 48 ? 128 : (S <= 160 ? 256 : (S <= 600 ? 512 : 1024)); }
+// CTA size by taxon count (measured on B200: 16-500 taxa, 64-128 trees per launch): the per-join scans
+// want many threads long before the matrix is large
+static int nj_threads(int S) { return S <= 32 ? 256 : (S <= 128 ? 512 : 1024); }
 
 extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
                             void *stream_) {
