@@ -49,6 +49,7 @@ WORKLOADS = {
 # the other BASELINE.json configurations: parity-test shapes, timed by `bench.py --side NAME` into
 # profiles/ (NOT the headline line; they print their own small JSON)
 SIDE = {
+    "c1": dict(S=27, L=934, B=4, D=3, desc="DS1-sized (27 taxa x 934 patterns, JC69): MCMC sweep of 4 chains and VI step of 8 samples, launch-by-launch vs one CUDA graph (configs[0])"),
     "c3": dict(S=200, L=50000, B=64, D=5, desc="MCMC, 64 chains, 200 taxa x 50k patterns, JC69, forward only (configs[2])"),
     "c4": dict(S=2000, B=256, D=5, desc="pairwise distance + batched NJ, 2000 taxa x 256 embeddings (configs[3])"),
     "c5": dict(S=500, L=1000000, B=1, D=5, desc="long alignment, 500 taxa x 1M patterns, fwd+grad (configs[4]; one GPU holds L/world)"),
@@ -367,7 +368,19 @@ def run_side(args):
     out = {"side": args.side, "config": cfg["desc"], "n_gpus": world}
     S, B, D = cfg["S"], cfg["B"], cfg["D"]
     rng = np.random.default_rng(7)
-    if args.side == "c4":
+    if args.side == "c1":
+        from dodonaphy_b200.pipeline import GraphedStep
+
+        prob = synth.make_problem(S, cfg["L"], 8, D=D, seed=1001)
+        hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69())
+        xs = torch.as_tensor(prob["xs"]).cuda()
+        chains, samples = xs[:B].contiguous(), xs
+        g_mcmc, g_vi = GraphedStep(hp, chains, grad=False), GraphedStep(hp, samples, grad=True)
+        out["mcmc_sweep_ms"] = timed(lambda: hp.value(chains), 200)
+        out["mcmc_sweep_graph_ms"] = timed(lambda: g_mcmc.run(chains), 200)
+        out["vi_step_ms"] = timed(lambda: hp.value_and_grad(samples), 200)
+        out["vi_step_graph_ms"] = timed(lambda: g_vi.run(samples), 200)
+    elif args.side == "c4":
         lo, hi = ddist.shard_bounds(B, rank, world)
         xs = torch.as_tensor(rng.normal(0, 0.05, (B, S, D))[lo:hi]).cuda()
         pdm = engine.pdm_forward(xs, -1.0, "torch")

@@ -118,3 +118,35 @@ class HotPath:
         out_ll_pinned.copy_(r["lnL"], non_blocking=True)
         out_gx_pinned.copy_(r["grad_x"], non_blocking=True)
         return r
+
+
+class GraphedStep:
+    """One step of the path captured ONCE as a CUDA graph and replayed.
+
+    Small problems (the reference's own DS1 case: 27 taxa x 934 patterns, a handful of chains) are
+    launch-bound: ~10 kernels of a few microseconds each behind Python / ctypes call overhead.  The
+    whole step -- every launch between the input buffer and the outputs -- is recorded into a graph on
+    first use; ``run(x)`` copies the new locations into the captured input buffer and replays.  The
+    substitution model, rates, temperature and curvature are baked in at capture time (they travel as
+    kernel parameters): capture again after changing them.  Outputs are the captured tensors,
+    overwritten by every replay.
+    """
+
+    def __init__(self, hot, x_example, grad=True):
+        self.hot = hot
+        self.x = x_example.detach().to(hot.device, dtype=torch.float64).contiguous().clone()
+        fn = hot.value_and_grad if grad else hot.value
+        side = torch.cuda.Stream(device=hot.device)
+        side.wait_stream(torch.cuda.current_stream(hot.device))
+        with torch.cuda.stream(side):  # warm-up off the capture: workspaces, plans, function attributes
+            for _ in range(2):
+                fn(self.x)
+        torch.cuda.current_stream(hot.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(self.x)
+
+    def run(self, x):
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -430,3 +430,25 @@ def test_laplace_hessian_matches_double_backward_oracle():
     out = m.laplace(n_samples=8) if bool((torch.linalg.eigvalsh(-H) > 0).all()) else None
     if out is not None:
         assert out["peel"].shape == (8, S - 1, 3) and np.isfinite(out["ln_p"]).all()
+
+
+def test_graphed_step_replays_the_whole_path():
+    """pipeline.GraphedStep: the captured CUDA graph returns what the launch-by-launch path returns,
+    for the capture input and for fresh inputs (both the gradient and the gradient-free route)."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import GraphedStep, HotPath
+
+    S, D, L, B = 27, 3, 934, 4
+    prob = synth.make_problem(S, L, B, D=D, seed=123)
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69())
+    x0 = torch.tensor(prob["xs"]).cuda()
+    x1 = x0 + 0.01 * torch.randn_like(x0)
+    for grad in (True, False):
+        step = GraphedStep(hp, x0, grad=grad)
+        for x in (x0, x1, x0):
+            got = {k: v.clone() for k, v in step.run(x).items()}
+            ref = hp.value_and_grad(x) if grad else hp.value(x)
+            torch.cuda.synchronize()
+            for k in ("lnL", "peel", "blens") + (("grad_x",) if grad else ()):
+                assert torch.equal(got[k], ref[k]), (grad, k)
