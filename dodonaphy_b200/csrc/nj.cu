@@ -1085,7 +1085,13 @@ extern "C" uint64_t dodo_nj_workspace_bytes(int B, int S) {
 
 // CTA size by taxon count (measured on B200: 16-500 taxa, 64-128 trees per launch): the per-join scans
 // want many threads long before the matrix is large
-static int nj_threads(int S) { return S <= 32 ? 256 : (S <= 128 ? 512 : 1024); }
+static int nj_threads(int S, int B = 1) {
+    const int t = S <= 32 ? 256 : (S <= 128 ? 512 : 1024);
+    // more trees than SMs: two 512-thread CTAs share an SM instead of queueing a second round of
+    // 1024-thread CTAs behind the first
+    if (t == 1024 && B > sm_count()) return 512;
+    return t;
+}
 
 extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
                             void *stream_) {
@@ -1095,7 +1101,7 @@ extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64
     size_t smem = 2 * (size_t)nj_ld(S) * sizeof(double) + 3 * (size_t)nj_ld(S) * sizeof(int);
     if (smem > 48 * 1024)
         DODO_CUDA(cudaFuncSetAttribute(nj_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_hard_kernel<<<B, nj_threads(S), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens);
+    nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }
@@ -1111,7 +1117,7 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
     size_t smem = (2 * (size_t)nj_ld(S) + 32) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
     if (smem > 48 * 1024)
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_soft_kernel<<<B, nj_threads(S), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);
+    nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

@@ -452,3 +452,31 @@ def test_graphed_step_replays_the_whole_path():
             torch.cuda.synchronize()
             for k in ("lnL", "peel", "blens") + (("grad_x",) if grad else ()):
                 assert torch.equal(got[k], ref[k]), (grad, k)
+
+
+def test_host_buffer_entry_point_graph_and_plain_agree():
+    """HotPath.value_and_grad_host: pinned host buffers in and out; the CUDA-graph replay and the
+    launch-by-launch path write identical results, also after the model changes (re-capture)."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    S, D, L, B = 12, 3, 300, 6
+    prob = synth.make_problem(S, L, B, D=D, seed=124)
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.gtr(prob["rates"], prob["freqs"]),
+                 rates=SubstModel.discrete_gamma(0.5, 4), mix=True)
+    x = torch.tensor(prob["xs"]).pin_memory()
+    outs = {}
+    for model in (hp.model, SubstModel.jc69()):
+        hp.model = model
+        for graph in (True, False, True):
+            ll = torch.empty(B, dtype=torch.float64).pin_memory()
+            gx = torch.empty((B, S, D), dtype=torch.float64).pin_memory()
+            hp.value_and_grad_host(x, ll, gx, graph=graph)
+            torch.cuda.synchronize()
+            outs.setdefault(model.kind, []).append((ll.clone(), gx.clone()))
+    for runs in outs.values():
+        for ll, gx in runs[1:]:
+            assert torch.equal(ll, runs[0][0]) and torch.equal(gx, runs[0][1])
+    kinds = list(outs)
+    assert not torch.equal(outs[kinds[0]][0][0], outs[kinds[1]][0][0])  # the model change was picked up
