@@ -202,5 +202,6 @@ class BaseModel:
         """MCMC: (B,S,D) proposals (one per chain) -> (lnL, peel, blens) as NumPy arrays, no gradient."""
         hot = self._hotpath()
         hot.curvature = float(self.curvature)
-        out = hot.value(torch.as_tensor(np.ascontiguousarray(locs, dtype=np.float64)).to(hot.device))
+        x = torch.as_tensor(np.ascontiguousarray(locs, dtype=np.float64))
+        out = hot.graphed(x, grad=False).run(x)  # every sweep has the same shape: replay one CUDA graph
         return out["lnL"].cpu().numpy(), out["peel"].cpu().numpy(), out["blens"].cpu().numpy()

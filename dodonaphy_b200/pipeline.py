@@ -114,7 +114,18 @@ class HotPath:
     # end-to-end call with host buffers (what a reference-side caller holding NumPy/CPU tensors does)
     def _fingerprint(self, shape):
         return (tuple(shape), bytes(self.model.c_struct()), None if self.rates is None else self.rates.tobytes(),
-                self.mix, float(self.tau), float(self.curvature), self.lift, self.matsumoto, self.connector)
+                self.mix, None if self.tau is None else float(self.tau), float(self.curvature), self.lift,
+                self.matsumoto, self.connector)
+
+    def graphed(self, x, grad):
+        """The step for inputs shaped like ``x`` as a captured CUDA graph (one live capture per
+        gradient / gradient-free route, re-captured when shape, model or settings change)."""
+        key = self._fingerprint(x.shape)
+        cache = self.__dict__.setdefault("_graphs", {})
+        hit = cache.get(bool(grad))
+        if hit is None or hit[0] != key:
+            hit = cache[bool(grad)] = (key, GraphedStep(self, x.to(self.device), grad=grad))
+        return hit[1]
 
     def value_and_grad_host(self, x_pinned, out_ll_pinned, out_gx_pinned, graph=True):
         """Host buffers in, host buffers out: pinned (B,S,D) locations -> lnL (B,) and d lnL/d locations
@@ -123,13 +134,7 @@ class HotPath:
         replayed, so a caller that synchronises every step pays ~3 API calls instead of the Python
         launch sequence; ``graph=False`` launches kernel by kernel."""
         if graph:
-            key = self._fingerprint(x_pinned.shape)
-            cache = self.__dict__.setdefault("_graphs", {})
-            step = cache.get(key)
-            if step is None:
-                cache.clear()  # one live capture: its buffers are sized for this shape
-                step = cache[key] = GraphedStep(self, x_pinned.to(self.device), grad=True)
-            r = step.run(x_pinned)
+            r = self.graphed(x_pinned, grad=True).run(x_pinned)
         else:
             r = self.value_and_grad(x_pinned.to(self.device, non_blocking=True))
         out_ll_pinned.copy_(r["lnL"], non_blocking=True)
