@@ -1,5 +1,5 @@
 import torch, numpy as np, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repository root
 from dodonaphy_b200 import engine
 S, B = 2000, 148
 xs = torch.as_tensor(np.random.default_rng(7).normal(0, 0.05, (B, S, 5))).cuda()

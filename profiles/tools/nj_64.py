@@ -1,5 +1,5 @@
 import torch, numpy as np, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repository root
 from dodonaphy_b200 import engine, synth
 prob = synth.make_problem(64, 100, 128, D=5, seed=1002)
 xs = torch.as_tensor(prob["xs"]).cuda()

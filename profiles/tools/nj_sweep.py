@@ -1,5 +1,5 @@
 import torch, numpy as np, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repository root
 from dodonaphy_b200 import engine
 S, B = int(sys.argv[1]), int(sys.argv[2])
 xs = torch.as_tensor(np.random.default_rng(3).normal(0, 0.05, (B, S, 5))).cuda()
