@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
     for (int n = S; n > 1; --n) {
         if (used == ld) {  // no free slot left: repack the live rows/columns densely in pool order
             const int nld = nj_ld(n);
-            for (size_t i = tid; i < (size_t)n * n; i += T) {
-                const int p = (int)(i / n), q = (int)(i - (size_t)p * n);
-                Dalt[(size_t)p * nld + q] = Dm[(size_t)act[p] * ld + act[q]];
+            for (int p = warp; p < n; p += nwarp) {
+                const double *src = Dm + (size_t)act[p] * ld;
+                double *dst = Dalt + (size_t)p * nld;
+                for (int q = lane; q < n; q += 32) dst[q] = src[act[q]];
             }
             for (int p = tid; p < n; p += T) { newd[p] = xs[act[p]]; act2[p] = id_of[act[p]]; }
             __syncthreads();
@@ -288,8 +289,13 @@ __device__ __forceinline__ double block_reduce(double v, double *sh, int op /*0 
     __syncthreads();
     if (lane == 0) sh[warp] = v;
     __syncthreads();
-    double r = sh[0];
-    for (int w = 1; w < nwarp; ++w) r = op == 0 ? r + sh[w] : (op == 1 ? fmin(r, sh[w]) : fmax(r, sh[w]));
+    // second stage: every warp folds the (<= 32) per-warp values with shuffles, in the same fixed order
+    double r = lane < nwarp ? sh[lane] : (op == 0 ? 0.0 : (op == 1 ? DBL_MAX : -DBL_MAX));
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        double o = __shfl_xor_sync(0xffffffffu, r, m);
+        r = op == 0 ? r + o : (op == 1 ? fmin(r, o) : fmax(r, o));
+    }
     return r;
 }
 
@@ -312,6 +318,15 @@ __device__ __forceinline__ double block_excl_scan(double v, double *sh, double &
     }
     total = tot;
     return off + inc - v;
+}
+
+// unravel_index (soft.py:7-10) of a (possibly fractional) flat index: row = trunc(idx / N),
+// col = fmod(idx, N).  idx - row * N is exact whenever row is the true quotient; the library fmod is
+// only needed when the rounded division lands on the wrong side of an integer.
+__device__ __forceinline__ void unravel(double idx, double N, double &rowf, double &colf) {
+    rowf = trunc(idx / N);
+    colf = fma(-rowf, N, idx);
+    if (!(colf >= 0.0 && colf < N)) colf = fmod(idx, N);
 }
 
 // exp(-a) for a >= 0; exactly 0 beyond the fp64 underflow point, without paying for the call
@@ -555,9 +570,10 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
     for (int n = S; n > 1; --n) {
         if (used == ld) {  // no free slot left: repack live rows/columns densely in pool order
             const int nld = nj_ld(n);
-            for (size_t i = tid; i < (size_t)n * n; i += T) {
-                const int p = (int)(i / n), q = (int)(i - (size_t)p * n);
-                Dalt[(size_t)p * nld + q] = Dm[(size_t)act[p] * ld + act[q]];
+            for (int p = warp; p < n; p += nwarp) {
+                const double *src = Dm + (size_t)act[p] * ld;
+                double *dst = Dalt + (size_t)p * nld;
+                for (int q = lane; q < n; q += 32) dst[q] = src[act[q]];
             }
             for (int p = tid; p < n; p += T) act2[p] = id_of[act[p]];
             __syncthreads();
@@ -586,7 +602,8 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
         if (full) soft_argmin_block<1>(c, tau, sh, idx, ok);
         else soft_argmin_block<0>(c, tau, sh, idx, ok);
         // unravel (soft.py:7-10) and round (peeler.py:196-198)
-        double rowf = trunc(idx / (double)N), colf = fmod(idx, (double)N);
+        double rowf, colf;
+        unravel(idx, (double)N, rowf, colf);
         int right = (int)rint(rowf), left = (int)rint(colf);
         int fbits = ok ? 0 : 4;
         bool bad = !(idx == idx) || right < 0 || right >= N || left < 0 || left >= N || right == left;
@@ -721,8 +738,10 @@ __global__ void __launch_bounds__(256) soft_argmin_kernel(const double *__restri
     bool ok;
     soft_argmin_block<2>(c, tau, sh, idx, ok);
     if (threadIdx.x == 0) {
-        out[blockIdx.x * 2 + 0] = trunc(idx / (double)cols);  // unravel_index (soft.py:7-10)
-        out[blockIdx.x * 2 + 1] = fmod(idx, (double)cols);
+        double rowf, colf;
+        unravel(idx, (double)cols, rowf, colf);
+        out[blockIdx.x * 2 + 0] = rowf;
+        out[blockIdx.x * 2 + 1] = colf;
     }
 }
 
@@ -903,7 +922,8 @@ __global__ void __launch_bounds__(1024) geo_soft_kernel(const double *__restrict
         double idx;
         bool ok;
         soft_argmin_block<2>(c, tau, sh, idx, ok);
-        const double rowf = trunc(idx / (double)S), colf = fmod(idx, (double)S);
+        double rowf, colf;
+        unravel(idx, (double)S, rowf, colf);
         const int f = (int)rint(rowf), g = (int)rint(colf);
         const bool bad = !(idx == idx) || f < 0 || f >= S || g < 0 || g >= S || f == g || !live[f] || !live[g];
         if (bad) {
