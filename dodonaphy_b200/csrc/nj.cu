@@ -1147,10 +1147,13 @@ extern "C" int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, c
     DODO_CHECK_ARG(d_peel && d_flags && d_grad_blens && d_ws && d_grad_pdm, "dodo_nj_soft_bwd: NULL argument");
     DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_soft_bwd: need B>=1, S>=2");
     cudaStream_t stream = (cudaStream_t)stream_;
+    // O(S) work per un-join behind four barriers: as few warps as cover the S slots
+    int bwd_threads = (S + 31) / 32 * 32;
+    bwd_threads = bwd_threads < 64 ? 64 : (bwd_threads > 1024 ? 1024 : bwd_threads);
     size_t smem = 32 * sizeof(double) + (2 * (size_t)S + (size_t)S) * sizeof(int);
     if (smem > 48 * 1024)
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_soft_bwd_kernel<<<B, nj_threads(S), smem, stream>>>(d_peel, d_flags, d_grad_blens, S, (double *)d_ws, d_grad_pdm);
+    nj_soft_bwd_kernel<<<B, bwd_threads, smem, stream>>>(d_peel, d_flags, d_grad_blens, S, (double *)d_ws, d_grad_pdm);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

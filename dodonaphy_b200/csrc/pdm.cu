@@ -82,7 +82,7 @@ __global__ void pdm_fwd_kernel(const double *__restrict__ x, const double *__res
 }
 
 // One CTA per sample; warp per row i, lanes over j; fixed-order reductions.
-__global__ void __launch_bounds__(256) pdm_bwd_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
+__global__ void __launch_bounds__(1024) pdm_bwd_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
                                                       const double *__restrict__ util, int S, int D,
                                                       const double *__restrict__ curv, int lift, int matsumoto,
                                                       const double *__restrict__ gpdm, double *__restrict__ gx,
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) pdm_bwd_kernel(const double *__restrict__
     const double *sh = sheet + (size_t)b * S * (D + 1);
     const double *ut = util + (size_t)b * S;
     const double *G = gpdm + (size_t)b * S * S;
-    __shared__ double cpart[8];
+    __shared__ double cpart[32];
     double csum = 0.0;
     for (int i = warp; i < S; i += nwarp) {
         double si[MAX_D + 1], acc[MAX_D + 1];
@@ -200,7 +200,8 @@ extern "C" int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double
     double *sheet, *util;
     int rc = run_lift(d_x, B, S, D, lift, d_ws, stream, &sheet, &util);
     if (rc != DODO_OK) return rc;
-    pdm_bwd_kernel<<<B, 256, 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_grad_pdm, d_grad_x,
+    // one warp per row of the tree's matrix: up to 32 rows in flight per CTA
+    pdm_bwd_kernel<<<B, S >= 48 ? 1024 : (S >= 16 ? 512 : 256), 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_grad_pdm, d_grad_x,
                                           d_grad_curv);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
