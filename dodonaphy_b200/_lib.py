@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_C", "libdodonaphy_b200.so")
+# DODO_LIB: load another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("DODO_LIB") or os.path.join(_PKG, "_C", "libdodonaphy_b200.so")
 
 DODO_OK, DODO_EINVAL, DODO_ECUDA, DODO_ENOTIMPL, DODO_EINEXACT = 0, -1, -2, -3, -4
 MODEL_JC69, MODEL_EIGEN = 0, 1
@@ -25,7 +26,7 @@ class PrunePlan(C.Structure):
     _fields_ = [("B", C.c_int32), ("S", C.c_int32), ("L", C.c_int32), ("K", C.c_int32),
                 ("flags", C.c_uint32), ("threads", C.c_int32), ("grid", C.c_int32),
                 ("tile_patterns", C.c_int32), ("n_tiles", C.c_int32), ("n_items", C.c_int32),
-                ("_pad", C.c_int32), ("ws_bytes", C.c_uint64),
+                ("cherry_slots", C.c_int32), ("ws_bytes", C.c_uint64),
                 ("off_ops", C.c_uint64), ("off_sched", C.c_uint64), ("off_pmat", C.c_uint64),
                 ("off_tiptab", C.c_uint64), ("off_scratch", C.c_uint64), ("off_ll_part", C.c_uint64),
                 ("off_g_part", C.c_uint64), ("off_gm_part", C.c_uint64)]

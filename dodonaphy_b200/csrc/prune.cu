@@ -58,8 +58,13 @@ __device__ __forceinline__ double uQx(const double *Q, const V4 &u, const V4 &x)
 // message comes from scratch rather than from the previous op).  The child with the larger
 // Strahler number is evaluated first, which bounds the number of simultaneously pending a-children
 // by log2(S).
+// Cherries (both children tips) that are the b-child of their parent are never written to scratch:
+// forward they stay in registers, backward they are recomputed from the two tip tables in shared
+// memory (flags bit3 on the parent: "b is a recomputed cherry"; bit4 on the cherry: "do not store").
 // ------------------------------------------------------------------------------------------
-__global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S, int4 *__restrict__ ops) {
+constexpr int FL_A_CHILD = 1, FL_ROOT = 2, FL_B_CHERRY = 8, FL_NO_STORE = 16, FL_CHERRY = 32;  // cherry id in bits 8+
+__global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S, int4 *__restrict__ ops,
+                                int *__restrict__ chop) {
     // one warp per sample: the peel is staged into shared memory by the warp, lane 0 runs the two
     // (inherently sequential) passes there, the warp writes the schedule back coalesced
     extern __shared__ __align__(16) int sched_sm[];
@@ -70,6 +75,8 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
     int4 *op = reinterpret_cast<int4 *>(sched_sm);               // [S-1] schedule being built
     int *Pl = reinterpret_cast<int *>(op + nI), *Pr = Pl + S, *Pp = Pr + S;  // peel rows
     int *Lc = Pp + S, *Rc = Lc + S, *st = Rc + S, *isz = st + S, *start = isz + S, *afl = start + S;
+    int *cho = afl + S;  // schedule position of cherry c
+    int nch = 0;
     for (int i = lane; i < nI; i += 32) {
         // memory safety for malformed input (the host shim validates and raises)
         Pl[i] = min(max((int)pl[i * 3 + 0], 0), Nn - 1);
@@ -98,7 +105,16 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
             else { a = l; bb = r; }
             const int s0 = (i == nI - 1) ? 0 : start[idx];
             const int oi = min(max(s0 + isz[idx] - 1, 0), nI - 1);
-            op[oi] = make_int4(a, bb, p, afl[idx] | ((i == nI - 1) ? 2 : 0));
+            int fl = afl[idx] | ((i == nI - 1) ? 2 : 0);
+            if (bb >= S && Lc[bb - S] < S && Rc[bb - S] < S) {
+                fl |= FL_B_CHERRY;
+                afl[bb - S] |= FL_NO_STORE;
+            }
+            if (l < S && r < S) {  // cherry: numbered in schedule order of discovery
+                fl |= FL_CHERRY | (nch << 8);
+                cho[nch++] = oi;
+            }
+            op[oi] = make_int4(a, bb, p, fl);
             if (li && ri) {
                 start[a - S] = s0;
                 start[bb - S] = s0 + isz[a - S];
@@ -108,9 +124,10 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
             }
         }
     }
-    __syncwarp();
+    nch = __shfl_sync(0xffffffffu, nch, 0);
     int4 *out = ops + (size_t)b * nI;
     for (int i = lane; i < nI; i += 32) out[i] = op[i];
+    for (int c = lane; c < S / 2; c += 32) chop[(size_t)b * (S / 2) + c] = c < nch ? cho[c] : -1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -120,10 +137,14 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
 //                 Ttip[S][5][4] : for tip edge t, the four columns of P and the row sums
 //                                 (== P . tip_partial for the masks A,C,G,T and N/?/-) }
 // ------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t tab_doubles(int S) { return (size_t)(S - 1) * 16 + (size_t)S * 20; }
+//                 Cher[chmax][25][4] : message of tabulated cherry c for every pair of tip rows
+//                                 (row of the left tip * 5 + row of the right tip), see cherry_kernel }
+__host__ __device__ inline size_t tab_doubles(int S, int chmax) {
+    return (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)chmax * 100;
+}
 
 __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens, const double *__restrict__ P_in,
-                                  int B, int S, int K, double *__restrict__ tab) {
+                                  int B, int S, int K, int eig, int chmax, double *__restrict__ tab) {
     const int E = 2 * S - 2;
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * E * K;
@@ -131,7 +152,7 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
     int k = gid % K;
     int e = (gid / K) % E;
     int b = gid / ((size_t)K * E);
-    double P[16];
+    double P[16], ex[4] = {0, 0, 0, 0};
     if (P_in != nullptr) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) P[i] = P_in[gid * 16 + i];
@@ -145,7 +166,6 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
 #pragma unroll
             for (int i = 0; i < 16; ++i) P[i] = ((i >> 2) == (i & 3)) ? pa : pb;
         } else {
-            double ex[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) ex[m] = exp(md.lam[m] * t);
 #pragma unroll
@@ -160,11 +180,15 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
                 }
         }
     }
-    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S);
+    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax);
     if (e >= S) {
         double2 *out = reinterpret_cast<double2 *>(slab + (size_t)(e - S) * 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) out[i] = make_double2(P[2 * i], P[2 * i + 1]);
+        if (eig) {  // internal edges are applied in factored form: only exp(lambda t) is read back
+            out[0] = make_double2(ex[0], ex[1]);
+            out[1] = make_double2(ex[2], ex[3]);
+        }
     } else {
         double2 *tt = reinterpret_cast<double2 *>(slab + (size_t)(S - 1) * 16 + (size_t)e * 20);
 #pragma unroll
@@ -199,7 +223,8 @@ struct PruneArgs {
     int B, S, L, K;
     int n_tiles, n_items, tile_patterns;
     int mix;
-    int jc;  // transition matrices have the JC69 structure (two distinct entries)
+    int pmode;  // how internal-edge transition matrices are applied (PM_*)
+    int ch_max; // cherries per tree whose messages are tabulated in the slab
 };
 
 constexpr int NT = 256;  // threads per CTA = site patterns per work item
@@ -209,13 +234,13 @@ constexpr int NT = 256;  // threads per CTA = site patterns per work item
 
 // Shared memory.  SMALL (tables and tip selectors resident): tables | gacc | fx | red | cx | ops | sel.
 // LARGE (big S: tables and masks stay in global memory, read through L1): gacc | fx | red | cx | ops.
-__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np) {
+__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np, int chmax) {
     const size_t nwarp = NT / 32, E = 2 * (size_t)S - 2;
-    size_t dbl = nwarp * E + (size_t)K * NT * np + nwarp + (small ? tab_doubles(S) : 0);
+    size_t dbl = nwarp * E + (size_t)K * NT * np + nwarp + (small ? tab_doubles(S, chmax) : 0);
     return (dbl + 1) & ~(size_t)1;  // keep what follows 16-byte aligned
 }
-__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np) {
-    return prune_smem_dbl(S, K, small, np) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
+__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np, int chmax) {
+    return prune_smem_dbl(S, K, small, np, chmax) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
            (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT * np : 0);
 }
 
@@ -409,6 +434,44 @@ __device__ __forceinline__ void matvec_jc(const double *P, const V4 (&x)[NP], V4
     }
 }
 
+// Eigen form (device-formed GTR matrices): P = U diag(e) V with U, V = U^-1 in the kernel-parameter
+// (constant) bank and only e = exp(lambda r t) read per edge: P x = U (e * (V x)).  32 FMAs with
+// constant operands instead of 16 FMAs behind eight shared-memory loads -- the kernel is bound by
+// shared-memory wavefronts, not by the fp64 pipe.  Agrees with (U diag(e) V) x to rounding (1e-15).
+template <bool SMALL, int NP>
+__device__ __forceinline__ void matvec_eig(const ModelDev &md, const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    const V4 e = ld4t<SMALL>(P);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const V4 v = x[q];
+        const double z0 = e.a * fma(md.Uinv[3], v.d, fma(md.Uinv[2], v.c, fma(md.Uinv[1], v.b, md.Uinv[0] * v.a)));
+        const double z1 = e.b * fma(md.Uinv[7], v.d, fma(md.Uinv[6], v.c, fma(md.Uinv[5], v.b, md.Uinv[4] * v.a)));
+        const double z2 = e.c * fma(md.Uinv[11], v.d, fma(md.Uinv[10], v.c, fma(md.Uinv[9], v.b, md.Uinv[8] * v.a)));
+        const double z3 = e.d * fma(md.Uinv[15], v.d, fma(md.Uinv[14], v.c, fma(md.Uinv[13], v.b, md.Uinv[12] * v.a)));
+        y[q].a = fma(md.U[3], z3, fma(md.U[2], z2, fma(md.U[1], z1, md.U[0] * z0)));
+        y[q].b = fma(md.U[7], z3, fma(md.U[6], z2, fma(md.U[5], z1, md.U[4] * z0)));
+        y[q].c = fma(md.U[11], z3, fma(md.U[10], z2, fma(md.U[9], z1, md.U[8] * z0)));
+        y[q].d = fma(md.U[15], z3, fma(md.U[14], z2, fma(md.U[13], z1, md.U[12] * z0)));
+    }
+}
+// P^T x = V^T (e * (U^T x))
+template <bool SMALL, int NP>
+__device__ __forceinline__ void matvecT_eig(const ModelDev &md, const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    const V4 e = ld4t<SMALL>(P);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const V4 v = x[q];
+        const double z0 = e.a * fma(md.U[12], v.d, fma(md.U[8], v.c, fma(md.U[4], v.b, md.U[0] * v.a)));
+        const double z1 = e.b * fma(md.U[13], v.d, fma(md.U[9], v.c, fma(md.U[5], v.b, md.U[1] * v.a)));
+        const double z2 = e.c * fma(md.U[14], v.d, fma(md.U[10], v.c, fma(md.U[6], v.b, md.U[2] * v.a)));
+        const double z3 = e.d * fma(md.U[15], v.d, fma(md.U[11], v.c, fma(md.U[7], v.b, md.U[3] * v.a)));
+        y[q].a = fma(md.Uinv[12], z3, fma(md.Uinv[8], z2, fma(md.Uinv[4], z1, md.Uinv[0] * z0)));
+        y[q].b = fma(md.Uinv[13], z3, fma(md.Uinv[9], z2, fma(md.Uinv[5], z1, md.Uinv[1] * z0)));
+        y[q].c = fma(md.Uinv[14], z3, fma(md.Uinv[10], z2, fma(md.Uinv[6], z1, md.Uinv[2] * z0)));
+        y[q].d = fma(md.Uinv[15], z3, fma(md.Uinv[11], z2, fma(md.Uinv[7], z1, md.Uinv[3] * z0)));
+    }
+}
+
 template <bool SMALL, int NP>
 __device__ __forceinline__ void matvec_n(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
     const V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL>(P + 4), r2 = ld4t<SMALL>(P + 8), r3 = ld4t<SMALL>(P + 12);
@@ -446,6 +509,48 @@ __device__ __forceinline__ void matvecT_n(const double *P, const V4 (&x)[NP], V4
     }
 }
 
+enum { PM_GENERIC = 0, PM_JC = 1, PM_EIG = 2 };
+// PM_EIG measured slower at 64 taxa x 10k x 128 x 4 (5.7 ms against 4.7 ms): U and U^-1 do not fit the
+// uniform register file next to Q, pi and the rates, so every use reloads them (+50 % instructions).
+#ifndef DODO_PRUNE_EIG
+#define DODO_PRUNE_EIG 0
+#endif
+// y = P x (TR = false) or P^T x (TR = true) in the way the launch selected (compile-time PM)
+template <bool SMALL, int NP, bool TR>
+__device__ __forceinline__ void apply_P(const int pmode, const ModelDev &md, const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    if (pmode == PM_JC) matvec_jc<SMALL, NP>(P, x, y);
+    else if (pmode == PM_EIG) { if (TR) matvecT_eig<SMALL, NP>(md, P, x, y); else matvec_eig<SMALL, NP>(md, P, x, y); }
+    else { if (TR) matvecT_n<SMALL, NP>(P, x, y); else matvec_n<SMALL, NP>(P, x, y); }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cherry tables: for the first chmax cherries of every tree (schedule order) the message
+// P_n (T_l[i] * T_r[j]) for each of the 5 x 5 pairs of tip-table rows, computed with exactly the
+// operations the pruning kernel would use, so that a lookup and a recomputation are interchangeable
+// bit for bit.  One thread per (sample, category, cherry, pair).
+// ------------------------------------------------------------------------------------------
+__global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restrict__ chop, int ops_batch, int B, int S,
+                              int K, int chmax, int pmode, ModelDev md, double *__restrict__ tab) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * K * chmax * 25) return;
+    const int pair = gid % 25;
+    const int c = (gid / 25) % chmax;
+    const int k = (gid / (25 * (size_t)chmax)) % K;
+    const int b = gid / (25 * (size_t)chmax * K);
+    const int ob = ops_batch == 1 ? 0 : b;
+    const int pos = chop[(size_t)ob * (S / 2) + c];
+    if (pos < 0) return;
+    const int4 o = ops[(size_t)ob * (S - 1) + pos];  // {left tip, right tip, node, flags}
+    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax);
+    const double *P = slab + (size_t)(o.z - S) * 16;
+    const double *Tl = slab + (size_t)(S - 1) * 16 + (size_t)o.x * 20 + (pair / 5) * 4;
+    const double *Tr = slab + (size_t)(S - 1) * 16 + (size_t)o.y * 20 + (pair % 5) * 4;
+    V4 x[1] = {V4{Tl[0] * Tr[0], Tl[1] * Tr[1], Tl[2] * Tr[2], Tl[3] * Tr[3]}}, y[1];
+    apply_P<false, 1, false>(pmode, md, P, x, y);
+    double *out = slab + (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)c * 100 + pair * 4;
+    out[0] = y[0].a; out[1] = y[0].b; out[2] = y[0].c; out[3] = y[0].d;
+}
+
 // MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
 // NP: site patterns per thread (1 or 2).  With NP = 2 the schedule decode, the branches, the address
 // arithmetic and -- above all -- the warp-wide fills of registers with the (warp-uniform) entries of P
@@ -458,7 +563,7 @@ __device__ __forceinline__ void matvecT_n(const double *P, const V4 (&x)[NP], V4
 //             this node is its b-child, else (a-child) fetched from scratch.
 // Latency is hidden by the resident warps plus an L2 prefetch three joins ahead in the backward
 // sweep; a register-level software pipeline was measured slower (more instructions).
-template <int MODE, bool SMALL, bool SCALE, int NP>
+template <int MODE, bool SMALL, bool SCALE, int NP, int PM>
 __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kernel(PruneArgs A, ModelDev md) {
     constexpr bool GRAD = MODE == 1;
     constexpr bool GMATS = MODE == 2;
@@ -472,16 +577,18 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
     const unsigned warp = tid >> 5;
     constexpr unsigned nwarp = NT / 32;
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
-    const bool jc = A.jc != 0;
-    const unsigned tabn = (unsigned)tab_doubles(S);
+    constexpr int pmode = PM;
+    const int ch_max = SMALL && !SCALE ? A.ch_max : 0;  // tabulated cherries (tables resident only)
+    const unsigned tabn = (unsigned)tab_doubles(S, A.ch_max);
     // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] | cx | ops | sel
     const unsigned o_gacc = SMALL ? tabn : 0u;
     const unsigned o_fx = o_gacc + nwarp * (unsigned)E;
     const unsigned o_red = o_fx + (unsigned)K * npt;
-    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP);                // int [K][npt]
+    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP, A.ch_max);      // int [K][npt]
     const unsigned o_ops = o_cx + ((unsigned)K * npt) / 2u;                         // int4 [S+2]
     const unsigned o_sel = o_ops + 2u * (unsigned)(S + 2);                          // u8 [S][npt]
     const unsigned o_T = (unsigned)(S - 1) * 16u;                                   // Ttip inside the slab
+    const unsigned o_C = o_T + (unsigned)S * 20u;                                   // Cher inside the slab
 #define GACC(i) smd[o_gacc + (i)]
 #define FX(k, q) smd[o_fx + ((unsigned)(k) * NP + (q)) * nthr + tid]
 #define RED(i) smd[o_red + (i)]
@@ -550,6 +657,27 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             const unsigned sel = SMALL ? (unsigned)SEL(t, q) : encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
             return tip_message<SMALL>(tab_at(o_T + (unsigned)t * 20u), sel);
         };
+        // tabulated cherry: one 32-byte row of its 5 x 5 table instead of two tip rows and a mat-vec
+        // (warp-uniform outcome; false when the cherry has no table or a lane holds a 2/3-state code)
+        auto cherry_lookup = [&](const int4 &oc, int q, V4 &out) -> bool {
+            if (!SMALL || SCALE) return false;
+            const int c = oc.w >> 8;
+            if (c >= ch_max) return false;
+            const unsigned ja = (unsigned)SEL(~oc.x, q) >> 4, jb = (unsigned)SEL(~oc.y, q) >> 4;
+            if (__any_sync(0xffffffffu, ja == 7u || jb == 7u)) return false;
+            out = lds4(&smd[o_C + (unsigned)c * 100u + (ja * 5u + jb) * 4u]);
+            return true;
+        };
+        // message of a cherry, recomputed exactly as the forward sweep formed it (oc = the cherry's op)
+        auto cherry_msg = [&](const int4 &oc, int q, int &cnt) -> V4 {
+            cnt = 0;
+            V4 t;
+            if (cherry_lookup(oc, q, t)) return t;
+            V4 x[1] = {vmul(tipmsg(~oc.x, q), tipmsg(~oc.y, q))}, y[1];
+            if (SCALE) scale_up(x[0], cnt);
+            apply_P<SMALL, 1, false>(pmode, md, tab_at((unsigned)oc.z * 16u), x, y);
+            return y[0];
+        };
 
         // ---------------- forward (post-order), one pass per rate category ----------------
         double fsum[NP], ll = 0.0;
@@ -591,12 +719,25 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 const int4 o = OPS(i);
                 V4 Lv[NP];
                 int cnt[NP];
-                join(o, Lv, cnt);
-                if (jc) matvec_jc<SMALL, NP>(tab_at((unsigned)o.z * 16u), Lv, Bv);
-                else matvec_n<SMALL, NP>(tab_at((unsigned)o.z * 16u), Lv, Bv);
+                bool tabulated = false;
+                if (SMALL && !SCALE && (o.w & FL_CHERRY)) {
+                    tabulated = true;
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        cnt[q] = 0;
+                        tabulated = tabulated && cherry_lookup(o, q, Lv[q]);
+                    }
+                }
+                if (tabulated) {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) Bv[q] = Lv[q];
+                } else {
+                    join(o, Lv, cnt);
+                    apply_P<SMALL, NP, false>(pmode, md, tab_at((unsigned)o.z * 16u), Lv, Bv);
+                }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) bc[q] = cnt[q];
-                if (MODE != 0 || (o.w & 1)) {
+                if ((MODE != 0 && !(o.w & FL_NO_STORE)) || (o.w & 1)) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         stg256(SCR(o.z, q), Bv[q]);
@@ -662,9 +803,19 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             if (of.x >= 0) prefetch_l2(SCR(of.x, q));
-                            if (of.y >= 0) prefetch_l2(SCR(of.y, q));
+                            if (of.y >= 0 && !(of.w & FL_B_CHERRY)) prefetch_l2(SCR(of.y, q));
                         }
                     }
+#if DODO_PF_L1
+                    {   // ... and what the next join needs from L2 into L1
+                        const int4 o1 = OPS(i - 1);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            if (o1.x >= 0) prefetch_l1(SCR(o1.x, q));
+                            if (o1.y >= 0 && !(o1.w & FL_B_CHERRY)) prefetch_l1(SCR(o1.y, q));
+                        }
+                    }
+#endif
                     if (o.w & 1) {  // a-child: its upper message was parked in its own slot by the parent
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
@@ -681,6 +832,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         if (o.x < 0) av[q] = tipmsg(~o.x, q);
                         else { av[q] = ldg256_bwd(SCR(o.x, q)); if (SCALE) ac[q] = __ldcg(CSCR(o.x, q)); }
                         if (o.y < 0) bv[q] = tipmsg(~o.y, q);
+                        else if (o.w & FL_B_CHERRY) bv[q] = cherry_msg(OPS(i - 1), q, bcn[q]);
                         else { bv[q] = ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
                         ua[q] = vmul(Wv[q], bv[q]);
                         ub[q] = vmul(Wv[q], av[q]);
@@ -701,8 +853,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     }
                     if (o.x >= 0) {
                         V4 wa[NP];
-                        if (jc) matvec_jc<SMALL, NP>(tab_at((unsigned)o.x * 16u), ua, wa);
-                        else matvecT_n<SMALL, NP>(tab_at((unsigned)o.x * 16u), ua, wa);
+                        apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.x * 16u), ua, wa);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             int ea = we[q] - bcn[q];
@@ -712,8 +863,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         }
                     }
                     if (o.y >= 0) {  // the next join (in this reversed order) is exactly node b
-                        if (jc) matvec_jc<SMALL, NP>(tab_at((unsigned)o.y * 16u), ub, Wv);
-                        else matvecT_n<SMALL, NP>(tab_at((unsigned)o.y * 16u), ub, Wv);
+                        apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.y * 16u), ub, Wv);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             we[q] -= ac[q];
@@ -744,7 +894,9 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
                     const V4 av = o.x < 0 ? tipmsg(~o.x, 0) : ldg256(SCR(o.x, 0));
-                    const V4 bv = o.y < 0 ? tipmsg(~o.y, 0) : ldg256(SCR(o.y, 0));
+                    int unused_cnt;
+                    const V4 bv = o.y < 0 ? tipmsg(~o.y, 0)
+                                          : ((o.w & FL_B_CHERRY) ? cherry_msg(OPS(i - 1), 0, unused_cnt) : ldg256(SCR(o.y, 0)));
                     const V4 Lv = vmul(av, bv);
                     V4 w;
                     if (i == nops) {
@@ -843,18 +995,43 @@ __global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, co
 }
 
 typedef void (*prune_fn_t)(PruneArgs, ModelDev);
-template <int MODE, int NP>
+template <int MODE, int NP, int PM>
 static prune_fn_t prune_pick(bool small, bool scale) {
-    if (small) return scale ? prune_kernel<MODE, true, true, NP> : prune_kernel<MODE, true, false, NP>;
-    return scale ? prune_kernel<MODE, false, true, NP> : prune_kernel<MODE, false, false, NP>;
+    if (small) return scale ? prune_kernel<MODE, true, true, NP, PM> : prune_kernel<MODE, true, false, NP, PM>;
+    return scale ? prune_kernel<MODE, false, true, NP, PM> : prune_kernel<MODE, false, false, NP, PM>;
 }
-static prune_fn_t prune_entry(int mode, bool small, bool scale, int np) {
-    if (mode == 2) return small ? prune_kernel<2, true, false, 1> : prune_kernel<2, false, false, 1>;
-    if (mode == 1) return np == 2 ? prune_pick<1, 2>(small, scale) : prune_pick<1, 1>(small, scale);
-    return np == 2 ? prune_pick<0, 2>(small, scale) : prune_pick<0, 1>(small, scale);
+template <int MODE, int NP>
+static prune_fn_t prune_pick_pm(bool small, bool scale, int pm) {
+    if (pm == PM_JC) return prune_pick<MODE, NP, PM_JC>(small, scale);
+    if (pm == PM_EIG) return prune_pick<MODE, NP, PM_EIG>(small, scale);
+    return prune_pick<MODE, NP, PM_GENERIC>(small, scale);
+}
+static prune_fn_t prune_entry(int mode, bool small, bool scale, int np, int pm) {
+    if (mode == 2) {  // d lnL/d P reads P itself: generic or JC69 forward, generic reverse sweep
+        if (pm == PM_JC) return small ? prune_kernel<2, true, false, 1, PM_JC> : prune_kernel<2, false, false, 1, PM_JC>;
+        return small ? prune_kernel<2, true, false, 1, PM_GENERIC> : prune_kernel<2, false, false, 1, PM_GENERIC>;
+    }
+#ifdef DODO_PRUNE_NP
+    if (np == 2) return mode == 1 ? prune_pick_pm<1, 2>(small, scale, pm) : prune_pick_pm<0, 2>(small, scale, pm);
+#endif
+    (void)np;
+    return mode == 1 ? prune_pick_pm<1, 1>(small, scale, pm) : prune_pick_pm<0, 1>(small, scale, pm);
 }
 // tables + selectors live in shared memory when that still leaves room for several CTAs per SM
-static bool prune_small(int S, int K, int np) { return prune_smem_bytes(S, K, true, np) <= (np == 2 ? 110 : 74) * 1024; }
+static size_t prune_small_budget(int np) { return (size_t)(np == 2 ? 110 : 74) * 1024; }
+static bool prune_small(int S, int K, int np) { return prune_smem_bytes(S, K, true, np, 0) <= prune_small_budget(np); }
+// Tabulated cherries per tree: whatever shared memory is left inside the budget that keeps the CTA
+// count per SM (100 doubles per cherry); none with rescaling (counters are not tabulated) or when
+// the tables are not resident.
+static int prune_cherry_slots(int S, int K, int np, bool small, bool scale) {
+#ifdef DODO_PRUNE_NO_CHERRY_TABLE
+    return 0;
+#endif
+    if (!small || scale) return 0;
+    const size_t left = prune_small_budget(np) - prune_smem_bytes(S, K, true, np, 0);
+    const int fit = (int)(left / 800);
+    return fit < S / 2 ? fit : S / 2;
+}
 // patterns per thread.  Two per thread halve the warp-uniform work (schedule decode, P fills) per
 // pattern but cost registers (116 vs 78 -> 2 instead of 3 CTAs per SM): measured 5.1 ms against
 // 4.75 ms at 64 taxa x 10k patterns x 128 samples x 4 categories, so one per thread is the default.
@@ -889,7 +1066,9 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     const int np = prune_np(B, L, flags);
     const bool small = prune_small(S, K, np);
     const bool scale = (flags & DODO_PRUNE_SCALE) != 0;
-    const size_t smem = prune_smem_bytes(S, K, small, np);
+    const int chmax = prune_cherry_slots(S, K, np, small, scale);
+    plan->cherry_slots = chmax;
+    const size_t smem = prune_smem_bytes(S, K, small, np, chmax);
     if (smem > 227 * 1024) {
         set_error("dodo_prune_plan: %d taxa need %zu bytes of shared memory per CTA (limit 227 KB)", S, smem);
         return DODO_ENOTIMPL;
@@ -903,7 +1082,7 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     int grid = grid_hint;
     if (grid <= 0) {
         // persistent grid: every CTA the SMs can hold at once (a multiple of the SM count)
-        prune_fn_t fn = prune_entry(prune_mode(flags), small, scale, np);
+        prune_fn_t fn = prune_entry(prune_mode(flags), small, scale, np, PM_GENERIC);  // same footprint for every PM
         if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
@@ -919,7 +1098,7 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     uint64_t off = 0;
     plan->off_ops = off;     off = align_up(off + (uint64_t)B * nI * sizeof(int4), 256);
     plan->off_sched = off;   off = align_up(off + (uint64_t)B * 6 * S * sizeof(int), 256);
-    plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S) * sizeof(double), 256);
+    plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S, chmax) * sizeof(double), 256);
     plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * threads * np * 32, 256);
     plan->off_tiptab = off;  // rescaling counters (int32 per stored message)
     if (scale) off = align_up(off + (uint64_t)grid * K * nI * threads * np * sizeof(int), 256);
@@ -964,22 +1143,31 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     md.kind = model->kind;
     for (int k = 0; k < MAX_K; ++k) md.rates[k] = (k < K) ? (rates ? rates[k] : 1.0) : 0.0;
 
+    const int pmode = d_P_in != nullptr ? PM_GENERIC
+                      : (model->kind == DODO_MODEL_JC69 ? PM_JC
+                         : ((DODO_PRUNE_EIG && !(plan->flags & DODO_PRUNE_GMATS)) ? PM_EIG : PM_GENERIC));  // d lnL/d P reads P itself
+    const int chmax = plan->cherry_slots;
     int4 *ops = (int4 *)(ws + plan->off_ops);
-    int *sched = (int *)(ws + plan->off_sched);
+    int *chop = (int *)(ws + plan->off_sched);  // [peel_batch][S/2] schedule position of cherry c
     double *tab = (double *)(ws + plan->off_pmat);
 
     {
         int nb = peel_batch;
-        (void)sched;
-        size_t sm = ((size_t)9 * S + 4) * sizeof(int) + (size_t)(S - 1) * sizeof(int4);
+        size_t sm = ((size_t)10 * S + 4) * sizeof(int) + (size_t)(S - 1) * sizeof(int4);
         if (sm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        schedule_kernel<<<nb, 32, sm, stream>>>(d_peel, nb, S, ops);
+        schedule_kernel<<<nb, 32, sm, stream>>>(d_peel, nb, S, ops, chop);
         DODO_LAUNCH_CHECK();
     }
     {
         size_t total = (size_t)B * E * K;
-        transition_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(md, d_blens, d_P_in, B, S, K, tab);
+        transition_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(md, d_blens, d_P_in, B, S, K,
+                                                                               pmode == PM_EIG ? 1 : 0, chmax, tab);
         DODO_LAUNCH_CHECK();
+        if (chmax > 0) {
+            size_t tc = (size_t)B * K * chmax * 25;
+            cherry_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, stream>>>(ops, chop, peel_batch, B, S, K, chmax, pmode, md, tab);
+            DODO_LAUNCH_CHECK();
+        }
     }
     PruneArgs A;
     A.tipmask = d_tipmask; A.ld_mask = ld_mask; A.weights = d_weights;
@@ -993,15 +1181,16 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.B = B; A.S = S; A.L = L; A.K = K;
     A.n_tiles = plan->n_tiles; A.n_items = plan->n_items; A.tile_patterns = plan->tile_patterns;
     A.mix = ((plan->flags & DODO_PRUNE_MIX) && K > 1) ? 1 : 0;
-    A.jc = (model->kind == DODO_MODEL_JC69 && d_P_in == nullptr) ? 1 : 0;
+    A.pmode = pmode;
+    A.ch_max = chmax;
     const int np = plan->tile_patterns / plan->threads;
     const bool small = prune_small(S, K, np);
-    size_t smem = prune_smem_bytes(S, K, small, np);
+    size_t smem = prune_smem_bytes(S, K, small, np, chmax);
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
     {
-        prune_fn_t fn = prune_entry(prune_mode(plan->flags), small, (plan->flags & DODO_PRUNE_SCALE) != 0, np);
+        prune_fn_t fn = prune_entry(prune_mode(plan->flags), small, (plan->flags & DODO_PRUNE_SCALE) != 0, np, pmode);
         if (smem > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<plan->grid, plan->threads, smem, stream>>>(A, md);
     }

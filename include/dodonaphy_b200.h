@@ -81,7 +81,7 @@ typedef struct {
     int32_t tile_patterns; /* site patterns per CTA work item                             */
     int32_t n_tiles;       /* ceil(L / tile_patterns)                                     */
     int32_t n_items;       /* B * n_tiles                                                 */
-    int32_t _pad;
+    int32_t cherry_slots; /* cherries per tree whose messages are tabulated (shared memory left over) */
     uint64_t ws_bytes;     /* device workspace the caller must provide                    */
     /* offsets (bytes) of the sub-buffers inside the workspace                            */
     uint64_t off_ops, off_sched, off_pmat, off_tiptab, off_scratch, off_ll_part, off_g_part, off_gm_part;
