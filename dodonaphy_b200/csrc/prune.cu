@@ -422,9 +422,12 @@ __device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0
 // P x / P^T x for NP patterns at once: every row of P is loaded once and applied to all of them
 // JC69: P = (a-b) I + b J is symmetric with two distinct entries, so P x = (a-b) x + b sum(x): one
 // 16-byte load and 8 flops instead of eight loads and 16 flops (warp-uniform runtime switch).
-template <bool SMALL, int NP>
-__device__ __forceinline__ void matvec_jc(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
-    const double2 ab = SMALL ? *reinterpret_cast<const double2 *>(P) : ldg2(P);
+template <bool SMALL>
+__device__ __forceinline__ double2 load_ab(const double *P) {
+    return SMALL ? *reinterpret_cast<const double2 *>(P) : ldg2(P);
+}
+template <int NP>
+__device__ __forceinline__ void matvec_jc_ab(const double2 ab, const V4 (&x)[NP], V4 (&y)[NP]) {
     const double amb = ab.x - ab.y;
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
@@ -432,6 +435,10 @@ __device__ __forceinline__ void matvec_jc(const double *P, const V4 (&x)[NP], V4
         const double bs = ab.y * ((v.a + v.b) + (v.c + v.d));
         y[q] = V4{fma(amb, v.a, bs), fma(amb, v.b, bs), fma(amb, v.c, bs), fma(amb, v.d, bs)};
     }
+}
+template <bool SMALL, int NP>
+__device__ __forceinline__ void matvec_jc(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
+    matvec_jc_ab<NP>(load_ab<SMALL>(P), x, y);
 }
 
 // Eigen form (device-formed GTR matrices): P = U diag(e) V with U, V = U^-1 in the kernel-parameter
@@ -579,6 +586,11 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
     const int S = A.S, K = A.K, E = 2 * S - 2, nops = S - 1;
     constexpr int pmode = PM;
     const int ch_max = SMALL && !SCALE ? A.ch_max : 0;  // tabulated cherries (tables resident only)
+    // b-child cherries are recomputed rather than stored
+#ifndef DODO_PRUNE_RECOMP_LARGE
+#define DODO_PRUNE_RECOMP_LARGE 1
+#endif
+    constexpr bool RECOMP = SMALL || DODO_PRUNE_RECOMP_LARGE;
     const unsigned tabn = (unsigned)tab_doubles(S, A.ch_max);
     // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] | cx | ops | sel
     const unsigned o_gacc = SMALL ? tabn : 0u;
@@ -731,13 +743,19 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 if (tabulated) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) Bv[q] = Lv[q];
+                } else if (pmode == PM_JC) {
+                    // issue the (a, b) load before the join: its latency would otherwise sit on the
+                    // critical path behind the rescaling branch
+                    const double2 ab = load_ab<SMALL>(tab_at((unsigned)o.z * 16u));
+                    join(o, Lv, cnt);
+                    matvec_jc_ab<NP>(ab, Lv, Bv);
                 } else {
                     join(o, Lv, cnt);
                     apply_P<SMALL, NP, false>(pmode, md, tab_at((unsigned)o.z * 16u), Lv, Bv);
                 }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) bc[q] = cnt[q];
-                if ((MODE != 0 && !(o.w & FL_NO_STORE)) || (o.w & 1)) {
+                if ((MODE != 0 && !(RECOMP && (o.w & FL_NO_STORE))) || (o.w & 1)) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         stg256(SCR(o.z, q), Bv[q]);
@@ -803,7 +821,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             if (of.x >= 0) prefetch_l2(SCR(of.x, q));
-                            if (of.y >= 0 && !(of.w & FL_B_CHERRY)) prefetch_l2(SCR(of.y, q));
+                            if (of.y >= 0 && !(RECOMP && (of.w & FL_B_CHERRY))) prefetch_l2(SCR(of.y, q));
                         }
                     }
 #if DODO_PF_L1
@@ -812,7 +830,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             if (o1.x >= 0) prefetch_l1(SCR(o1.x, q));
-                            if (o1.y >= 0 && !(o1.w & FL_B_CHERRY)) prefetch_l1(SCR(o1.y, q));
+                            if (o1.y >= 0 && !(RECOMP && (o1.w & FL_B_CHERRY))) prefetch_l1(SCR(o1.y, q));
                         }
                     }
 #endif
@@ -823,6 +841,11 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                             if (SCALE) we[q] = __ldcg(CSCR(o.z, q));
                         }
                     }
+                    double2 ab_a = make_double2(0.0, 0.0), ab_b = ab_a;
+                    if (pmode == PM_JC) {  // early, as in the forward sweep
+                        if (o.x >= 0) ab_a = load_ab<SMALL>(tab_at((unsigned)o.x * 16u));
+                        if (o.y >= 0) ab_b = load_ab<SMALL>(tab_at((unsigned)o.y * 16u));
+                    }
                     V4 av[NP], bv[NP], ua[NP], ub[NP];
                     int ac[NP], bcn[NP];
                     double ga = 0.0, gb = 0.0;
@@ -832,7 +855,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         if (o.x < 0) av[q] = tipmsg(~o.x, q);
                         else { av[q] = ldg256_bwd(SCR(o.x, q)); if (SCALE) ac[q] = __ldcg(CSCR(o.x, q)); }
                         if (o.y < 0) bv[q] = tipmsg(~o.y, q);
-                        else if (o.w & FL_B_CHERRY) bv[q] = cherry_msg(OPS(i - 1), q, bcn[q]);
+                        else if (RECOMP && (o.w & FL_B_CHERRY)) bv[q] = cherry_msg(OPS(i - 1), q, bcn[q]);
                         else { bv[q] = ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
                         ua[q] = vmul(Wv[q], bv[q]);
                         ub[q] = vmul(Wv[q], av[q]);
@@ -853,7 +876,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     }
                     if (o.x >= 0) {
                         V4 wa[NP];
-                        apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.x * 16u), ua, wa);
+                        if (pmode == PM_JC) matvec_jc_ab<NP>(ab_a, ua, wa);
+                        else apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.x * 16u), ua, wa);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             int ea = we[q] - bcn[q];
@@ -863,7 +887,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         }
                     }
                     if (o.y >= 0) {  // the next join (in this reversed order) is exactly node b
-                        apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.y * 16u), ub, Wv);
+                        if (pmode == PM_JC) matvec_jc_ab<NP>(ab_b, ub, Wv);
+                        else apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.y * 16u), ub, Wv);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             we[q] -= ac[q];
@@ -896,7 +921,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     const V4 av = o.x < 0 ? tipmsg(~o.x, 0) : ldg256(SCR(o.x, 0));
                     int unused_cnt;
                     const V4 bv = o.y < 0 ? tipmsg(~o.y, 0)
-                                          : ((o.w & FL_B_CHERRY) ? cherry_msg(OPS(i - 1), 0, unused_cnt) : ldg256(SCR(o.y, 0)));
+                                          : ((RECOMP && (o.w & FL_B_CHERRY)) ? cherry_msg(OPS(i - 1), 0, unused_cnt) : ldg256(SCR(o.y, 0)));
                     const V4 Lv = vmul(av, bv);
                     V4 w;
                     if (i == nops) {
