@@ -62,7 +62,7 @@ __host__ __device__ inline size_t nj_ws_doubles(int S) {
 // ------------------------------------------------------------------------------------------ hard
 __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
                                                        int64_t *__restrict__ peel, double *__restrict__ blens) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     double *Dm = ws + (size_t)b * nj_ws_doubles(S);
@@ -150,19 +150,25 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
         const int parent = S + (S - n);
         const int ns = used++;  // the new node's slot
         const double d12 = Dm[(size_t)sa * ld + sb];
-        // ---- distances of the new node, running row sums (Cpeeler.pyx:81-95)
+        // ---- distances of the new node, running row sums (Cpeeler.pyx:81-95); the survivors move up in
+        // the pool (pool = survivors in order, then the new node) and the new row/column is written
         for (int p = tid; p < n; p += T) {
             if (p == pa || p == pb) continue;
             const int sx = act[p];
             const double *rx = Dm + (size_t)sx * ld;
             double v1 = __dadd_rn(__dadd_rn(0.0, rx[sa]), rx[sb]);
             double dist = __dmul_rn(0.5, __dsub_rn(v1, d12));
-            newd[sx] = dist;
             double x = __dadd_rn(xs[sx], dist);
             x = __dsub_rn(x, Dm[(size_t)sa * ld + sx]);
             x = __dsub_rn(x, Dm[(size_t)sb * ld + sx]);
             xs[sx] = x;
+            const int pc = p - (p > pa) - (p > pb);
+            newd[pc] = dist;  // dense, in pool order: summed sequentially below
+            act2[pc] = sx;
+            Dm[(size_t)ns * ld + sx] = dist;
+            Dm[(size_t)sx * ld + ns] = dist;
         }
+        if (tid == 0) act2[n - 2] = ns;
         __syncthreads();
         if (tid == 0) {
             // branch lengths (Cpeeler.pyx:98-112) with the joined nodes' row sums as they stand
@@ -181,26 +187,27 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
             pl[(S - n) * 3 + 0] = n1;
             pl[(S - n) * 3 + 1] = n2;
             pl[(S - n) * 3 + 2] = parent;
-            // new node's row sum: sequential in pool order (Cpeeler.pyx:92)
+            // new node's row sum: sequential in pool order (Cpeeler.pyx:92).  One dependent add per
+            // survivor is the critical path of a join at a few hundred taxa, so the operands come
+            // from a dense array with the loads running ahead of the adds.
             double acc = 0.0;
-            for (int p = 0; p < n; ++p) {
-                if (p == pa || p == pb) continue;
-                acc = __dadd_rn(acc, newd[act[p]]);
+            const int m = n - 2;
+            int p = 0;
+#pragma unroll 2
+            for (; p + 8 <= m; p += 8) {
+                const double2 u0 = *reinterpret_cast<const double2 *>(newd + p);
+                const double2 u1 = *reinterpret_cast<const double2 *>(newd + p + 2);
+                const double2 u2 = *reinterpret_cast<const double2 *>(newd + p + 4);
+                const double2 u3 = *reinterpret_cast<const double2 *>(newd + p + 6);
+                acc = __dadd_rn(acc, u0.x); acc = __dadd_rn(acc, u0.y);
+                acc = __dadd_rn(acc, u1.x); acc = __dadd_rn(acc, u1.y);
+                acc = __dadd_rn(acc, u2.x); acc = __dadd_rn(acc, u2.y);
+                acc = __dadd_rn(acc, u3.x); acc = __dadd_rn(acc, u3.y);
             }
+            for (; p < m; ++p) acc = __dadd_rn(acc, newd[p]);
             xs[ns] = acc;
             id_of[ns] = parent;
         }
-        // pool = survivors in order, then the new node
-        for (int p = tid; p < n; p += T) {
-            if (p == pa || p == pb) continue;
-            const int sx = act[p];
-            const double dist = newd[sx];
-            Dm[(size_t)ns * ld + sx] = dist;
-            Dm[(size_t)sx * ld + ns] = dist;
-            act2[p - (p > pa) - (p > pb)] = sx;
-        }
-        if (tid == 0) act2[n - 2] = ns;
-        __syncthreads();
         for (int p = tid; p < n - 1; p += T) act[p] = act2[p];
         __syncthreads();
     }
