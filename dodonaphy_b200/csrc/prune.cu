@@ -137,8 +137,12 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
 //                 Ttip[S][5][4] : for tip edge t, the four columns of P and the row sums
 //                                 (== P . tip_partial for the masks A,C,G,T and N/?/-) }
 // ------------------------------------------------------------------------------------------
-//                 Cher[chmax][25][4] : message of tabulated cherry c for every pair of tip rows
-//                                 (row of the left tip * 5 + row of the right tip), see cherry_kernel }
+//                 Cher[chmax][4][25] : message of tabulated cherry c for every pair of tip rows, one
+//                                 plane per state; entry order cherry_entry() keeps the 16 one-hot
+//                                 pairs in distinct shared-memory banks (see cherry_kernel) }
+__host__ __device__ __forceinline__ unsigned cherry_entry(unsigned ja, unsigned jb) {  // rows 0..3 one-hot, 4 = any
+    return (ja < 4u && jb < 4u) ? ja * 4u + jb : (ja == 4u ? 16u + jb : 21u + ja);
+}
 __host__ __device__ inline size_t tab_doubles(int S, int chmax) {
     return (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)chmax * 100;
 }
@@ -554,8 +558,8 @@ __global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restric
     const double *Tr = slab + (size_t)(S - 1) * 16 + (size_t)o.y * 20 + (pair % 5) * 4;
     V4 x[1] = {V4{Tl[0] * Tr[0], Tl[1] * Tr[1], Tl[2] * Tr[2], Tl[3] * Tr[3]}}, y[1];
     apply_P<false, 1, false>(pmode, md, P, x, y);
-    double *out = slab + (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)c * 100 + pair * 4;
-    out[0] = y[0].a; out[1] = y[0].b; out[2] = y[0].c; out[3] = y[0].d;
+    double *out = slab + (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)c * 100 + cherry_entry(pair / 5, pair % 5);
+    out[0] = y[0].a; out[25] = y[0].b; out[50] = y[0].c; out[75] = y[0].d;
 }
 
 // MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
@@ -677,7 +681,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             if (c >= ch_max) return false;
             const unsigned ja = (unsigned)SEL(~oc.x, q) >> 4, jb = (unsigned)SEL(~oc.y, q) >> 4;
             if (__any_sync(0xffffffffu, ja == 7u || jb == 7u)) return false;
-            out = lds4(&smd[o_C + (unsigned)c * 100u + (ja * 5u + jb) * 4u]);
+            const double *e = &smd[o_C + (unsigned)c * 100u + cherry_entry(ja, jb)];
+            out = V4{e[0], e[25], e[50], e[75]};
             return true;
         };
         // message of a cherry, recomputed exactly as the forward sweep formed it (oc = the cherry's op)
