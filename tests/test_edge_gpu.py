@@ -154,3 +154,68 @@ def test_pdm_shapes():
     for S, D in ((1, 3), (2, 1), (5, 15), (33, 2)):
         x = rng.normal(0, 0.2, (S, D))
         np.testing.assert_allclose(engine.pdm_forward(_dev(x), -1.0).cpu().numpy(), hyp.get_pdm_torch(x), rtol=1e-10, atol=1e-13)
+
+
+def _shaped_tree(S, shape, rng):
+    """peel (S-1,3) + blens for a perfectly balanced tree (S/2 cherries, S a power of two) or a
+    caterpillar (one cherry)."""
+    peel, nxt = [], S
+    if shape == "balanced":
+        level = list(range(S))
+        while len(level) > 1:
+            up = []
+            for i in range(0, len(level), 2):
+                peel.append((level[i], level[i + 1], nxt))
+                up.append(nxt)
+                nxt += 1
+            level = up
+    else:
+        cur = 0
+        for t in range(1, S):
+            peel.append((cur, t, nxt) if t % 2 else (t, cur, nxt))
+            cur = nxt
+            nxt += 1
+    return np.asarray(peel, dtype=np.int64), rng.uniform(0.01, 0.3, 2 * S - 2)
+
+
+@pytest.mark.parametrize("shape", ["balanced", "caterpillar"])
+@pytest.mark.parametrize("model", ["JC69", "GTR"])
+def test_cherry_tables_and_recomputed_cherries(shape, model):
+    """64 taxa x 4 categories: a balanced tree has 32 cherries, more than the shared memory left
+    over can tabulate, so tabulated, recomputed and stored cherries all occur; 2 % fully ambiguous
+    cells plus a few two-state codes force the per-warp fallback of the table lookup.  Value,
+    branch-length gradient, d lnL/d P and the rescaling variant against the oracle."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+
+    rng = np.random.default_rng(11)
+    S, L, K = 64, 700, 4
+    peel, blens = _shaped_tree(S, shape, rng)
+    masks = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    masks[rng.random((S, L)) < 0.02] = 15
+    masks[rng.random((S, L)) < 0.002] = 5
+    weights = rng.integers(1, 5, size=L)
+    rates = SubstModel.discrete_gamma(0.5, K)
+    pr, pf = synth.gtr_params(rng)
+    sm = SubstModel.jc69() if model == "JC69" else SubstModel.gtr(pr, pf)
+    ref, gref = _oracle(masks, weights, peel, blens, rates, model, True, pr, pf)
+    eng = PruneEngine(masks, weights)
+    for scale in (False, True):
+        ll, g = eng.loglik(_dev(peel), _dev(blens), sm, rates=rates, mix=True, grad=True, scale=scale)
+        assert ll.item() == pytest.approx(ref, rel=1e-9)
+        np.testing.assert_allclose(g[0].cpu().numpy(), gref, rtol=1e-9, atol=1e-9 * np.abs(gref).max())
+    ll0, _ = eng.loglik(_dev(peel), _dev(blens), sm, rates=rates, mix=True, grad=False)
+    assert ll0.item() == pytest.approx(ref, rel=1e-9)
+    # caller-supplied matrices: d lnL / d P through the same cherry paths
+    from oracle import phylo
+
+    t = torch.tensor(blens)[:, None] * torch.tensor(rates)[None, :]
+    fr = torch.full([4], 0.25, dtype=torch.float64) if model == "JC69" else torch.tensor(pf)
+    mats = (phylo.jc69_p_t_torch(t) if model == "JC69" else phylo.gtr_p_t_torch(t, torch.tensor(pr), torch.tensor(pf))).detach()
+    mats = mats.reshape(2 * S - 2, K, 4, 4).clone().requires_grad_(True)
+    llm = phylo.treelikelihood_torch([torch.tensor(phylo.mask_to_partial(m)) for m in masks], torch.tensor(weights), peel, mats, fr, gamma_mix=True)
+    llm.backward()
+    out = eng.loglik_mats(_dev(peel), mats.detach()[None].cuda(), fr.numpy(), grad=True, mix=True)
+    assert out["lnL"].item() == pytest.approx(ref, rel=1e-9)
+    gm = mats.grad.numpy()
+    np.testing.assert_allclose(out["grad_mats"][0].cpu().numpy(), gm, rtol=1e-9, atol=1e-9 * np.abs(gm).max())
