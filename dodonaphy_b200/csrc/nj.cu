@@ -122,7 +122,25 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
             const int sa = act[pa];
             const double xa = xs[sa];
             const double *row = Dm + (size_t)sa * ld;
-            for (int pb = pa + 1 + lane; pb < n; pb += 32) {
+            int pb = pa + 1 + lane;
+            // four independent loads in flight per lane (the scan is otherwise latency-bound)
+            for (; pb + 96 < n; pb += 128) {
+                int sb[4];
+                double d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sb[k] = act[pb + 32 * k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = row[sb[k]];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, d[k]), xa), xs[sb[k]]);
+                    if (q < best.q) {
+                        best.q = q;
+                        best.key = ((unsigned long long)pa << 32) | (unsigned)(pb + 32 * k);
+                    }
+                }
+            }
+            for (; pb < n; pb += 32) {
                 const int sb = act[pb];
                 double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, row[sb]), xa), xs[sb]);
                 if (q < best.q) {
@@ -387,9 +405,37 @@ __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, doubl
         for (int prow = 1 + warp; prow < c.n; prow += nwarp) {
             const int srow = c.act[prow];
             const double frow = (double)c.id_of[srow] * (double)c.N;
-            for (int pcol = lane; pcol < prow; pcol += 32) {
+            const double *rowp = c.Dm + (size_t)srow * c.S;
+            const double rsr = c.rs[srow];
+            // compute_Q (peeler.py:223-248) as in soft_Q, with the row's operands hoisted
+            auto entry = [&](int scol, double dij, double dji) {
+                const double rsc = c.rs[scol];
+                const double a = (c.nm2 * dij - rsr) - rsc;
+                const double b = (c.nm2 * dji - rsc) - rsr;
+                const double q = 0.5 * (a + b);
+                // almost every entry is outside the window: the flat index (an int -> double
+                // conversion on the quarter-rate pipe) is only formed for the few that are not
+                if (q <= lm + W) visit(q, frow + (double)c.id_of[scol]);
+            };
+            int pcol = lane;
+            // four independent loads in flight per lane: one load per trip leaves the scan bound by
+            // memory latency (1 KB in flight per warp), not by bandwidth
+            for (; pcol + 96 < prow; pcol += 128) {
+                int sc[4];
+                double d[4], dt[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sc[k] = c.act[pcol + 32 * k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = rowp[sc[k]];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dt[k] = c.symmetric ? d[k] : c.Dm[(size_t)sc[k] * c.S + srow];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) entry(sc[k], d[k], dt[k]);
+            }
+            for (; pcol < prow; pcol += 32) {
                 const int scol = c.act[pcol];
-                visit(soft_Q(c, srow, scol), frow + (double)c.id_of[scol]);
+                const double dij = rowp[scol];
+                entry(scol, dij, c.symmetric ? dij : c.Dm[(size_t)scol * c.S + srow]);
             }
         }
     } else {
@@ -539,6 +585,31 @@ __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, doub
     idx_out = isum / z2;
 }
 
+// Row sums of the soft NJ state are kept as unevaluated sums hi + lo (double-double) and updated per
+// join with error-free transformations: r_x <- r_x - d(x,l) - d(x,r) + d(x,u).  The value the joins
+// see (hi) is the mathematical row sum rounded once, i.e. at least as close to it as the reference's
+// fresh torch.sum (peeler.py:240) in any summation order -- without re-reading the whole matrix
+// every join (the row-sum pass was 2/3 of the kernel's DRAM traffic at 2000 taxa).
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+}
+__device__ __forceinline__ void dd_add(double &hi, double &lo, double x) {
+    double s, e;
+    two_sum(hi, x, s, e);
+    e = __dadd_rn(e, lo);
+    hi = __dadd_rn(s, e);
+    lo = __dsub_rn(e, __dsub_rn(hi, s));
+}
+__device__ __forceinline__ void dd_add_dd(double &hi, double &lo, double xh, double xl) {
+    double s, e;
+    two_sum(hi, xh, s, e);
+    e = __dadd_rn(e, __dadd_rn(lo, xl));
+    hi = __dadd_rn(s, e);
+    lo = __dsub_rn(e, __dsub_rn(hi, s));
+}
+
 __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
                                                        double *__restrict__ blens, int32_t *__restrict__ flags) {
@@ -551,10 +622,11 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
     double *Dalt = Dm + (size_t)LD * LD;  // repack target (storage scheme: see nj_ws_doubles)
     int ld = LD, used = S;
     const double *P = pdm + (size_t)b * S * S;
-    double *rs = reinterpret_cast<double *>(smem_raw);  // [LD] by storage slot
-    double *newd = rs + LD;                             // [LD]
-    double *sh = newd + LD;                             // [32]
-    int *act = reinterpret_cast<int *>(sh + 32);        // [LD]
+    double *rs = reinterpret_cast<double *>(smem_raw);  // [LD] by storage slot: row sums (hi)
+    double *rs_lo = rs + LD;                            // [LD] ... and their low parts
+    double *newd = rs_lo + LD;                          // [LD]
+    double *sh = newd + LD;                             // [64]
+    int *act = reinterpret_cast<int *>(sh + 64);        // [LD]
     int *act2 = act + LD;                               // [LD]
     int *id_of = act2 + LD;                             // [LD]
     int *pos_of = id_of + LD;                           // [N]
@@ -573,6 +645,26 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
     for (int s = tid; s < S; s += T) { act[s] = s; id_of[s] = s; }
     for (int i = tid; i < N; i += T) pos_of[i] = i < S ? i : -1;
     __syncthreads();
+    // row sums over the active set (peeler.py:240, :261): one warp per row, compensated
+    auto row_sums = [&](int n) {
+        for (int p = warp; p < n; p += nwarp) {
+            const int sx = act[p];
+            const double *row = Dm + (size_t)sx * ld;
+            double hi = 0.0, lo = 0.0;
+            for (int q = lane; q < n; q += 32) {
+                int sy = act[q];
+                if (sy != sx) dd_add(hi, lo, row[sy]);
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double oh = __shfl_xor_sync(0xffffffffu, hi, m), ol = __shfl_xor_sync(0xffffffffu, lo, m);
+                dd_add_dd(hi, lo, oh, ol);
+            }
+            if (lane == 0) { rs[sx] = hi; rs_lo[sx] = lo; }
+        }
+        __syncthreads();
+    };
+    row_sums(S);
 
     for (int n = S; n > 1; --n) {
         if (used == ld) {  // no free slot left: repack live rows/columns densely in pool order
@@ -582,27 +674,18 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
                 double *dst = Dalt + (size_t)p * nld;
                 for (int q = lane; q < n; q += 32) dst[q] = src[act[q]];
             }
-            for (int p = tid; p < n; p += T) act2[p] = id_of[act[p]];
+            for (int p = tid; p < n; p += T) { act2[p] = id_of[act[p]]; newd[p] = rs[act[p]]; }
             __syncthreads();
-            for (int p = tid; p < n; p += T) { id_of[p] = act2[p]; act[p] = p; }
+            for (int p = tid; p < n; p += T) { id_of[p] = act2[p]; rs[p] = newd[p]; newd[p] = rs_lo[act[p]]; }
+            __syncthreads();
+            for (int p = tid; p < n; p += T) { rs_lo[p] = newd[p]; act[p] = p; }
             double *t = Dm; Dm = Dalt; Dalt = t;
             ld = nld;
             used = n;
             __syncthreads();
         }
-        // fresh row sums over the active set (peeler.py:240, :261)
-        for (int p = warp; p < n; p += nwarp) {
-            const int sx = act[p];
-            const double *row = Dm + (size_t)sx * ld;
-            double acc = 0.0;
-            for (int q = lane; q < n; q += 32) {
-                int sy = act[q];
-                if (sy != sx) acc += row[sy];
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) rs[sx] = acc;
-        }
-        __syncthreads();
+        // an asymmetric input has no single d(x, l) to take out of a row sum: recompute
+        if (!symmetric && n < S) row_sums(n);
         SoftCtx c{Dm, rs, act, id_of, pos_of, ld, N, n, (double)(n - 2), 0, symmetric};
         double idx;
         bool ok;
@@ -631,12 +714,36 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
         if (!(d_pl > DBL_EPSILON)) { fbits |= (d_pl == DBL_EPSILON) ? 0 : 1; d_pl = DBL_EPSILON; }
         double d_pr = d_lr - d_pl;
         if (!(d_pr > DBL_EPSILON)) { fbits |= (d_pr == DBL_EPSILON) ? 0 : 2; d_pr = DBL_EPSILON; }
+        double usum_h = 0.0, usum_l = 0.0;  // this thread's share of the new node's row sum
         for (int p = tid; p < n; p += T) {
             if (p == pc || p == pr) continue;
             const int sx = act[p];
-            newd[sx] = 0.5 * ((Dm[(size_t)sl * ld + sx] + Dm[(size_t)sr * ld + sx]) - d_lr);
+            const double dl = Dm[(size_t)sl * ld + sx], dr = Dm[(size_t)sr * ld + sx];
+            const double u = 0.5 * ((dl + dr) - d_lr);
+            newd[sx] = u;
+            if (symmetric) {
+                double hi = rs[sx], lo = rs_lo[sx];
+                dd_add(hi, lo, -dl);
+                dd_add(hi, lo, -dr);
+                dd_add(hi, lo, u);
+                rs[sx] = hi; rs_lo[sx] = lo;
+                dd_add(usum_h, usum_l, u);
+            }
+        }
+        if (symmetric) {  // row sum of the new node: fixed-order double-double reduction over the block
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double oh = __shfl_xor_sync(0xffffffffu, usum_h, m), ol = __shfl_xor_sync(0xffffffffu, usum_l, m);
+                dd_add_dd(usum_h, usum_l, oh, ol);
+            }
+            if (lane == 0) { sh[warp] = usum_h; sh[32 + warp] = usum_l; }
         }
         __syncthreads();
+        if (symmetric && tid == 0) {
+            double hi = 0.0, lo = 0.0;
+            for (int w = 0; w < nwarp; ++w) dd_add_dd(hi, lo, sh[w], sh[32 + w]);
+            rs[ns] = hi; rs_lo[ns] = lo;
+        }
         if (tid == 0) {
             pl[(S - n) * 3 + 0] = left;
             pl[(S - n) * 3 + 1] = right;
@@ -1126,7 +1233,7 @@ extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64
     DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_hard: need B>=1, S>=2");
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t smem = 2 * (size_t)nj_ld(S) * sizeof(double) + 3 * (size_t)nj_ld(S) * sizeof(int);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens);
     DODO_LAUNCH_CHECK();
@@ -1141,8 +1248,8 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
     cudaStream_t stream = (cudaStream_t)stream_;
     const int full = tau < 0.0 ? 1 : 0;  // negative tau selects the exhaustive N^2 enumeration
     const double t = fabs(tau);
-    size_t smem = (2 * (size_t)nj_ld(S) + 32) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
-    if (smem > 48 * 1024)
+    size_t smem = (3 * (size_t)nj_ld(S) + 64) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
+    if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);
     DODO_LAUNCH_CHECK();
@@ -1158,7 +1265,7 @@ extern "C" int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, c
     int bwd_threads = (S + 31) / 32 * 32;
     bwd_threads = bwd_threads < 64 ? 64 : (bwd_threads > 1024 ? 1024 : bwd_threads);
     size_t smem = 32 * sizeof(double) + (2 * (size_t)S + (size_t)S) * sizeof(int);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_soft_bwd_kernel<<<B, bwd_threads, smem, stream>>>(d_peel, d_flags, d_grad_blens, S, (double *)d_ws, d_grad_pdm);
     DODO_LAUNCH_CHECK();
@@ -1181,7 +1288,7 @@ extern "C" int dodo_geo_soft(const double *d_x, int B, int S, int D, double tau,
     cudaStream_t stream = (cudaStream_t)stream_;
     DODO_CUDA(cudaMemsetAsync(d_slots, 0xff, (size_t)B * (S - 1) * 2 * sizeof(int32_t), stream));
     size_t smem = (32 + GEO_MAX_D) * sizeof(double) + 2 * (size_t)S * sizeof(int);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(geo_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     geo_soft_kernel<<<B, nj_threads(S), smem, stream>>>(d_x, S, D, tau, (double *)d_ws, d_peel, d_int_locs, d_blens,
                                                         d_slots, d_tape, d_flags);
@@ -1208,7 +1315,7 @@ extern "C" int dodo_geo_hard(const double *d_sheet, int B, int S, int D1, void *
     DODO_CHECK_ARG(D1 >= 2 && D1 <= GEO_MAX_D, "dodo_geo_hard: sheet points need 2..16 coordinates");
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t smem = 32 * sizeof(double) + 32 * sizeof(unsigned long long) + 2 * (size_t)S * sizeof(int);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(geo_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     geo_hard_kernel<<<B, nj_threads(S), smem, stream>>>(d_sheet, S, D1, (double *)d_ws, d_peel, d_int_locs);
     DODO_LAUNCH_CHECK();
