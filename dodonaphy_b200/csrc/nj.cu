@@ -60,6 +60,9 @@ __host__ __device__ inline size_t nj_ws_doubles(int S) {
 }
 
 // ------------------------------------------------------------------------------------------ hard
+#ifndef HARD_MLP
+#define HARD_MLP 8
+#endif
 __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
                                                        int64_t *__restrict__ peel, double *__restrict__ blens) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -123,16 +126,16 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
             const double xa = xs[sa];
             const double *row = Dm + (size_t)sa * ld;
             int pb = pa + 1 + lane;
-            // four independent loads in flight per lane (the scan is otherwise latency-bound)
-            for (; pb + 96 < n; pb += 128) {
-                int sb[4];
-                double d[4];
+            // HARD_MLP independent loads in flight per lane (the scan is otherwise latency-bound)
+            for (; pb + 32 * (HARD_MLP - 1) < n; pb += 32 * HARD_MLP) {
+                int sb[HARD_MLP];
+                double d[HARD_MLP];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) sb[k] = act[pb + 32 * k];
+                for (int k = 0; k < HARD_MLP; ++k) sb[k] = act[pb + 32 * k];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) d[k] = row[sb[k]];
+                for (int k = 0; k < HARD_MLP; ++k) d[k] = row[sb[k]];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < HARD_MLP; ++k) {
                     const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, d[k]), xa), xs[sb[k]]);
                     if (q < best.q) {
                         best.q = q;
