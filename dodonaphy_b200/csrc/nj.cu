@@ -628,8 +628,8 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
     double *rs = reinterpret_cast<double *>(smem_raw);  // [LD] by storage slot: row sums (hi)
     double *rs_lo = rs + LD;                            // [LD] ... and their low parts
     double *newd = rs_lo + LD;                          // [LD]
-    double *sh = newd + LD;                             // [64]
-    int *act = reinterpret_cast<int *>(sh + 64);        // [LD]
+    double *sh = newd + LD;                             // [32]
+    int *act = reinterpret_cast<int *>(sh + 32);        // [LD]
     int *act2 = act + LD;                               // [LD]
     int *id_of = act2 + LD;                             // [LD]
     int *pos_of = id_of + LD;                           // [N]
@@ -717,7 +717,6 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
         if (!(d_pl > DBL_EPSILON)) { fbits |= (d_pl == DBL_EPSILON) ? 0 : 1; d_pl = DBL_EPSILON; }
         double d_pr = d_lr - d_pl;
         if (!(d_pr > DBL_EPSILON)) { fbits |= (d_pr == DBL_EPSILON) ? 0 : 2; d_pr = DBL_EPSILON; }
-        double usum_h = 0.0, usum_l = 0.0;  // this thread's share of the new node's row sum
         for (int p = tid; p < n; p += T) {
             if (p == pc || p == pr) continue;
             const int sx = act[p];
@@ -730,22 +729,19 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
                 dd_add(hi, lo, -dr);
                 dd_add(hi, lo, u);
                 rs[sx] = hi; rs_lo[sx] = lo;
-                dd_add(usum_h, usum_l, u);
             }
-        }
-        if (symmetric) {  // row sum of the new node: fixed-order double-double reduction over the block
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                const double oh = __shfl_xor_sync(0xffffffffu, usum_h, m), ol = __shfl_xor_sync(0xffffffffu, usum_l, m);
-                dd_add_dd(usum_h, usum_l, oh, ol);
-            }
-            if (lane == 0) { sh[warp] = usum_h; sh[32 + warp] = usum_l; }
         }
         __syncthreads();
-        if (symmetric && tid == 0) {
+        if (symmetric && warp == 0) {  // row sum of the new node: one warp, fixed order, double-double
             double hi = 0.0, lo = 0.0;
-            for (int w = 0; w < nwarp; ++w) dd_add_dd(hi, lo, sh[w], sh[32 + w]);
-            rs[ns] = hi; rs_lo[ns] = lo;
+            for (int p = lane; p < n; p += 32)
+                if (p != pc && p != pr) dd_add(hi, lo, newd[act[p]]);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const double oh = __shfl_xor_sync(0xffffffffu, hi, m), ol = __shfl_xor_sync(0xffffffffu, lo, m);
+                dd_add_dd(hi, lo, oh, ol);
+            }
+            if (lane == 0) { rs[ns] = hi; rs_lo[ns] = lo; }
         }
         if (tid == 0) {
             pl[(S - n) * 3 + 0] = left;
@@ -1251,7 +1247,7 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
     cudaStream_t stream = (cudaStream_t)stream_;
     const int full = tau < 0.0 ? 1 : 0;  // negative tau selects the exhaustive N^2 enumeration
     const double t = fabs(tau);
-    size_t smem = (3 * (size_t)nj_ld(S) + 64) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
+    size_t smem = (3 * (size_t)nj_ld(S) + 32) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);
