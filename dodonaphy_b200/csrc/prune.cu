@@ -16,8 +16,11 @@
 //   * the backward sweep is the same schedule reversed (a valid pre-order), carries the upper
 //     message in registers, reads each stored message once and reduces d lnL / d t_e over the 32
 //     patterns of the warp with a fixed-order butterfly -> run-to-run reproducible.
-// HBM traffic per (pattern, category): one 32 B write + one 32 B read per internal node -- about
-// half of the "materialise every partial" model used for the roofline denominator.
+//   * cherries (both children tips) that feed their parent directly are never stored: backward they
+//     are recomputed, or -- while shared memory is left -- looked up in a per-(sample, category) table
+//     of their 5 x 5 possible messages (cherry_kernel).
+// HBM traffic per (pattern, category): one 32 B write + one 32 B read per stored internal node -- about
+// 2/5 of the "materialise every partial" model used for the roofline denominator.
 #include <stdarg.h>
 #include <string.h>
 
@@ -83,7 +86,7 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
         Pr[i] = min(max((int)pl[i * 3 + 1], 0), Nn - 1);
         Pp[i] = min(max((int)pl[i * 3 + 2], S), Nn - 1);
         isz[i] = 0; afl[i] = 0; start[i] = 0; Lc[i] = 0; Rc[i] = 0; st[i] = 1;
-        op[i] = make_int4(0, 0, S + i, i == nI - 1 ? 2 : 0);
+        op[i] = make_int4(0, 0, S + i, i == nI - 1 ? FL_ROOT : 0);
     }
     __syncwarp();
     if (lane == 0) {
@@ -105,7 +108,7 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
             else { a = l; bb = r; }
             const int s0 = (i == nI - 1) ? 0 : start[idx];
             const int oi = min(max(s0 + isz[idx] - 1, 0), nI - 1);
-            int fl = afl[idx] | ((i == nI - 1) ? 2 : 0);
+            int fl = afl[idx] | ((i == nI - 1) ? FL_ROOT : 0);
             if (bb >= S && Lc[bb - S] < S && Rc[bb - S] < S) {
                 fl |= FL_B_CHERRY;
                 afl[bb - S] |= FL_NO_STORE;
@@ -118,7 +121,7 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
             if (li && ri) {
                 start[a - S] = s0;
                 start[bb - S] = s0 + isz[a - S];
-                afl[a - S] = 1;
+                afl[a - S] = FL_A_CHILD;
             } else if (bb >= S) {
                 start[bb - S] = s0;
             }
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) bc[q] = cnt[q];
-                if ((MODE != 0 && !(RECOMP && (o.w & FL_NO_STORE))) || (o.w & 1)) {
+                if ((MODE != 0 && !(RECOMP && (o.w & FL_NO_STORE))) || (o.w & FL_A_CHILD)) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         stg256(SCR(o.z, q), Bv[q]);
@@ -839,7 +842,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         }
                     }
 #endif
-                    if (o.w & 1) {  // a-child: its upper message was parked in its own slot by the parent
+                    if (o.w & FL_A_CHILD) {  // a-child: its upper message was parked in its own slot by the parent
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             Wv[q] = ldg256(SCR(o.z, q));
@@ -934,7 +937,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         gpi0 = fma(sc, Lv.a, gpi0); gpi1 = fma(sc, Lv.b, gpi1);
                         gpi2 = fma(sc, Lv.c, gpi2); gpi3 = fma(sc, Lv.d, gpi3);
                     } else {
-                        const V4 u = (o.w & 1) ? ldg256(SCR(o.z, 0)) : uprev;
+                        const V4 u = (o.w & FL_A_CHILD) ? ldg256(SCR(o.z, 0)) : uprev;
                         outer_reduce_store(u, Lv, gpart + (size_t)(o.z + S) * 16, lane);
                         w = matvecT_t<SMALL>(tab_at((unsigned)o.z * 16u), u);
                     }
