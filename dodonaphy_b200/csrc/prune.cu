@@ -270,6 +270,9 @@ __device__ __forceinline__ V4 ldg256(const V4 *p) {
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef DODO_PRUNE_PAIR_REDUCE
+#define DODO_PRUNE_PAIR_REDUCE 1
+#endif
 #ifndef DODO_PF_L2_DIST
 #define DODO_PF_L2_DIST 3
 #endif
@@ -351,6 +354,24 @@ __device__ __forceinline__ double warp_sum2(double x, double y, unsigned lane) {
     keep += shfl_xor_d(keep, 2);
     keep += shfl_xor_d(keep, 1);
     return keep;
+}
+
+// four sums at once: v0..v3 end in lanes 0, 8, 16, 24 with 6 shuffles (fixed order) -- the edge
+// gradients of two consecutive joins share one butterfly: 3 shuffles and a 5-step dependent chain
+// per join instead of 5 and 5
+__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, unsigned lane) {
+    const bool h16 = lane & 16u, h8 = lane & 8u;
+    double k0 = h16 ? v2 : v0, k1 = h16 ? v3 : v1;
+    const double s0 = h16 ? v0 : v2, s1 = h16 ? v1 : v3;
+    k0 += shfl_xor_d(s0, 16);
+    k1 += shfl_xor_d(s1, 16);
+    double r = h8 ? k1 : k0;
+    const double sn = h8 ? k0 : k1;
+    r += shfl_xor_d(sn, 8);
+    r += shfl_xor_d(r, 4);
+    r += shfl_xor_d(r, 2);
+    r += shfl_xor_d(r, 1);
+    return r;
 }
 
 // sum over the warp of the 4x4 outer products u (x) v; entry (i,j) ends in lane 2*(4i+j) and is
@@ -820,6 +841,12 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     Wv[q] = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
                     we[q] = SCALE ? (A.mix ? cmin[q] : CX(k, q)) : 0;
                 }
+                // edge gradients of two consecutive joins share one reduction (resident tables only:
+                // the large-tree variants have no registers to park a pair in)
+                constexpr bool PAIR = DODO_PRUNE_PAIR_REDUCE && SMALL;
+                double pend_ga = 0.0, pend_gb = 0.0;
+                int pend_x = 0, pend_y = 0;
+                bool have_pending = false;
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
@@ -877,10 +904,22 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         }
                         ga = __dadd_rn(ga, gaq); gb = __dadd_rn(gb, gbq);
                     }
-                    const double g2 = warp_sum2(ga, gb, lane);
-                    if ((lane & 15u) == 0u) {
-                        const int c = lane ? o.y : o.x;
-                        GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
+                    if (!PAIR) {
+                        const double g2 = warp_sum2(ga, gb, lane);
+                        if ((lane & 15u) == 0u) {
+                            const int c = lane ? o.y : o.x;
+                            GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
+                        }
+                    } else if (have_pending) {  // warp-uniform: every second join reduces its own and the parked pair
+                        const double g4 = warp_sum4(pend_ga, pend_gb, ga, gb, lane);
+                        if ((lane & 7u) == 0u) {
+                            const int c = lane == 0u ? pend_x : (lane == 8u ? pend_y : (lane == 16u ? o.x : o.y));
+                            GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g4;
+                        }
+                        have_pending = false;
+                    } else {
+                        pend_ga = ga; pend_gb = gb; pend_x = o.x; pend_y = o.y;
+                        have_pending = true;
                     }
                     if (o.x >= 0) {
                         V4 wa[NP];
@@ -902,6 +941,13 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                             we[q] -= ac[q];
                             if (SCALE) { int neg = -we[q]; scale_both(Wv[q], neg); we[q] = -neg; }
                         }
+                    }
+                }
+                if (PAIR && have_pending) {  // odd number of joins: the last pair goes alone
+                    const double g2 = warp_sum2(pend_ga, pend_gb, lane);
+                    if ((lane & 15u) == 0u) {
+                        const int c = lane ? pend_y : pend_x;
+                        GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
                     }
                 }
             }
