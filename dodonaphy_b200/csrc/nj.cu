@@ -790,15 +790,24 @@ __global__ void __launch_bounds__(1024) nj_soft_bwd_kernel(const int64_t *__rest
     const double *gb = gblens + (size_t)b * (2 * S - 2);
     double *out = gpdm + (size_t)b * S * S;
 
+    __shared__ int t_last;
     for (size_t i = tid; i < (size_t)S * S; i += T) Ab[i] = 0.0;
     for (int s = tid; s < S; s += T) { st_of[s] = s; active[s] = 0; }
+    if (tid == 0) t_last = 0;
     __syncthreads();
+    // the last join whose two branch lengths carry a cotangent: later joins only see zeros (one-hot
+    // cotangents of the batched Jacobian skip half of the replay on average)
+    for (int t = tid; t < S - 1; t += T)
+        if (gb[(int)pl[t * 3 + 0]] != 0.0 || gb[(int)pl[t * 3 + 1]] != 0.0) atomicMax(&t_last, t);
+    __syncthreads();
+    const int t_start = t_last;
     if (tid == 0) {
         for (int t = 0; t < S - 1; ++t) st_of[(int)pl[t * 3 + 2]] = st_of[(int)pl[t * 3 + 0]];
         active[st_of[(int)pl[(S - 2) * 3 + 2]]] = 1;
+        for (int t = S - 2; t > t_start; --t) active[st_of[(int)pl[t * 3 + 1]]] = 1;  // un-joins without adjoints
     }
     __syncthreads();
-    for (int t = S - 2; t >= 0; --t) {
+    for (int t = t_start; t >= 0; --t) {
         const int left = (int)pl[t * 3 + 0], right = (int)pl[t * 3 + 1];
         const int sl = st_of[left], sr = st_of[right];
         const int n = S - t;

@@ -100,15 +100,24 @@ __global__ void __launch_bounds__(1024) pdm_bwd_kernel(const double *__restrict_
         double si[MAX_D + 1], acc[MAX_D + 1];
         for (int d = 0; d <= D; ++d) { si[d] = sh[(size_t)i * (D + 1) + d]; acc[d] = 0.0; }
         const double ui = ut[i];
-        for (int j = lane; j < S; j += 32) {
-            if (j == i) continue;
+        // pairs without a cotangent are skipped a warp at a time (the one-hot cotangents of the batched
+        // Jacobian leave most of the matrix zero), rows without any skip their reductions as well
+        bool row_any = false;
+        for (int jb = 0; jb < S; jb += 32) {
+            const int j = jb + lane;
+            const bool use = j < S && j != i;
+            double gij = 0.0, gji = 0.0;
+            if (use) { gij = G[(size_t)i * S + j]; gji = G[(size_t)j * S + i]; }
+            const bool nz = use && (gij != 0.0 || gji != 0.0);
+            if (!__any_sync(0xffffffffu, nz)) continue;
+            row_any = true;
+            if (!nz) continue;
             const double *sj = sh + (size_t)j * (D + 1);
             const double uj = ut[j];
             double Hraw = pair_H(si, sj, D, ui, uj);
             bool live = Hraw < -TORCH_CLAMP;
             double H = fmin(Hraw, -TORCH_CLAMP);
             double D0 = sc * acosh(-H);
-            double gij = G[(size_t)i * S + j], gji = G[(size_t)j * S + i];
             if (matsumoto) { double th = tanh(D0); gij *= th; gji *= th; }
             csum += gij * D0;
             if (live) {
@@ -116,6 +125,13 @@ __global__ void __launch_bounds__(1024) pdm_bwd_kernel(const double *__restrict_
                 double ratio = uj / ui;
                 for (int d = 0; d <= D; ++d) acc[d] += gs * (sj[d] - ratio * si[d]);
             }
+        }
+        if (!row_any) {  // warp-uniform
+            if (lane == 0) {
+                double *out = gx + ((size_t)b * S + i) * D;
+                for (int d = 0; d < D; ++d) out[d] = 0.0;
+            }
+            continue;
         }
         for (int d = 0; d <= D; ++d) acc[d] = warp_sum(acc[d]);
         if (lane == 0) {
@@ -201,7 +217,9 @@ extern "C" int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double
     int rc = run_lift(d_x, B, S, D, lift, d_ws, stream, &sheet, &util);
     if (rc != DODO_OK) return rc;
     // one warp per row of the tree's matrix: up to 32 rows in flight per CTA
-    pdm_bwd_kernel<<<B, S >= 48 ? 1024 : (S >= 16 ? 512 : 256), 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_grad_pdm, d_grad_x,
+    // ... unless the batch alone fills the machine (the batched Jacobian: thousands of small trees)
+    const int bwd_threads = B >= 8 * sm_count() ? 256 : (S >= 48 ? 1024 : (S >= 16 ? 512 : 256));
+    pdm_bwd_kernel<<<B, bwd_threads, 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_grad_pdm, d_grad_x,
                                           d_grad_curv);
     DODO_LAUNCH_CHECK();
     return DODO_OK;

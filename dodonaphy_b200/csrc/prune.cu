@@ -1097,7 +1097,10 @@ static prune_fn_t prune_entry(int mode, bool small, bool scale, int np, int pm) 
     return mode == 1 ? prune_pick_pm<1, 1>(small, scale, pm) : prune_pick_pm<0, 1>(small, scale, pm);
 }
 // tables + selectors live in shared memory when that still leaves room for several CTAs per SM
-static size_t prune_small_budget(int np) { return (size_t)(np == 2 ? 110 : 74) * 1024; }
+#ifndef DODO_PRUNE_SMEM_KB
+#define DODO_PRUNE_SMEM_KB 74
+#endif
+static size_t prune_small_budget(int np) { return (size_t)(np == 2 ? 110 : DODO_PRUNE_SMEM_KB) * 1024; }
 static bool prune_small(int S, int K, int np) { return prune_smem_bytes(S, K, true, np, 0) <= prune_small_budget(np); }
 // Tabulated cherries per tree: whatever shared memory is left inside the budget that keeps the CTA
 // count per SM (100 doubles per cherry); none with rescaling (counters are not tabulated) or when
