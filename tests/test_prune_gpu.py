@@ -197,3 +197,41 @@ def test_rescaling_where_the_reference_underflows(K, mix):
     assert torch.isfinite(ll).all()
     assert ll.item() == pytest.approx(ref.item(), rel=RTOL)
     _assert_grad(g[0].cpu().numpy(), bt.grad.numpy())
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tabulated_recomputed_and_stored_cherries_agree_bit_for_bit(seed):
+    """Random tree sizes and category counts: the unscaled kernel tabulates cherries while shared
+    memory lasts, the rescaled one recomputes them -- lnL and gradient must not differ in a single bit
+    (same operations in the same order), and both must match the oracle to 1e-9."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import phylo
+
+    rng = np.random.default_rng(4000 + seed)
+    S = int(rng.integers(4, 90))
+    K = int(rng.choice([1, 2, 4, 8]))
+    L = int(rng.integers(40, 400))
+    prob = synth.make_problem(S, L, 2, D=3, seed=500 + seed)
+    prob["masks"][rng.random(prob["masks"].shape) < 0.01] = 6  # a few two-state codes
+    peels, blens = _nj_batch(prob)
+    eng = _engine(prob["masks"], prob["weights"])
+    model = SubstModel.jc69() if seed % 2 else SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(0.7, K)
+    a, ga = eng.loglik(_dev(peels), _dev(blens), model, rates=rates, mix=True, grad=True, scale=False)
+    b, gb = eng.loglik(_dev(peels), _dev(blens), model, rates=rates, mix=True, grad=True, scale=True)
+    assert torch.equal(a, b) and torch.equal(ga, gb)
+    tips = [torch.tensor(phylo.mask_to_partial(m)) for m in prob["masks"]]
+    for i in range(2):
+        bt = torch.tensor(blens[i], requires_grad=True)
+        t = bt[:, None] * torch.tensor(rates)[None, :]
+        if seed % 2:
+            mats, fr = phylo.jc69_p_t_torch(t), torch.full([4], 0.25, dtype=torch.float64)
+        else:
+            mats = phylo.gtr_p_t_torch(t, torch.tensor(prob["rates"]), torch.tensor(prob["freqs"]))
+            fr = torch.tensor(prob["freqs"])
+        ll = phylo.treelikelihood_torch(tips, torch.tensor(prob["weights"]), peels[i], mats, fr, gamma_mix=True)
+        ll.backward()
+        assert a[i].item() == pytest.approx(ll.item(), rel=1e-9)
+        g = bt.grad.numpy()
+        np.testing.assert_allclose(ga[i].cpu().numpy(), g, rtol=1e-9, atol=1e-9 * np.abs(g).max())
