@@ -251,14 +251,35 @@ __host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int
            (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT * np : 0);
 }
 
-__device__ __forceinline__ V4 lds4(const double *p) {
-    double2 x = *reinterpret_cast<const double2 *>(p), y = *reinterpret_cast<const double2 *>(p + 2);
-    return V4{x.x, x.y, y.x, y.y};
+// Table pointers.  With the tables in global memory (LARGE) a table pointer is an ordinary pointer.
+// With resident tables (SMALL) it carries a 32-bit shared-window address (see sptr()) and is only ever
+// dereferenced through ld.shared below: addressed from the `smd` symbol, every lane-dependent access
+// re-derived the window base from a special register (S2R + MOV + LEA per access, ~4 per join).
+__device__ __forceinline__ unsigned lds_u8(unsigned shared_addr) {
+    unsigned r;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(shared_addr));
+    return r;
 }
-template <bool SMALL>
-__device__ __forceinline__ V4 ld4t(const double *p) {
-    if (SMALL) return lds4(p);
-    double2 x = ldg2(p), y = ldg2(p + 2);
+__device__ __forceinline__ const double *sptr(unsigned shared_addr) {
+    return reinterpret_cast<const double *>((size_t)shared_addr);
+}
+template <int OFF>
+__device__ __forceinline__ double2 lds2(const double *p) {  // two doubles at p + OFF (shared-window address)
+    double2 r;
+    asm("ld.shared.v2.f64 {%0,%1}, [%2+%3];" : "=d"(r.x), "=d"(r.y) : "r"((unsigned)(size_t)p), "n"(OFF * 8));
+    return r;
+}
+template <int OFF>
+__device__ __forceinline__ double lds1(const double *p) {
+    double r;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(r) : "r"((unsigned)(size_t)p), "n"(OFF * 8));
+    return r;
+}
+template <bool SMALL, int OFF = 0>
+__device__ __forceinline__ V4 ld4t(const double *p) {  // four doubles at p + OFF
+    double2 x, y;
+    if (SMALL) { x = lds2<OFF>(p); y = lds2<OFF + 2>(p); }
+    else { x = ldg2(p + OFF); y = ldg2(p + OFF + 2); }
     return V4{x.x, x.y, y.x, y.y};
 }
 
@@ -296,7 +317,7 @@ __device__ __forceinline__ void stg256(V4 *p, const V4 &v) {
 // y = P x / y = P^T x with P (row-major, warp-uniform address -> broadcast)
 template <bool SMALL>
 __device__ __forceinline__ V4 matvec_t(const double *P, const V4 &x) {
-    V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL>(P + 4), r2 = ld4t<SMALL>(P + 8), r3 = ld4t<SMALL>(P + 12);
+    V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL, 4>(P), r2 = ld4t<SMALL, 8>(P), r3 = ld4t<SMALL, 12>(P);
     V4 y;
     y.a = fma(r0.d, x.d, fma(r0.c, x.c, fma(r0.b, x.b, r0.a * x.a)));
     y.b = fma(r1.d, x.d, fma(r1.c, x.c, fma(r1.b, x.b, r1.a * x.a)));
@@ -308,11 +329,11 @@ template <bool SMALL>
 __device__ __forceinline__ V4 matvecT_t(const double *P, const V4 &x) {
     V4 r = ld4t<SMALL>(P);
     V4 y{r.a * x.a, r.b * x.a, r.c * x.a, r.d * x.a};
-    r = ld4t<SMALL>(P + 4);
+    r = ld4t<SMALL, 4>(P);
     y.a = fma(r.a, x.b, y.a), y.b = fma(r.b, x.b, y.b), y.c = fma(r.c, x.b, y.c), y.d = fma(r.d, x.b, y.d);
-    r = ld4t<SMALL>(P + 8);
+    r = ld4t<SMALL, 8>(P);
     y.a = fma(r.a, x.c, y.a), y.b = fma(r.b, x.c, y.b), y.c = fma(r.c, x.c, y.c), y.d = fma(r.d, x.c, y.d);
-    r = ld4t<SMALL>(P + 12);
+    r = ld4t<SMALL, 12>(P);
     y.a = fma(r.a, x.d, y.a), y.b = fma(r.b, x.d, y.b), y.c = fma(r.c, x.d, y.c), y.d = fma(r.d, x.d, y.d);
     return y;
 }
@@ -333,12 +354,10 @@ __device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, unsigned s
     if (__any_sync(0xffffffffu, j == 7u)) {
         if (j == 7u) {  // two/three-state codes: add the columns in state order (mask 0: nothing allowed)
             v = V4{0, 0, 0, 0};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                if (sel & (1u << jj)) {
-                    V4 c = ld4t<SMALL>(T + jj * 4);
-                    v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d;
-                }
+            if (sel & 1u) { V4 c = ld4t<SMALL, 0>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 2u) { V4 c = ld4t<SMALL, 4>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 4u) { V4 c = ld4t<SMALL, 8>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 8u) { V4 c = ld4t<SMALL, 12>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
         }
     }
     return v;
@@ -452,7 +471,7 @@ __device__ __forceinline__ double pow2_256(int d) {  // 2^(256 d), flushing to 0
 // 16-byte load and 8 flops instead of eight loads and 16 flops (warp-uniform runtime switch).
 template <bool SMALL>
 __device__ __forceinline__ double2 load_ab(const double *P) {
-    return SMALL ? *reinterpret_cast<const double2 *>(P) : ldg2(P);
+    return SMALL ? lds2<0>(P) : ldg2(P);
 }
 template <int NP>
 __device__ __forceinline__ void matvec_jc_ab(const double2 ab, const V4 (&x)[NP], V4 (&y)[NP]) {
@@ -509,7 +528,7 @@ __device__ __forceinline__ void matvecT_eig(const ModelDev &md, const double *P,
 
 template <bool SMALL, int NP>
 __device__ __forceinline__ void matvec_n(const double *P, const V4 (&x)[NP], V4 (&y)[NP]) {
-    const V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL>(P + 4), r2 = ld4t<SMALL>(P + 8), r3 = ld4t<SMALL>(P + 12);
+    const V4 r0 = ld4t<SMALL>(P), r1 = ld4t<SMALL, 4>(P), r2 = ld4t<SMALL, 8>(P), r3 = ld4t<SMALL, 12>(P);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         const V4 v = x[q];
@@ -524,19 +543,19 @@ __device__ __forceinline__ void matvecT_n(const double *P, const V4 (&x)[NP], V4
     V4 r = ld4t<SMALL>(P);
 #pragma unroll
     for (int q = 0; q < NP; ++q) y[q] = V4{r.a * x[q].a, r.b * x[q].a, r.c * x[q].a, r.d * x[q].a};
-    r = ld4t<SMALL>(P + 4);
+    r = ld4t<SMALL, 4>(P);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         y[q].a = fma(r.a, x[q].b, y[q].a), y[q].b = fma(r.b, x[q].b, y[q].b);
         y[q].c = fma(r.c, x[q].b, y[q].c), y[q].d = fma(r.d, x[q].b, y[q].d);
     }
-    r = ld4t<SMALL>(P + 8);
+    r = ld4t<SMALL, 8>(P);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         y[q].a = fma(r.a, x[q].c, y[q].a), y[q].b = fma(r.b, x[q].c, y[q].b);
         y[q].c = fma(r.c, x[q].c, y[q].c), y[q].d = fma(r.d, x[q].c, y[q].d);
     }
-    r = ld4t<SMALL>(P + 12);
+    r = ld4t<SMALL, 12>(P);
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
         y[q].a = fma(r.a, x[q].d, y[q].a), y[q].b = fma(r.b, x[q].d, y[q].b);
@@ -635,9 +654,15 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #define CX(k, q) (reinterpret_cast<int *>(&smd[o_cx])[((unsigned)(k) * NP + (q)) * nthr + tid])
 #define OPS(i) (reinterpret_cast<const int4 *>(&smd[o_ops])[(i)])
 #define OPSW(i) (reinterpret_cast<int4 *>(&smd[o_ops])[(i)])
-#define SEL(t, q) (reinterpret_cast<uint8_t *>(&smd[o_sel])[((unsigned)(t) * NP + (q)) * nthr + tid])
+#define SELW(t, q) (reinterpret_cast<uint8_t *>(&smd[o_sel])[((unsigned)(t) * NP + (q)) * nthr + tid])
+#define SEL(t, q) lds_u8(sel_base + ((unsigned)(t) * NP + (q)) * nthr)
 #define SCR(node, q) (scr + ((unsigned)(node) * NP + (q)) * nthr)
 #define CSCR(node, q) (cscr + ((unsigned)(node) * NP + (q)) * nthr)
+    // shared-window address of smd, made opaque so that it lives in a register instead of being
+    // re-derived from the special register at every lane-dependent access
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(smd);
+    asm volatile("" : "+r"(sbase));
+    const unsigned sel_base = sbase + o_sel * 8u + tid;
     if (GRAD) {
         for (unsigned i = tid; i < nwarp * (unsigned)E; i += nthr) GACC(i) = 0.0;
     }
@@ -677,7 +702,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             if (SMALL) {  // tip selectors of this thread's patterns (thread-private columns)
                 for (int t = 0; t < S; ++t)
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) SEL(t, q) = (uint8_t)encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
+                    for (int q = 0; q < NP; ++q) SELW(t, q) = (uint8_t)encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
             }
         }
         const double *tabg = tab_b;  // LARGE: tables of the current category in global memory
@@ -692,7 +717,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 tabg = tab_b + (size_t)k * tabn;
             }
         };
-        auto tab_at = [&](unsigned off) -> const double * { return SMALL ? &smd[off] : tabg + off; };
+        auto tab_at = [&](unsigned off) -> const double * { return SMALL ? sptr(sbase + off * 8u) : tabg + off; };
         auto tipmsg = [&](int t, int q) -> V4 {
             const unsigned sel = SMALL ? (unsigned)SEL(t, q) : encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
             return tip_message<SMALL>(tab_at(o_T + (unsigned)t * 20u), sel);
@@ -705,8 +730,8 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             if (c >= ch_max) return false;
             const unsigned ja = (unsigned)SEL(~oc.x, q) >> 4, jb = (unsigned)SEL(~oc.y, q) >> 4;
             if (__any_sync(0xffffffffu, ja == 7u || jb == 7u)) return false;
-            const double *e = &smd[o_C + (unsigned)c * 100u + cherry_entry(ja, jb)];
-            out = V4{e[0], e[25], e[50], e[75]};
+            const double *e = sptr(sbase + (o_C + (unsigned)c * 100u + cherry_entry(ja, jb)) * 8u);
+            out = V4{lds1<0>(e), lds1<25>(e), lds1<50>(e), lds1<75>(e)};
             return true;
         };
         // message of a cherry, recomputed exactly as the forward sweep formed it (oc = the cherry's op)
@@ -1025,6 +1050,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #undef OPS
 #undef OPSW
 #undef SEL
+#undef SELW
 #undef SCR
 #undef CSCR
 }
