@@ -127,7 +127,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm (the only place bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(prob, cfg, n_trees, repeats=1):
+def cpu_reference(prob, cfg, n_trees, repeats=1, threads=None):
     """Reference CPU arithmetic for n_trees samples of the workload; returns (seconds per pass,
     description).  Topology stage: the reference's soft NJ needs 209 s and 18.8 GB per 64-taxon tree
     (SURVEY.md Appendix B), so its hard NJ (compiled Cpeeler.nj_np when available) stands in."""
@@ -135,7 +135,7 @@ def cpu_reference(prob, cfg, n_trees, repeats=1):
 
     from oracle import hyp, nj, phylo, refload
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     ref = refload.load()
     rates = torch.tensor(phylo.discrete_gamma_rates(cfg["alpha"], cfg["K"]))
     tips = [torch.tensor(phylo.mask_to_partial(m)) for m in prob["masks"]]
@@ -332,6 +332,9 @@ def run_ours(args, cfg):
             dt, desc, kind, cores = cpu_reference(prob, cfg, args.cpu_trees)
             line["cpu_baseline"] = {"value": S * L * args.cpu_trees / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": desc, "seconds": dt}
+            n1 = max(1, args.cpu_trees // 8)  # the same arithmetic on one thread (SURVEY.md 8d asks for both)
+            dt1, _, _, _ = cpu_reference(prob, cfg, n1, threads=1)
+            line["cpu_baseline"]["single_thread"] = {"value": S * L * n1 / dt1, "samples": n1, "seconds": dt1}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -426,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-trees", type=int, default=32, help="samples in the bounded CPU-baseline pass")
+    ap.add_argument("--cpu-trees", type=int, default=128, help="samples in the bounded CPU-baseline pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
