@@ -14,6 +14,7 @@
 // Matrix state lives in the caller's workspace (L2-resident: 8 S^2 bytes per tree); the active list
 // and per-node scalars live in shared memory.  Storage slot of a new node = slot of its left child.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -1228,6 +1229,10 @@ extern "C" uint64_t dodo_nj_workspace_bytes(int B, int S) {
 // CTA size by taxon count (measured on B200: 16-500 taxa, 64-128 trees per launch): the per-join scans
 // want many threads long before the matrix is large
 static int nj_threads(int S, int B = 1) {
+    if (const char *e = getenv("DODO_NJ_THREADS")) {  // tuning sweeps (profiles/tools/nj_sweep.py)
+        const int t = atoi(e);
+        if (t >= 64 && t <= 1024 && t % 32 == 0) return t;
+    }
     const int t = S <= 32 ? 256 : (S <= 128 ? 512 : 1024);
     // more trees than SMs: two 512-thread CTAs share an SM instead of queueing a second round of
     // 1024-thread CTAs behind the first
