@@ -510,7 +510,8 @@ __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, doubl
     __syncthreads();
     idx_out = sh[0];
     guard_ok = sh[1] != 0.0;
-    __syncthreads();
+    // no trailing barrier: sh and the candidate buffers are next written behind the leading barrier of a
+    // block_reduce (or the caller's own barrier), which every thread reaches only after these reads
     return true;
 }
 
@@ -718,12 +719,20 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
         if (!(d_pl > DBL_EPSILON)) { fbits |= (d_pl == DBL_EPSILON) ? 0 : 1; d_pl = DBL_EPSILON; }
         double d_pr = d_lr - d_pl;
         if (!(d_pr > DBL_EPSILON)) { fbits |= (d_pr == DBL_EPSILON) ? 0 : 2; d_pr = DBL_EPSILON; }
+        const int plo = min(pc, pr), phi = max(pc, pr);
         for (int p = tid; p < n; p += T) {
             if (p == pc || p == pr) continue;
             const int sx = act[p];
             const double dl = Dm[(size_t)sl * ld + sx], dr = Dm[(size_t)sr * ld + sx];
             const double u = 0.5 * ((dl + dr) - d_lr);
             newd[sx] = u;
+            // the survivor moves up in the pool (pool = survivors in order, then the new node) and the
+            // new node's row/column is written
+            const int p2 = p - (p > plo) - (p > phi);
+            act2[p2] = sx;
+            pos_of[id_of[sx]] = p2;
+            Dm[(size_t)ns * ld + sx] = u;
+            Dm[(size_t)sx * ld + ns] = u;
             if (symmetric) {
                 double hi = rs[sx], lo = rs_lo[sx];
                 dd_add(hi, lo, -dl);
@@ -754,23 +763,11 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
             id_of[ns] = parent;
             pos_of[left] = -1;
             pos_of[right] = -1;
-        }
-        const int plo = min(pc, pr), phi = max(pc, pr);
-        for (int p = tid; p < n; p += T) {
-            if (p == pc || p == pr) continue;
-            const int sx = act[p];
-            const double u = newd[sx];
-            Dm[(size_t)ns * ld + sx] = u;
-            Dm[(size_t)sx * ld + ns] = u;
-            act2[p - (p > plo) - (p > phi)] = sx;
-        }
-        if (tid == 0) act2[n - 2] = ns;
-        __syncthreads();
-        for (int p = tid; p < n - 1; p += T) {
-            act[p] = act2[p];
-            pos_of[id_of[act2[p]]] = p;
+            pos_of[parent] = n - 2;
+            act2[n - 2] = ns;
         }
         __syncthreads();
+        { int *t = act; act = act2; act2 = t; }  // the new pool order takes over
     }
 }
 
