@@ -812,12 +812,6 @@ __global__ void __launch_bounds__(1024) nj_soft_bwd_kernel(const int64_t *__rest
         const int f = fl[t];
         const double nact = fmax((double)n, 3.0);
         // un-join: slot sl (currently the parent) becomes `left`, slot sr becomes active as `right`
-        double usum = 0.0;
-        for (int sx = tid; sx < S; sx += T) {
-            if (!active[sx] || sx == sl) continue;
-            usum += Ab[(size_t)sl * S + sx] + Ab[(size_t)sx * S + sl];
-        }
-        usum = block_reduce(usum, sh, 0);
         double g_pl = gb[left], g_pr = gb[right];
         double g_lr = 0.0, g_rl = 0.0, g_rr = 0.0;
         if (!(f & 2)) { g_lr += g_pr; g_pl -= g_pr; }
@@ -826,15 +820,19 @@ __global__ void __launch_bounds__(1024) nj_soft_bwd_kernel(const int64_t *__rest
             g_rl = g_pl / (2.0 * (nact - 2.0));
             g_rr = -g_rl;
         }
+        // one pass: the adjoint of the parent's distances is summed (for d(l, r)) while it is handed
+        // to the two children; the reduction's barriers also publish the updates
+        double usum = 0.0;
         for (int sx = tid; sx < S; sx += T) {
             if (!active[sx] || sx == sl) continue;
             double ub = Ab[(size_t)sl * S + sx] + Ab[(size_t)sx * S + sl];
+            usum += ub;
             Ab[(size_t)sl * S + sx] = 0.5 * ub + g_rl;
             Ab[(size_t)sr * S + sx] = 0.5 * ub + g_rr;
             Ab[(size_t)sx * S + sl] = 0.0;
             Ab[(size_t)sx * S + sr] = 0.0;
         }
-        __syncthreads();
+        usum = block_reduce(usum, sh, 0);
         if (tid == 0) {
             Ab[(size_t)sl * S + sr] = -0.5 * usum + g_lr + g_rl;
             Ab[(size_t)sr * S + sl] = g_rr;
