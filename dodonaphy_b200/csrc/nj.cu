@@ -11,8 +11,11 @@
 // dodo_nj_soft_bwd  vector-Jacobian product d blens / d pdm (what torch autograd computes through
 //                the one-hot row selections of peeler.py:196-213): a reverse replay of the joins.
 //
-// Matrix state lives in the caller's workspace (L2-resident: 8 S^2 bytes per tree); the active list
-// and per-node scalars live in shared memory.  Storage slot of a new node = slot of its left child.
+// Matrix state lives in the caller's workspace (8 S^2 bytes per tree, L1/L2-resident for small trees,
+// streamed from HBM at thousands of taxa); the active list and per-node scalars live in shared memory.
+// A new node takes a fresh storage slot and live rows are repacked when the spares run out (nj_spare).
+// Both scans keep several independent matrix loads in flight per lane; the soft variant keeps its row
+// sums in double-double and updates them per join instead of re-reading the matrix (see two_sum).
 #include <float.h>
 #include <stdlib.h>
 
