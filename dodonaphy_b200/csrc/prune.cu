@@ -1108,7 +1108,9 @@ static prune_fn_t prune_pick(bool small, bool scale) {
 template <int MODE, int NP>
 static prune_fn_t prune_pick_pm(bool small, bool scale, int pm) {
     if (pm == PM_JC) return prune_pick<MODE, NP, PM_JC>(small, scale);
+#if DODO_PRUNE_EIG
     if (pm == PM_EIG) return prune_pick<MODE, NP, PM_EIG>(small, scale);
+#endif
     return prune_pick<MODE, NP, PM_GENERIC>(small, scale);
 }
 static prune_fn_t prune_entry(int mode, bool small, bool scale, int np, int pm) {
