@@ -321,7 +321,7 @@ def run_ours(args, cfg):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 8),
                         "d2h_bytes_per_step": int((ll_pin.numel() + gx_pin.numel()) * 8), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "dodo::prune_kernel<1,true,false> (fused P(t)+pruning forward + branch-length gradient)", "achieved": achieved,
+                "roofline": {"bound": "hbm", "kernel": "dodo::prune_kernel<1,true,false,1,0> (MODE=grad, resident tables, no rescaling, 1 pattern/thread, generic P: fused P(t)+pruning forward + branch-length gradient)", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                              "kernel_share_of_step": k_ms / ms_step, "traffic": traffic},
