@@ -875,6 +875,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
+#if DODO_PF_L2_DIST > 0
                     {
                         // pull what the join a few steps ahead needs out of HBM into L2
                         const int4 of = OPS(i > DODO_PF_L2_DIST ? i - DODO_PF_L2_DIST : 0);
@@ -884,6 +885,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                             if (of.y >= 0 && !(RECOMP && (of.w & FL_B_CHERRY))) prefetch_l2(SCR(of.y, q));
                         }
                     }
+#endif
 #if DODO_PF_L1
                     {   // ... and what the next join needs from L2 into L1
                         const int4 o1 = OPS(i - 1);
