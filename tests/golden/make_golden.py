@@ -12,6 +12,7 @@ Outputs (committed; small):
   pdm.npz        Chyp_torch.get_pdm / Chyp_np.get_pdm outputs + torch-autograd gradients.
   nj_hard.npz    Cpeeler.nj_np outputs.
   nj_soft.npz    peeler.nj_torch outputs + autograd gradient of a random linear functional of blens.
+  nj_soft_c2.npz the same for ONE 64-taxon tree (the headline shape; ~19 GB and minutes in the reference).
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
   charts.npz     tangent-space / sheet / ball chart changes of Chyp_torch (t02p, p2t0, ...).
@@ -209,6 +210,24 @@ def make_nj_soft(r):
     print("nj_soft cases:", n)
 
 
+def make_nj_soft_c2(r):
+    """ONE 64-taxon tree through the reference's own soft NJ (peeler.nj_torch, tau = 1e-8) at the
+    shape the headline metric is quoted on (BASELINE.json configs[1]: 64 taxa, d5; sample 0 of the
+    bench's synthetic problem).  The reference needs ~19 GB and minutes for this single tree
+    (SURVEY.md Appendix B), so it is not part of the default run: python make_golden.py nj_soft_c2"""
+    prob = synth.make_problem(64, 8, 2, D=5, seed=1002)
+    rng = np.random.default_rng(64)
+    x = prob["xs"][0]
+    pdm = r.Chyp_torch.get_pdm(torch.tensor(x)).detach().clone().requires_grad_(True)
+    peel, blens = r.peeler.nj_torch(pdm, tau=1e-8)
+    c = rng.normal(size=2 * 64 - 2)
+    (blens * torch.tensor(c)).sum().backward()
+    np.savez_compressed(os.path.join(HERE, "nj_soft_c2.npz"), x=x, pdm=pdm.detach().numpy().copy(), tau=1e-8,
+                        peel=np.asarray(peel, dtype=np.int64), blens=blens.detach().numpy().copy(), c=c,
+                        g_pdm=pdm.grad.numpy().copy())
+    print("nj_soft_c2: peel tail", np.asarray(peel)[-3:].tolist())
+
+
 def make_prune(r):
     out = {}
     cases = [(4, 40, 41), (8, 120, 42), (27, 300, 43), (64, 500, 44), (130, 200, 45)]
@@ -327,5 +346,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
+    slow = dict(nj_soft_c2=make_nj_soft_c2)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
-        makers[name](r)
+        {**makers, **slow}[name](r)

@@ -184,6 +184,22 @@ def test_nj_soft_fixtures():
         np.testing.assert_allclose(ours + ours.T, ref + ref.T, rtol=1e-9, atol=1e-12)
 
 
+def test_nj_soft_fixture_at_the_headline_size():
+    """One 64-taxon tree (the C2 shape) through the reference's own soft NJ: the restatement must give
+    the same peel, branch lengths and gradient."""
+    g = load_golden("nj_soft_c2.npz")
+    tau = float(g["tau"])
+    peel, blens = nj.nj_soft(g["pdm"], tau)
+    assert np.array_equal(peel, g["peel"])
+    np.testing.assert_allclose(blens, g["blens"], rtol=1e-12, atol=1e-15)
+    pdm = torch.tensor(g["pdm"], requires_grad=True)
+    p2, b2 = nj.nj_soft_torch(pdm, tau)
+    assert np.array_equal(p2, g["peel"])
+    (b2 * torch.tensor(g["c"])).sum().backward()
+    ours, ref = pdm.grad.numpy(), g["g_pdm"]
+    np.testing.assert_allclose(ours + ours.T, ref + ref.T, rtol=1e-9, atol=1e-12)
+
+
 def test_q_matrix_wikipedia():
     """test/test_peeler.py:228-303: Q of the 5-taxon textbook example."""
     D = np.array([[0, 5, 9, 9, 8], [5, 0, 10, 10, 9], [9, 10, 0, 8, 7], [9, 10, 8, 0, 3], [8, 9, 7, 3, 0]], dtype=np.float64)

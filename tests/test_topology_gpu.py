@@ -107,6 +107,28 @@ def test_nj_soft_reference_fixtures(exhaustive):
         np.testing.assert_allclose(2 * gp, ref + ref.T, rtol=1e-9, atol=1e-12)
 
 
+def test_nj_soft_reference_fixture_at_the_headline_size():
+    """The reference's own soft NJ on one 64-taxon tree of the C2 workload (tests/golden/nj_soft_c2.npz):
+    peel bit-exact, branch lengths and the gradient w.r.t. the distances to 1e-9; and the whole device
+    chain from the locations (distance kernel -> soft NJ) gives the same peel."""
+    from dodonaphy_b200 import engine
+
+    g = load_golden("nj_soft_c2.npz")
+    tau = float(g["tau"])
+    peel, blens, flags = engine.nj_soft(_dev(g["pdm"]), tau, return_flags=True)
+    assert int((flags & 12).sum().item()) == 0
+    assert np.array_equal(peel.cpu().numpy(), g["peel"])
+    np.testing.assert_allclose(blens.cpu().numpy(), g["blens"], rtol=1e-9, atol=1e-15)
+    gp = engine.nj_soft_backward(peel, flags, _dev(g["c"])).cpu().numpy()
+    ref = g["g_pdm"]
+    np.testing.assert_allclose(2 * gp, ref + ref.T, rtol=1e-9, atol=1e-12)
+    pdm_dev = engine.pdm_forward(_dev(g["x"]), -1.0, "torch")
+    np.testing.assert_allclose(pdm_dev.cpu().numpy(), g["pdm"], rtol=1e-10, atol=1e-14)
+    peel2, blens2 = engine.nj_soft(pdm_dev, tau)
+    assert np.array_equal(peel2.cpu().numpy().reshape(g["peel"].shape), g["peel"])
+    np.testing.assert_allclose(blens2.cpu().numpy().reshape(-1), g["blens"], rtol=1e-9, atol=1e-15)
+
+
 @pytest.mark.parametrize("S,B", [(27, 4), (64, 8), (130, 2)])
 def test_nj_soft_batched_vs_oracle(S, B):
     from dodonaphy_b200 import engine
