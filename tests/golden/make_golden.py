@@ -13,6 +13,7 @@ Outputs (committed; small):
   nj_hard.npz    Cpeeler.nj_np outputs.
   nj_soft.npz    peeler.nj_torch outputs + autograd gradient of a random linear functional of blens.
   nj_soft_c2.npz the same for ONE 64-taxon tree (the headline shape; ~19 GB and minutes in the reference).
+  prune_c2.npz   lnL + gradients of the reference at the full headline size (64 taxa x 10 000 patterns).
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
   charts.npz     tangent-space / sheet / ball chart changes of Chyp_torch (t02p, p2t0, ...).
@@ -254,6 +255,41 @@ def make_prune(r):
     print("prune cases:", n)
 
 
+def make_prune_c2(r):
+    """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
+    10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
+    four discrete-gamma rates as a category axis (the reference's broadcasting then sums the
+    per-category lnL, phylo.py:137-139).  Only the answers are stored: the alignment is regenerated
+    from the seed by the test (its checksum is stored too).  python make_golden.py prune_c2"""
+    from dodonaphy_b200.engine import SubstModel
+
+    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    masks, weights = prob["masks"], prob["weights"]
+    pdm = np.ascontiguousarray(r.Chyp_np.get_pdm(prob["xs"][0]))
+    peel, blens = r.Cpeeler.nj_np(pdm)
+    peel = np.asarray(peel, dtype=np.int64)
+    out = dict(peel=peel, blens=np.asarray(blens), rates=prob["rates"], freqs=prob["freqs"],
+               mask_sum=int(masks.astype(np.int64).sum()), mask_dot=int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()),
+               weight_sum=int(weights.sum()))
+    for name, model in (("jc", "JC69"), ("gtr", "GTR")):
+        res = ref_ll_and_grads(r, masks, weights, peel, blens, model, prob["rates"], prob["freqs"])
+        out[f"{name}_lnL"], out[f"{name}_g_blens"] = res["lnL"], res["g_blens"]
+        if model == "GTR":
+            out["gtr_g_raw_rates"], out["gtr_g_raw_freqs"] = res["g_raw_rates"], res["g_raw_freqs"]
+            out["gtr_raw_rates"], out["gtr_raw_freqs"] = res["raw_rates"], res["raw_freqs"]
+    cat = SubstModel.discrete_gamma(0.5, 4)
+    b = torch.tensor(blens, requires_grad=True)
+    pm = r.phylomodel.PhyloModel("GTR")
+    pm._freqs = pm.freqs_transform.inv(torch.tensor(prob["freqs"])).clone().detach()
+    pm._sub_rates = pm.sub_rates_transform.inv(torch.tensor(prob["rates"])).clone().detach()
+    mats = pm.get_transition_mats(b[:, None] * torch.tensor(cat)[None, :])  # (E, K, 4, 4)
+    ll = r.phylo.calculate_treelikelihood(ref_partials(r, masks), torch.tensor(weights), peel, mats, pm.freqs)
+    ll.backward()
+    out["cat_rates"], out["gtrk4_lnL"], out["gtrk4_g_blens"] = np.asarray(cat), ll.item(), b.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "prune_c2.npz"), **out)
+    print("prune_c2: lnL", out["jc_lnL"], out["gtr_lnL"], out["gtrk4_lnL"])
+
+
 def make_pdm_jac(r):
     """Chyp_np.get_pdm(..., get_jacobian=True) (Chyp_np.pyx:369-410): analytic Jacobian of the pair
     distances w.r.t. the sheet coordinates."""
@@ -346,6 +382,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, prune_c2=make_prune_c2)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

@@ -162,3 +162,45 @@ def test_c2_full_size_headline_workload():
     ok = torch.isclose(fd, an, rtol=2e-4, atol=1e-3)
     assert same or ok.float().mean().item() > 0.9
     assert ok.float().mean().item() > 0.9, (fd[:4], an[:4])
+
+
+def test_c2_full_size_against_the_reference_itself():
+    """64 taxa x 10 000 patterns (sample 0 of the bench's problem): the REFERENCE's lnL and autograd
+    gradients (tests/golden/prune_c2.npz, generated by importing the reference) for JC69, GTR and GTR
+    with the four gamma rates as the reference's category axis (per-category lnL summed) -- through
+    the engine (device-formed P) and through the reference-shaped API (caller's mats, torch autograd
+    down to the unconstrained GTR leaves).  1e-9 relative."""
+    from conftest import load_golden
+    from dodonaphy_b200 import phylo, synth
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+    from dodonaphy_b200.phylomodel import PhyloModel
+    from oracle import phylo as ophylo
+
+    g = load_golden("prune_c2.npz")
+    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    masks, weights = prob["masks"], prob["weights"]
+    assert int(masks.astype(np.int64).sum()) == int(g["mask_sum"]) and int(weights.sum()) == int(g["weight_sum"])
+    assert int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) == int(g["mask_dot"])
+    np.testing.assert_array_equal(prob["rates"], g["rates"])
+    peel, blens = g["peel"], g["blens"]
+    eng = PruneEngine(masks, weights)
+
+    def check(ll, grad, key):
+        assert ll.item() == pytest.approx(float(g[f"{key}_lnL"]), rel=1e-9)
+        ref = g[f"{key}_g_blens"]
+        np.testing.assert_allclose(grad.cpu().numpy().reshape(-1), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+    gtr = SubstModel.gtr(prob["rates"], prob["freqs"])
+    for scale in (False, True):
+        check(*eng.loglik(_dev(peel), _dev(blens), SubstModel.jc69(), grad=True, scale=scale), "jc")
+        check(*eng.loglik(_dev(peel), _dev(blens), gtr, grad=True, scale=scale), "gtr")
+        check(*eng.loglik(_dev(peel), _dev(blens), gtr, rates=g["cat_rates"], mix=False, grad=True, scale=scale), "gtrk4")
+    # the reference-shaped call: calculate_treelikelihood(partials, weights, peel, mats, freqs) + autograd
+    partials = [torch.tensor(ophylo.mask_to_partial(m)) for m in masks]
+    pm = PhyloModel("GTR", torch.tensor(prob["rates"]), torch.tensor(prob["freqs"]))
+    bt = torch.tensor(blens, requires_grad=True)
+    ll = phylo.calculate_treelikelihood(partials, torch.tensor(weights), peel, pm.get_transition_mats(bt), pm.freqs)
+    ll.backward()
+    check(ll, bt.grad, "gtr")
+    for ours, key in ((pm._sub_rates.grad, "gtr_g_raw_rates"), (pm._freqs.grad, "gtr_g_raw_freqs")):
+        np.testing.assert_allclose(ours.numpy(), g[key], rtol=1e-8, atol=1e-9 * np.abs(g[key]).max())

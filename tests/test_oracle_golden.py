@@ -200,6 +200,30 @@ def test_nj_soft_fixture_at_the_headline_size():
     np.testing.assert_allclose(ours + ours.T, ref + ref.T, rtol=1e-9, atol=1e-12)
 
 
+def test_prune_fixture_at_the_headline_size():
+    """The restatement of the pruning arithmetic against the reference's answers at 64 taxa x 10 000
+    patterns (JC69; GTR; GTR with the category axis summed as the reference's broadcasting does)."""
+    from dodonaphy_b200 import synth
+
+    g = load_golden("prune_c2.npz")
+    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    assert int(prob["masks"].astype(np.int64).sum()) == int(g["mask_sum"])
+    tips = [torch.tensor(phylo.mask_to_partial(m)) for m in prob["masks"]]
+    w = torch.tensor(prob["weights"])
+    for key, K in (("jc", 1), ("gtr", 1), ("gtrk4", 4)):
+        bt = torch.tensor(g["blens"], requires_grad=True)
+        t = bt[:, None] * (torch.tensor(g["cat_rates"]) if K == 4 else torch.ones(1, dtype=torch.float64))[None, :]
+        if key == "jc":
+            mats, fr = phylo.jc69_p_t_torch(t), torch.full([4], 0.25, dtype=torch.float64)
+        else:
+            mats, fr = phylo.gtr_p_t_torch(t, torch.tensor(g["rates"]), torch.tensor(g["freqs"])), torch.tensor(g["freqs"])
+        ll = phylo.treelikelihood_torch(tips, w, g["peel"], mats, fr, gamma_mix=False)
+        ll.backward()
+        assert ll.item() == pytest.approx(float(g[f"{key}_lnL"]), rel=1e-11)
+        ref = g[f"{key}_g_blens"]
+        np.testing.assert_allclose(bt.grad.numpy(), ref, rtol=1e-9, atol=1e-10 * np.abs(ref).max())
+
+
 def test_q_matrix_wikipedia():
     """test/test_peeler.py:228-303: Q of the 5-taxon textbook example."""
     D = np.array([[0, 5, 9, 9, 8], [5, 0, 10, 10, 9], [9, 10, 0, 8, 7], [9, 10, 8, 0, 3], [8, 9, 7, 3, 0]], dtype=np.float64)
