@@ -14,6 +14,18 @@ import numpy as np
 EPS = np.finfo(np.float64).eps
 
 
+def det_distances(S, D, seed):
+    """Euclidean distances of seeded points built from elementwise IEEE operations only (no BLAS, no
+    reductions whose order could depend on the host): the same bits on every machine, so a reference
+    answer computed elsewhere stays valid for the regenerated input (tests/golden/configs.npz)."""
+    x = np.random.default_rng(seed).normal(0.0, 1.0, (S, D))
+    acc = np.zeros((S, S))
+    for k in range(D):
+        d = x[:, None, k] - x[None, :, k]
+        acc = acc + d * d
+    return np.sqrt(acc)
+
+
 def embed_locations(S, D, rng, scale=0.05):
     return rng.normal(0.0, scale, size=(S, D))
 

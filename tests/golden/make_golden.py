@@ -14,6 +14,7 @@ Outputs (committed; small):
   nj_soft.npz    peeler.nj_torch outputs + autograd gradient of a random linear functional of blens.
   nj_soft_c2.npz the same for ONE 64-taxon tree (the headline shape; ~19 GB and minutes in the reference).
   prune_c2.npz   lnL + gradients of the reference at the full headline size (64 taxa x 10 000 patterns).
+  configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
   charts.npz     tangent-space / sheet / ball chart changes of Chyp_torch (t02p, p2t0, ...).
@@ -290,6 +291,64 @@ def make_prune_c2(r):
     print("prune_c2: lnL", out["jc_lnL"], out["gtr_lnL"], out["gtrk4_lnL"])
 
 
+det_distances = synth.det_distances  # bit-reproducible input distances (elementwise IEEE operations only)
+
+
+def configs_c5_likelihood(r, prob):
+    """500 taxa: on a tree unrelated to the alignment the reference's unscaled product underflows to
+    -inf, so the likelihood answers use the reference's own NJ tree of the sample's locations (stored;
+    the bit-reproducible 500-taxon NJ case above is separate)."""
+    pdm = np.ascontiguousarray(r.Chyp_np.get_pdm(prob["xs"][0]))
+    peel, blens = r.Cpeeler.nj_np(pdm)
+    peel = np.asarray(peel, dtype=np.int64)
+    pn = [p.numpy() for p in ref_partials(r, prob["masks"])]
+    res = ref_ll_and_grads(r, prob["masks"], prob["weights"], peel, blens, "JC69")
+    return dict(c5_ll_peel=peel, c5_ll_blens=np.asarray(blens), c5_lnL=res["lnL"], c5_g_blens=res["g_blens"],
+                c5_lnL_cython=float(r.Cphylo.compute_LL_np(pn, prob["weights"], peel, blens)))
+
+
+def make_configs_c5(r):
+    """Refresh only the 500-taxon likelihood answers inside configs.npz (seconds, not minutes)."""
+    old = dict(np.load(os.path.join(HERE, "configs.npz")))
+    prob = synth.make_problem(500, 20000, 1, D=5, seed=1005)
+    old.update(configs_c5_likelihood(r, prob))
+    print("c5 lnL", old["c5_lnL"], old["c5_lnL_cython"])
+    np.savez_compressed(os.path.join(HERE, "configs.npz"), **old)
+
+
+def make_configs(r):
+    """The reference itself at the shapes of BASELINE.json configs[2..4] (python make_golden.py configs):
+    c3  200 taxa x 20 000 patterns, JC69, two chains: Cpeeler.nj_np tree + Cphylo.compute_LL_np value;
+    c4  ONE 2000-taxon tree through Cpeeler.nj_np (minutes of Python-object arithmetic);
+    c5  500 taxa x 20 000 patterns, JC69: compute_LL_np value and the torch path's lnL + autograd gradient.
+    Distances come from det_distances (bit-reproducible input); alignments from the seeded generator."""
+    out = {}
+    prob = synth.make_problem(200, 20000, 64, D=5, seed=1003)
+    out["c3_mask_sum"] = int(prob["masks"].astype(np.int64).sum())
+    pn = [p.numpy() for p in ref_partials(r, prob["masks"])]
+    for i in range(2):
+        pdm = det_distances(200, 5, 3000 + i) * 0.05
+        peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(pdm))
+        peel = np.asarray(peel, dtype=np.int64)
+        out[f"c3_{i}_peel"], out[f"c3_{i}_blens"] = peel, np.asarray(blens)
+        out[f"c3_{i}_lnL"] = float(r.Cphylo.compute_LL_np(pn, prob["weights"], peel, blens))
+    prob = synth.make_problem(500, 20000, 1, D=5, seed=1005)
+    out["c5_mask_sum"] = int(prob["masks"].astype(np.int64).sum())
+    pdm = det_distances(500, 5, 5000) * 0.02
+    peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(pdm))
+    peel = np.asarray(peel, dtype=np.int64)
+    out["c5_peel"], out["c5_blens"] = peel, np.asarray(blens)
+    out.update(configs_c5_likelihood(r, prob))
+    print("c3 lnL", out["c3_0_lnL"], out["c3_1_lnL"], "c5 lnL", out["c5_lnL"], out["c5_lnL_cython"])
+    import time
+    t0 = time.time()
+    pdm = det_distances(2000, 5, 4000)
+    peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(pdm))
+    out["c4_peel"], out["c4_blens"] = np.asarray(peel, dtype=np.int64), np.asarray(blens)
+    print("c4: reference nj_np at 2000 taxa took %.0f s" % (time.time() - t0))
+    np.savez_compressed(os.path.join(HERE, "configs.npz"), **out)
+
+
 def make_pdm_jac(r):
     """Chyp_np.get_pdm(..., get_jacobian=True) (Chyp_np.pyx:369-410): analytic Jacobian of the pair
     distances w.r.t. the sheet coordinates."""
@@ -382,6 +441,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, prune_c2=make_prune_c2)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

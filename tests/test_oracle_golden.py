@@ -224,6 +224,21 @@ def test_prune_fixture_at_the_headline_size():
         np.testing.assert_allclose(bt.grad.numpy(), ref, rtol=1e-9, atol=1e-10 * np.abs(ref).max())
 
 
+def test_hard_nj_fixtures_at_the_config_sizes():
+    """tests/golden/configs.npz: the reference's Cpeeler.nj_np on bit-reproducible distances at 200, 500
+    and 2000 taxa -- the C restatement returns the same peel and branch lengths bit for bit."""
+    from dodonaphy_b200 import synth
+    from oracle import cbuild
+
+    g = load_golden("configs.npz")
+    cases = [(synth.det_distances(200, 5, 3000) * 0.05, "c3_0"), (synth.det_distances(200, 5, 3001) * 0.05, "c3_1"),
+             (synth.det_distances(500, 5, 5000) * 0.02, "c5"), (synth.det_distances(2000, 5, 4000), "c4")]
+    for pdm, key in cases:
+        peel, blens = cbuild.nj_hard_c(pdm)
+        assert np.array_equal(peel, g[f"{key}_peel"]), key
+        assert np.array_equal(blens, g[f"{key}_blens"]), key
+
+
 def test_q_matrix_wikipedia():
     """test/test_peeler.py:228-303: Q of the 5-taxon textbook example."""
     D = np.array([[0, 5, 9, 9, 8], [5, 0, 10, 10, 9], [9, 10, 0, 8, 7], [9, 10, 8, 0, 3], [8, 9, 7, 3, 0]], dtype=np.float64)
