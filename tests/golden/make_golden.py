@@ -14,6 +14,8 @@ Outputs (committed; small):
   nj_soft.npz    peeler.nj_torch outputs + autograd gradient of a random linear functional of blens.
   nj_soft_c2.npz the same for ONE 64-taxon tree (the headline shape; ~19 GB and minutes in the reference).
   prune_c2.npz   lnL + gradients of the reference at the full headline size (64 taxa x 10 000 patterns).
+  chain_c2.npz   one headline-size VI sample end to end in the reference: locations -> distances -> soft NJ
+                 -> GTR P(t) -> lnL, and autograd back to the locations.
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
@@ -256,6 +258,39 @@ def make_prune(r):
     print("prune cases:", n)
 
 
+def make_chain_c2(r):
+    """The whole differentiable chain of ONE headline-size VI sample through the reference:
+    locations (64 x 5) -> Chyp_torch.get_pdm -> peeler.nj_torch(tau = 1e-8) -> GTR P(t) ->
+    phylo.calculate_treelikelihood over 10 000 patterns -> torch autograd back to the locations
+    (vi.py:467-491 / base_model.py:219-247).  K = 1 and the four gamma rates as the reference's summed
+    category axis.  ~19 GB and minutes (the soft NJ); python make_golden.py chain_c2"""
+    from dodonaphy_b200.engine import SubstModel
+
+    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    masks, weights = prob["masks"], prob["weights"]
+    x = torch.tensor(prob["xs"][0], requires_grad=True)
+    pdm = r.Chyp_torch.get_pdm(x)
+    peel, blens = r.peeler.nj_torch(pdm, tau=1e-8)
+    pm = r.phylomodel.PhyloModel("GTR")
+    pm._freqs = pm.freqs_transform.inv(torch.tensor(prob["freqs"])).clone().detach().requires_grad_(True)
+    pm._sub_rates = pm.sub_rates_transform.inv(torch.tensor(prob["rates"])).clone().detach().requires_grad_(True)
+    parts, w = ref_partials(r, masks), torch.tensor(weights)
+    ll = r.phylo.calculate_treelikelihood(parts, w, peel, pm.get_transition_mats(blens), pm.freqs)
+    ll.backward(retain_graph=True)
+    out = dict(x=prob["xs"][0], peel=np.asarray(peel, dtype=np.int64), blens=blens.detach().numpy().copy(), lnL=ll.item(),
+               g_x=x.grad.numpy().copy(), g_raw_rates=pm._sub_rates.grad.numpy().copy(), g_raw_freqs=pm._freqs.grad.numpy().copy(),
+               rates=prob["rates"], freqs=prob["freqs"], weight_sum=int(weights.sum()),
+               mask_dot=int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()))
+    x.grad = None
+    cat = SubstModel.discrete_gamma(0.5, 4)
+    ll4 = r.phylo.calculate_treelikelihood(ref_partials(r, masks), w, peel,
+                                           pm.get_transition_mats(blens[:, None] * torch.tensor(cat)[None, :]), pm.freqs)
+    ll4.backward()
+    out["cat_rates"], out["k4_lnL"], out["k4_g_x"] = np.asarray(cat), ll4.item(), x.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "chain_c2.npz"), **out)
+    print("chain_c2: lnL", out["lnL"], out["k4_lnL"], "|g_x|max", np.abs(out["g_x"]).max())
+
+
 def make_prune_c2(r):
     """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
     10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
@@ -441,6 +476,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

@@ -254,3 +254,31 @@ def test_configs_2_to_4_against_the_reference_itself():
     assert ll.item() == pytest.approx(float(g["c5_lnL_cython"]), rel=1e-9)
     ref = g["c5_g_blens"]
     np.testing.assert_allclose(gr.cpu().numpy().reshape(-1), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+def test_c2_one_sample_end_to_end_against_the_reference_itself():
+    """tests/golden/chain_c2.npz: ONE VI sample of the headline workload through the reference's own
+    chain -- locations (64 x 5) -> Chyp_torch.get_pdm -> peeler.nj_torch(tau=1e-8) -> GTR P(t) ->
+    calculate_treelikelihood over 10 000 patterns -> torch autograd back to the locations.  The fused
+    device path must reproduce the topology bit for bit and lnL, branch lengths and d lnL / d locations
+    to 1e-9 (K = 1 and the four gamma rates as the reference's summed category axis)."""
+    from conftest import load_golden
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    g = load_golden("chain_c2.npz")
+    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    masks, weights = prob["masks"], prob["weights"]
+    if int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) != int(g["mask_dot"]) or int(weights.sum()) != int(g["weight_sum"]):
+        pytest.skip("the synthetic alignment regenerated on this host differs from the one the reference answers were computed for")
+    gtr = SubstModel.gtr(g["rates"], g["freqs"])
+    x = _dev(g["x"])[None]
+    for rates, key_ll, key_g in ((None, "lnL", "g_x"), (g["cat_rates"], "k4_lnL", "k4_g_x")):
+        hp = HotPath(masks, weights, gtr, rates=rates, mix=False, tau=1e-8)
+        out = hp.value_and_grad(x)
+        assert np.array_equal(out["peel"][0].cpu().numpy(), g["peel"])
+        np.testing.assert_allclose(out["blens"][0].cpu().numpy(), g["blens"], rtol=1e-9, atol=1e-15)
+        assert out["lnL"][0].item() == pytest.approx(float(g[key_ll]), rel=1e-9)
+        ref = g[key_g]
+        np.testing.assert_allclose(out["grad_x"][0].cpu().numpy(), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
