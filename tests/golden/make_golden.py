@@ -16,6 +16,7 @@ Outputs (committed; small):
   prune_c2.npz   lnL + gradients of the reference at the full headline size (64 taxa x 10 000 patterns).
   chain_c2.npz   one headline-size VI sample end to end in the reference: locations -> distances -> soft NJ
                  -> GTR P(t) -> lnL, and autograd back to the locations.
+  chains.npz     the reference's gradient-free MCMC chain end to end (locations -> lnL) at the configs[0] and [2] shapes.
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
@@ -291,6 +292,33 @@ def make_chain_c2(r):
     print("chain_c2: lnL", out["lnL"], out["k4_lnL"], "|g_x|max", np.abs(out["g_x"]).max())
 
 
+def make_chains(r):
+    """The gradient-free MCMC chain of the reference end to end (chain.py:145-169: Chyp_np.get_pdm ->
+    Cpeeler.nj_np -> Cphylo.compute_LL_np) for four chains at the configs[2] shape (200 taxa x 20 000
+    patterns) and four at the configs[0] shape (the DS1 alignment, 27 taxa, d3).  Stored: locations,
+    lnL and tree length -- both are invariant to how the last exactly-tied joins are ordered, which
+    depends on the last bit of the distances.  python make_golden.py chains"""
+    out = {}
+    prob = synth.make_problem(200, 20000, 64, D=5, seed=1003)
+    out["c3_mask_sum"] = int(prob["masks"].astype(np.int64).sum())
+    pn = [p.numpy() for p in ref_partials(r, prob["masks"])]
+    for i in range(4):
+        x = prob["xs"][i]
+        peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(r.Chyp_np.get_pdm(x)))
+        out[f"c3_{i}_x"], out[f"c3_{i}_lnL"] = x, float(r.Cphylo.compute_LL_np(pn, prob["weights"], np.asarray(peel), blens))
+        out[f"c3_{i}_len"] = float(np.sum(blens))
+    d = np.load(os.path.join(HERE, "ds1.npz"))
+    pn = [p.numpy() for p in ref_partials(r, d["masks"])]
+    rng = np.random.default_rng(27)
+    for i in range(4):
+        x = rng.normal(0, 0.05, (27, 3))
+        peel, blens = r.Cpeeler.nj_np(np.ascontiguousarray(r.Chyp_np.get_pdm(x)))
+        out[f"c1_{i}_x"], out[f"c1_{i}_lnL"] = x, float(r.Cphylo.compute_LL_np(pn, d["weights"], np.asarray(peel), blens))
+        out[f"c1_{i}_len"] = float(np.sum(blens))
+    np.savez_compressed(os.path.join(HERE, "chains.npz"), **out)
+    print("chains: c3 lnL", [out[f"c3_{i}_lnL"] for i in range(4)], "c1 lnL", [out[f"c1_{i}_lnL"] for i in range(4)])
+
+
 def make_prune_c2(r):
     """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
     10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
@@ -476,6 +504,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

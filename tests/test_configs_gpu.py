@@ -282,3 +282,29 @@ def test_c2_one_sample_end_to_end_against_the_reference_itself():
         assert out["lnL"][0].item() == pytest.approx(float(g[key_ll]), rel=1e-9)
         ref = g[key_g]
         np.testing.assert_allclose(out["grad_x"][0].cpu().numpy(), ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+def test_mcmc_chain_end_to_end_against_the_reference_itself():
+    """tests/golden/chains.npz: the reference's gradient-free chain (Chyp_np.get_pdm -> Cpeeler.nj_np ->
+    Cphylo.compute_LL_np) from the locations to lnL at the configs[2] shape (200 taxa x 20 000
+    patterns) and the configs[0] shape (DS1: 27 taxa x 934 patterns).  lnL and tree length do not
+    depend on how the exactly-tied last joins are ordered: 1e-9 through the whole device chain."""
+    from conftest import load_golden
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    g = load_golden("chains.npz")
+    d = load_golden("ds1.npz")
+    hp = HotPath(d["masks"], d["weights"], SubstModel.jc69())
+    out = hp.value(_dev(np.stack([g[f"c1_{i}_x"] for i in range(4)])))
+    for i in range(4):
+        assert out["lnL"][i].item() == pytest.approx(float(g[f"c1_{i}_lnL"]), rel=1e-9)
+        assert out["blens"][i].sum().item() == pytest.approx(float(g[f"c1_{i}_len"]), rel=1e-9)
+    prob = synth.make_problem(200, 20000, 64, D=5, seed=1003)
+    _same_alignment_or_skip(prob["masks"], g["c3_mask_sum"])
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69())
+    out = hp.value(_dev(np.stack([g[f"c3_{i}_x"] for i in range(4)])))
+    for i in range(4):
+        assert out["lnL"][i].item() == pytest.approx(float(g[f"c3_{i}_lnL"]), rel=1e-9)
+        assert out["blens"][i].sum().item() == pytest.approx(float(g[f"c3_{i}_len"]), rel=1e-9)
