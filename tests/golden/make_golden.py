@@ -16,6 +16,7 @@ Outputs (committed; small):
   prune_c2.npz   lnL + gradients of the reference at the full headline size (64 taxa x 10 000 patterns).
   chain_c2.npz   one headline-size VI sample end to end in the reference: locations -> distances -> soft NJ
                  -> GTR P(t) -> lnL, and autograd back to the locations.
+  blens_jac.npz  the reference's autograd Jacobian of the decoded branch lengths w.r.t. the locations (vi.py:376-387).
   chains.npz     the reference's gradient-free MCMC chain end to end (locations -> lnL) at the configs[0] and [2] shapes.
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
@@ -319,6 +320,25 @@ def make_chains(r):
     print("chains: c3 lnL", [out[f"c3_{i}_lnL"] for i in range(4)], "c1 lnL", [out[f"c1_{i}_lnL"] for i in range(4)])
 
 
+def make_blens_jac(r):
+    """vi.py:376-387 with the reference's own functions: torch.autograd.functional.jacobian of the decoded
+    branch lengths w.r.t. the flattened locations (Chyp_torch.get_pdm -> peeler.nj_torch(tau = 1e-8)) and
+    log sqrt|det(J J^T)|, for 7, 12 and 17 taxa.  python make_golden.py blens_jac"""
+    rng = np.random.default_rng(77)
+    out = {"n": 3}
+    for i, (S, D) in enumerate([(7, 3), (12, 2), (17, 5)]):
+        x = rng.normal(0, 0.08, (S, D))
+
+        def get_blens(flat):
+            return r.peeler.nj_torch(r.Chyp_torch.get_pdm(flat.reshape(S, D)), tau=1e-8)[1]
+
+        J = torch.autograd.functional.jacobian(get_blens, torch.tensor(x).flatten())
+        out[f"{i}_x"], out[f"{i}_J"] = x, J.numpy().copy()
+        out[f"{i}_logdet"] = float(torch.log(torch.sqrt(torch.abs(torch.linalg.det(J @ J.T)))))
+    np.savez_compressed(os.path.join(HERE, "blens_jac.npz"), **out)
+    print("blens_jac: log|det| terms", [out[f"{i}_logdet"] for i in range(3)])
+
+
 def make_prune_c2(r):
     """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
     10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
@@ -504,6 +524,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

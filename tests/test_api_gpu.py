@@ -215,6 +215,27 @@ def test_blens_jacobian_batched_vs_autograd_oracle():
         np.testing.assert_allclose(J[b].cpu().numpy(), ref.numpy(), rtol=1e-8, atol=1e-10)
 
 
+def test_blens_jacobian_against_the_reference_itself():
+    """tests/golden/blens_jac.npz: torch.autograd.functional.jacobian through the reference's own
+    Chyp_torch.get_pdm -> peeler.nj_torch chain (vi.py:376-387), 7 / 12 / 17 taxa."""
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    g = load_golden("blens_jac.npz")
+    for i in range(int(g["n"])):
+        x = g[f"{i}_x"]
+        S, D = x.shape
+        masks = np.ones((S, 4), dtype=np.uint8)
+        hp = HotPath(masks, np.ones(4), SubstModel.jc69(), tau=1e-8, curvature=-1.0)
+        J, half_logdet = hp.blens_jacobian(torch.as_tensor(x).cuda()[None])
+        ref = g[f"{i}_J"]
+        np.testing.assert_allclose(J[0].cpu().numpy(), ref, rtol=1e-8, atol=1e-9 * np.abs(ref).max())
+        # the determinant itself is numerically zero in the reference as well (the last join halves one
+        # distance, so two rows of J coincide): only its being tiny is comparable
+        if np.isfinite(float(g[f"{i}_logdet"])) and float(g[f"{i}_logdet"]) > -20:
+            assert half_logdet[0].item() == pytest.approx(float(g[f"{i}_logdet"]), rel=1e-6)
+
+
 def test_compress_alignment_on_device():
     """phylo.compress_alignment (phylo.py:16-58) with the sort/unique on the GPU."""
     from dodonaphy_b200 import phylo
