@@ -17,6 +17,7 @@ Outputs (committed; small):
   chain_c2.npz   one headline-size VI sample end to end in the reference: locations -> distances -> soft NJ
                  -> GTR P(t) -> lnL, and autograd back to the locations.
   blens_jac.npz  the reference's autograd Jacobian of the decoded branch lengths w.r.t. the locations (vi.py:376-387).
+  hmap.npz       the reference's own HMAP object: MAP loss, its parts and autograd gradients (hmap.py:185-192).
   chains.npz     the reference's gradient-free MCMC chain end to end (locations -> lnL) at the configs[0] and [2] shapes.
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
@@ -339,6 +340,36 @@ def make_blens_jac(r):
     print("blens_jac: log|det| terms", [out[f"{i}_logdet"] for i in range(3)])
 
 
+def make_hmap(r):
+    """The reference's own HMAP object (hmap.py:20-64,185-192,310-334): MAP loss = -(lnL + gamma-Dirichlet
+    prior) at given tip locations, with torch autograd to the locations and the curvature leaf.
+    Cases: 8 taxa x 60 patterns and the DS1 alignment (27 taxa), "up" and "wrap" embedders.
+    python make_golden.py hmap"""
+    import importlib
+
+    hm = importlib.import_module("dodonaphy.hmap")
+    d = np.load(os.path.join(HERE, "ds1.npz"))
+    prob = synth.make_problem(8, 60, 1, D=3, seed=77)
+    rng = np.random.default_rng(99)
+    cases = [(prob["masks"], prob["weights"], prob["xs"][0], "up"), (prob["masks"], prob["weights"], prob["xs"][0], "wrap"),
+             (d["masks"], d["weights"], rng.normal(0, 0.05, (27, 3)), "up")]
+    out = {"n": len(cases)}
+    for i, (masks, weights, x, emb) in enumerate(cases):
+        parts = ref_partials(r, masks)
+        m = hm.HMAP(parts, torch.tensor(weights), dim=x.shape[1], soft_temp=1e-8, loss_fn="likelihood", path_write=None,
+                    prior="gammadir", embedder=emb, connector="nj")
+        m.params_optim["leaf_loc"] = torch.tensor(x, requires_grad=True)
+        loss = m.compute_loss()
+        loss.backward()
+        out[f"{i}_masks"], out[f"{i}_weights"], out[f"{i}_x"], out[f"{i}_embedder"] = masks, weights, x, emb
+        out[f"{i}_loss"], out[f"{i}_ln_p"], out[f"{i}_ln_prior"] = loss.item(), m.ln_p.item(), m.ln_prior.item()
+        out[f"{i}_g_x"] = m.params_optim["leaf_loc"].grad.numpy().copy()
+        out[f"{i}_g_curv"] = float(m.params_optim["curvature"].grad)
+        out[f"{i}_peel"] = np.asarray(m.peel, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "hmap.npz"), **out)
+    print("hmap: losses", [out[f"{i}_loss"] for i in range(len(cases))], "g_curv", [out[f"{i}_g_curv"] for i in range(len(cases))])
+
+
 def make_prune_c2(r):
     """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
     10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
@@ -524,6 +555,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

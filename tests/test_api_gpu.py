@@ -368,6 +368,29 @@ def test_hmap_loss_gradient_and_learn():
     assert m.best_peel.shape == (S - 1, 3) and m.best_locs.shape == (S, D)
 
 
+def test_hmap_against_the_reference_object_itself():
+    """tests/golden/hmap.npz: the reference's own HMAP instance (hmap.py:185-192): loss, lnL, prior,
+    topology, and autograd gradients w.r.t. the tip locations and the curvature leaf, for the "up"
+    and "wrap" embedders (8 taxa) and on the DS1 alignment (27 taxa)."""
+    from dodonaphy_b200.hmap import HMAP
+
+    g = load_golden("hmap.npz")
+    for i in range(int(g["n"])):
+        x = g[f"{i}_x"]
+        m = HMAP(_partials(g[f"{i}_masks"])[:x.shape[0]], torch.tensor(g[f"{i}_weights"]), dim=x.shape[1], soft_temp=1e-8,
+                 loss_fn="likelihood", path_write=None, prior="gammadir", embedder=str(g[f"{i}_embedder"]), connector="nj")
+        m.init_embedding_params(x)
+        loss = m.compute_loss()
+        loss.sum().backward()
+        assert float(loss.detach()) == pytest.approx(float(g[f"{i}_loss"]), rel=1e-9)
+        assert float(m.ln_p.detach()) == pytest.approx(float(g[f"{i}_ln_p"]), rel=1e-9)
+        assert float(m.ln_prior.detach()) == pytest.approx(float(g[f"{i}_ln_prior"]), rel=1e-9)
+        assert np.array_equal(np.asarray(m.peel).reshape(-1, 3), g[f"{i}_peel"])
+        ref = g[f"{i}_g_x"]
+        np.testing.assert_allclose(m.params_optim["leaf_loc"].grad.numpy(), ref, rtol=1e-8, atol=1e-9 * np.abs(ref).max())
+        assert float(m.params_optim["curvature"].grad) == pytest.approx(float(g[f"{i}_g_curv"]), rel=1e-8)
+
+
 def test_hmap_gtr_parameters_receive_gradient():
     """Learnable GTR: the fused batched pass (d lnL/d P, d lnL/d pi from the kernel, chain rule to the
     unconstrained leaves) and the reference's call-by-call route (base_model.py:239-247) give the same
