@@ -17,6 +17,7 @@ Outputs (committed; small):
   chain_c2.npz   one headline-size VI sample end to end in the reference: locations -> distances -> soft NJ
                  -> GTR P(t) -> lnL, and autograd back to the locations.
   blens_jac.npz  the reference's autograd Jacobian of the decoded branch lengths w.r.t. the locations (vi.py:376-387).
+  vi.npz         the reference's own DodonaphyVI object: elbo_siwae, its per-sample terms and gradients (vi.py:315-341).
   hmap.npz       the reference's own HMAP object: MAP loss, its parts and autograd gradients (hmap.py:185-192).
   chains.npz     the reference's gradient-free MCMC chain end to end (locations -> lnL) at the configs[0] and [2] shapes.
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
@@ -355,7 +356,7 @@ def make_hmap(r):
              (d["masks"], d["weights"], rng.normal(0, 0.05, (27, 3)), "up")]
     out = {"n": len(cases)}
     for i, (masks, weights, x, emb) in enumerate(cases):
-        parts = ref_partials(r, masks)
+        parts = ref_partials(r, masks)[:masks.shape[0]]  # tips only: BaseModel allocates the internal nodes itself
         m = hm.HMAP(parts, torch.tensor(weights), dim=x.shape[1], soft_temp=1e-8, loss_fn="likelihood", path_write=None,
                     prior="gammadir", embedder=emb, connector="nj")
         m.params_optim["leaf_loc"] = torch.tensor(x, requires_grad=True)
@@ -368,6 +369,51 @@ def make_hmap(r):
         out[f"{i}_peel"] = np.asarray(m.peel, dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "hmap.npz"), **out)
     print("hmap: losses", [out[f"{i}_loss"] for i in range(len(cases))], "g_curv", [out[f"{i}_g_curv"] for i in range(len(cases))])
+
+
+def make_vi(r):
+    """The reference's own DodonaphyVI object (vi.py:161-202,315-341): elbo_siwae over two importance
+    samples, its per-sample terms (ln p, ln prior, ln q; the log-Jacobian is -inf -> 0 for both, vi.py:199-201)
+    and autograd gradients w.r.t. leaf_mu / leaf_sigma.  The sampled locations are stored, so the test
+    feeds the same draws instead of relying on the generator's stream.  python make_golden.py vi"""
+    import importlib
+    import warnings
+
+    vim = importlib.import_module("dodonaphy.vi")
+    S, D, L, imp = 8, 3, 60, 2
+    prob = synth.make_problem(S, L, 1, D=D, seed=55)
+    vi = vim.DodonaphyVI(ref_partials(r, prob["masks"])[:S], torch.tensor(prob["weights"]), D, embedder="up", connector="nj",
+                         soft_temp=1e-8, path_write=None)
+    mu, sg = torch.tensor(prob["x"]), torch.full((S, D), -9.0)
+    vi.set_params_optim({"leaf_mu": mu.clone(), "leaf_sigma": sg.clone()})
+    rec, orig = [], vi.rsample_tree
+
+    def wrapped(*a, **k):
+        rec.append(orig(*a, **k))
+        return rec[-1]
+
+    vi.rsample_tree = wrapped
+    drawn, orig_draw = [], vi.rsample_Euclid  # the sample dict holds the MEAN under "leaf_locs": record the draws
+
+    def draw(*a, **k):
+        loc, log_q = orig_draw(*a, **k)
+        drawn.append(loc.detach().numpy().copy())
+        return loc, log_q
+
+    vi.rsample_Euclid = draw
+    torch.manual_seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        elbo = vi.elbo_siwae(importance=imp)
+    elbo.backward()
+    assert all(float(t["jacobian"]) == 0.0 for t in rec)
+    out = dict(masks=prob["masks"], weights=prob["weights"], mu=mu.numpy(), sigma=sg.numpy(), elbo=elbo.item(),
+               x=np.stack(drawn),
+               ln_p=np.array([float(t["ln_p"]) for t in rec]), ln_prior=np.array([float(t["ln_prior"]) for t in rec]),
+               log_q=np.array([float(t["logQ"]) for t in rec]),
+               g_mu=vi.params_optim["leaf_mu"].grad.numpy().copy(), g_sigma=vi.params_optim["leaf_sigma"].grad.numpy().copy())
+    np.savez_compressed(os.path.join(HERE, "vi.npz"), **out)
+    print("vi: elbo", out["elbo"], "terms", out["ln_p"], out["ln_prior"], out["log_q"])
 
 
 def make_prune_c2(r):
@@ -555,6 +601,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, vi=make_vi, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

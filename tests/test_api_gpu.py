@@ -432,6 +432,34 @@ def test_hmap_gtr_parameters_receive_gradient():
     np.testing.assert_allclose(-grads[True][1]["freqs"].numpy(), (g_rf + prior_f).numpy(), rtol=1e-8, atol=1e-9)
 
 
+def test_vi_against_the_reference_object_itself():
+    """tests/golden/vi.npz: the reference's own DodonaphyVI instance -- elbo_siwae over two importance
+    samples (vi.py:315-341), its per-sample ln p / ln prior / ln q, and autograd gradients w.r.t. leaf_mu and
+    leaf_sigma.  The reference's sampled locations are fed back as noise; its log-Jacobian term was
+    -inf -> 0 for both samples (vi.py:199-201), so the batched step runs without it."""
+    from dodonaphy_b200.vi import DodonaphyVI
+
+    g = load_golden("vi.npz")
+    mu, sg = torch.tensor(g["mu"]), torch.tensor(g["sigma"])
+    S, D = mu.shape
+    xs = torch.tensor(g["x"]).reshape(-1, S, D)
+    imp = xs.shape[0]
+    vi = DodonaphyVI(_partials(g["masks"])[:S], torch.tensor(g["weights"]), D, embedder="up", connector="nj", soft_temp=1e-8,
+                     include_jacobian=False)
+    vi.set_params_optim(mu, sg)
+    noise = ((xs - mu) / torch.exp(0.5 * sg)).reshape(imp, 1, S, D)
+    x, log_q = vi.rsample(imp, noise)
+    np.testing.assert_allclose(log_q.detach().numpy().reshape(-1), g["log_q"], rtol=1e-9)
+    ln_p, ln_prior, _, _, _ = vi.elbo_terms(x.reshape(-1, S, D))
+    np.testing.assert_allclose(ln_p.detach().cpu().numpy(), g["ln_p"], rtol=1e-9)
+    np.testing.assert_allclose(ln_prior.detach().cpu().numpy(), g["ln_prior"], rtol=1e-9)
+    elbo = vi.elbo_siwae(imp, noise=noise)
+    elbo.backward()
+    assert elbo.item() == pytest.approx(float(g["elbo"]), rel=1e-9)
+    for ours, ref in ((vi.params_optim["leaf_mu"].grad[0].numpy(), g["g_mu"][0]), (vi.params_optim["leaf_sigma"].grad[0].numpy(), g["g_sigma"][0])):
+        np.testing.assert_allclose(ours, ref, rtol=1e-6, atol=1e-7 * np.abs(ref).max())
+
+
 def test_vi_learns_gtr_parameters_in_the_batched_step():
     """vi.py:228-249 with model_name='GTR' and gamma rate categories: one batched ELBO step puts
     gradient on the rate / frequency leaves."""
