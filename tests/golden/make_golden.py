@@ -18,6 +18,7 @@ Outputs (committed; small):
                  -> GTR P(t) -> lnL, and autograd back to the locations.
   blens_jac.npz  the reference's autograd Jacobian of the decoded branch lengths w.r.t. the locations (vi.py:376-387).
   vi.npz         the reference's own DodonaphyVI object: elbo_siwae, its per-sample terms and gradients (vi.py:315-341).
+  laplace.npz    the reference's own Laplace object: log posterior and its autograd Hessian (laplace.py:9-25,40).
   hmap.npz       the reference's own HMAP object: MAP loss, its parts and autograd gradients (hmap.py:185-192).
   chains.npz     the reference's gradient-free MCMC chain end to end (locations -> lnL) at the configs[0] and [2] shapes.
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
@@ -416,6 +417,25 @@ def make_vi(r):
     print("vi: elbo", out["elbo"], "terms", out["ln_p"], out["ln_prior"], out["log_q"])
 
 
+def make_laplace(r):
+    """The reference's own Laplace object (laplace.py:9-25,40): log posterior at the flattened tip
+    locations and its torch.autograd.functional.hessian, 6 taxa x 50 patterns, d2.
+    python make_golden.py laplace"""
+    import importlib
+
+    lp = importlib.import_module("dodonaphy.laplace")
+    S, D, L = 6, 2, 50
+    prob = synth.make_problem(S, L, 1, D=D, seed=79)
+    m = lp.Laplace(ref_partials(r, prob["masks"])[:S], torch.tensor(prob["weights"]), dim=D, soft_temp=1e-8, loss_fn="likelihood",
+                   path_write=None, prior="gammadir", embedder="up", connector="nj")
+    x0 = torch.tensor(prob["xs"][0]).flatten()
+    val = m.get_ln_posterior(x0)
+    H = torch.autograd.functional.hessian(m.get_ln_posterior, x0, vectorize=True)
+    np.savez_compressed(os.path.join(HERE, "laplace.npz"), masks=prob["masks"], weights=prob["weights"], x=prob["xs"][0],
+                        ln_posterior=float(val), hessian=H.numpy().copy())
+    print("laplace: ln posterior", float(val), "|H|max", float(H.abs().max()))
+
+
 def make_prune_c2(r):
     """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
     10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
@@ -601,6 +621,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, vi=make_vi, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, vi=make_vi, laplace=make_laplace, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

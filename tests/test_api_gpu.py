@@ -504,6 +504,23 @@ def test_laplace_hessian_matches_double_backward_oracle():
         assert out["peel"].shape == (8, S - 1, 3) and np.isfinite(out["ln_p"]).all()
 
 
+def test_laplace_against_the_reference_object_itself():
+    """tests/golden/laplace.npz: the reference's own Laplace instance -- get_ln_posterior (laplace.py:9-25)
+    and the Hessian torch.autograd.functional.hessian takes of it (laplace.py:40).  Ours: one fused pass
+    for the value, batched central differences of the analytic gradient for the Hessian (1e-5 of its
+    largest entry)."""
+    from dodonaphy_b200.laplace import Laplace
+
+    g = load_golden("laplace.npz")
+    S, D = g["x"].shape
+    m = Laplace(_partials(g["masks"])[:S], torch.tensor(g["weights"]), dim=D, soft_temp=1e-8, prior="gammadir")
+    m.init_embedding_params(g["x"])
+    val = m.get_ln_posterior(torch.tensor(g["x"]).flatten())
+    assert float(val.detach()) == pytest.approx(float(g["ln_posterior"]), rel=1e-9)
+    H, Href = m.hessian().numpy(), g["hessian"]
+    assert np.abs(H - Href).max() <= 1e-5 * np.abs(Href).max()
+
+
 def test_graphed_step_replays_the_whole_path():
     """pipeline.GraphedStep: the captured CUDA graph returns what the launch-by-launch path returns,
     for the capture input and for fresh inputs (both the gradient and the gradient-free route)."""
