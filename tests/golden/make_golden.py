@@ -353,20 +353,23 @@ def make_hmap(r):
     d = np.load(os.path.join(HERE, "ds1.npz"))
     prob = synth.make_problem(8, 60, 1, D=3, seed=77)
     rng = np.random.default_rng(99)
-    cases = [(prob["masks"], prob["weights"], prob["xs"][0], "up"), (prob["masks"], prob["weights"], prob["xs"][0], "wrap"),
-             (d["masks"], d["weights"], rng.normal(0, 0.05, (27, 3)), "up")]
+    cases = [(prob["masks"], prob["weights"], prob["xs"][0], "up", "nj"), (prob["masks"], prob["weights"], prob["xs"][0], "wrap", "nj"),
+             (d["masks"], d["weights"], rng.normal(0, 0.05, (27, 3)), "up", "nj"),
+             (prob["masks"], prob["weights"], prob["xs"][0] * 4.0, "up", "geodesics")]  # ball points of norm ~0.3
     out = {"n": len(cases)}
-    for i, (masks, weights, x, emb) in enumerate(cases):
+    for i, (masks, weights, x, emb, conn) in enumerate(cases):
         parts = ref_partials(r, masks)[:masks.shape[0]]  # tips only: BaseModel allocates the internal nodes itself
         m = hm.HMAP(parts, torch.tensor(weights), dim=x.shape[1], soft_temp=1e-8, loss_fn="likelihood", path_write=None,
-                    prior="gammadir", embedder=emb, connector="nj")
+                    prior="gammadir", embedder=emb, connector=conn)
         m.params_optim["leaf_loc"] = torch.tensor(x, requires_grad=True)
+        out[f"{i}_connector"] = conn
         loss = m.compute_loss()
         loss.backward()
         out[f"{i}_masks"], out[f"{i}_weights"], out[f"{i}_x"], out[f"{i}_embedder"] = masks, weights, x, emb
         out[f"{i}_loss"], out[f"{i}_ln_p"], out[f"{i}_ln_prior"] = loss.item(), m.ln_p.item(), m.ln_prior.item()
         out[f"{i}_g_x"] = m.params_optim["leaf_loc"].grad.numpy().copy()
-        out[f"{i}_g_curv"] = float(m.params_optim["curvature"].grad)
+        gc = m.params_optim["curvature"].grad  # None where the connector does not use the curvature leaf
+        out[f"{i}_g_curv"] = float(gc) if gc is not None else float("nan")
         out[f"{i}_peel"] = np.asarray(m.peel, dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "hmap.npz"), **out)
     print("hmap: losses", [out[f"{i}_loss"] for i in range(len(cases))], "g_curv", [out[f"{i}_g_curv"] for i in range(len(cases))])

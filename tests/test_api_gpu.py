@@ -378,7 +378,8 @@ def test_hmap_against_the_reference_object_itself():
     for i in range(int(g["n"])):
         x = g[f"{i}_x"]
         m = HMAP(_partials(g[f"{i}_masks"])[:x.shape[0]], torch.tensor(g[f"{i}_weights"]), dim=x.shape[1], soft_temp=1e-8,
-                 loss_fn="likelihood", path_write=None, prior="gammadir", embedder=str(g[f"{i}_embedder"]), connector="nj")
+                 loss_fn="likelihood", path_write=None, prior="gammadir", embedder=str(g[f"{i}_embedder"]),
+                 connector=str(g[f"{i}_connector"]))
         m.init_embedding_params(x)
         loss = m.compute_loss()
         loss.sum().backward()
@@ -388,7 +389,8 @@ def test_hmap_against_the_reference_object_itself():
         assert np.array_equal(np.asarray(m.peel).reshape(-1, 3), g[f"{i}_peel"])
         ref = g[f"{i}_g_x"]
         np.testing.assert_allclose(m.params_optim["leaf_loc"].grad.numpy(), ref, rtol=1e-8, atol=1e-9 * np.abs(ref).max())
-        assert float(m.params_optim["curvature"].grad) == pytest.approx(float(g[f"{i}_g_curv"]), rel=1e-8)
+        if np.isfinite(float(g[f"{i}_g_curv"])):
+            assert float(m.params_optim["curvature"].grad) == pytest.approx(float(g[f"{i}_g_curv"]), rel=1e-8)
 
 
 def test_hmap_gtr_parameters_receive_gradient():
