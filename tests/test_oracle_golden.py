@@ -239,6 +239,32 @@ def test_hard_nj_fixtures_at_the_config_sizes():
         assert np.array_equal(blens, g[f"{key}_blens"]), key
 
 
+def test_whole_chain_fixture_at_the_headline_size():
+    """tests/golden/chain_c2.npz: one VI sample of the headline workload end to end in the reference.  The
+    restatements chained the same way (distance -> soft NJ -> GTR P(t) -> pruning -> autograd) give the
+    same topology, lnL and gradient w.r.t. the 64 x 5 locations."""
+    from dodonaphy_b200 import synth
+
+    g = load_golden("chain_c2.npz")
+    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    masks = prob["masks"]
+    if int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) != int(g["mask_dot"]):
+        pytest.skip("the synthetic alignment regenerated on this host differs from the one the reference answers were computed for")
+    x = torch.tensor(g["x"], requires_grad=True)
+    z = torch.sqrt((x * x).sum(1) + 1)
+    H = torch.minimum(x @ x.T - torch.outer(z, z), torch.tensor(-1.0000001, dtype=torch.float64))
+    pdm = torch.acosh(-H) * (1 - torch.eye(64, dtype=torch.float64))
+    peel, blens = nj.nj_soft_torch(pdm, 1e-8)
+    assert np.array_equal(peel, g["peel"])
+    tips = [torch.tensor(phylo.mask_to_partial(m)) for m in masks]
+    mats = phylo.gtr_p_t_torch(blens[:, None], torch.tensor(g["rates"]), torch.tensor(g["freqs"]))
+    ll = phylo.treelikelihood_torch(tips, torch.tensor(prob["weights"]), peel, mats, torch.tensor(g["freqs"]), gamma_mix=False)
+    ll.backward()
+    assert ll.item() == pytest.approx(float(g["lnL"]), rel=1e-11)
+    ref = g["g_x"]
+    np.testing.assert_allclose(x.grad.numpy(), ref, rtol=1e-8, atol=1e-9 * np.abs(ref).max())
+
+
 def test_q_matrix_wikipedia():
     """test/test_peeler.py:228-303: Q of the 5-taxon textbook example."""
     D = np.array([[0, 5, 9, 9, 8], [5, 0, 10, 10, 9], [9, 10, 0, 8, 7], [9, 10, 8, 0, 3], [8, 9, 7, 3, 0]], dtype=np.float64)
