@@ -21,6 +21,7 @@ Outputs (committed; small):
   laplace.npz    the reference's own Laplace object: log posterior and its autograd Hessian (laplace.py:9-25,40).
   hmap.npz       the reference's own HMAP object: MAP loss, its parts and autograd gradients (hmap.py:185-192).
   chains.npz     the reference's gradient-free MCMC chain end to end (locations -> lnL) at the configs[0] and [2] shapes.
+  pdm_c4.npz     sampled entries of the reference's 2000-taxon distance matrices (NumPy and torch variants).
   configs.npz    the reference at the shapes of configs[2..4]: 200- and 500-taxon trees + lnL, one 2000-taxon NJ tree.
   prune.npz      phylo.calculate_treelikelihood lnL + autograd gradients (JC69 and GTR).
   pdm_jac.npz    Chyp_np.get_pdm(get_jacobian=True) pair Jacobians.
@@ -439,6 +440,20 @@ def make_laplace(r):
     print("laplace: ln posterior", float(val), "|H|max", float(H.abs().max()))
 
 
+def make_pdm_c4(r):
+    """Chyp_np.get_pdm and Chyp_torch.get_pdm of the reference at the configs[3] size (2000 taxa, d5, seeded
+    locations): 4000 sampled entries of each 2000 x 2000 matrix (the full matrices are 32 MB).
+    python make_golden.py pdm_c4"""
+    rng = np.random.default_rng(2000)
+    x = rng.normal(0, 0.05, (2000, 5))
+    ii, jj = rng.integers(0, 2000, 4000), rng.integers(0, 2000, 4000)
+    dn = r.Chyp_np.get_pdm(x)
+    dt = r.Chyp_torch.get_pdm(torch.tensor(x)).numpy()
+    np.savez_compressed(os.path.join(HERE, "pdm_c4.npz"), seed=2000, ii=ii, jj=jj, np_vals=dn[ii, jj], torch_vals=dt[ii, jj],
+                        np_row_sum=dn.sum(1)[:16], torch_total=float(dt.sum()))
+    print("pdm_c4: mean distance", float(dt.mean()))
+
+
 def make_prune_c2(r):
     """The reference's lnL and autograd gradients at the FULL size of the headline workload (64 taxa x
     10 000 patterns, sample 0 of bench.py's synthetic problem, seed 1002): JC69, GTR, and GTR with the
@@ -624,6 +639,6 @@ if __name__ == "__main__":
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
                   pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
-    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, vi=make_vi, laplace=make_laplace, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
+    slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, vi=make_vi, laplace=make_laplace, pdm_c4=make_pdm_c4, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)

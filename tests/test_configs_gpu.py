@@ -308,3 +308,21 @@ def test_mcmc_chain_end_to_end_against_the_reference_itself():
     for i in range(4):
         assert out["lnL"][i].item() == pytest.approx(float(g[f"c3_{i}_lnL"]), rel=1e-9)
         assert out["blens"][i].sum().item() == pytest.approx(float(g[f"c3_{i}_len"]), rel=1e-9)
+
+
+def test_c4_shape_distances_against_the_reference_itself():
+    """tests/golden/pdm_c4.npz: 4000 sampled entries (plus row sums and the grand total) of the reference's
+    own Chyp_np.get_pdm / Chyp_torch.get_pdm matrices for 2000 seeded taxa (configs[3])."""
+    from conftest import load_golden
+    from dodonaphy_b200 import engine
+
+    g = load_golden("pdm_c4.npz")
+    x = np.random.default_rng(int(g["seed"])).normal(0, 0.05, (2000, 5))
+    ii, jj = g["ii"], g["jj"]
+    dn = engine.pdm_forward(_dev(x), -1.0, "numpy").cpu().numpy().reshape(2000, 2000)
+    dt = engine.pdm_forward(_dev(x), -1.0, "torch").cpu().numpy().reshape(2000, 2000)
+    off = ii != jj  # the NumPy variant's diagonal is sqrt(2 eps)-sized rounding noise in the reference
+    np.testing.assert_allclose(dn[ii, jj][off], g["np_vals"][off], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(dt[ii, jj], g["torch_vals"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose((dn.sum(1) - np.diag(dn))[:16], g["np_row_sum"] - 0.0, rtol=1e-9, atol=1e-6)
+    assert float(dt.sum()) == pytest.approx(float(g["torch_total"]), rel=1e-10)
