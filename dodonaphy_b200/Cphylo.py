@@ -39,6 +39,27 @@ def calculate_treelikelihood(partials, weights, post_indexing, mats, freqs):
     return np.float64(out["lnL"].item())
 
 
+def compute_prior_gamma_dir_np(blen, aT=1.0, bT=0.1, a=1.0, c=1.0):
+    """Gamma-Dirichlet(aT, bT, a, c) log prior of one tree's branch lengths (Cphylo.pyx:53-114;
+    called per proposal from chain.py:129).  Host NumPy like the reference: 2S-2 numbers, off the
+    device path.  The NumPy twin floors the tree length and every branch at machine epsilon (:105-107)
+    where the torch twin clamps at 1e-4 (utils.py:258-260); both are kept as they are.  The batched
+    device version is ``priors.gamma_dir_device``."""
+    import math
+
+    blen = np.asarray(blen, dtype=np.float64)
+    eps = np.finfo(np.double).eps
+    n_leaf = int(len(blen) / 2 + 1)
+    tree_len = np.maximum(np.sum(blen), eps)
+    tipb = np.sum(np.log(np.maximum(blen[:n_leaf], eps)))
+    intb = np.sum(np.log(np.maximum(blen[n_leaf:], eps)))
+    ln_prior = (a - 1) * tipb + (a * c - 1) * intb
+    ln_prior = ln_prior + (aT - a * n_leaf - a * c * (n_leaf - 3)) * np.log(tree_len) - bT * tree_len
+    ln_prior = (ln_prior + aT * np.log(bT) - math.lgamma(aT) + math.lgamma(a * n_leaf + a * c * (n_leaf - 3))
+                - n_leaf * math.lgamma(a) - (n_leaf - 3) * math.lgamma(a * c))
+    return ln_prior - np.sum(np.log(np.arange(n_leaf * 2 - 5, 0, -2)))
+
+
 def compute_branch_lengths_np(S, peel, leaf_x, int_x, curvature=-1.0, matsumoto=False):
     """Branch lengths of a geodesic-connected tree from node locations (Cphylo.pyx:116-160): the
     hyperbolic distance from each child to its parent, floored at machine epsilon.

@@ -17,11 +17,29 @@ namespace dodo {
 constexpr int MAX_D = 15;  // embedding dimension (sheet has D+1 coordinates)
 constexpr double TORCH_CLAMP = 1.0000001;
 
+// sum_d x_d^2 exactly as the reference's host libraries round it: squares rounded one by one
+// (np.power / torch.pow), then NumPy's pairwise_sum of a contiguous row -- a plain left-to-right sum
+// below 8 terms, eight running partial sums combined as ((0+1)+(2+3))+((4+5)+(6+7)) plus a sequential
+// tail from 8 to 15 terms (torch's row reduction is the plain sum at these lengths).  No FMA
+// contraction: the last joins of hard NJ are exact mathematical ties of Q and follow the last bit.
+__device__ __forceinline__ double row_norm2(const double *__restrict__ x, int D) {
+    if (D < 8) {
+        double n2 = 0.0;
+        for (int d = 0; d < D; ++d) n2 = __dadd_rn(n2, __dmul_rn(x[d], x[d]));
+        return n2;
+    }
+    double r[8];
+    for (int d = 0; d < 8; ++d) r[d] = __dmul_rn(x[d], x[d]);
+    double n2 = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                          __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (int d = 8; d < D; ++d) n2 = __dadd_rn(n2, __dmul_rn(x[d], x[d]));
+    return n2;
+}
+
 __device__ __forceinline__ void lift_point(const double *__restrict__ x, int D, int lift, double *s) {
-    double n2 = 0.0;
-    for (int d = 0; d < D; ++d) n2 = fma(x[d], x[d], n2);
+    const double n2 = row_norm2(x, D);
     if (lift == DODO_LIFT_UP) {
-        s[0] = sqrt(n2 + 1.0);
+        s[0] = sqrt(__dadd_rn(n2, 1.0));
         for (int d = 0; d < D; ++d) s[d + 1] = x[d];
     } else {
         double r = sqrt(fmax(n2, DBL_EPSILON));
@@ -41,15 +59,18 @@ __global__ void lift_kernel(const double *__restrict__ x, int n, int D, int lift
     double xx = 0.0;
     for (int d = 0; d <= D; ++d) {
         sheet[(size_t)gid * (D + 1) + d] = s[d];
-        xx = fma(s[d], s[d], xx);
+        xx = fma(s[d], s[d], xx);  // diagonal of X: the same chain as pair_H
     }
-    util[gid] = sqrt(xx + 1.0);
+    util[gid] = sqrt(__dadd_rn(xx, 1.0));
 }
 
+// H_ij = X_ij - u~_i u~_j with X = s s^T.  X is the k-ordered FMA chain a BLAS dgemm/dsyrk micro-kernel
+// runs for an inner dimension this small (one accumulator per entry, k ascending, alpha = 1); the outer
+// product and the subtraction are separate roundings in the reference (np.outer / torch.outer, then `-`).
 __device__ __forceinline__ double pair_H(const double *si, const double *sj, int D, double ui, double uj) {
     double X = 0.0;
     for (int d = 0; d <= D; ++d) X = fma(si[d], sj[d], X);
-    return X - ui * uj;
+    return __dsub_rn(X, __dmul_rn(ui, uj));
 }
 
 __global__ void pdm_fwd_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
@@ -140,8 +161,7 @@ __global__ void __launch_bounds__(1024) pdm_bwd_kernel(const double *__restrict_
             if (lift == DODO_LIFT_UP) {
                 for (int d = 0; d < D; ++d) out[d] = acc[d + 1] + acc[0] * xi[d] / si[0];
             } else {
-                double n2 = 0.0;
-                for (int d = 0; d < D; ++d) n2 = fma(xi[d], xi[d], n2);
+                const double n2 = row_norm2(xi, D);
                 double r = sqrt(fmax(n2, DBL_EPSILON));
                 double shr = sinh(r), chr = cosh(r);
                 double f = shr / r;

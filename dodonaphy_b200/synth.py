@@ -107,13 +107,21 @@ def gtr_params(rng):
     return rates, freqs
 
 
-def make_problem(S, L, B, D=5, seed=1001, jitter=0.01, scale=0.05):
+def make_problem(S, L, B, D=5, seed=1001, jitter=0.01, scale=0.05, guide=None):
     """One synthetic configuration.  Returns a dict with
     x (S,D) base locations, xs (B,S,D) per-sample locations, masks (S,L) uint8, weights (L,) int64,
-    guide_peel, guide_blens, rates(6), freqs(4)."""
+    guide_peel, guide_blens, rates(6), freqs(4).
+
+    ``guide`` = (peel, blens) fixes the tree the alignment is simulated on.  The guide tree computed
+    here goes through the host's BLAS and libm, and NJ's last joins are exact ties that follow the
+    last bit -- so parity tests that compare with stored reference answers pass the committed guide
+    tree of their seed (tests/golden/guides.npz): everything after it is elementwise and seeded."""
     rng = np.random.default_rng(seed)
     x = embed_locations(S, D, rng, scale)
-    peel, blens = guide_tree(hyperboloid_pdm(x))
+    if guide is None:
+        peel, blens = guide_tree(hyperboloid_pdm(x))
+    else:
+        peel, blens = np.asarray(guide[0], dtype=np.int64), np.asarray(guide[1], dtype=np.float64)
     masks = simulate_alignment(peel, blens, L, rng)
     weights = rng.integers(1, 5, size=L).astype(np.int64)
     rates, freqs = gtr_params(rng)

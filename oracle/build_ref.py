@@ -36,6 +36,13 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref", "dodonaphy")
 MODULES = ["Ctransforms", "Chyp_np", "Chyp_torch", "Cphylo", "Cpeeler", "Cutils"]
+# the reference's pure-Python modules (its callers: vi.py, chain.py, mcmc.py, base_model.py ... and
+# its torch path phylo.py / phylomodel.py / peeler.py / soft.py).  They are placed, unmodified, next
+# to the compiled modules in the git-ignored oracle/_ref/ so that they travel to the GPU box with the
+# snapshot: tests/test_dropin_gpu.py runs the reference's OWN DodonaphyVI / Chain over this library's
+# modules there, and bench.py --impl reference times the reference's own calculate_treelikelihood.
+# Nothing is committed (oracle/_ref/ is in .gitignore).
+DATA_FILES = ["test/data/ds1/dna.nex", "test/data/ds1/dna.nj.newick", "test/test_peel_data.txt"]
 
 
 def ext_suffix():
@@ -46,9 +53,31 @@ def is_built():
     return all(os.path.exists(os.path.join(OUT, m + ext_suffix())) for m in MODULES)
 
 
+def python_present():
+    return os.path.exists(os.path.join(OUT, "vi.py")) and os.path.exists(os.path.join(HERE, "_ref", "data", "dna.nex"))
+
+
+def copy_python(reference="/root/reference"):
+    """Place the reference's pure-Python modules and the DS1 inputs in oracle/_ref (git-ignored)."""
+    src = os.path.join(reference, "dodonaphy")
+    if not os.path.isdir(src):
+        return python_present()
+    os.makedirs(OUT, exist_ok=True)
+    for f in sorted(os.listdir(src)):
+        if f.endswith(".py"):
+            shutil.copyfile(os.path.join(src, f), os.path.join(OUT, f))
+    data = os.path.join(HERE, "_ref", "data")
+    os.makedirs(data, exist_ok=True)
+    for rel in DATA_FILES:
+        if os.path.exists(os.path.join(reference, rel)):
+            shutil.copyfile(os.path.join(reference, rel), os.path.join(data, os.path.basename(rel)))
+    return python_present()
+
+
 def build(reference="/root/reference", force=False, verbose=False):
     """Compile the reference's Cython modules into oracle/_ref/dodonaphy/.  Returns True when
     oracle/_ref is usable afterwards, False when the reference sources are absent."""
+    copy_python(reference)
     if is_built() and not force:
         return True
     src_dir = os.path.join(reference, "dodonaphy", "cython")

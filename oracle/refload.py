@@ -4,9 +4,10 @@
 
 * ``oracle/_ref/dodonaphy/*.so``  -- the reference's Cython modules compiled by
   ``oracle/build_ref.py`` (binaries; travel to the GPU box with the snapshot), and
-* ``/root/reference/dodonaphy/*.py`` -- the reference's pure-Python modules, *only when that
-  directory exists* (this container).  On the GPU box it does not exist, and only the compiled
-  modules (``Cphylo``, ``Cpeeler``, ``Chyp_np``, ``Chyp_torch``) are available.
+* the reference's pure-Python modules: the unmodified files ``oracle/build_ref.py`` placed next to the
+  compiled ones in the git-ignored ``oracle/_ref/dodonaphy/`` (they travel to the GPU box with the
+  snapshot), else ``/root/reference/dodonaphy/*.py`` when that directory exists (this container).
+  With neither, only the compiled modules (``Cphylo``, ``Cpeeler``, ``Chyp_np``, ``Chyp_torch``) load.
 
 It returns a small namespace describing what could be loaded.  Stubs installed:
 ``dendropy*``, ``matplotlib*``, ``hydraPlus`` as MagicMock modules, ``np.NaN``/``np.infty`` aliases.
@@ -21,7 +22,8 @@ from unittest import mock
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO_DIR = os.path.join(HERE, "_ref", "dodonaphy")
-REF_PY_DIR = "/root/reference/dodonaphy"
+REF_PY_DIR = REF_SO_DIR if os.path.isfile(os.path.join(REF_SO_DIR, "phylo.py")) else "/root/reference/dodonaphy"
+REF_DATA_DIR = os.path.join(HERE, "_ref", "data")
 
 _state = {}
 
@@ -89,7 +91,7 @@ def load():
     sys.meta_path.append(_StubFinder())
 
     pkg = types.ModuleType("dodonaphy")
-    pkg.__path__ = [REF_SO_DIR] + ([REF_PY_DIR] if have_py else [])
+    pkg.__path__ = [REF_SO_DIR] + ([REF_PY_DIR] if have_py and REF_PY_DIR != REF_SO_DIR else [])
     pkg.__package__ = "dodonaphy"
     sys.modules["dodonaphy"] = pkg
     if not have_py:

@@ -170,17 +170,17 @@ def test_c2_full_size_against_the_reference_itself():
     with the four gamma rates as the reference's category axis (per-category lnL summed) -- through
     the engine (device-formed P) and through the reference-shaped API (caller's mats, torch autograd
     down to the unconstrained GTR leaves).  1e-9 relative."""
-    from conftest import load_golden
+    from conftest import golden_problem, load_golden
     from dodonaphy_b200 import phylo, synth
     from dodonaphy_b200.engine import PruneEngine, SubstModel
     from dodonaphy_b200.phylomodel import PhyloModel
     from oracle import phylo as ophylo
 
     g = load_golden("prune_c2.npz")
-    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    prob = golden_problem("c2")
     masks, weights = prob["masks"], prob["weights"]
-    if int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) != int(g["mask_dot"]) or int(weights.sum()) != int(g["weight_sum"]):
-        pytest.skip("the synthetic alignment regenerated on this host differs from the one the reference answers were computed for")
+    assert int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) == int(g["mask_dot"])
+    assert int(weights.sum()) == int(g["weight_sum"])
     np.testing.assert_array_equal(prob["rates"], g["rates"])
     peel, blens = g["peel"], g["blens"]
     eng = PruneEngine(masks, weights)
@@ -206,18 +206,17 @@ def test_c2_full_size_against_the_reference_itself():
         np.testing.assert_allclose(ours.numpy(), g[key], rtol=1e-8, atol=1e-9 * np.abs(g[key]).max())
 
 
-def _same_alignment_or_skip(masks, checksum):
-    """The stored answers belong to one particular regenerated alignment (the generator's guide tree
-    goes through BLAS); on a host whose BLAS rounds differently the comparison is not applicable."""
-    if int(masks.astype(np.int64).sum()) != int(checksum):
-        pytest.skip("the synthetic alignment regenerated on this host differs from the one the reference answers were computed for")
+def _same_alignment(masks, checksum):
+    """The stored answers belong to one particular alignment: regenerated from its seed on the committed
+    guide tree (conftest.golden_problem), it is the same on every host."""
+    assert int(masks.astype(np.int64).sum()) == int(checksum)
 
 
 def test_configs_2_to_4_against_the_reference_itself():
     """tests/golden/configs.npz: the reference's own Cpeeler.nj_np / Cphylo.compute_LL_np / torch path at
     the shapes of configs[2..4].  Hard NJ on bit-reproducible distances: peel AND branch lengths equal
     bit for bit (200, 500 and 2000 taxa); lnL (and the gradient at 500 taxa) to 1e-9."""
-    from conftest import load_golden
+    from conftest import golden_problem, load_golden
     from dodonaphy_b200 import engine, synth
     from dodonaphy_b200.engine import PruneEngine, SubstModel
 
@@ -247,8 +246,8 @@ def test_configs_2_to_4_against_the_reference_itself():
     assert np.array_equal(blens.cpu().numpy().reshape(-1), g["c5_blens"])
     # likelihood answers: on the reference's NJ tree of the sample's own locations (on an unrelated tree
     # the reference's unscaled product is -inf at 500 taxa)
-    prob = synth.make_problem(500, 20000, 1, D=5, seed=1005)
-    _same_alignment_or_skip(prob["masks"], g["c5_mask_sum"])
+    prob = golden_problem("c5")
+    _same_alignment(prob["masks"], g["c5_mask_sum"])
     ll, gr = PruneEngine(prob["masks"], prob["weights"]).loglik(_dev(g["c5_ll_peel"]), _dev(g["c5_ll_blens"]), jc, grad=True)
     assert ll.item() == pytest.approx(float(g["c5_lnL"]), rel=1e-9)
     assert ll.item() == pytest.approx(float(g["c5_lnL_cython"]), rel=1e-9)
@@ -262,16 +261,16 @@ def test_c2_one_sample_end_to_end_against_the_reference_itself():
     calculate_treelikelihood over 10 000 patterns -> torch autograd back to the locations.  The fused
     device path must reproduce the topology bit for bit and lnL, branch lengths and d lnL / d locations
     to 1e-9 (K = 1 and the four gamma rates as the reference's summed category axis)."""
-    from conftest import load_golden
+    from conftest import golden_problem, load_golden
     from dodonaphy_b200 import synth
     from dodonaphy_b200.engine import SubstModel
     from dodonaphy_b200.pipeline import HotPath
 
     g = load_golden("chain_c2.npz")
-    prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
+    prob = golden_problem("c2")
     masks, weights = prob["masks"], prob["weights"]
-    if int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) != int(g["mask_dot"]) or int(weights.sum()) != int(g["weight_sum"]):
-        pytest.skip("the synthetic alignment regenerated on this host differs from the one the reference answers were computed for")
+    assert int((masks.astype(np.int64) * (np.arange(masks.shape[1]) % 97 + 1)).sum()) == int(g["mask_dot"])
+    assert int(weights.sum()) == int(g["weight_sum"])
     gtr = SubstModel.gtr(g["rates"], g["freqs"])
     x = _dev(g["x"])[None]
     for rates, key_ll, key_g in ((None, "lnL", "g_x"), (g["cat_rates"], "k4_lnL", "k4_g_x")):
@@ -289,7 +288,7 @@ def test_mcmc_chain_end_to_end_against_the_reference_itself():
     Cphylo.compute_LL_np) from the locations to lnL at the configs[2] shape (200 taxa x 20 000
     patterns) and the configs[0] shape (DS1: 27 taxa x 934 patterns).  lnL and tree length do not
     depend on how the exactly-tied last joins are ordered: 1e-9 through the whole device chain."""
-    from conftest import load_golden
+    from conftest import golden_problem, load_golden
     from dodonaphy_b200 import synth
     from dodonaphy_b200.engine import SubstModel
     from dodonaphy_b200.pipeline import HotPath
@@ -301,8 +300,8 @@ def test_mcmc_chain_end_to_end_against_the_reference_itself():
     for i in range(4):
         assert out["lnL"][i].item() == pytest.approx(float(g[f"c1_{i}_lnL"]), rel=1e-9)
         assert out["blens"][i].sum().item() == pytest.approx(float(g[f"c1_{i}_len"]), rel=1e-9)
-    prob = synth.make_problem(200, 20000, 64, D=5, seed=1003)
-    _same_alignment_or_skip(prob["masks"], g["c3_mask_sum"])
+    prob = golden_problem("c3")
+    _same_alignment(prob["masks"], g["c3_mask_sum"])
     hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69())
     out = hp.value(_dev(np.stack([g[f"c3_{i}_x"] for i in range(4)])))
     for i in range(4):
@@ -313,7 +312,7 @@ def test_mcmc_chain_end_to_end_against_the_reference_itself():
 def test_c4_shape_distances_against_the_reference_itself():
     """tests/golden/pdm_c4.npz: 4000 sampled entries (plus row sums and the grand total) of the reference's
     own Chyp_np.get_pdm / Chyp_torch.get_pdm matrices for 2000 seeded taxa (configs[3])."""
-    from conftest import load_golden
+    from conftest import golden_problem, load_golden
     from dodonaphy_b200 import engine
 
     g = load_golden("pdm_c4.npz")
