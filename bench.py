@@ -335,9 +335,161 @@ def run_ours(args, cfg):
             n1 = max(1, args.cpu_trees // 8)  # the same arithmetic on one thread (SURVEY.md 8d asks for both)
             dt1, _, _, _ = cpu_reference(prob, cfg, n1, threads=1)
             line["cpu_baseline"]["single_thread"] = {"value": S * L * n1 / dt1, "samples": n1, "seconds": dt1}
+    strong = None
+    if not args.no_strong:
+        strong = strong_legs(args, rank, world, dist)
+    if rank == 0:
+        if strong is not None:
+            line["strong"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# Strong-scaling legs: the multi-GPU configurations BASELINE.json names, total work FIXED as N grows,
+# measured in the same job as the headline.  Each leg reports the time of the whole problem on ONE rank
+# (rank 0 alone, the others idle at the barrier) and sharded over all N ranks, device-timed (CUDA
+# events, barrier + synchronize on both sides, max over ranks).
+# ---------------------------------------------------------------------------------------------
+def _timed_all_ranks(fn, steps, warmup, world, dist, active=True):
+    """ms per call of ``fn`` over ``steps`` calls; ranks with ``active=False`` only take part in the
+    barriers (used for the 1-rank reference time inside an N-rank job)."""
+    import torch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if active:
+        for _ in range(warmup):
+            fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    if active:
+        for _ in range(steps):
+            fn()
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_legs(args, rank, world, dist, which=("c2", "c3", "c5")):
+    import torch
+
+    from dodonaphy_b200 import dist as ddist, engine, synth
+    from dodonaphy_b200.engine import PruneEngine, SubstModel
+    from dodonaphy_b200.pipeline import GraphedStep, HotPath
+
+    steps, warmup = max(3, min(args.steps, 10)), 3
+    legs = {}
+
+    def finish(name, desc, units, ms1, msn, extra):
+        legs[name] = {"config": desc, "n_gpus": world, "ms_1gpu": ms1, "ms": msn, "value": units / (msn * 1e-3), "unit": UNIT,
+                      "speedup": ms1 / msn, "efficiency": ms1 / (world * msn), **extra}
+
+    if "c2" in which:
+        # (i) the headline workload with 128 samples IN TOTAL (vi.py:328-333 shards by sample)
+        cfg = WORKLOADS["c2"]
+        S, L, B, D, K = cfg["S"], cfg["L"], cfg["B"], cfg["D"], cfg["K"]
+        prob = synth.make_problem(S, L, B, D=D, seed=cfg["seed"])
+        hp = HotPath(prob["masks"], prob["weights"], SubstModel.gtr(prob["rates"], prob["freqs"]),
+                     rates=SubstModel.discrete_gamma(cfg["alpha"], K), mix=True, tau=cfg["tau"])
+        lo, hi = ddist.shard_bounds(B, rank, world)
+        x_all, x_loc = torch.as_tensor(prob["xs"]).cuda(), torch.as_tensor(prob["xs"][lo:hi]).cuda()
+        gathered = torch.empty(B, dtype=torch.float64, device="cuda")
+        ms1 = None
+        if rank == 0 or world == 1:
+            g1 = GraphedStep(hp, x_all, grad=True)
+        ms1 = _timed_all_ranks((lambda: g1.run(x_all)) if rank == 0 else None, steps, warmup, world, dist, active=rank == 0)
+        if world > 1:
+            gn = GraphedStep(hp, x_loc, grad=True)
+            even = B % world == 0
+
+            def step_n():
+                r = gn.run(x_loc)
+                if even:
+                    dist.all_gather_into_tensor(gathered, r["lnL"])
+                else:
+                    ddist.gather_samples(r["lnL"], B)
+
+            msn = _timed_all_ranks(step_n, steps, warmup, world, dist)
+        else:
+            msn = ms1
+        finish("c2_128_samples_total", cfg["desc"] + " -- 128 samples in total, sharded by sample", S * L * B, ms1, msn,
+               {"samples_per_gpu": hi - lo, "exchange": "all_gather of per-sample lnL", "graph": True})
+        del hp, x_all, x_loc
+        torch.cuda.empty_cache()
+
+    if "c3" in which:
+        # (ii) configs[2]: 64 chains in total, 200 taxa x 50k patterns, JC69, forward only (mcmc.py:136-146)
+        cfg = SIDE["c3"]
+        S, L, B, D = cfg["S"], cfg["L"], cfg["B"], cfg["D"]
+        prob = synth.make_problem(S, 20000, B, D=D, seed=1003)
+        reps = -(-L // prob["masks"].shape[1])
+        masks = np.tile(prob["masks"], (1, reps))[:, :L]
+        weights = np.tile(prob["weights"], reps)[:L]
+        hp = HotPath(masks, weights, SubstModel.jc69())
+        lo, hi = ddist.shard_bounds(B, rank, world)
+        x_all, x_loc = torch.as_tensor(prob["xs"]).cuda(), torch.as_tensor(prob["xs"][lo:hi]).cuda()
+        gathered = torch.empty(B, dtype=torch.float64, device="cuda")
+        if rank == 0 or world == 1:
+            g1 = GraphedStep(hp, x_all, grad=False)
+        ms1 = _timed_all_ranks((lambda: g1.run(x_all)) if rank == 0 else None, steps, warmup, world, dist, active=rank == 0)
+        if world > 1:
+            gn = GraphedStep(hp, x_loc, grad=False)
+
+            def step_n():
+                r = gn.run(x_loc)
+                if B % world == 0:
+                    dist.all_gather_into_tensor(gathered, r["lnL"])
+                else:
+                    ddist.gather_samples(r["lnL"], B)
+
+            msn = _timed_all_ranks(step_n, steps, warmup, world, dist)
+        else:
+            msn = ms1
+        finish("c3_64_chains_total", cfg["desc"] + " -- sharded by chain", S * L * B, ms1, msn,
+               {"chains_per_gpu": hi - lo, "exchange": "all_gather of per-chain lnL", "graph": True})
+        del hp, x_all, x_loc
+        torch.cuda.empty_cache()
+
+    if "c5" in which:
+        # (iii) configs[4]: 500 taxa x 1M patterns, lnL + gradient, site blocks + ONE all_reduce of 1 + 2S-2 doubles
+        cfg = SIDE["c5"]
+        S, L, D = cfg["S"], cfg["L"], cfg["D"]
+        prob = synth.make_problem(S, 20000, 1, D=D, seed=1005)
+        reps = -(-L // prob["masks"].shape[1])
+        masks = np.tile(prob["masks"], (1, reps))[:, :L]
+        weights = np.tile(prob["weights"], reps)[:L]
+        peel, blens = engine.nj_hard(engine.pdm_forward(torch.as_tensor(prob["xs"][0]).cuda(), -1.0, "numpy"))
+        ms1 = None
+        if rank == 0 or world == 1:
+            full = ddist.SiteShardedStep(PruneEngine(masks, weights), SubstModel.jc69(), peel, blens, grad=True, reduce=False)
+        ms1 = _timed_all_ranks((lambda: full.run()) if rank == 0 else None, steps, warmup, world, dist, active=rank == 0)
+        extra = {"exchange": "one all_reduce of 1 + 2S-2 = 999 doubles per evaluation (NCCL), captured in the step's CUDA graph"}
+        if world > 1:
+            ll_full = full.lnl.clone() if rank == 0 else None
+            if rank == 0:
+                del full
+            torch.cuda.empty_cache()
+            lo, hi = ddist.shard_bounds(L, rank, world)
+            part = ddist.SiteShardedStep(PruneEngine(np.ascontiguousarray(masks[:, lo:hi]), weights[lo:hi]), SubstModel.jc69(),
+                                         peel, blens, grad=True)
+            msn = _timed_all_ranks(lambda: part.run(), steps, warmup, world, dist)
+            extra.update(patterns_per_gpu=hi - lo, graph=part.graph is not None)
+            if rank == 0:
+                extra["lnL_rel_diff_vs_1gpu"] = abs(float(part.lnl[0]) - float(ll_full[0])) / abs(float(ll_full[0]))
+        else:
+            msn = ms1
+            extra.update(patterns_per_gpu=L, graph=full.graph is not None)
+        finish("c5_1M_site_patterns", cfg["desc"] + " -- site blocks", S * L, ms1, msn, extra)
+    return legs
 
 
 def run_side(args):
@@ -431,6 +583,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-trees", type=int, default=128, help="samples in the bounded CPU-baseline pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs (configs[1] with 128 samples in total, configs[2], configs[4])")
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--side", default=None, choices=sorted(SIDE), help="time a non-headline configuration instead")

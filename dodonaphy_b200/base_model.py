@@ -34,7 +34,8 @@ class _BatchedLogLik(torch.autograd.Function):
         # the leaf is log(-kappa) (base_model.py:109-124): kappa = -exp(leaf), d kappa / d leaf = kappa
         hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
         x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
-        out = hot.value_and_grad(x, to_locations=False)
+        # flagged soft-NJ samples: redone exhaustively / raised, like the one-tree route (peeler._SoftNJ)
+        out = hot.resolve(x, hot.value_and_grad(x, to_locations=False), to_locations=False)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
         ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens") if k in out}
@@ -63,7 +64,7 @@ class _BatchedLogLikModel(torch.autograd.Function):
     def forward(ctx, locs, curvature_leaf, raw_rates, raw_freqs, hot):
         hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
         x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
-        dec = hot.decode(x)
+        dec = hot.decode_checked(x)
         peel, blens = dec["peel"], dec["blens"]
         P, pi = PhyloModel.transition_mats_from_raw(raw_rates.detach(), raw_freqs.detach(), blens, hot.rates)
         out = hot.prune.loglik_mats(peel, P, pi.numpy(), grad=True, mix=hot.mix)

@@ -1207,9 +1207,48 @@ __global__ void __launch_bounds__(1024) geo_hard_kernel(const double *__restrict
     }
 }
 
+// Batched callers' policy for soft-NJ status flags: a sample whose joins carry a bit of `mask` has a
+// topology the reference would not have produced (guard tripped: must be redone exhaustively; invalid
+// selection: the reference indexes a masked node there).  Its lnL and gradient row are poisoned with
+// NaN so that it cannot be consumed silently, and the two kinds are counted for the host.
+__global__ void nj_guard_kernel(const int32_t *__restrict__ flags, int B, int nJ, uint32_t mask, int E,
+                                double *__restrict__ loglik, double *__restrict__ grad, int32_t *__restrict__ counts) {
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    unsigned bits = 0;
+    for (int t = threadIdx.x; t < nJ; t += blockDim.x) bits |= (unsigned)flags[(size_t)b * nJ + t];
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    __shared__ unsigned sh_bits[8];
+    if ((threadIdx.x & 31) == 0) sh_bits[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    bits = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) bits |= sh_bits[w];
+    bits &= mask;
+    if (!bits) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (threadIdx.x == 0) {
+        if (loglik) loglik[b] = nan;
+        if (bits & 4u) atomicAdd(counts + 0, 1);
+        if (bits & 8u) atomicAdd(counts + 1, 1);
+    }
+    if (grad)
+        for (int e = threadIdx.x; e < E; e += blockDim.x) grad[(size_t)b * E + e] = nan;
+}
+
 }  // namespace dodo
 
 using namespace dodo;
+
+extern "C" int dodo_nj_guard(const int32_t *d_flags, int B, int S, uint32_t mask, double *d_loglik,
+                             double *d_grad_blens, int32_t *d_counts, void *stream_) {
+    DODO_CHECK_ARG(d_flags && d_counts, "dodo_nj_guard: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_guard: need B>=1, S>=2");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DODO_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(int32_t), stream));
+    nj_guard_kernel<<<B, 64, 0, stream>>>(d_flags, B, S - 1, mask, 2 * S - 2, d_loglik, d_grad_blens, d_counts);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
 
 extern "C" int dodo_soft_argmin(const double *d_Q, int B, int rows, int cols, double tau, double *d_rowcol, void *stream_) {
     DODO_CHECK_ARG(d_Q && d_rowcol, "dodo_soft_argmin: NULL argument");

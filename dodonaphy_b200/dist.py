@@ -75,6 +75,65 @@ def reduce_site_blocks(lnl, grad_blens=None, group=None):
     return packed[:, 0].reshape(lnl.shape), packed[:, 1:].reshape(grad_blens.shape)
 
 
+class SiteShardedStep:
+    """One evaluation of a site-sharded likelihood as ONE replayable unit: this rank's pruning pass
+    writes lnL and d lnL/d blens of its pattern block into a single packed buffer (B, 1 + 2S-2), and the
+    all_reduce over ranks runs on that buffer in place -- kernels and collective captured together in a
+    CUDA graph (NCCL collectives are capturable), so an evaluation costs one graph launch instead of
+    the Python launch sequence plus a pack / reduce / unpack round trip.  ``run(peel, blens)`` copies the
+    new tree into the captured inputs and replays; results are views of the packed buffer."""
+
+    def __init__(self, engine, model, peel, blens, rates=None, mix=False, grad=True, group=None, graph=True, reduce=True):
+        self.engine, self.model, self.rates, self.mix, self.grad, self.group = engine, model, rates, mix, grad, group
+        dev = engine.device
+        self.peel = peel.detach().to(dev, dtype=torch.int64).reshape(-1, engine.S - 1, 3).contiguous().clone()
+        self.blens = blens.detach().to(dev, dtype=torch.float64).reshape(-1, engine.E).contiguous().clone()
+        B = int(self.blens.shape[0])
+        if B == 1:
+            self.packed = torch.zeros(1 + engine.E if grad else 1, dtype=torch.float64, device=dev)
+            self.lnl = self.packed[:1]
+            self.g = self.packed[1:].reshape(1, engine.E) if grad else None
+        else:  # separate regions of one buffer: [B lnL | B x E gradients]
+            self.packed = torch.zeros(B * (1 + engine.E) if grad else B, dtype=torch.float64, device=dev)
+            self.lnl = self.packed[:B]
+            self.g = self.packed[B:].reshape(B, engine.E) if grad else None
+        self.world = dist.get_world_size(group) if (reduce and dist.is_initialized()) else 1
+        self.graph = None
+        if graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step()
+                self.graph = g
+            except Exception as exc:  # a collective that cannot be captured here: launch by launch
+                self.graph_error = repr(exc)
+                torch.cuda.synchronize(dev)
+
+    def _step(self):
+        self.engine.loglik(self.peel, self.blens, self.model, rates=self.rates, mix=self.mix, grad=self.grad,
+                           out=(self.lnl, self.g))
+        if self.world > 1:
+            dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group)
+
+    def run(self, peel=None, blens=None):
+        if peel is not None:
+            self.peel.copy_(peel.reshape(self.peel.shape), non_blocking=True)
+        if blens is not None:
+            self.blens.copy_(blens.reshape(self.blens.shape), non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return self.lnl, self.g
+
+
 class SiteShardedLikelihood:
     """Long-alignment likelihood (BASELINE.json configs[4]): this rank's block of site patterns on
     this rank's GPU, one all_reduce per evaluation."""

@@ -168,6 +168,8 @@ class PruneEngine:
         rates : K category rates (host); None => K = 1
         scale : power-of-two rescaling against underflow (bit-identical to the unscaled result where
                 that one is finite); None => on for >= 200 taxa
+        out   : optional (lnL (B,), grad_blens (B, 2S-2) or None) device tensors to write into (e.g. two
+                views of one packed buffer that a collective then reduces in place)
         Returns (lnL (B,), grad_blens (B, 2S-2) or None), both device tensors.
         """
         with torch.cuda.device(self.device):
@@ -196,8 +198,15 @@ class PruneEngine:
                 scale = self.S >= 200
             flags = (_lib.PRUNE_GRAD if grad else 0) | (_lib.PRUNE_MIX if (mix and K > 1) else 0) | (_lib.PRUNE_SCALE if scale else 0)
             plan, ws = self._plan(B, K, flags)
-            ll = torch.empty(B, dtype=torch.float64, device=self.device)
-            g = torch.empty((B, self.E), dtype=torch.float64, device=self.device) if grad else None
+            if out is not None:
+                ll, g = out
+                if ll.shape != (B,) or ll.dtype != torch.float64 or not ll.is_contiguous():
+                    raise ValueError("out[0] must be a contiguous float64 tensor of shape (B,)")
+                if grad and (g is None or g.shape != (B, self.E) or g.dtype != torch.float64 or not g.is_contiguous()):
+                    raise ValueError("out[1] must be a contiguous float64 tensor of shape (B, 2S-2)")
+            else:
+                ll = torch.empty(B, dtype=torch.float64, device=self.device)
+                g = torch.empty((B, self.E), dtype=torch.float64, device=self.device) if grad else None
             cm = model.c_struct()
             rates_c = (C.c_double * K)(*rates_arr.tolist())
             _lib.check(self.lib.dodo_prune(C.byref(plan), C.byref(cm), rates_c, _ptr(self.tipmask), self.L,
@@ -238,16 +247,40 @@ class PruneEngine:
 # --------------------------------------------------------------------------------------------
 # K1 / K2 batched device functions
 # --------------------------------------------------------------------------------------------
-_ws_cache = {}
+class Workspaces:
+    """Device scratch buffers of the K1 / K2 kernels, one per tag, owned by whoever calls the kernels
+    (a ``HotPath``, a ``GraphedStep``, or the module-level default used by the one-tree shims).
+
+    Kernels receive raw pointers into these buffers, and a captured CUDA graph keeps replaying them:
+    a buffer must therefore never be freed while something may still address it.  Growing a buffer
+    keeps the outgrown one alive once the owner has been ``freeze``-d (done by ``GraphedStep`` at
+    capture), and nothing is ever dropped behind the owner's back.  One owner = one stream: the
+    buffers carry no ordering of their own."""
+
+    def __init__(self):
+        self._bufs = {}
+        self._retired = []
+        self.frozen = False
+
+    def get(self, tag, nbytes, device):
+        key = (tag, str(device))
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            if buf is not None and self.frozen:
+                self._retired.append(buf)
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def freeze(self):
+        self.frozen = True
 
 
-def _workspace(tag, nbytes, device):
-    key = (tag, device)
-    buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
-    return buf
+_default_ws = Workspaces()
+
+
+def _workspace(tag, nbytes, device, ws=None):
+    return (_default_ws if ws is None else ws).get(tag, nbytes, device)
 
 
 def _as_batch(x, ndim):
@@ -264,33 +297,25 @@ def _as_batch(x, ndim):
     return x.contiguous(), squeeze
 
 
-_curv_cache = {}
-
-
 def _curv_tensor(curvature, device):
+    """Device scalar for the curvature argument.  A Python number becomes a fresh one-element tensor
+    filled by a kernel (no pageable host->device copy, hence no stream synchronisation, and nothing
+    cached that a captured graph could outlive); a CUDA tensor is used as it is."""
     if isinstance(curvature, torch.Tensor):
         if curvature.is_cuda:
             return curvature.detach().to(device=device, dtype=torch.float64).reshape(-1)[:1].contiguous()
         curvature = float(curvature.detach().reshape(-1)[0])
-    # a pageable host->device copy synchronises the stream: keep one device scalar per value
-    key = (float(curvature), str(device))
-    t = _curv_cache.get(key)
-    if t is None:
-        if len(_curv_cache) > 64:
-            _curv_cache.clear()
-        t = torch.tensor([float(curvature)], dtype=torch.float64, device=device)
-        _curv_cache[key] = t
-    return t
+    return torch.full((1,), float(curvature), dtype=torch.float64, device=device)
 
 
-def pdm_forward(x, curvature=-1.0, variant="torch", lift="up", matsumoto=False):
+def pdm_forward(x, curvature=-1.0, variant="torch", lift="up", matsumoto=False, ws=None):
     """Batched pairwise hyperbolic distances.  x: (B,S,D) or (S,D) -> (B,S,S) or (S,S) on device."""
     lib = _lib.load()
     x, squeeze = _as_batch(x, 3)
     B, S, D = (int(v) for v in x.shape)
     with torch.cuda.device(x.device):
         out = torch.empty((B, S, S), dtype=torch.float64, device=x.device)
-        ws = _workspace("pdm", lib.dodo_pdm_workspace_bytes(B, S, D), x.device)
+        ws = _workspace("pdm", lib.dodo_pdm_workspace_bytes(B, S, D), x.device, ws)
         cv = _curv_tensor(curvature, x.device)
         _lib.check(lib.dodo_pdm_fwd(_ptr(x), B, S, D, _ptr(cv), _lib.PDM_TORCH if variant == "torch" else _lib.PDM_NUMPY,
                                     _lib.LIFT_UP if lift == "up" else _lib.LIFT_WRAP, int(bool(matsumoto)),
@@ -298,7 +323,7 @@ def pdm_forward(x, curvature=-1.0, variant="torch", lift="up", matsumoto=False):
     return out[0] if squeeze else out
 
 
-def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False):
+def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False, ws=None):
     """VJP of pdm_forward (torch variant).  Returns (grad_x like x, grad_curvature (B,))."""
     lib = _lib.load()
     x, squeeze = _as_batch(x, 3)
@@ -309,7 +334,7 @@ def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False):
     with torch.cuda.device(x.device):
         gx = torch.empty_like(x)
         gc = torch.empty(B, dtype=torch.float64, device=x.device)
-        ws = _workspace("pdm", lib.dodo_pdm_workspace_bytes(B, S, D), x.device)
+        ws = _workspace("pdm", lib.dodo_pdm_workspace_bytes(B, S, D), x.device, ws)
         cv = _curv_tensor(curvature, x.device)
         _lib.check(lib.dodo_pdm_bwd(_ptr(x), B, S, D, _ptr(cv), _lib.PDM_TORCH,
                                     _lib.LIFT_UP if lift == "up" else _lib.LIFT_WRAP, int(bool(matsumoto)),
@@ -317,7 +342,7 @@ def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False):
     return (gx[0] if squeeze else gx), gc
 
 
-def nj_hard(pdm):
+def nj_hard(pdm, ws=None):
     """Batched hard NJ (Cpeeler.nj_np).  pdm (B,S,S) or (S,S) -> peel int64 (B,S-1,3), blens (B,2S-2)."""
     lib = _lib.load()
     pdm, squeeze = _as_batch(pdm, 3)
@@ -327,12 +352,12 @@ def nj_hard(pdm):
     with torch.cuda.device(pdm.device):
         peel = torch.empty((B, S - 1, 3), dtype=torch.int64, device=pdm.device)
         blens = torch.empty((B, 2 * S - 2), dtype=torch.float64, device=pdm.device)
-        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device)
+        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device, ws)
         _lib.check(lib.dodo_nj_hard(_ptr(pdm), B, S, _ptr(ws), _ptr(peel), _ptr(blens), _stream()))
     return (peel[0], blens[0]) if squeeze else (peel, blens)
 
 
-def nj_soft(pdm, tau, exhaustive=False, return_flags=False):
+def nj_soft(pdm, tau, exhaustive=False, return_flags=False, ws=None):
     """Batched soft NJ (peeler.nj_torch with tau).  Returns peel, blens[, flags (B,S-1) int32].
     ``exhaustive`` evaluates soft.argmin over all N^2 padded entries instead of the active pairs."""
     lib = _lib.load()
@@ -347,7 +372,7 @@ def nj_soft(pdm, tau, exhaustive=False, return_flags=False):
         peel = torch.zeros((B, S - 1, 3), dtype=torch.int64, device=pdm.device)
         blens = torch.zeros((B, 2 * S - 2), dtype=torch.float64, device=pdm.device)
         flags = torch.zeros((B, S - 1), dtype=torch.int32, device=pdm.device)
-        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device)
+        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device, ws)
         _lib.check(lib.dodo_nj_soft(_ptr(pdm), B, S, -tau if exhaustive else tau, _ptr(ws), _ptr(peel), _ptr(blens),
                                     _ptr(flags), _stream()))
     if squeeze:
@@ -355,7 +380,7 @@ def nj_soft(pdm, tau, exhaustive=False, return_flags=False):
     return (peel, blens, flags) if return_flags else (peel, blens)
 
 
-def nj_soft_backward(peel, flags, grad_blens):
+def nj_soft_backward(peel, flags, grad_blens, ws=None):
     """VJP of soft-NJ branch lengths w.r.t. the distance matrix: returns symmetric (B,S,S)."""
     lib = _lib.load()
     g, squeeze = _as_batch(grad_blens, 2)
@@ -365,15 +390,27 @@ def nj_soft_backward(peel, flags, grad_blens):
     flags = flags.reshape(B, S - 1).to(device=g.device, dtype=torch.int32).contiguous()
     with torch.cuda.device(g.device):
         out = torch.empty((B, S, S), dtype=torch.float64, device=g.device)
-        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), g.device)
+        ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), g.device, ws)
         _lib.check(lib.dodo_nj_soft_bwd(_ptr(peel), _ptr(flags), _ptr(g), B, S, _ptr(ws), _ptr(out), _stream()))
     return out[0] if squeeze else out
+
+
+def nj_guard(flags, loglik=None, grad_blens=None, mask=12):
+    """Poison (NaN) lnL / gradient rows of the samples whose soft-NJ flags (B, S-1) carry a bit of
+    ``mask`` and count them: returns an int32 device tensor [#guard tripped (bit 2), #invalid selection
+    (bit 3)].  No host synchronisation (``HotPath.resolve`` is the host side of the policy)."""
+    lib = _lib.load()
+    B, nj = int(flags.shape[0]), int(flags.shape[1])
+    with torch.cuda.device(flags.device):
+        counts = torch.empty(2, dtype=torch.int32, device=flags.device)
+        _lib.check(lib.dodo_nj_guard(_ptr(flags), B, nj + 1, int(mask), _ptr(loglik), _ptr(grad_blens), _ptr(counts), _stream()))
+    return counts
 
 
 # --------------------------------------------------------------------------------------------
 # geodesic connector (K2g)
 # --------------------------------------------------------------------------------------------
-def geo_soft(x, tau=1e-8):
+def geo_soft(x, tau=1e-8, ws=None):
     """Batched peeler.make_soft_peel_tips: ball locations (B,S,D) or (S,D) ->
     dict(peel, int_locs, blens, flags, slots, tape); slots/tape feed ``geo_soft_backward``."""
     lib = _lib.load()
@@ -389,7 +426,7 @@ def geo_soft(x, tau=1e-8):
                    flags=torch.zeros((B, S - 1), dtype=torch.int32, device=dev),
                    slots=torch.empty((B, S - 1, 2), dtype=torch.int32, device=dev),
                    tape=torch.zeros((B, S - 1, 2, D), dtype=torch.float64, device=dev))
-        ws = _workspace("geo", lib.dodo_geo_workspace_bytes(B, S, D), dev)
+        ws = _workspace("geo", lib.dodo_geo_workspace_bytes(B, S, D), dev, ws)
         _lib.check(lib.dodo_geo_soft(_ptr(x), B, S, D, float(tau), _ptr(ws), _ptr(out["peel"]), _ptr(out["int_locs"]),
                                      _ptr(out["blens"]), _ptr(out["slots"]), _ptr(out["tape"]), _ptr(out["flags"]),
                                      _stream()))

@@ -127,17 +127,16 @@ class HMAP(BaseModel):
 
     # ------------------------------------------------------------------ optimisation
     def record_if_best(self):
-        if self.loss < -self.best_posterior or self.current_epoch == 0:
-            self.best_posterior = -self.loss.detach().clone().reshape(())
-            self.best_ln_p = self.ln_p.detach().clone()
-            self.best_ln_prior = self.ln_prior.detach().clone()
-            self.best_peel = self.peel
-            self.best_blens = self.blens.detach().clone()
-            self.best_epoch = self.current_epoch
-            self.best_freqs = self.phylomodel.freqs.detach().clone()
-            self.best_sub_rates = self.phylomodel.sub_rates.detach().clone()
-            self.best_curvature = torch.as_tensor(self.curvature).detach().clone()
-            self.best_locs = self.get_locs().detach().clone()
+        """Keep a detached snapshot of the best state seen so far under the reference's attribute
+        names (``best_posterior``, ``best_ln_p``, ``best_locs`` ..., hmap.py:236-247)."""
+        if self.current_epoch != 0 and not bool(self.loss < -self.best_posterior):
+            return
+        tensors = dict(posterior=-self.loss.reshape(()), ln_p=self.ln_p, ln_prior=self.ln_prior, blens=self.blens,
+                       freqs=self.phylomodel.freqs, sub_rates=self.phylomodel.sub_rates,
+                       curvature=torch.as_tensor(self.curvature), locs=self.get_locs())
+        for name, value in tensors.items():
+            setattr(self, f"best_{name}", value.detach().clone())
+        self.best_peel, self.best_epoch = self.peel, self.current_epoch
 
     def learn(self, epochs, learn_rate, save_locations=False, start=""):
         """Adam with the reference's 1/(epoch+1)^(1/4) learning-rate decay; returns the history of

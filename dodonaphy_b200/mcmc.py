@@ -39,6 +39,10 @@ class DodonaphyMCMC:
         """One generation for all chains (Metropolis with a symmetric Gaussian proposal)."""
         import torch
 
+        # chain.py:75,455-458: the reference keeps cov = I * step_scale and proposes x + cov @ u with
+        # u ~ N(0, I), i.e. a displacement of standard deviation step_scale per coordinate (its `cov` is
+        # applied as a matrix, not as a covariance).  The Jacobian term of its acceptance ratio is
+        # identically zero on this route (chain.py:414 sets log_abs_det_jacobian = 0.0).
         prop = self.x + self.step_scale * self.rng.standard_normal(self.x.shape)
         ln_p, peel, blens = self.model.log_likelihood_batch_np(prop)
         ln_prior = priors.compute_prior_gamma_dir(torch.as_tensor(blens)).numpy()

@@ -26,6 +26,7 @@ class HotPath:
         self.curvature = curvature
         self.lift = lift
         self.matsumoto = matsumoto
+        self.ws = engine.Workspaces()  # K1 / K2 scratch owned by this object (never shared, never dropped)
 
     @classmethod
     def from_engine(cls, prune_engine, model, rates=None, mix=False, tau=1e-8, curvature=-1.0, lift="up", matsumoto=False,
@@ -38,23 +39,27 @@ class HotPath:
         self.model = model
         self.rates = None if rates is None else np.ascontiguousarray(rates, dtype=np.float64)
         self.mix, self.tau, self.curvature, self.lift, self.matsumoto = bool(mix), tau, curvature, lift, matsumoto
+        self.ws = engine.Workspaces()
         return self
 
     # -- tree decoding: the differentiable connector and its reverse ------------------------------
-    def decode(self, x):
-        """x (B,S,D) -> dict(peel, blens, + what ``decode_backward`` needs).  'nj': distance kernel +
+    def decode(self, x, exhaustive=False):
+        """x (B,S,D) -> dict(peel, blens, flags + what ``decode_backward`` needs).  'nj': distance kernel +
         soft NJ (vi.py:476-484); 'geodesics': the LCA connector on x taken as ball coordinates
-        (vi.py:479-482; curvature -1 only, as in the reference)."""
+        (vi.py:479-482; curvature -1 only, as in the reference).  ``flags`` (B,S-1): bit 2 = the soft
+        argmin's closed-form treatment of inactive entries is not provably exact for that join (redo with
+        ``exhaustive=True``), bit 3 = it selected an inactive node.  Nothing is checked here: see
+        ``value_and_grad`` / ``resolve``."""
         if self.connector == "geodesics":
             if abs(float(self.curvature) + 1.0) > 1e-8:
                 raise NotImplementedError(f"Curvature must be -1, got {self.curvature}")
-            out = engine.geo_soft(x, 1e-8)
+            out = engine.geo_soft(x, 1e-8, ws=self.ws)
             out["flags"] = out["flags"] & 8  # only an invalid selection matters downstream
             return out
         if self.connector != "nj":
             raise NotImplementedError(f"connector {self.connector!r} has no differentiable device path")
-        pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto)
-        peel, blens, flags = engine.nj_soft(pdm, self.tau, return_flags=True)
+        pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto, ws=self.ws)
+        peel, blens, flags = engine.nj_soft(pdm, self.tau, exhaustive=exhaustive, return_flags=True, ws=self.ws)
         return dict(peel=peel, blens=blens, flags=flags)
 
     def decode_backward(self, x, dec, grad_blens):
@@ -62,18 +67,59 @@ class HotPath:
         if self.connector == "geodesics":
             gx = engine.geo_soft_backward(dec["peel"], dec["slots"], dec["tape"], grad_blens)
             return gx, torch.zeros(gx.shape[0], dtype=torch.float64, device=gx.device)
-        gpdm = engine.nj_soft_backward(dec["peel"], dec["flags"], grad_blens)
-        return engine.pdm_backward(x, gpdm, self.curvature, self.lift, self.matsumoto)
+        gpdm = engine.nj_soft_backward(dec["peel"], dec["flags"], grad_blens, ws=self.ws)
+        return engine.pdm_backward(x, gpdm, self.curvature, self.lift, self.matsumoto, ws=self.ws)
 
-    def value_and_grad(self, x, to_locations=True):
+    def value_and_grad(self, x, to_locations=True, exhaustive=False):
         """x: (B,S,D) device tensor.  Returns dict(lnL (B,), grad_x (B,S,D), grad_curvature (B,),
-        peel (B,S-1,3), blens (B,2S-2)) -- the differentiable (VI) path.  ``to_locations=False`` stops
-        at d lnL/d blens (the caller chains ``decode_backward`` itself)."""
-        dec = self.decode(x)
+        peel (B,S-1,3), blens (B,2S-2), flags, bad) -- the differentiable (VI) path.
+        ``to_locations=False`` stops at d lnL/d blens (the caller chains ``decode_backward`` itself).
+
+        Samples whose soft-NJ flags carry bit 2 or bit 3 have a topology the reference would not have
+        produced: their lnL and gradients come back as NaN (poisoned on the device, so the step stays
+        free of host synchronisation and can be captured in a graph) and ``bad`` = device int32
+        [#guard tripped, #invalid selection].  ``resolve`` applies the reference-faithful policy."""
+        dec = self.decode(x, exhaustive=exhaustive)
         ll, gbl = self.prune.loglik(dec["peel"], dec["blens"], self.model, rates=self.rates, mix=self.mix, grad=True)
+        dec["bad"] = engine.nj_guard(dec["flags"], ll, gbl)
         dec.update(lnL=ll, grad_blens=gbl)
         if to_locations:
             dec["grad_x"], dec["grad_curvature"] = self.decode_backward(x, dec, gbl)
+        return dec
+
+    def resolve(self, x, out, to_locations=True):
+        """Host side of the flag policy (one device->host read of two counters): samples whose exactness
+        guard tripped are re-evaluated with the exhaustive N^2 soft argmin -- the reference's result in
+        every regime -- and patched into ``out``; an invalid selection raises, as the one-tree route
+        ``peeler.nj_torch`` does.  Call it where the results are about to leave the device anyway."""
+        n_guard, n_invalid = (int(v) for v in out["bad"].tolist())
+        if n_invalid:
+            raise RuntimeError("soft NJ: the soft argmin selected an inactive node for "
+                               f"{n_invalid} sample(s) (temperature too high for these distances)")
+        if n_guard:
+            idx = ((out["flags"] & 4) != 0).any(dim=1).nonzero().reshape(-1)
+            sub = self.value_and_grad(x[idx].contiguous(), to_locations=to_locations, exhaustive=True)
+            if int(sub["bad"][1]):
+                raise RuntimeError("soft NJ: the soft argmin selected an inactive node")
+            for k, v in sub.items():
+                if k != "bad" and isinstance(v, torch.Tensor) and k in out and v.shape[0] == idx.numel():
+                    out[k][idx] = v
+            out["bad"] = torch.zeros_like(out["bad"])
+        return out
+
+    def decode_checked(self, x):
+        """``decode`` + the same host policy, for callers that synchronise right after decoding."""
+        dec = self.decode(x)
+        bad = int((dec["flags"] & 12).max().item()) if dec["flags"].numel() else 0
+        if bad & 8:
+            raise RuntimeError("soft NJ: the soft argmin selected an inactive node (temperature too high for these distances)")
+        if bad & 4:
+            idx = ((dec["flags"] & 4) != 0).any(dim=1).nonzero().reshape(-1)
+            sub = self.decode(x[idx].contiguous(), exhaustive=True)
+            if int((sub["flags"] & 8).max().item()):
+                raise RuntimeError("soft NJ: the soft argmin selected an inactive node")
+            for k, v in sub.items():
+                dec[k][idx] = v
         return dec
 
     def blens_jacobian(self, x, peel=None, flags=None, logdet=True):
@@ -85,17 +131,27 @@ class HotPath:
         so two rows of J coincide and the determinant is numerically ~0 in the reference as well.)"""
         B, S, D = (int(v) for v in x.shape)
         E = 2 * S - 2
-        cot = torch.eye(E, dtype=torch.float64, device=x.device).repeat(B, 1)
         if self.connector == "geodesics":
             dec = self.decode(x)
+            cot = torch.eye(E, dtype=torch.float64, device=x.device).repeat(B, 1)
             rep = {k: dec[k].repeat_interleave(E, 0) for k in ("peel", "slots", "tape")}
             gx, _ = self.decode_backward(None, rep, cot)
         else:
             if peel is None:
-                dec = self.decode(x)
+                dec = self.decode_checked(x)
                 peel, flags = dec["peel"], dec["flags"]
-            rep = dict(peel=peel.repeat_interleave(E, 0), flags=flags.repeat_interleave(E, 0))
-            gx, _ = self.decode_backward(x.repeat_interleave(E, 0), rep, cot)
+            # every replay needs an S x S adjoint workspace: chunk the B*E replays to a memory budget
+            # (2000 taxa: 32 MB per replay) instead of asking for all of them at once
+            per = max(1, int(engine._lib.load().dodo_nj_workspace_bytes(1, S)))
+            chunk = max(1, min(B, int((2 << 30) // (per * E))))
+            parts = []
+            eye = torch.eye(E, dtype=torch.float64, device=x.device)
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
+                rep = dict(peel=peel[lo:hi].repeat_interleave(E, 0), flags=flags[lo:hi].repeat_interleave(E, 0))
+                g, _ = self.decode_backward(x[lo:hi].repeat_interleave(E, 0), rep, eye.repeat(hi - lo, 1))
+                parts.append(g)
+            gx = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         J = gx.reshape(B, E, S * D)
         if not logdet:
             return J
@@ -106,8 +162,8 @@ class HotPath:
         """Gradient-free MCMC path (Chyp_np.get_pdm -> Cpeeler.nj_np -> Cphylo.compute_LL_np)."""
         if self.connector != "nj":
             raise NotImplementedError("the batched gradient-free path decodes with hard NJ only")
-        pdm = engine.pdm_forward(x, self.curvature, "numpy", "up", self.matsumoto)
-        peel, blens = engine.nj_hard(pdm)
+        pdm = engine.pdm_forward(x, self.curvature, "numpy", "up", self.matsumoto, ws=self.ws)
+        peel, blens = engine.nj_hard(pdm, ws=self.ws)
         ll, _ = self.prune.loglik(peel, blens, self.model, rates=self.rates, mix=self.mix, grad=False)
         return dict(lnL=ll, peel=peel, blens=blens)
 
@@ -137,6 +193,7 @@ class HotPath:
             r = self.graphed(x_pinned, grad=True).run(x_pinned)
         else:
             r = self.value_and_grad(x_pinned.to(self.device, non_blocking=True))
+        # flagged samples arrive as NaN (see value_and_grad); r["bad"] holds their counts
         out_ll_pinned.copy_(r["lnL"], non_blocking=True)
         out_gx_pinned.copy_(r["grad_x"], non_blocking=True)
         return r
@@ -155,7 +212,15 @@ class GraphedStep:
     """
 
     def __init__(self, hot, x_example, grad=True):
-        self.hot = hot
+        # the graph addresses its scratch by raw pointer: give it workspaces of its own (a private
+        # view of the HotPath sharing the tips and the prune plans, which are never reallocated), so that
+        # nothing the owner does later -- a bigger batch, the batched Jacobian -- can free them
+        import copy
+
+        self.hot = hot = copy.copy(hot)
+        hot.ws = engine.Workspaces()
+        hot.ws.freeze()
+        hot.__dict__.pop("_graphs", None)
         self.x = x_example.detach().to(hot.device, dtype=torch.float64).contiguous().clone()
         fn = hot.value_and_grad if grad else hot.value
         side = torch.cuda.Stream(device=hot.device)

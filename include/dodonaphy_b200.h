@@ -147,6 +147,14 @@ int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void *d_ws, int6
  * d_rowcol [B][2] = (soft_row, soft_col) as doubles, ties resolved towards the last entry. */
 int dodo_soft_argmin(const double *d_Q, int B, int rows, int cols, double tau, double *d_rowcol,
                      void *stream);
+/* Policy for batched callers (the one-tree route peeler.nj_torch re-runs or raises on the host): every
+ * sample whose d_flags [B][S-1] carry a bit of `mask` (4 = exactness guard tripped, 8 = the soft argmin
+ * selected an inactive node -- where the reference, peeler.py:196-205, would index a masked row) gets
+ * d_loglik[b] = NaN and d_grad_blens[b][:] = NaN (either may be NULL), so a topology the reference would
+ * not have produced cannot be consumed silently; d_counts int32 [2] receives the number of samples with
+ * bit 2 / bit 3 set.  Enqueued on `stream`, no host synchronisation. */
+int dodo_nj_guard(const int32_t *d_flags, int B, int S, uint32_t mask, double *d_loglik,
+                  double *d_grad_blens, int32_t *d_counts, void *stream);
 /* VJP of blens w.r.t. pdm given the recorded joins: d_grad_pdm [B][S][S] (symmetric) */
 int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, const double *d_grad_blens,
                      int B, int S, void *d_ws, double *d_grad_pdm, void *stream);

@@ -200,3 +200,45 @@ def test_reference_HMAP_runs_unchanged(reference):
     assert got["ln_prior"] == pytest.approx(want["ln_prior"], rel=1e-9)
     assert got["g_curv"] == pytest.approx(want["g_curv"], rel=1e-7)
     np.testing.assert_allclose(got["g"], want["g"], rtol=1e-7, atol=1e-9 * np.abs(want["g"]).max())
+
+
+def test_hard_nj_peel_match_rate_from_locations():
+    """north_star: "NJ topologies and peel orders bit-exact".  On IDENTICAL distance matrices the hard-NJ
+    kernel is bit-identical to Cpeeler.nj_np (tests/test_configs_gpu.py, 200 / 500 / 2000 taxa).  From
+    LOCATIONS the distances themselves come from different libraries (the reference: OpenBLAS dsyrk + the
+    host's arccosh; here: an FMA chain + CUDA's acosh) and agree to rounding, not bit for bit; NJ's Q has
+    exact mathematical ties once <= 4 nodes remain, so the order of the LAST joins follows the last bit.
+    This test measures that against the compiled reference (Chyp_np.get_pdm -> Cpeeler.nj_np) over the 64
+    chains of configs[2] (200 taxa) and 16 DS1-sized embeddings: every tree must be the same unrooted tree
+    with the same branch lengths (1e-9) and every peel must agree in all joins before the tied ones; the
+    rate of fully bit-identical peels and distance matrices is printed."""
+    from dodonaphy_b200 import engine, synth
+    from oracle import refload
+
+    r = refload.load()
+    assert r.compiled, "oracle/_ref holds no compiled reference modules"
+    for name, S, D, xs in (("configs[2] chains", 200, 5, synth.make_problem(200, 100, 64, D=5, seed=1003)["xs"]),
+                           ("DS1-sized", 27, 3, np.random.default_rng(8).normal(0.0, 0.05, (16, 27, 3)))):
+        pdm = engine.pdm_forward(torch.as_tensor(xs).cuda(), -1.0, "numpy")
+        peel, blens = engine.nj_hard(pdm)
+        pdm, peel, blens = pdm.cpu().numpy(), peel.cpu().numpy(), blens.cpu().numpy()
+        same_peel = same_pdm = 0
+        first_diff = []
+        for b in range(xs.shape[0]):
+            ref_pdm = np.ascontiguousarray(r.Chyp_np.get_pdm(xs[b]))
+            ref_peel, ref_blens = r.Cpeeler.nj_np(ref_pdm)
+            ref_peel = np.asarray(ref_peel)
+            off = ~np.eye(S, dtype=bool)
+            np.testing.assert_allclose(pdm[b][off], ref_pdm[off], rtol=1e-11, atol=1e-15)
+            same_pdm += int(np.array_equal(pdm[b][off], ref_pdm[off]))
+            assert _splits(peel[b], S) == _splits(ref_peel, S)
+            assert blens[b].sum() == pytest.approx(ref_blens.sum(), rel=1e-9)
+            rows = np.nonzero((peel[b] != ref_peel).any(axis=1))[0]
+            if len(rows) == 0:
+                same_peel += 1
+                np.testing.assert_allclose(blens[b], ref_blens, rtol=1e-9, atol=1e-15)
+            else:
+                first_diff.append(int(rows[0]))
+                assert rows[0] >= S - 4, "peels differ before the exactly-tied last joins"
+        print(f"\n[match rate] {name}: {same_peel}/{xs.shape[0]} peels and {same_pdm}/{xs.shape[0]} distance matrices "
+              f"bit-identical to the reference's; first differing join (of {S - 1}): {sorted(set(first_diff))}")

@@ -219,3 +219,82 @@ def test_cherry_tables_and_recomputed_cherries(shape, model):
     assert out["lnL"].item() == pytest.approx(ref, rel=1e-9)
     gm = mats.grad.numpy()
     np.testing.assert_allclose(out["grad_mats"][0].cpu().numpy(), gm, rtol=1e-9, atol=1e-9 * np.abs(gm).max())
+
+
+def test_batched_path_applies_the_soft_nj_flag_policy():
+    """A tripped exactness guard (flag bit 2) or an invalid selection (bit 3) must not be consumed
+    silently by the batched routes: the device step poisons those samples with NaN and counts them
+    (dodo_nj_guard); ``HotPath.resolve`` / ``BaseModel.log_likelihood_batch`` redo guard-tripped samples
+    with the exhaustive N^2 soft argmin -- the reference's result in every regime (soft.py:38-53 over the
+    whole padded matrix, oracle.nj.nj_soft) -- and raise on an invalid selection, exactly as the one-tree
+    route peeler.nj_torch does."""
+    from dodonaphy_b200 import engine, synth
+    from dodonaphy_b200.base_model import BaseModel
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+    from oracle import hyp, nj
+    from oracle.phylo import mask_to_partial
+
+    S, D, B, tau = 8, 3, 6, 1e-3
+    prob = synth.make_problem(S, 120, B, D=D, seed=12)
+    xs = prob["xs"] * 0.1  # distances of a few 1e-2: inactive entries are no longer invisible at tau = 1e-3
+    x = _dev(xs)
+    pdm = engine.pdm_forward(x, -1.0, "torch")
+    _, _, flags = engine.nj_soft(pdm, tau, return_flags=True)
+    tripped = ((flags & 4) != 0).any(dim=1).cpu().numpy()
+    assert tripped.any() and int((flags & 8).sum().item()) == 0, "the case is meant to trip the guard only"
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69(), tau=tau)
+    out = hp.value_and_grad(x)
+    n_guard, n_invalid = out["bad"].tolist()
+    assert n_guard == int(tripped.sum()) and n_invalid == 0
+    assert np.array_equal(torch.isnan(out["lnL"]).cpu().numpy(), tripped)
+    assert np.array_equal(torch.isnan(out["grad_blens"]).all(dim=1).cpu().numpy(), tripped)
+    ok = hp.resolve(x, out)
+    assert torch.isfinite(ok["lnL"]).all() and torch.isfinite(ok["grad_x"]).all() and ok["bad"].tolist() == [0, 0]
+    # the same through the autograd front end, against the oracle's soft NJ per sample
+    tips = [torch.tensor(mask_to_partial(m)) for m in prob["masks"]]
+    bm = BaseModel("vi", tips, torch.tensor(prob["weights"]), D, soft_temp=tau)
+    locs = torch.tensor(xs, requires_grad=True)
+    ll, peel, blens = bm.log_likelihood_batch(locs)
+    ll.sum().backward()
+    assert torch.isfinite(ll).all() and torch.isfinite(locs.grad).all()
+    np.testing.assert_array_equal(peel.cpu().numpy(), ok["peel"].cpu().numpy())
+    np.testing.assert_allclose(ll.detach().numpy(), ok["lnL"].cpu().numpy(), rtol=1e-12)
+    for b in range(B):
+        p_ref, b_ref = nj.nj_soft(hyp.get_pdm_torch(xs[b]), tau)
+        assert np.array_equal(peel[b].cpu().numpy(), p_ref), b
+        np.testing.assert_allclose(blens[b].detach().cpu().numpy(), b_ref, rtol=1e-9, atol=1e-15)
+    # an invalid selection raises instead of returning the lnL of a garbage topology
+    hot = HotPath(prob["masks"], prob["weights"], SubstModel.jc69(), tau=50.0)
+    bad = hot.value_and_grad(x)
+    if bad["bad"].tolist()[1] > 0:
+        with pytest.raises(RuntimeError):
+            hot.resolve(x, bad)
+    bm_hot = BaseModel("vi", tips, torch.tensor(prob["weights"]), D, soft_temp=50.0)
+    d = np.full((B, S, D), np.nan)
+    with pytest.raises(RuntimeError):
+        bm_hot.log_likelihood_batch(torch.tensor(d))
+
+
+def test_graphs_own_their_workspaces():
+    """A captured step keeps replaying raw workspace pointers: growing the owner's buffers afterwards (a
+    bigger batch, the batched Jacobian's B*(2S-2) replays) must not free what the graph addresses."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import GraphedStep, HotPath
+
+    S, D = 10, 3
+    prob = synth.make_problem(S, 200, 24, D=D, seed=4)
+    hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69())
+    x_small, x_big = _dev(prob["xs"][:4]), _dev(prob["xs"])
+    want = {k: v.clone() for k, v in hp.value_and_grad(x_small).items() if k in ("lnL", "grad_x")}
+    g = GraphedStep(hp, x_small, grad=True)
+    hp.value_and_grad(x_big)                 # larger pdm / nj workspaces for the owner
+    hp.blens_jacobian(x_big)                 # ... and much larger ones
+    torch.cuda.empty_cache()
+    filler = [torch.full((1 << 20,), 7.0, device="cuda") for _ in range(8)]  # recycle whatever was freed
+    out = g.run(x_small)
+    torch.cuda.synchronize()
+    assert torch.equal(out["lnL"], want["lnL"]) and torch.equal(out["grad_x"], want["grad_x"])
+    assert all(float(f[0]) == 7.0 and float(f[-1]) == 7.0 for f in filler)
+    assert g.hot.ws is not hp.ws
