@@ -63,22 +63,43 @@ def hyper_to_poincare(location):
     return location[1:] / (1 + location[0])
 
 
+class _PairDistance(torch.autograd.Function):
+    """Distances of n independent pairs through the CUDA kernel (csrc/hypdist.cu) with its VJP."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, curvature, form):
+        kappa = float(curvature.detach().reshape(-1)[0])
+        a, b = x1.detach(), x2.detach()
+        out = _engine.hypdist_forward(a, b, kappa, form)
+        ctx.save_for_backward(a, b)
+        ctx.meta = (kappa, form, x1.device, x2.device, curvature.shape, curvature.device)
+        return out.to(x1.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b = ctx.saved_tensors
+        kappa, form, d1, d2, cshape, cdev = ctx.meta
+        g1, g2, gk = _engine.hypdist_backward(a, b, grad_out.contiguous(), kappa, form)
+        return g1.to(d1), g2.to(d2), gk.sum().reshape(cshape).to(cdev), None
+
+
+def _pair_distance(x1, x2, curvature, form):
+    curv = curvature if isinstance(curvature, torch.Tensor) else torch.tensor([float(curvature)], dtype=torch.float64)
+    x1 = torch.as_tensor(x1, dtype=torch.float64)
+    x2 = torch.as_tensor(x2, dtype=torch.float64)
+    return _PairDistance.apply(x1, x2, curv.to(torch.float64), form)
+
+
 def hyperbolic_distance_lorentz(x1, x2, curvature=-torch.ones(1)):
-    """Poincare-ball points, distance through the hyperboloid (Chyp_torch.pyx:137-154)."""
-    if torch.isclose(curvature, torch.zeros(1, dtype=curvature.dtype)).all():
-        return torch.norm(x2 - x1)
-    inner = torch.clamp(-lorentz_product(poincare_to_hyper(x1), poincare_to_hyper(x2)), min=1.0 + eps)
-    return 1.0 / torch.sqrt(-curvature) * torch.acosh(inner)
+    """Poincare-ball points, distance through the hyperboloid (Chyp_torch.pyx:137-154).  x1, x2: (D,) as
+    in the reference, or (n, D) for n pairs at once; differentiable w.r.t. both points and the curvature."""
+    return _pair_distance(x1, x2, curvature, "lorentz")
 
 
 def hyperbolic_distance(x1, x2, curvature=-torch.ones(1)):
-    """Poincare-ball formula at curvature -1, Lorentz form otherwise (Chyp_torch.pyx:119-134)."""
-    if abs(curvature + 1.0) > 1e-9:
-        return hyperbolic_distance_lorentz(x1, x2, curvature)
-    inv = 2 * torch.sum((x2 - x1) ** 2) / (1 - torch.linalg.norm(x1) ** 2) / (1 - torch.linalg.norm(x2) ** 2)
-    if torch.isnan(inv):
-        return hyperbolic_distance_lorentz(x1, x2, curvature)
-    return torch.acosh(1 + inv)
+    """Poincare-ball formula at curvature -1, Lorentz form otherwise (Chyp_torch.pyx:119-134); (D,) or
+    batched (n, D) like ``hyperbolic_distance_lorentz``."""
+    return _pair_distance(x1, x2, curvature, "poincare")
 
 
 # ---------------------------------------------------------------------------------------------

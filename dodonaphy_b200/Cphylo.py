@@ -72,14 +72,16 @@ def compute_branch_lengths_np(S, peel, leaf_x, int_x, curvature=-1.0, matsumoto=
 
     leaf_x = np.asarray(leaf_x, dtype=np.float64)
     int_x = np.asarray(int_x, dtype=np.float64)
+    peel = np.asarray(peel)[: S - 1]
+    children = peel[:, :2].reshape(-1).astype(np.int64)
+    parents = np.repeat(peel[:, 2].astype(np.int64), 2)
+    is_leaf = children < S
+    here = np.where(is_leaf[:, None], leaf_x[np.where(is_leaf, children, 0)], int_x[np.where(is_leaf, 0, children - S - 1)])
+    up = int_x[parents - S - 1]
+    # all 2S-2 branches as ONE launch of the pairs kernel (the reference loops over them in Python)
+    hd = Chyp_np.hyperbolic_distance(Chyp_np.project_up_2d(here), Chyp_np.project_up_2d(up), curvature)
+    if matsumoto:
+        hd = np.log(np.cosh(hd))
     blens = np.zeros(2 * S - 2, dtype=np.float64)
-    tiny = np.finfo(np.double).eps
-    for left, right, parent in np.asarray(peel)[: S - 1]:
-        up = Chyp_np.project_up(int_x[int(parent) - S - 1])
-        for child in (int(left), int(right)):
-            here = leaf_x[child] if child < S else int_x[child - S - 1]
-            hd = Chyp_np.hyperbolic_distance(Chyp_np.project_up(here), up, curvature)
-            if matsumoto:
-                hd = np.log(np.cosh(hd))
-            blens[child] = np.maximum(hd, tiny)
+    blens[children] = np.maximum(hd, np.finfo(np.double).eps)  # later rows win, as in the reference's loop
     return blens

@@ -15,11 +15,18 @@ MODEL_JC69, MODEL_EIGEN = 0, 1
 PRUNE_GRAD, PRUNE_MIX, PRUNE_SCALE, PRUNE_GMATS = 1, 2, 4, 8
 PDM_TORCH, PDM_NUMPY = 0, 1
 LIFT_UP, LIFT_WRAP = 0, 1
+DIST_POINCARE, DIST_LORENTZ, DIST_SHEET_UP = 0, 1, 2
+PRIOR_TORCH, PRIOR_NUMPY = 0, 1
 
 
 class Model(C.Structure):
     _fields_ = [("U", C.c_double * 16), ("Uinv", C.c_double * 16), ("lam", C.c_double * 4),
                 ("Q", C.c_double * 16), ("pi", C.c_double * 4), ("kind", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("aT", C.c_double), ("bT", C.c_double), ("a", C.c_double), ("c", C.c_double), ("variant", C.c_int32),
+                ("_pad", C.c_int32), ("d_ln_prior", C.c_void_p), ("d_grad_blens", C.c_void_p)]
 
 
 class PrunePlan(C.Structure):
@@ -47,11 +54,15 @@ _SIGNATURES = {
                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dodo_pdm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dodo_hypdist_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "dodo_hypdist_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dodo_nj_workspace_bytes": (C.c_uint64, [C.c_int, C.c_int]),
+    "dodo_prior_gamma_dir": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(Prior), C.c_void_p]),
     "dodo_nj_hard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_void_p]),
+                               C.POINTER(Prior), C.c_void_p]),
     "dodo_nj_soft": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_void_p, C.c_void_p]),
+                               C.c_void_p, C.c_void_p, C.POINTER(Prior), C.c_void_p]),
     "dodo_nj_guard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dodo_soft_argmin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "dodo_nj_soft_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

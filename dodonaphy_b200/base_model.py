@@ -24,6 +24,11 @@ from .phylomodel import PhyloModel
 from .pipeline import HotPath
 
 
+def _ln_prior_of(out):
+    """ln prior from the NJ epilogue when the hot path carries a prior, zeros otherwise."""
+    return out["ln_prior"] if out.get("ln_prior") is not None else torch.zeros_like(out["blens"][:, 0])
+
+
 class _BatchedLogLik(torch.autograd.Function):
     """(lnL, peel, blens) of B embeddings in one fused pass.  lnL and blens both carry gradient to the
     locations and to the curvature leaf: the backward adds the caller's cotangent on blens (e.g. from a
@@ -38,16 +43,18 @@ class _BatchedLogLik(torch.autograd.Function):
         out = hot.resolve(x, hot.value_and_grad(x, to_locations=False), to_locations=False)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
-        ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens") if k in out}
+        ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens", "grad_prior") if k in out}
         ctx.mark_non_differentiable(out["peel"])
-        return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device)
+        return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device), _ln_prior_of(out).to(locs.device)
 
     @staticmethod
-    def backward(ctx, g_ll, _g_peel, g_blens):
+    def backward(ctx, g_ll, _g_peel, g_blens, g_prior):
         x, hot = ctx.x, ctx.hot
         gb = g_ll.to(x.device).reshape(-1, 1) * ctx.dec["grad_blens"]
         if g_blens is not None:
             gb = gb + g_blens.to(x.device)
+        if g_prior is not None and "grad_prior" in ctx.dec:  # prior from the NJ kernel's epilogue
+            gb = gb + g_prior.to(x.device).reshape(-1, 1) * ctx.dec["grad_prior"]
         hot.curvature = ctx.kappa
         gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())
         return gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]), None
@@ -73,10 +80,10 @@ class _BatchedLogLikModel(torch.autograd.Function):
         ctx.x, ctx.dec = x, dec
         ctx.save_for_backward(blens, out["grad_mats"], out["grad_pi"], raw_rates.detach(), raw_freqs.detach())
         ctx.mark_non_differentiable(peel)
-        return out["lnL"].to(locs.device), peel, blens.to(locs.device)
+        return out["lnL"].to(locs.device), peel, blens.to(locs.device), _ln_prior_of(dec).to(locs.device)
 
     @staticmethod
-    def backward(ctx, g_ll, _g_peel, g_blens):
+    def backward(ctx, g_ll, _g_peel, g_blens, g_prior):
         blens, gP, gpi, raw_rates, raw_freqs = ctx.saved_tensors
         x, hot = ctx.x, ctx.hot
         w = g_ll.to(x.device).reshape(-1)
@@ -88,6 +95,8 @@ class _BatchedLogLikModel(torch.autograd.Function):
             gb, g_rates, g_freqs = torch.autograd.grad(obj, (bl, rr, rf))
         if g_blens is not None:
             gb = gb + g_blens.to(x.device)
+        if g_prior is not None and ctx.dec.get("grad_prior") is not None:
+            gb = gb + g_prior.to(x.device).reshape(-1, 1) * ctx.dec["grad_prior"]
         hot.curvature = ctx.kappa
         gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())
         return (gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]),
@@ -190,19 +199,28 @@ class BaseModel:
         self._hot.tau = self.soft_temp
         return self._hot
 
-    def log_likelihood_batch(self, locs):
+    def log_likelihood_batch(self, locs, prior=None):
         """VI: (B,S,D) sampled locations -> (lnL (B,), peel (B,S-1,3), blens (B,2S-2)); lnL carries
         gradient to ``locs``, to the curvature leaf and -- for a learnable GTR model -- to the
-        unconstrained rate and frequency leaves."""
+        unconstrained rate and frequency leaves.  With ``prior`` (an ``engine.GammaDirPrior``) a fourth
+        item, ln prior (B,), comes from the epilogue of the same NJ kernel launch (base_model.py:475-527
+        evaluated where the branch lengths are produced) and is differentiable like lnL."""
         pm = self.phylomodel
-        if not (pm.fix_sub_rates and pm.fix_freqs):
-            return _BatchedLogLikModel.apply(locs, self._curvature, pm._sub_rates, pm._freqs, self._hotpath())
-        return _BatchedLogLik.apply(locs, self._curvature, self._hotpath())
-
-    def log_likelihood_batch_np(self, locs):
-        """MCMC: (B,S,D) proposals (one per chain) -> (lnL, peel, blens) as NumPy arrays, no gradient."""
         hot = self._hotpath()
+        hot.prior = prior
+        if not (pm.fix_sub_rates and pm.fix_freqs):
+            out = _BatchedLogLikModel.apply(locs, self._curvature, pm._sub_rates, pm._freqs, hot)
+        else:
+            out = _BatchedLogLik.apply(locs, self._curvature, hot)
+        return out if prior is not None else out[:3]
+
+    def log_likelihood_batch_np(self, locs, prior=None):
+        """MCMC: (B,S,D) proposals (one per chain) -> (lnL, peel, blens[, ln prior]) as NumPy arrays, no
+        gradient; ``prior`` as in ``log_likelihood_batch`` (hard-NJ kernel epilogue)."""
+        hot = self._hotpath()
+        hot.prior = prior
         hot.curvature = float(self.curvature)
         x = torch.as_tensor(np.ascontiguousarray(locs, dtype=np.float64))
         out = hot.graphed(x, grad=False).run(x)  # every sweep has the same shape: replay one CUDA graph
-        return out["lnL"].cpu().numpy(), out["peel"].cpu().numpy(), out["blens"].cpu().numpy()
+        res = (out["lnL"].cpu().numpy(), out["peel"].cpu().numpy(), out["blens"].cpu().numpy())
+        return res + (out["ln_prior"].cpu().numpy(),) if prior is not None else res

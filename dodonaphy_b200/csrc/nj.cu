@@ -19,6 +19,9 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace dodo {
@@ -63,12 +66,66 @@ __host__ __device__ inline size_t nj_ws_doubles(int S) {
     return 2 * (size_t)nj_ld(S) * nj_ld(S) + ((4 * (size_t)S + 15) & ~(size_t)15);
 }
 
+// ------------------------------------------------------------------------------------------ prior
+// Gamma-Dirichlet(aT, bT, a, c) log prior of one tree's branch lengths and its gradient
+// (BaseModel.compute_prior_gamma_dir dodonaphy/base_model.py:475-527 with utils.LogDirPrior
+// dodonaphy/utils.py:251-267; NumPy twin Cphylo.pyx:53-114), evaluated by ONE warp as the epilogue of
+// the NJ kernel that has just produced the branch lengths (or on its own, dodo_prior_gamma_dir), so the
+// 2S-2 numbers never travel to the host per sample.  Fixed-order reductions.
+struct PriorDev {
+    double aT, bT, a, c, konst;  // konst: normalising constants + topology term, from the host (lgamma)
+    int variant;                 // DODO_PRIOR_TORCH: clamp at 1e-4 when any branch is <= 0; DODO_PRIOR_NUMPY: eps floors
+    double *ln_prior;            // [B]
+    double *grad;                // [B][2S-2] or NULL
+};
+
+__device__ void prior_warp(const double *__restrict__ bl, int S, const PriorDev &pr, int b, int lane) {
+    const int E = 2 * S - 2;
+    double tot = 0.0;
+    int nonpos = 0;
+    for (int e = lane; e < E; e += 32) {
+        const double v = bl[e];
+        tot += v;
+        nonpos |= !(v > 0.0);
+    }
+    tot = warp_sum(tot);
+    nonpos = __any_sync(0xffffffffu, nonpos);
+    const bool np_variant = pr.variant == DODO_PRIOR_NUMPY;
+    const double floor_v = np_variant ? DBL_EPSILON : (nonpos ? 1e-4 : 0.0);
+    double tipb = 0.0, intb = 0.0;
+    for (int e = lane; e < E; e += 32) {
+        const double v = floor_v > 0.0 ? fmax(bl[e], floor_v) : bl[e];
+        if (e < S) tipb += log(v); else intb += log(v);
+    }
+    tipb = warp_sum(tipb);
+    intb = warp_sum(intb);
+    const double treeL = np_variant ? fmax(tot, DBL_EPSILON) : tot;
+    const double coef = pr.aT - pr.a * S - pr.a * pr.c * (S - 3);
+    if (lane == 0)
+        pr.ln_prior[b] = (pr.a - 1.0) * tipb + (pr.a * pr.c - 1.0) * intb + coef * log(treeL) - pr.bT * treeL + pr.konst;
+    if (pr.grad != nullptr) {
+        double *g = pr.grad + (size_t)b * E;
+        for (int e = lane; e < E; e += 32) {
+            const double v = bl[e];
+            const bool clamped = floor_v > 0.0 && v < floor_v;  // a clamp passes no gradient below its floor
+            const double w = e < S ? pr.a - 1.0 : pr.a * pr.c - 1.0;
+            g[e] = (clamped ? 0.0 : w / v) + coef / treeL - pr.bT;
+        }
+    }
+}
+
+__global__ void prior_kernel(const double *__restrict__ blens, int B, int S, PriorDev pr) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b < B) prior_warp(blens + (size_t)b * (2 * S - 2), S, pr, b, threadIdx.x & 31);
+}
+
 // ------------------------------------------------------------------------------------------ hard
 #ifndef HARD_MLP
 #define HARD_MLP 8
 #endif
 __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
-                                                       int64_t *__restrict__ peel, double *__restrict__ blens) {
+                                                       int64_t *__restrict__ peel, double *__restrict__ blens,
+                                                       PriorDev prior) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
@@ -236,6 +293,7 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
         for (int p = tid; p < n - 1; p += T) act[p] = act2[p];
         __syncthreads();
     }
+    if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);  // epilogue (bl complete: barrier above)
 }
 
 // ------------------------------------------------------------------------------------------ soft
@@ -620,7 +678,8 @@ __device__ __forceinline__ void dd_add_dd(double &hi, double &lo, double xh, dou
 
 __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
-                                                       double *__restrict__ blens, int32_t *__restrict__ flags) {
+                                                       double *__restrict__ blens, int32_t *__restrict__ flags,
+                                                       PriorDev prior) {
     extern __shared__ unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
@@ -710,6 +769,7 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
             // the reference would index a masked node here (garbage); flag it and stop this tree
             if (tid == 0) {
                 for (int t = S - n; t < S - 1; ++t) fl[t] = 8;
+                if (prior.ln_prior != nullptr) prior.ln_prior[b] = __longlong_as_double(0x7ff8000000000000ll);
             }
             return;
         }
@@ -772,6 +832,7 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
         __syncthreads();
         { int *t = act; act = act2; act2 = t; }  // the new pool order takes over
     }
+    if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);  // epilogue (bl complete: barrier above)
 }
 
 // reverse replay: adjoint of blens w.r.t. the input distance matrix
@@ -1277,23 +1338,59 @@ static int nj_threads(int S, int B = 1) {
     return t;
 }
 
+// host part of the prior: normalising constants and the uniform-topology term (base_model.py:506-521)
+static int make_prior(const dodo_prior_t *p, int S, PriorDev *out) {
+    memset(out, 0, sizeof(*out));
+    if (p == nullptr) return DODO_OK;
+    DODO_CHECK_ARG(p->d_ln_prior != nullptr, "prior: d_ln_prior is NULL");
+    DODO_CHECK_ARG(p->variant == DODO_PRIOR_TORCH || p->variant == DODO_PRIOR_NUMPY, "prior: bad variant");
+    DODO_CHECK_ARG(p->aT > 0.0 && p->bT > 0.0 && p->a > 0.0 && p->c > 0.0, "prior: parameters must be positive");
+    DODO_CHECK_ARG(S >= 3, "prior: the gamma-Dirichlet prior needs at least 3 taxa");
+    const double n = (double)S;
+    double k = p->aT * log(p->bT) - lgamma(p->aT) + lgamma(p->a * n + p->a * p->c * (n - 3.0)) - n * lgamma(p->a) -
+               (n - 3.0) * lgamma(p->a * p->c);
+    double topo = 0.0;
+    for (int i = 2 * S - 5; i > 0; i -= 2) topo += log((double)i);
+    out->aT = p->aT; out->bT = p->bT; out->a = p->a; out->c = p->c;
+    out->konst = k - topo;
+    out->variant = p->variant;
+    out->ln_prior = p->d_ln_prior;
+    out->grad = p->d_grad_blens;
+    return DODO_OK;
+}
+
+extern "C" int dodo_prior_gamma_dir(const double *d_blens, int B, int S, const dodo_prior_t *prior, void *stream_) {
+    DODO_CHECK_ARG(d_blens && prior, "dodo_prior_gamma_dir: NULL argument");
+    DODO_CHECK_ARG(B >= 1, "dodo_prior_gamma_dir: need B>=1");
+    PriorDev pr;
+    int rc = make_prior(prior, S, &pr);
+    if (rc != DODO_OK) return rc;
+    prior_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream_>>>(d_blens, B, S, pr);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
 extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
-                            void *stream_) {
+                            const dodo_prior_t *prior, void *stream_) {
     DODO_CHECK_ARG(d_pdm && d_ws && d_peel && d_blens, "dodo_nj_hard: NULL argument");
     DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_hard: need B>=1, S>=2");
+    PriorDev pr;
+    { int rc = make_prior(prior, S, &pr); if (rc != DODO_OK) return rc; }
     cudaStream_t stream = (cudaStream_t)stream_;
     size_t smem = 2 * (size_t)nj_ld(S) * sizeof(double) + 3 * (size_t)nj_ld(S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens);
+    nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }
 
 extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void *d_ws, int64_t *d_peel,
-                            double *d_blens, int32_t *d_flags, void *stream_) {
+                            double *d_blens, int32_t *d_flags, const dodo_prior_t *prior, void *stream_) {
     DODO_CHECK_ARG(d_pdm && d_ws && d_peel && d_blens && d_flags, "dodo_nj_soft: NULL argument");
     DODO_CHECK_ARG(B >= 1 && S >= 2, "dodo_nj_soft: need B>=1, S>=2");
+    PriorDev pr;
+    { int rc = make_prior(prior, S, &pr); if (rc != DODO_OK) return rc; }
     DODO_CHECK_ARG(tau != 0.0 && tau == tau, "dodo_nj_soft: tau must be a non-zero number");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int full = tau < 0.0 ? 1 : 0;  // negative tau selects the exhaustive N^2 enumeration
@@ -1301,7 +1398,7 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
     size_t smem = (3 * (size_t)nj_ld(S) + 32) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags);
+    nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags, pr);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

@@ -342,8 +342,94 @@ def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False, ws=Non
     return (gx[0] if squeeze else gx), gc
 
 
-def nj_hard(pdm, ws=None):
-    """Batched hard NJ (Cpeeler.nj_np).  pdm (B,S,S) or (S,S) -> peel int64 (B,S-1,3), blens (B,2S-2)."""
+_DIST_FORMS = {"poincare": _lib.DIST_POINCARE, "lorentz": _lib.DIST_LORENTZ, "sheet_up": _lib.DIST_SHEET_UP}
+
+
+def _pairs(x1, x2):
+    x1 = x1 if isinstance(x1, torch.Tensor) else torch.as_tensor(x1)
+    x2 = x2 if isinstance(x2, torch.Tensor) else torch.as_tensor(x2)
+    if not x1.is_cuda:
+        _lib.require_cuda()
+    x1 = x1.cuda().to(torch.float64)
+    x2 = x2.to(x1.device, dtype=torch.float64)
+    if x1.shape != x2.shape or x1.dim() not in (1, 2):
+        raise ValueError("x1 and x2 must both be (D,) or (n, D)")
+    single = x1.dim() == 1
+    return (x1.reshape(-1, x1.shape[-1]).contiguous(), x2.reshape(-1, x2.shape[-1]).contiguous(), single)
+
+
+def hypdist_forward(x1, x2, curvature=-1.0, form="poincare", matsumoto=False):
+    """Distances of n independent pairs of points: x1, x2 (n, D) or (D,) -> (n,) or a 0-dim tensor on the
+    device.  ``form``: 'poincare' (Chyp_torch.hyperbolic_distance), 'lorentz'
+    (Chyp_torch.hyperbolic_distance_lorentz), 'sheet_up' (Chyp_np.hyperbolic_distance)."""
+    lib = _lib.load()
+    a, b, single = _pairs(x1, x2)
+    n, D = int(a.shape[0]), int(a.shape[1])
+    with torch.cuda.device(a.device):
+        out = torch.empty(n, dtype=torch.float64, device=a.device)
+        _lib.check(lib.dodo_hypdist_fwd(_ptr(a), _ptr(b), n, D, _ptr(_curv_tensor(curvature, a.device)), _DIST_FORMS[form],
+                                        int(bool(matsumoto)), _ptr(out), _stream()))
+    return out[0] if single else out
+
+
+def hypdist_backward(x1, x2, grad_out, curvature=-1.0, form="poincare", matsumoto=False):
+    """VJP of ``hypdist_forward``: returns (grad_x1, grad_x2 like the inputs, grad_curvature (n,))."""
+    lib = _lib.load()
+    a, b, single = _pairs(x1, x2)
+    n, D = int(a.shape[0]), int(a.shape[1])
+    g = grad_out.to(a.device, dtype=torch.float64).reshape(n).contiguous()
+    with torch.cuda.device(a.device):
+        g1, g2 = torch.empty_like(a), torch.empty_like(b)
+        gk = torch.empty(n, dtype=torch.float64, device=a.device)
+        _lib.check(lib.dodo_hypdist_bwd(_ptr(a), _ptr(b), n, D, _ptr(_curv_tensor(curvature, a.device)), _DIST_FORMS[form],
+                                        int(bool(matsumoto)), _ptr(g), _ptr(g1), _ptr(g2), _ptr(gk), _stream()))
+    return (g1[0], g2[0], gk) if single else (g1, g2, gk)
+
+
+class GammaDirPrior:
+    """Parameters of the gamma-Dirichlet(aT, bT, a, c) branch-length prior (base_model.py:475-527) for the
+    NJ kernels' epilogue / ``prior_gamma_dir``.  ``variant``: 'torch' (utils.LogDirPrior) or 'numpy'
+    (Cphylo.compute_prior_gamma_dir_np)."""
+
+    def __init__(self, aT=1.0, bT=None, a=1.0, c=1.0, variant="torch", grad=True):
+        if bT is None:
+            # the reference's torch default is the float32 tensor torch.full((1,), 0.1) (base_model.py:476), whose
+            # value 0.100000001490116 enters the float64 arithmetic as it is; the NumPy twin's is the double 0.1
+            bT = torch.full((1,), 0.1) if variant == "torch" else 0.1
+        self.aT, self.bT, self.a, self.c = (float(v.reshape(-1)[0]) if isinstance(v, torch.Tensor) else float(v)
+                                            for v in (aT, bT, a, c))
+        self.variant, self.grad = variant, grad
+
+    def c_struct(self, ln_prior, grad_blens):
+        p = _lib.Prior()
+        p.aT, p.bT, p.a, p.c = self.aT, self.bT, self.a, self.c
+        p.variant = _lib.PRIOR_TORCH if self.variant == "torch" else _lib.PRIOR_NUMPY
+        p.d_ln_prior = ln_prior.data_ptr()
+        p.d_grad_blens = grad_blens.data_ptr() if grad_blens is not None else None
+        return p
+
+    def outputs(self, B, E, device):
+        ln_prior = torch.empty(B, dtype=torch.float64, device=device)
+        g = torch.empty((B, E), dtype=torch.float64, device=device) if self.grad else None
+        return ln_prior, g
+
+
+def prior_gamma_dir(blens, prior=None):
+    """Log prior (B,) and its gradient (B, 2S-2) for a batch of branch lengths already on the device."""
+    lib = _lib.load()
+    prior = GammaDirPrior() if prior is None else prior
+    b, squeeze = _as_batch(blens, 2)
+    B, E = int(b.shape[0]), int(b.shape[1])
+    with torch.cuda.device(b.device):
+        lp, g = prior.outputs(B, E, b.device)
+        ps = prior.c_struct(lp, g)
+        _lib.check(lib.dodo_prior_gamma_dir(_ptr(b), B, E // 2 + 1, C.byref(ps), _stream()))
+    return (lp[0], None if g is None else g[0]) if squeeze else (lp, g)
+
+
+def nj_hard(pdm, ws=None, prior=None):
+    """Batched hard NJ (Cpeeler.nj_np).  pdm (B,S,S) or (S,S) -> peel int64 (B,S-1,3), blens (B,2S-2);
+    with ``prior`` (a GammaDirPrior) also (ln_prior (B,), grad (B,2S-2) or None) from the kernel's epilogue."""
     lib = _lib.load()
     pdm, squeeze = _as_batch(pdm, 3)
     B, S = int(pdm.shape[0]), int(pdm.shape[1])
@@ -353,12 +439,20 @@ def nj_hard(pdm, ws=None):
         peel = torch.empty((B, S - 1, 3), dtype=torch.int64, device=pdm.device)
         blens = torch.empty((B, 2 * S - 2), dtype=torch.float64, device=pdm.device)
         ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device, ws)
-        _lib.check(lib.dodo_nj_hard(_ptr(pdm), B, S, _ptr(ws), _ptr(peel), _ptr(blens), _stream()))
+        pr = None
+        if prior is not None:
+            pr = prior.outputs(B, 2 * S - 2, pdm.device)
+            ps = prior.c_struct(*pr)
+        _lib.check(lib.dodo_nj_hard(_ptr(pdm), B, S, _ptr(ws), _ptr(peel), _ptr(blens), C.byref(ps) if prior is not None else None,
+                                    _stream()))
+    if prior is not None:
+        return (peel[0], blens[0], pr) if squeeze else (peel, blens, pr)
     return (peel[0], blens[0]) if squeeze else (peel, blens)
 
 
-def nj_soft(pdm, tau, exhaustive=False, return_flags=False, ws=None):
-    """Batched soft NJ (peeler.nj_torch with tau).  Returns peel, blens[, flags (B,S-1) int32].
+def nj_soft(pdm, tau, exhaustive=False, return_flags=False, ws=None, prior=None):
+    """Batched soft NJ (peeler.nj_torch with tau).  Returns peel, blens[, flags (B,S-1) int32][, (ln_prior,
+    grad_blens) when ``prior`` is given: evaluated in the kernel's epilogue].
     ``exhaustive`` evaluates soft.argmin over all N^2 padded entries instead of the active pairs."""
     lib = _lib.load()
     pdm, squeeze = _as_batch(pdm, 3)
@@ -373,11 +467,16 @@ def nj_soft(pdm, tau, exhaustive=False, return_flags=False, ws=None):
         blens = torch.zeros((B, 2 * S - 2), dtype=torch.float64, device=pdm.device)
         flags = torch.zeros((B, S - 1), dtype=torch.int32, device=pdm.device)
         ws = _workspace("nj", lib.dodo_nj_workspace_bytes(B, S), pdm.device, ws)
+        pr = None
+        if prior is not None:
+            pr = prior.outputs(B, 2 * S - 2, pdm.device)
+            ps = prior.c_struct(*pr)
         _lib.check(lib.dodo_nj_soft(_ptr(pdm), B, S, -tau if exhaustive else tau, _ptr(ws), _ptr(peel), _ptr(blens),
-                                    _ptr(flags), _stream()))
+                                    _ptr(flags), C.byref(ps) if prior is not None else None, _stream()))
     if squeeze:
         peel, blens, flags = peel[0], blens[0], flags[0]
-    return (peel, blens, flags) if return_flags else (peel, blens)
+    out = (peel, blens, flags) if return_flags else (peel, blens)
+    return out + (pr,) if prior is not None else out
 
 
 def nj_soft_backward(peel, flags, grad_blens, ws=None):

@@ -17,6 +17,7 @@ import torch
 
 from . import priors
 from .base_model import BaseModel
+from .engine import GammaDirPrior
 
 
 class HMAP(BaseModel):
@@ -81,7 +82,11 @@ class HMAP(BaseModel):
         call-by-call route (connect -> compute_LL) instead of the single batched pass."""
         if self.connector not in ("nj", "geodesics"):
             self.connect()
-        if fused:
+        self._fused_tree_prior = None
+        if fused and self.prior == "gammadir":  # the tree prior comes out of the same soft-NJ launch
+            ll, peel, blens, lp = self.log_likelihood_batch(self.get_locs().unsqueeze(0), prior=GammaDirPrior())
+            self.peel, self.blens, self.ln_p, self._fused_tree_prior = peel[0].cpu().numpy(), blens[0], ll[0], lp[0]
+        elif fused:
             ll, peel, blens = self.log_likelihood_batch(self.get_locs().unsqueeze(0))
             self.peel, self.blens, self.ln_p = peel[0].cpu().numpy(), blens[0], ll[0]
         else:
@@ -107,6 +112,8 @@ class HMAP(BaseModel):
         if self.prior == "uniform":
             return self.compute_prior_unif(self.get_locs(), scale=10.0)
         if self.prior == "gammadir":
+            if getattr(self, "_fused_tree_prior", None) is not None:
+                return self._fused_tree_prior
             return priors.compute_prior_gamma_dir(self.blens)
         raise ValueError("Birth death model implementation isn't differentiable. "
                          "It cannot be used for gradient based map estimation.")

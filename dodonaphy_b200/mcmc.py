@@ -10,8 +10,8 @@ tuning), priors other than the gamma-Dirichlet, tree files and logs are outside 
 """
 import numpy as np
 
-from . import priors
 from .base_model import BaseModel
+from .engine import GammaDirPrior
 
 
 class DodonaphyMCMC:
@@ -25,27 +25,23 @@ class DodonaphyMCMC:
         self.temps = 1.0 / (1.0 + heat * np.arange(n_chains))  # chain_temp of mcmc.py:300-312
         self.rng = np.random.default_rng(seed)
         self.x = None
+        self._prior = GammaDirPrior(variant="numpy", grad=False)
 
     def initialise_chains(self, leaf_x):
-        import torch
-
         self.x = np.repeat(np.asarray(leaf_x, dtype=np.float64)[None], self.n_chains, axis=0)
-        self.ln_p, self.peel, self.blens = self.model.log_likelihood_batch_np(self.x)
-        self.ln_prior = priors.compute_prior_gamma_dir(torch.as_tensor(self.blens)).numpy()
+        # Cphylo.compute_prior_gamma_dir_np (chain.py:129) in the hard-NJ kernel's epilogue
+        self.ln_p, self.peel, self.blens, self.ln_prior = self.model.log_likelihood_batch_np(self.x, prior=self._prior)
         self.accepted = np.zeros(self.n_chains, dtype=np.int64)
         self.iterations = 0
 
     def sweep(self):
         """One generation for all chains (Metropolis with a symmetric Gaussian proposal)."""
-        import torch
-
         # chain.py:75,455-458: the reference keeps cov = I * step_scale and proposes x + cov @ u with
         # u ~ N(0, I), i.e. a displacement of standard deviation step_scale per coordinate (its `cov` is
         # applied as a matrix, not as a covariance).  The Jacobian term of its acceptance ratio is
         # identically zero on this route (chain.py:414 sets log_abs_det_jacobian = 0.0).
         prop = self.x + self.step_scale * self.rng.standard_normal(self.x.shape)
-        ln_p, peel, blens = self.model.log_likelihood_batch_np(prop)
-        ln_prior = priors.compute_prior_gamma_dir(torch.as_tensor(blens)).numpy()
+        ln_p, peel, blens, ln_prior = self.model.log_likelihood_batch_np(prop, prior=self._prior)
         ln_r = self.temps * ((ln_p + ln_prior) - (self.ln_p + self.ln_prior))
         take = np.log(self.rng.random(self.n_chains)) < ln_r
         self.x[take], self.ln_p[take], self.ln_prior[take] = prop[take], ln_p[take], ln_prior[take]

@@ -15,8 +15,9 @@ from . import engine
 
 class HotPath:
     def __init__(self, tipmask, weights, model, rates=None, mix=False, tau=1e-8, curvature=-1.0,
-                 lift="up", matsumoto=False, device=None, connector="nj"):
+                 lift="up", matsumoto=False, device=None, connector="nj", prior=None):
         self.connector = connector
+        self.prior = prior  # engine.GammaDirPrior: evaluated in the NJ kernel's epilogue
         self.prune = engine.PruneEngine(tipmask, weights, device=device)
         self.device = self.prune.device
         self.model = model
@@ -33,6 +34,7 @@ class HotPath:
                     connector="nj"):
         """Share an existing PruneEngine (tips already resident on the device)."""
         self = cls.__new__(cls)
+        self.prior = None
         self.connector = connector
         self.prune = prune_engine
         self.device = prune_engine.device
@@ -55,10 +57,16 @@ class HotPath:
                 raise NotImplementedError(f"Curvature must be -1, got {self.curvature}")
             out = engine.geo_soft(x, 1e-8, ws=self.ws)
             out["flags"] = out["flags"] & 8  # only an invalid selection matters downstream
+            if self.prior is not None:
+                out["ln_prior"], out["grad_prior"] = engine.prior_gamma_dir(out["blens"], self.prior)
             return out
         if self.connector != "nj":
             raise NotImplementedError(f"connector {self.connector!r} has no differentiable device path")
         pdm = engine.pdm_forward(x, self.curvature, "torch", self.lift, self.matsumoto, ws=self.ws)
+        if self.prior is not None:
+            peel, blens, flags, (lp, gp) = engine.nj_soft(pdm, self.tau, exhaustive=exhaustive, return_flags=True, ws=self.ws,
+                                                          prior=self.prior)
+            return dict(peel=peel, blens=blens, flags=flags, ln_prior=lp, grad_prior=gp)
         peel, blens, flags = engine.nj_soft(pdm, self.tau, exhaustive=exhaustive, return_flags=True, ws=self.ws)
         return dict(peel=peel, blens=blens, flags=flags)
 
@@ -163,15 +171,21 @@ class HotPath:
         if self.connector != "nj":
             raise NotImplementedError("the batched gradient-free path decodes with hard NJ only")
         pdm = engine.pdm_forward(x, self.curvature, "numpy", "up", self.matsumoto, ws=self.ws)
-        peel, blens = engine.nj_hard(pdm, ws=self.ws)
+        out = {}
+        if self.prior is not None:
+            peel, blens, (out["ln_prior"], _) = engine.nj_hard(pdm, ws=self.ws, prior=self.prior)
+        else:
+            peel, blens = engine.nj_hard(pdm, ws=self.ws)
         ll, _ = self.prune.loglik(peel, blens, self.model, rates=self.rates, mix=self.mix, grad=False)
-        return dict(lnL=ll, peel=peel, blens=blens)
+        out.update(lnL=ll, peel=peel, blens=blens)
+        return out
 
     # end-to-end call with host buffers (what a reference-side caller holding NumPy/CPU tensors does)
     def _fingerprint(self, shape):
+        pr = None if self.prior is None else (self.prior.aT, self.prior.bT, self.prior.a, self.prior.c, self.prior.variant)
         return (tuple(shape), bytes(self.model.c_struct()), None if self.rates is None else self.rates.tobytes(),
                 self.mix, None if self.tau is None else float(self.tau), float(self.curvature), self.lift,
-                self.matsumoto, self.connector)
+                self.matsumoto, self.connector, pr)
 
     def graphed(self, x, grad):
         """The step for inputs shaped like ``x`` as a captured CUDA graph (one live capture per

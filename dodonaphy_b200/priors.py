@@ -25,10 +25,12 @@ def log_dir_prior(blens, aT=1.0, bT=0.1, a=1.0, c=1.0):
     return out if blens.dim() == 2 else out[0]
 
 
-def compute_prior_gamma_dir(blens, aT=1.0, bT=0.1, a=1.0, c=1.0):
+def compute_prior_gamma_dir(blens, aT=1.0, bT=None, a=1.0, c=1.0):
     """Log prior of every tree of the batch (normalising constants and the 1/(2S-5)!! topology
-    term included)."""
-    aT, bT, a, c = (float(torch.as_tensor(v).reshape(-1)[0]) for v in (aT, bT, a, c))
+    term included).  The reference's default bT is the float32 tensor torch.full((1,), 0.1)
+    (base_model.py:476): its value 0.100000001490116 enters the float64 arithmetic as it is."""
+    bT = torch.full((1,), 0.1) if bT is None else bT
+    aT, bT, a, c = (float(v.reshape(-1)[0]) if isinstance(v, torch.Tensor) else float(v) for v in (aT, bT, a, c))
     n_leaf = blens.shape[-1] // 2 + 1
     const = (aT * math.log(bT) - math.lgamma(aT) + math.lgamma(a * n_leaf + a * c * (n_leaf - 3))
              - n_leaf * math.lgamma(a) - (n_leaf - 3) * math.lgamma(a * c))

@@ -16,6 +16,7 @@ import torch
 
 from . import priors
 from .base_model import BaseModel
+from .engine import GammaDirPrior
 
 
 class DodonaphyVI(BaseModel):
@@ -60,9 +61,11 @@ class DodonaphyVI(BaseModel):
 
     def elbo_terms(self, x):
         """ln p, ln prior, ln|J| for a batch of locations (B, S, D)."""
-        ln_p, peel, blens = self.log_likelihood_batch(x)
-        ln_prior = (priors.compute_prior_gamma_dir(blens) if self.prior_fn == "gammadir"
-                    else priors.compute_prior_exponential(blens, rate=10.0))
+        if self.prior_fn == "gammadir":  # evaluated in the epilogue of the soft-NJ kernel launch
+            ln_p, peel, blens, ln_prior = self.log_likelihood_batch(x, prior=GammaDirPrior())
+        else:
+            ln_p, peel, blens = self.log_likelihood_batch(x)
+            ln_prior = priors.compute_prior_exponential(blens, rate=10.0)
         if self.include_jacobian:
             hot = self._hotpath()
             _, jac = hot.blens_jacobian(x.detach().to(hot.device), logdet=True)

@@ -130,6 +130,27 @@ int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double *d_curvatu
                  double *d_grad_curv, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K1p: batched POINTWISE hyperbolic distances -- n independent pairs (x1[i], x2[i]) of D-dimensional
+ * points (D <= 16) -- and their vector-Jacobian product.  Replaces the single-pair utilities the
+ * reference calls in Python loops over a tree's branches (BaseModel.compute_branch_lengths,
+ * dodonaphy/base_model.py:127-181; Cphylo.compute_branch_lengths_np, dodonaphy/cython/Cphylo.pyx:116-156):
+ *   DODO_DIST_POINCARE  Chyp_torch.hyperbolic_distance (dodonaphy/cython/Chyp_torch.pyx:119-134): Poincare-ball
+ *                       formula at curvature -1, the Lorentz form otherwise or when the invariant is NaN
+ *   DODO_DIST_LORENTZ   Chyp_torch.hyperbolic_distance_lorentz (:137-154) through poincare_to_hyper (:184-210)
+ *   DODO_DIST_SHEET_UP  Chyp_np.hyperbolic_distance (dodonaphy/cython/Chyp_np.pyx:279-296): project_up lift
+ * d_x1, d_x2 [n][D]; d_curvature device double [1]; d_out [n].  VJP: d_grad_out [n] -> d_grad_x1, d_grad_x2
+ * [n][D] and d_grad_curv [n] (one partial per pair; clamped pairs pass no gradient to the locations).
+ * ------------------------------------------------------------------------------------------ */
+#define DODO_DIST_POINCARE 0
+#define DODO_DIST_LORENTZ 1
+#define DODO_DIST_SHEET_UP 2
+int dodo_hypdist_fwd(const double *d_x1, const double *d_x2, int64_t n, int D, const double *d_curvature,
+                     int form, int matsumoto, double *d_out, void *stream);
+int dodo_hypdist_bwd(const double *d_x1, const double *d_x2, int64_t n, int D, const double *d_curvature,
+                     int form, int matsumoto, const double *d_grad_out, double *d_grad_x1, double *d_grad_x2,
+                     double *d_grad_curv, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2: batched neighbour joining, one tree per CTA.
  * dodo_nj_hard replaces Cpeeler.nj_np (dodonaphy/cython/Cpeeler.pyx:15-125): bit-identical peel
  * and blens (same operation order, no FMA contraction, first strict minimum in pool order).
@@ -137,12 +158,31 @@ int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double *d_curvatu
  * (dodonaphy/soft.py:38-53) evaluated in O(active pairs) per join.
  * ------------------------------------------------------------------------------------------ */
 uint64_t dodo_nj_workspace_bytes(int B, int S);
+/* Branch-length prior evaluated as the EPILOGUE of the NJ kernel that has just produced the branch
+ * lengths (pass NULL for none), or on its own by dodo_prior_gamma_dir: the gamma-Dirichlet(aT, bT, a, c)
+ * prior of MrBayes that the reference evaluates per sample on the host --
+ * BaseModel.compute_prior_gamma_dir (dodonaphy/base_model.py:475-527) with utils.LogDirPrior
+ * (dodonaphy/utils.py:251-267), called at vi.py:436-437 / hmap.py:385-397; NumPy twin
+ * Cphylo.compute_prior_gamma_dir_np (dodonaphy/cython/Cphylo.pyx:53-114), called at chain.py:129.
+ * d_ln_prior [B] receives the log density incl. normalising constants and the uniform-topology term;
+ * d_grad_blens [B][2S-2] (may be NULL) its gradient w.r.t. the branch lengths.  variant: TORCH clamps
+ * the branches at 1e-4 when any is <= 0 (utils.py:258-260), NUMPY floors everything at eps (:105-107). */
+#define DODO_PRIOR_TORCH 0
+#define DODO_PRIOR_NUMPY 1
+typedef struct {
+    double aT, bT, a, c;
+    int32_t variant;
+    int32_t _pad;
+    double *d_ln_prior;
+    double *d_grad_blens;
+} dodo_prior_t;
+int dodo_prior_gamma_dir(const double *d_blens, int B, int S, const dodo_prior_t *prior, void *stream);
 /* d_pdm [B][S][S] (not modified); d_peel int64 [B][S-1][3]; d_blens [B][2S-2] */
 int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
-                 void *stream);
+                 const dodo_prior_t *prior, void *stream);
 /* d_flags int32 [B][S-1]: bit0 = d_pl clamped, bit1 = d_pr clamped, bit2 = exactness guard tripped */
 int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void *d_ws, int64_t *d_peel,
-                 double *d_blens, int32_t *d_flags, void *stream);
+                 double *d_blens, int32_t *d_flags, const dodo_prior_t *prior, void *stream);
 /* soft.argmin (dodonaphy/soft.py:38-53) on B dense row-major matrices [B][rows][cols]:
  * d_rowcol [B][2] = (soft_row, soft_col) as doubles, ties resolved towards the last entry. */
 int dodo_soft_argmin(const double *d_Q, int B, int rows, int cols, double tau, double *d_rowcol,

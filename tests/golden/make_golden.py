@@ -634,11 +634,53 @@ def make_geodesic(r):
     print("geodesic: soft", len(soft), "hard", len(hard), "dogbone peel", out["h0_peel"].tolist())
 
 
+def make_hypdist(r):
+    """The reference's pointwise distances (Chyp_torch.pyx:119-154, Chyp_np.pyx:279-296) on random pairs of
+    ball points -- generic, near the boundary, coincident (clamped) -- with torch autograd gradients to both
+    points and the curvature for the two torch forms.  python make_golden.py hypdist"""
+    rng = np.random.default_rng(41)
+    out = {}
+    k = 0
+    for D in (2, 3, 5):
+        for radius in (0.3, 0.9, 0.999):
+            for kappa in (-1.0, -0.6):
+                n = 6
+                dirs = rng.normal(size=(2, n, D))
+                dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+                x1 = dirs[0] * rng.uniform(0, radius, (n, 1))
+                x2 = dirs[1] * rng.uniform(0, radius, (n, 1))
+                x2[0] = x1[0]  # a coincident pair: the Lorentz inner product is clamped
+                res = {"x1": x1, "x2": x2, "kappa": np.array(kappa)}
+                for form, fn in (("poincare", r.Chyp_torch.hyperbolic_distance), ("lorentz", r.Chyp_torch.hyperbolic_distance_lorentz)):
+                    d, g1, g2, gk = [], [], [], []
+                    for i in range(n):
+                        a = torch.tensor(x1[i], requires_grad=True)
+                        b = torch.tensor(x2[i], requires_grad=True)
+                        c = torch.tensor([kappa], dtype=torch.float64, requires_grad=True)
+                        v = fn(a, b, c).reshape(())
+                        d.append(v.item())
+                        if v.requires_grad and torch.isfinite(v):
+                            ga, gb, gc = torch.autograd.grad(v, (a, b, c), allow_unused=True)
+                        else:
+                            ga = gb = gc = None
+                        g1.append(np.zeros(D) if ga is None else ga.numpy())
+                        g2.append(np.zeros(D) if gb is None else gb.numpy())
+                        gk.append(0.0 if gc is None else float(gc))
+                    res[f"{form}_d"], res[f"{form}_g1"], res[f"{form}_g2"], res[f"{form}_gk"] = np.array(d), np.stack(g1), np.stack(g2), np.array(gk)
+                res["np_d"] = np.array([r.Chyp_np.hyperbolic_distance(x1[i], x2[i], kappa) for i in range(n)])
+                for key, v in res.items():
+                    out[f"{k}_{key}"] = v
+                k += 1
+    out["n"] = k
+    np.savez_compressed(os.path.join(HERE, "hypdist.npz"), **out)
+    print("hypdist:", k, "cases;", out["0_poincare_d"], out["0_lorentz_d"], out["0_np_d"])
+
+
 if __name__ == "__main__":
     r = refload.load()
     assert r.compiled and r.python, "needs /root/reference and oracle/_ref (python oracle/build_ref.py)"
     makers = dict(ds1=make_ds1, pdm=make_pdm, nj_hard=make_nj_hard, nj_soft=make_nj_soft, prune=make_prune,
-                  pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic)
+                  pdm_jac=make_pdm_jac, charts=make_charts, geodesic=make_geodesic, hypdist=make_hypdist)
     slow = dict(nj_soft_c2=make_nj_soft_c2, chain_c2=make_chain_c2, chains=make_chains, blens_jac=make_blens_jac, hmap=make_hmap, vi=make_vi, laplace=make_laplace, pdm_c4=make_pdm_c4, prune_c2=make_prune_c2, configs=make_configs, configs_c5=make_configs_c5)  # only when named explicitly
     for name in (sys.argv[1:] or list(makers)):  # optional: names of the fixtures to regenerate
         {**makers, **slow}[name](r)
