@@ -431,6 +431,58 @@ __device__ __forceinline__ double exp_neg(double a) { return a > 750.0 ? 0.0 : e
 // back to the general multi-pass evaluation below, so the result is the same in every regime.
 constexpr int CAND_LOCAL = 4, CAND_CAP = 128;
 
+// soft.argmin (soft.py:42-52) from the candidates inside the 750 tau window (one thread; the candidates are
+// sorted in place by flat index = the reference's cumsum order); every other entry enters in closed form.
+// idx = the soft index, guard = 1.0 when the closed-form treatment of the inactive entries is exact in fp64.
+__device__ void soft_eval_candidates(double *cand_s, double *cand_f, int n, double m, double tau, double NN, bool FULL,
+                                     double &idx, double &guard) {
+    {
+        const double away = fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau;
+        if (n == 1 && cand_s[0] == m && 1.0 / tau > 750.0 && (FULL || away > 750.0)) {
+            // the usual case: one entry carries all the weight (p = c = 1, every other weight is exactly 0)
+            idx = cand_f[0];
+            guard = 1.0;
+        } else {
+            for (int i = 1; i < n; ++i) {  // order by flat index (the reference's cumsum order)
+                double ks = cand_s[i], kf = cand_f[i];
+                int j = i - 1;
+                while (j >= 0 && cand_f[j] > kf) { cand_s[j + 1] = cand_s[j]; cand_f[j + 1] = cand_f[j]; --j; }
+                cand_s[j + 1] = ks; cand_f[j + 1] = kf;
+            }
+            double Z = 0.0;
+            for (int i = 0; i < n; ++i) {  // the first softmax's weights replace the scores (each is used three times)
+                cand_s[i] = exp_neg(fabs(cand_s[i] - m) / tau);
+                Z += cand_s[i];
+            }
+            double run = 0.0, M = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double e = cand_s[i];
+                run += e;
+                M = fmax(M, (e / Z) * (run / Z));
+            }
+            const double e0 = exp_neg(M / tau);
+            double z2 = 0.0, isum = 0.0, fs = 0.0;
+            run = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double e = cand_s[i];
+                double e2 = e0;
+                if (e != 0.0) {
+                    run += e;
+                    e2 = exp_neg(fabs(M - (e / Z) * (run / Z)) / tau);
+                }
+                z2 += e2;
+                isum = fma(e2, cand_f[i], isum);
+                fs += cand_f[i];
+            }
+            z2 += (NN - (double)n) * e0;
+            isum += e0 * (NN * (NN - 1.0) * 0.5 - fs);
+            idx = isum / z2;
+            double worst = FULL ? 0.0 : exp_neg(fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
+            guard = (FULL || NN * worst <= 1e-18 * fmin(1.0, tau) * Z) ? 1.0 : 0.0;
+        }
+    }
+}
+
 template <int MODE>
 __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
     constexpr bool FULL = MODE != 0;
@@ -526,48 +578,7 @@ __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, doubl
     const bool ok = !cand_over && n <= CAND_CAP && n >= 1;
     if (!ok) { __syncthreads(); return false; }
     const double NN = MODE == 0 ? (double)c.N * (double)c.N : (double)P;
-    if (tid == 0) {
-        const double away = fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau;
-        if (n == 1 && cand_s[0] == m && 1.0 / tau > 750.0 && (FULL || away > 750.0)) {
-            // the usual case: one entry carries all the weight (p = c = 1, every other weight is exactly 0)
-            sh[0] = cand_f[0];
-            sh[1] = 1.0;
-        } else {
-            for (int i = 1; i < n; ++i) {  // order by flat index (the reference's cumsum order)
-                double ks = cand_s[i], kf = cand_f[i];
-                int j = i - 1;
-                while (j >= 0 && cand_f[j] > kf) { cand_s[j + 1] = cand_s[j]; cand_f[j + 1] = cand_f[j]; --j; }
-                cand_s[j + 1] = ks; cand_f[j + 1] = kf;
-            }
-            double Z = 0.0;
-            for (int i = 0; i < n; ++i) Z += exp_neg(fabs(cand_s[i] - m) / tau);
-            double run = 0.0, M = 0.0;
-            for (int i = 0; i < n; ++i) {
-                double e = exp_neg(fabs(cand_s[i] - m) / tau);
-                run += e;
-                M = fmax(M, (e / Z) * (run / Z));
-            }
-            const double e0 = exp_neg(M / tau);
-            double z2 = 0.0, isum = 0.0, fs = 0.0;
-            run = 0.0;
-            for (int i = 0; i < n; ++i) {
-                double e = exp_neg(fabs(cand_s[i] - m) / tau);
-                double e2 = e0;
-                if (e != 0.0) {
-                    run += e;
-                    e2 = exp_neg(fabs(M - (e / Z) * (run / Z)) / tau);
-                }
-                z2 += e2;
-                isum = fma(e2, cand_f[i], isum);
-                fs += cand_f[i];
-            }
-            z2 += (NN - (double)n) * e0;
-            isum += e0 * (NN * (NN - 1.0) * 0.5 - fs);
-            sh[0] = isum / z2;
-            double worst = FULL ? 0.0 : exp_neg(fmin(fabs(0.0 - m), fabs(LARGE - m)) / tau);
-            sh[1] = (FULL || NN * worst <= 1e-18 * fmin(1.0, tau) * Z) ? 1.0 : 0.0;
-        }
-    }
+    if (tid == 0) soft_eval_candidates(cand_s, cand_f, n, m, tau, NN, FULL, sh[0], sh[1]);
     __syncthreads();
     idx_out = sh[0];
     guard_ok = sh[1] != 0.0;
@@ -679,12 +690,16 @@ __device__ __forceinline__ void dd_add_dd(double &hi, double &lo, double xh, dou
 __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
                                                        double *__restrict__ blens, int32_t *__restrict__ flags,
-                                                       PriorDev prior) {
+                                                       PriorDev prior, int lean_first) {
     extern __shared__ unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     const int N = 2 * S - 1;
     double *Dm = ws + (size_t)b * nj_ws_doubles(S);
+    if (lean_first) {  // nj_soft_lean_kernel ran first: only the trees it handed over are done here
+        const int todo = *reinterpret_cast<const int *>(Dm);
+        if (__syncthreads_or(0) || todo == 0) return;  // (the barrier orders the read before the writes below)
+    }
     const int LD = nj_ld(S);
     double *Dalt = Dm + (size_t)LD * LD;  // repack target (storage scheme: see nj_ws_doubles)
     int ld = LD, used = S;
@@ -833,6 +848,283 @@ __global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restri
         { int *t = act; act = act2; act2 = t; }  // the new pool order takes over
     }
     if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);  // epilogue (bl complete: barrier above)
+}
+
+// ------------------------------------------------------------------------------------------ lean soft
+// Small trees (<= NJ_LEAN_MAX taxa) are latency-bound: one CTA per tree, S-1 dependent joins.  The
+// general kernel above spends ~650 instructions per warp and six block-wide barriers on every join
+// regardless of n (ncu: 40 % of the stall samples at barriers, 31 % issue slots at 64 taxa): 4.4 us per
+// join.  This variant is built for a short dependent chain per join instead:
+//   * the matrix is resident in shared memory and kept DENSE (slots 0..n-1 live: the new node takes the
+//     lower of the two joined slots, the last live slot moves into the other), so the scan needs no
+//     indirection; node ids travel with the slots (the flat index of peeler.py:194 only needs the ids);
+//   * W <= 8 warps per tree and TWO barriers per join: [scan + warp reduction] | [merge, decision, new
+//     distances + slot move + row-sum updates in one pass, with the per-slot scalars double-buffered so
+//     that nobody overwrites what a slower thread still reads];
+//   * the scan tracks the smallest and the second smallest Q per thread: the regime nearly every join is in
+//     -- ONE entry inside the 750 tau window below which the softmax weights are exactly 0 in fp64
+//     (soft_argmin_fast's `n == 1` branch: idx = flat index of that entry) -- is recognised from those
+//     two numbers; otherwise (always for the last joins: with <= 4 nodes left Q has exact mathematical
+//     ties) the candidates are gathered and evaluated by the same soft_eval_candidates;
+//   * the new node's row sum follows from the old ones, r_u = (r_l + r_r - n d_lr) / 2, evaluated in
+//     double-double by one lane while the others update the matrix (the general kernel sums the new row:
+//     both are the mathematical row sum to ~1e-32, then rounded);
+//   * one lane forms the branch lengths (an fp64 division) off the critical path.
+// What it does not handle -- an asymmetric input, tau >= 1/750, more than CAND_CAP candidates, an invalid
+// selection -- is left to the general kernel: this kernel writes todo = 1 into the first word of the
+// tree's workspace and stops; nj_soft_kernel, launched right behind it with `lean_first`, redoes exactly
+// those trees from scratch and skips the others.  Same expressions as the general kernel for Q, the
+// branch lengths, the new distances and the double-double row-sum updates.
+constexpr int NJ_LEAN_MAX = 160;
+__host__ __device__ inline size_t nj_lean_smem_bytes(int S, int W) {
+    return ((size_t)S * (S | 1) + 4 * (size_t)S + 3 * (size_t)W + 2 + 2 * 128) * sizeof(double) +
+           (2 * (size_t)S + (2 * (size_t)S - 1) + W + 2) * sizeof(int);
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) nj_soft_lean_kernel(const double *__restrict__ pdm, int S, double tau,
+                                                            double *__restrict__ ws, int64_t *__restrict__ peel,
+                                                            double *__restrict__ blens, int32_t *__restrict__ flags,
+                                                            PriorDev prior) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T = 32 * W;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = 2 * S - 1, ld = S | 1;
+    double *D = reinterpret_cast<double *>(smem_raw);  // [S][ld] dense: slots 0..n-1 live
+    double *rsH = D + (size_t)S * ld;                  // [2][S] row sums (hi) by slot, double-buffered
+    double *rsL = rsH + 2 * S;                         // [2][S] low parts
+    double *red = rsL + 2 * S;                         // [3 W] per-warp (m1, m2, dmin)
+    double *res = red + 3 * W;                         // [2] soft index, guard
+    double *cand_s = res + 2;                          // [CAND_CAP] candidates of the multi-candidate joins
+    double *cand_f = cand_s + CAND_CAP;                // [CAND_CAP]
+    int *sidb = reinterpret_cast<int *>(cand_f + CAND_CAP);  // [2][S] slot -> node id, double-buffered
+    int *slot_of = sidb + 2 * S;                             // [N] node id -> slot or -1
+    unsigned *redk = reinterpret_cast<unsigned *>(slot_of + N);  // [W]
+    int *cand_n = reinterpret_cast<int *>(redk + W);
+    int *todo = reinterpret_cast<int *>(ws + (size_t)b * nj_ws_doubles(S));
+    const double *P = pdm + (size_t)b * S * S;
+    int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    double *bl = blens + (size_t)b * (2 * S - 2);
+    int32_t *fl = flags + (size_t)b * (S - 1);
+    auto sync = [&]() { if (W == 1) __syncwarp(); else __syncthreads(); };
+
+    if (tid == 0) *todo = 0;
+    for (int i = tid; i < S * S; i += T) {
+        const int r = i / S, c = i - r * S;
+        D[r * ld + c] = (r == c) ? 0.0 : P[i];  // dists.fill_diagonal_(0.0), peeler.py:178
+    }
+    for (int s = tid; s < S; s += T) sidb[s] = s;
+    for (int i = tid; i < N; i += T) slot_of[i] = i < S ? i : -1;
+    sync();
+    int asym = 0;
+    for (int i = tid; i < S * S; i += T) {
+        const int r = i / S, c = i - r * S;
+        if (r < c && D[r * ld + c] != D[c * ld + r]) asym = 1;
+    }
+    if (__syncthreads_or(asym) || !(1.0 / tau > 750.0)) {
+        if (tid == 0) *todo = 1;
+        return;
+    }
+    for (int r = warp; r < S; r += W) {  // row sums (peeler.py:240): one warp per row, double-double
+        double hi = 0.0, lo = 0.0;
+        for (int c = lane; c < S; c += 32)
+            if (c != r) dd_add(hi, lo, D[r * ld + c]);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double oh = __shfl_xor_sync(0xffffffffu, hi, m), ol = __shfl_xor_sync(0xffffffffu, lo, m);
+            dd_add_dd(hi, lo, oh, ol);
+        }
+        if (lane == 0) { rsH[r] = hi; rsL[r] = lo; }
+    }
+    sync();
+    const double Wd = 750.0 * tau;
+    const double Wd_sure = Wd * (1.0 + 1e-9);  // x > Wd_sure  =>  x / tau > 750 whatever the rounding
+    int cur = 0;
+    int pend_parent = -1, pend_keep = 0, pend_left = 0, pend_right = 0, pend_moved = -1, pend_freed = 0;  // tid 0 only
+    for (int n = S; n > 1; --n) {
+        const double *rs = rsH + cur * S;
+        const int *sid = sidb + cur * S;
+        if (tid == 0 && pend_parent >= 0) {  // the previous join's id -> slot changes (read behind the barriers below)
+            slot_of[pend_left] = -1;
+            slot_of[pend_right] = -1;
+            slot_of[pend_parent] = pend_keep;
+            if (pend_moved >= 0) slot_of[pend_moved] = pend_freed;
+        }
+        const double nm2 = (double)(n - 2);
+        // ---- smallest and second smallest Q over the live pairs (compute_Q, peeler.py:223-248): four rows
+        // per trip share the column operand and give the loads independent work
+        double m1 = DBL_MAX, m2 = DBL_MAX, dmin = 0.0;  // dmin: the distance behind m1 (= d(l, r) of the join)
+        unsigned key = 0x00010000u;
+        for (int r0 = 1 + warp; r0 < n; r0 += 4 * W) {
+            double rsr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rsr[j] = (r0 + j * W < n) ? rs[r0 + j * W] : 0.0;
+            const int rtop = min(r0 + 3 * W, n - 1);
+            for (int c = lane; c < rtop; c += 32) {
+                const double rsc = rs[c];
+                double dv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rj = r0 + j * W;
+                    dv[j] = (rj < n && c < rj) ? D[rj * ld + c] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rj = r0 + j * W;
+                    const double dij = dv[j];
+                    const double qa = (nm2 * dij - rsr[j]) - rsc;
+                    const double qb = (nm2 * dij - rsc) - rsr[j];
+                    double q = 0.5 * (qa + qb);
+                    if (!(rj < n && c < rj)) q = DBL_MAX;
+                    const bool lt1 = q < m1, lt2 = q < m2;
+                    m2 = lt1 ? m1 : (lt2 ? q : m2);
+                    m1 = lt1 ? q : m1;
+                    dmin = lt1 ? dij : dmin;
+                    key = lt1 ? (((unsigned)rj << 16) | (unsigned)c) : key;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double o1 = __shfl_xor_sync(0xffffffffu, m1, m), o2 = __shfl_xor_sync(0xffffffffu, m2, m);
+            const double od = __shfl_xor_sync(0xffffffffu, dmin, m);
+            const unsigned ok = __shfl_xor_sync(0xffffffffu, key, m);
+            const bool lt = o1 < m1;  // an exact tie leaves m2 == m1: not the one-candidate regime
+            const double lo1 = lt ? o1 : m1, hi1 = lt ? m1 : o1, oth = lt ? o2 : m2;
+            m2 = oth < hi1 ? oth : hi1;
+            m1 = lo1;
+            dmin = lt ? od : dmin;
+            key = lt ? ok : key;
+        }
+        if (W > 1) {
+            if (lane == 0) { red[3 * warp] = m1; red[3 * warp + 1] = m2; red[3 * warp + 2] = dmin; redk[warp] = key; }
+            __syncthreads();
+            m1 = red[0]; m2 = red[1]; dmin = red[2]; key = redk[0];
+#pragma unroll
+            for (int w = 1; w < W; ++w) {
+                const double o1 = red[3 * w], o2 = red[3 * w + 1], od = red[3 * w + 2];
+                const unsigned ok = redk[w];
+                const bool lt = o1 < m1;
+                const double lo1 = lt ? o1 : m1, hi1 = lt ? m1 : o1, oth = lt ? o2 : m2;
+                m2 = oth < hi1 ? oth : hi1;
+                m1 = lo1;
+                dmin = lt ? od : dmin;
+                key = lt ? ok : key;
+            }
+        }
+        // m = min(min Q, 0) (the strict upper triangle of the padded matrix holds zeros, torch.tril).  The
+        // usual case is soft_argmin_fast's one-candidate branch: m is attained by exactly one live pair and
+        // nothing else (live, zero or 1e9 entry) is within 750 tau of it.
+        int fbits = 0;
+        int left, right, sl, sr;
+        double d_lr;
+        if (m1 < 0.0 && m2 > m1 + Wd && -m1 > Wd_sure && LARGE - m1 > Wd_sure) {
+            const int sa = (int)(key >> 16), sb = (int)(key & 0xffffu);
+            const int ia = sid[sa], ib = sid[sb];
+            right = max(ia, ib);  // flat = row * N + col with row > col (tril)
+            left = min(ia, ib);
+            sl = ia < ib ? sa : sb;
+            sr = ia < ib ? sb : sa;
+            d_lr = dmin;  // == D[sl][sr] (the matrix is symmetric bit for bit); taken from the scan because the
+                          // pass below overwrites that entry while slower threads may still be here
+        } else {
+            // several entries inside the window, or a minimum too close to the zeros: gather the candidates and
+            // evaluate the two softmaxes as soft_argmin_fast does
+            const double mm = fmin(m1, 0.0);
+            if (tid == 0) *cand_n = 0;
+            sync();
+            for (int r = 1 + warp; r < n; r += W) {
+                const double rsr = rs[r];
+                const double *rowp = D + r * ld;
+                for (int c = lane; c < r; c += 32) {
+                    const double dij = rowp[c], rsc = rs[c];
+                    const double qa = (nm2 * dij - rsr) - rsc;
+                    const double qb = (nm2 * dij - rsc) - rsr;
+                    const double q = 0.5 * (qa + qb);
+                    if (q <= mm + Wd) {
+                        const int slot = atomicAdd(cand_n, 1);
+                        const int ia = sid[r], ib = sid[c];
+                        if (slot < CAND_CAP) { cand_s[slot] = q; cand_f[slot] = (double)max(ia, ib) * (double)N + (double)min(ia, ib); }
+                    }
+                }
+            }
+            sync();
+            const int nc = *cand_n;
+            if (nc < 1 || nc > CAND_CAP) {  // the general multi-pass evaluation: not here
+                if (tid == 0) *todo = 1;
+                return;
+            }
+            if (tid == 0) soft_eval_candidates(cand_s, cand_f, nc, mm, tau, (double)N * (double)N, false, res[0], res[1]);
+            sync();
+            const double idx = res[0];
+            if (res[1] == 0.0) fbits = 4;
+            double rowf, colf;
+            unravel(idx, (double)N, rowf, colf);
+            right = (int)rint(rowf);
+            left = (int)rint(colf);
+            const bool bad = !(idx == idx) || right < 0 || right >= N || left < 0 || left >= N || right == left;
+            sl = bad ? -1 : slot_of[left];
+            sr = bad ? -1 : slot_of[right];
+            if (sl < 0 || sr < 0) {  // invalid selection: flagged by the general kernel
+                if (tid == 0) *todo = 1;
+                return;
+            }
+            d_lr = D[sl * ld + sr];
+            sync();  // (everyone holds d_lr before the pass below overwrites that entry)
+        }
+        const int keep = min(sl, sr), freed = max(sl, sr), last = n - 1;
+        const int parent = S + (S - n);
+        const int nxt = cur ^ 1;
+        // ---- one pass: distances of the new node (get_new_dist_soft, peeler.py:251-265) into slot `keep`, the
+        // last live slot moved into `freed` (keep < freed <= last), running row sums.  Thread x reads column
+        // x of rows sl, sr, last and writes column x of rows keep, freed and row x: no two threads meet.
+        for (int x = tid; x < n; x += T) {
+            if (x == sl || x == sr) continue;
+            const double dl = D[sl * ld + x], dr = D[sr * ld + x];
+            const double u = 0.5 * ((dl + dr) - d_lr);
+            const int dx = x == last ? freed : x;
+            if (x != last && freed != last) {
+                const double v = D[last * ld + x];
+                D[freed * ld + x] = v;
+                D[x * ld + freed] = v;
+            }
+            D[keep * ld + dx] = u;
+            D[dx * ld + keep] = u;
+            double hi = rs[x], lo = rsL[cur * S + x];
+            dd_add(hi, lo, -dl);
+            dd_add(hi, lo, -dr);
+            dd_add(hi, lo, u);
+            rsH[nxt * S + dx] = hi; rsL[nxt * S + dx] = lo;
+            sidb[nxt * S + dx] = sid[x];
+        }
+        if (tid == 0) {  // branch lengths (peeler.py:199-213) and the peel row
+            const double nact = fmax((double)n, 3.0);
+            double d_pl = 0.5 * d_lr + (rs[sl] - rs[sr]) / (2.0 * (nact - 2.0));
+            if (!(d_pl > DBL_EPSILON)) { fbits |= (d_pl == DBL_EPSILON) ? 0 : 1; d_pl = DBL_EPSILON; }
+            double d_pr = d_lr - d_pl;
+            if (!(d_pr > DBL_EPSILON)) { fbits |= (d_pr == DBL_EPSILON) ? 0 : 2; d_pr = DBL_EPSILON; }
+            pl[(S - n) * 3 + 0] = left;
+            pl[(S - n) * 3 + 1] = right;
+            pl[(S - n) * 3 + 2] = parent;
+            bl[left] = d_pl;
+            bl[right] = d_pr;
+            fl[S - n] = fbits;
+            pend_parent = parent; pend_keep = keep; pend_left = left; pend_right = right;
+            pend_moved = freed != last ? sid[last] : -1;
+            pend_freed = freed;
+        }
+        if (tid == (W > 1 ? 32 : 1)) {  // row sum of the new node: (r_l + r_r - n d_lr) / 2 in double-double
+            double hi = rs[sl], lo = rsL[cur * S + sl];
+            dd_add_dd(hi, lo, rs[sr], rsL[cur * S + sr]);
+            const double nn = (double)n, p = nn * d_lr, pe = fma(nn, d_lr, -p);  // n d_lr = p + pe exactly
+            dd_add_dd(hi, lo, -p, -pe);
+            rsH[nxt * S + keep] = 0.5 * hi; rsL[nxt * S + keep] = 0.5 * lo;
+            sidb[nxt * S + keep] = parent;
+        }
+        sync();
+        cur = nxt;
+    }
+    if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);  // epilogue: bl written by lane 0
 }
 
 // reverse replay: adjoint of blens w.r.t. the input distance matrix
@@ -1398,7 +1690,22 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
     size_t smem = (3 * (size_t)nj_ld(S) + 32) * sizeof(double) + (3 * (size_t)nj_ld(S) + 2 * (size_t)S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags, pr);
+    int lean_first = 0;
+    if (!full && S <= NJ_LEAN_MAX && !getenv("DODO_NJ_NO_LEAN")) {
+        int W = S <= 32 ? 4 : 8;  // measured (profiles/tools/nj_sweep.py): 27 taxa 0.065 ms at W = 4, 64 taxa 0.138 ms at W = 8
+        if (const char *e = getenv("DODO_NJ_LEAN_W")) {  // tuning sweeps
+            const int w = atoi(e);
+            if (w == 1 || w == 2 || w == 4 || w == 8) W = w;
+        }
+        const size_t lsm = nj_lean_smem_bytes(S, W);
+        auto fn = W == 1 ? nj_soft_lean_kernel<1> : (W == 2 ? nj_soft_lean_kernel<2> : (W == 4 ? nj_soft_lean_kernel<4> : nj_soft_lean_kernel<8>));
+        if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+        fn<<<B, 32 * W, lsm, stream>>>(d_pdm, S, t, (double *)d_ws, d_peel, d_blens, d_flags, pr);
+        DODO_LAUNCH_CHECK();
+        lean_first = 1;
+    }
+    nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags, pr,
+                                                          lean_first);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

@@ -137,8 +137,14 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
 // Transition tables, laid out so that one (sample, category) slab is contiguous and can be staged
 // into shared memory with coalesced 16-byte copies:
 //   tab[b][k] = { Pint[S-1][16] : P of the edge above internal node S+i (row-major; root row unused)
-//                 Ttip[S][5][4] : for tip edge t, the four columns of P and the row sums
-//                                 (== P . tip_partial for the masks A,C,G,T and N/?/-) }
+//                 Ttip[S][2][5][2] : for tip edge t, five rows r_j (the four columns of P and the row sums
+//                                 == P . tip_partial for the masks A,C,G,T and N/?/-), split in halves:
+//                                 {r_j[0], r_j[1]} at 2j, {r_j[2], r_j[3]} at 10 + 2j.  A lane-dependent
+//                                 ld.shared.v2.f64 is served per quarter-warp, 16 bytes x 8 bank groups: with
+//                                 the five half-rows 16 bytes apart every lane of a quarter hits its own group
+//                                 (or the same address), 4 wavefronts per load; with whole rows 32 bytes
+//                                 apart rows 0 and 4 collide and every load costs 8 (measured,
+//                                 profiles/tools/micro/lds_wavefronts.cu) }
 // ------------------------------------------------------------------------------------------
 //                 Cher[chmax][4][25] : message of tabulated cherry c for every pair of tip rows, one
 //                                 plane per state; entry order cherry_entry() keeps the 16 one-hot
@@ -200,13 +206,13 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
         double2 *tt = reinterpret_cast<double2 *>(slab + (size_t)(S - 1) * 16 + (size_t)e * 20);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            tt[j * 2 + 0] = make_double2(P[0 + j], P[4 + j]);
-            tt[j * 2 + 1] = make_double2(P[8 + j], P[12 + j]);
+            tt[j] = make_double2(P[0 + j], P[4 + j]);
+            tt[5 + j] = make_double2(P[8 + j], P[12 + j]);
         }
         double rs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) rs[i] = ((P[i * 4 + 0] + P[i * 4 + 1]) + P[i * 4 + 2]) + P[i * 4 + 3];
-        tt[8] = make_double2(rs[0], rs[1]);
+        tt[4] = make_double2(rs[0], rs[1]);
         tt[9] = make_double2(rs[2], rs[3]);
     }
 }
@@ -347,17 +353,28 @@ __device__ __forceinline__ unsigned encode_sel(unsigned m) {
 }
 
 // message of a tip = P . (indicator of the states allowed by its mask)
+template <bool SMALL, int ROW>
+__device__ __forceinline__ V4 tip_row(const double *T) {  // row ROW of the split table (compile-time)
+    double2 x, y;
+    if (SMALL) { x = lds2<2 * ROW>(T); y = lds2<10 + 2 * ROW>(T); }
+    else { x = ldg2(T + 2 * ROW); y = ldg2(T + 10 + 2 * ROW); }
+    return V4{x.x, x.y, y.x, y.y};
+}
 template <bool SMALL>
-__device__ __forceinline__ V4 tip_message(const double *T /*[5][4]*/, unsigned sel) {
+__device__ __forceinline__ V4 tip_message(const double *T /*[2][5][2]*/, unsigned sel) {
     const unsigned j = sel >> 4;
-    V4 v = ld4t<SMALL>(T + (j & 3u) * 4 + (j & 4u) * 4);
+    const double *Tj = T + 2u * (j & 3u) + 2u * (j & 4u);  // j = 7 reads row 7 of the 10: replaced below
+    double2 x, y;
+    if (SMALL) { x = lds2<0>(Tj); y = lds2<10>(Tj); }
+    else { x = ldg2(T + 2u * min(j, 4u)); y = ldg2(T + 10 + 2u * min(j, 4u)); }
+    V4 v{x.x, x.y, y.x, y.y};
     if (__any_sync(0xffffffffu, j == 7u)) {
         if (j == 7u) {  // two/three-state codes: add the columns in state order (mask 0: nothing allowed)
             v = V4{0, 0, 0, 0};
-            if (sel & 1u) { V4 c = ld4t<SMALL, 0>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
-            if (sel & 2u) { V4 c = ld4t<SMALL, 4>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
-            if (sel & 4u) { V4 c = ld4t<SMALL, 8>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
-            if (sel & 8u) { V4 c = ld4t<SMALL, 12>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 1u) { V4 c = tip_row<SMALL, 0>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 2u) { V4 c = tip_row<SMALL, 1>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 4u) { V4 c = tip_row<SMALL, 2>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
+            if (sel & 8u) { V4 c = tip_row<SMALL, 3>(T); v.a += c.a; v.b += c.b; v.c += c.c; v.d += c.d; }
         }
     }
     return v;
@@ -597,9 +614,9 @@ __global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restric
     const int4 o = ops[(size_t)ob * (S - 1) + pos];  // {left tip, right tip, node, flags}
     double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax);
     const double *P = slab + (size_t)(o.z - S) * 16;
-    const double *Tl = slab + (size_t)(S - 1) * 16 + (size_t)o.x * 20 + (pair / 5) * 4;
-    const double *Tr = slab + (size_t)(S - 1) * 16 + (size_t)o.y * 20 + (pair % 5) * 4;
-    V4 x[1] = {V4{Tl[0] * Tr[0], Tl[1] * Tr[1], Tl[2] * Tr[2], Tl[3] * Tr[3]}}, y[1];
+    const double *Tl = slab + (size_t)(S - 1) * 16 + (size_t)o.x * 20 + (pair / 5) * 2;  // split rows: see Ttip
+    const double *Tr = slab + (size_t)(S - 1) * 16 + (size_t)o.y * 20 + (pair % 5) * 2;
+    V4 x[1] = {V4{Tl[0] * Tr[0], Tl[1] * Tr[1], Tl[10] * Tr[10], Tl[11] * Tr[11]}}, y[1];
     apply_P<false, 1, false>(pmode, md, P, x, y);
     double *out = slab + (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)c * 100 + cherry_entry(pair / 5, pair % 5);
     out[0] = y[0].a; out[25] = y[0].b; out[50] = y[0].c; out[75] = y[0].d;

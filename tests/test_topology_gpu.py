@@ -162,3 +162,41 @@ def test_nj_soft_all_ties():
     peel, blens = engine.nj_soft(_dev(pd), 1e-8)
     validate_peel(peel.cpu().numpy(), 6)
     assert peel.cpu().numpy().tolist() == [[4, 5, 6], [3, 6, 7], [2, 7, 8], [1, 8, 9], [0, 9, 10]]
+
+
+@pytest.mark.gpu
+def test_lean_soft_nj_agrees_with_the_general_kernel(monkeypatch):
+    """Trees of up to 160 taxa go through nj_soft_lean_kernel (matrix resident in shared memory, two barriers per
+    join); everything it does not handle is handed to the general kernel.  Both must return the same peel
+    and flags, and branch lengths equal to rounding (the lean kernel derives the new node's row sum from the old
+    ones instead of summing the new row: both are the exact sum to ~1e-32 before the final rounding)."""
+    import torch
+
+    from dodonaphy_b200 import engine
+
+    rng = np.random.default_rng(11)
+    cases = []
+    for S, B in ((3, 4), (4, 4), (5, 3), (17, 5), (33, 4), (64, 6), (65, 3), (130, 2), (160, 2)):
+        cases.append(torch.tensor(rng.normal(0, 0.08, (B, S, 4))).cuda())
+    dup = rng.normal(0, 0.08, (2, 12, 3))
+    dup[:, 5] = dup[:, 2]  # two identical taxa: exact ties in Q at every join
+    dup[:, 9] = dup[:, 2]
+    cases.append(torch.tensor(dup).cuda())
+    for x in cases:
+        pdm = engine.pdm_forward(x, -1.0, "torch")
+        for tau in (1e-8, 1e-4):
+            monkeypatch.delenv("DODO_NJ_NO_LEAN", raising=False)
+            p1, b1, f1 = engine.nj_soft(pdm, tau, return_flags=True)
+            monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
+            p0, b0, f0 = engine.nj_soft(pdm, tau, return_flags=True)
+            assert torch.equal(p0, p1) and torch.equal(f0, f1)
+            np.testing.assert_allclose(b1.cpu().numpy(), b0.cpu().numpy(), rtol=1e-12, atol=1e-15)
+    # handed over as a whole: an asymmetric matrix and a temperature outside the one-candidate regime
+    pdm = engine.pdm_forward(cases[3], -1.0, "torch").clone()
+    pdm[:, 1, 2] += 1e-3
+    for tau in (1e-8, 0.01):
+        monkeypatch.delenv("DODO_NJ_NO_LEAN", raising=False)
+        p1, b1, f1 = engine.nj_soft(pdm, tau, return_flags=True)
+        monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
+        p0, b0, f0 = engine.nj_soft(pdm, tau, return_flags=True)
+        assert torch.equal(p0, p1) and torch.equal(f0, f1) and torch.equal(b0, b1)
