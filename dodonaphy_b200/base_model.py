@@ -62,41 +62,44 @@ class _BatchedLogLik(torch.autograd.Function):
 
 class _BatchedLogLikModel(torch.autograd.Function):
     """As ``_BatchedLogLik`` with a learnable GTR model: gradient also reaches the unconstrained
-    rate / frequency leaves (phylomodel.py:19-45).  P(t) of the whole batch is formed as a (B,E,K,4,4)
-    device tensor, the pruning kernel returns d lnL/d P and d lnL/d pi (DODO_PRUNE_GMATS), and the
-    chain rule to branch lengths and model leaves is one autograd pass over that small tensor --
-    the batched form of the reference's non-bito branch (base_model.py:239-247)."""
+    rate / frequency leaves (phylomodel.py:19-45) -- the batched form of the reference's non-bito branch
+    (base_model.py:239-247: explicit ``get_transition_mats`` + ``calculate_treelikelihood`` under autograd).
+    P(t) is formed on the device from the current eigen-system; the pruning kernel returns d lnL/d P per edge
+    and category (DODO_PRUNE_GMATS) and d lnL/d pi; ``dodo_model_chain`` contracts them on the device into
+    d lnL/d blens and one 4 x 4 matrix per sample, W_b with d lnL_b/d Q = U^-T W_b U^T.  What is left for the
+    host is the 4 x 4 map (rates, freqs) -> normalised Q, differentiated by autograd on 16 numbers."""
 
     @staticmethod
     def forward(ctx, locs, curvature_leaf, raw_rates, raw_freqs, hot):
         hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
         x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
-        dec = hot.decode_checked(x)
-        peel, blens = dec["peel"], dec["blens"]
-        P, pi = PhyloModel.transition_mats_from_raw(raw_rates.detach(), raw_freqs.detach(), blens, hot.rates)
-        out = hot.prune.loglik_mats(peel, P, pi.numpy(), grad=True, mix=hot.mix)
+        out = hot.resolve(x, hot.value_and_grad_model(x), model=True)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
-        ctx.x, ctx.dec = x, dec
-        ctx.save_for_backward(blens, out["grad_mats"], out["grad_pi"], raw_rates.detach(), raw_freqs.detach())
-        ctx.mark_non_differentiable(peel)
-        return out["lnL"].to(locs.device), peel, blens.to(locs.device), _ln_prior_of(dec).to(locs.device)
+        ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens", "grad_prior", "W", "grad_pi") if k in out}
+        ctx.save_for_backward(raw_rates.detach(), raw_freqs.detach())
+        ctx.model = hot.model
+        ctx.mark_non_differentiable(out["peel"])
+        return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device), _ln_prior_of(out).to(locs.device)
 
     @staticmethod
     def backward(ctx, g_ll, _g_peel, g_blens, g_prior):
-        blens, gP, gpi, raw_rates, raw_freqs = ctx.saved_tensors
+        raw_rates, raw_freqs = ctx.saved_tensors
         x, hot = ctx.x, ctx.hot
         w = g_ll.to(x.device).reshape(-1)
-        with torch.enable_grad():
-            bl = blens.detach().requires_grad_(True)
-            rr, rf = raw_rates.clone().requires_grad_(True), raw_freqs.clone().requires_grad_(True)
-            P, pi = PhyloModel.transition_mats_from_raw(rr, rf, bl, hot.rates)
-            obj = (P * (gP * w.reshape(-1, 1, 1, 1, 1))).sum() + (pi * (gpi * w.reshape(-1, 1)).sum(0).cpu()).sum()
-            gb, g_rates, g_freqs = torch.autograd.grad(obj, (bl, rr, rf))
+        gb = w.reshape(-1, 1) * ctx.dec["grad_blens"]
         if g_blens is not None:
             gb = gb + g_blens.to(x.device)
         if g_prior is not None and ctx.dec.get("grad_prior") is not None:
             gb = gb + g_prior.to(x.device).reshape(-1, 1) * ctx.dec["grad_prior"]
+        # model leaves: sum_b w_b (U^-T W_b U^T) : dQ  +  sum_b w_b grad_pi_b : d pi  -- 20 numbers to the host
+        packed = torch.cat([(w.reshape(-1, 1, 1) * ctx.dec["W"]).sum(0).reshape(-1), (w.reshape(-1, 1) * ctx.dec["grad_pi"]).sum(0)]).cpu()
+        U, Uinv = torch.as_tensor(ctx.model.U), torch.as_tensor(ctx.model.Uinv)
+        GQ = Uinv.T @ packed[:16].reshape(4, 4) @ U.T
+        with torch.enable_grad():
+            rr, rf = raw_rates.clone().requires_grad_(True), raw_freqs.clone().requires_grad_(True)
+            Q, pi = PhyloModel.rate_matrix_from_raw(rr, rf)
+            g_rates, g_freqs = torch.autograd.grad((Q * GQ).sum() + (pi * packed[16:]).sum(), (rr, rf))
         hot.curvature = ctx.kappa
         gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())
         return (gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]),

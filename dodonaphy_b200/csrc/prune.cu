@@ -1118,6 +1118,81 @@ __global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, co
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Chain rule of a device-formed reversible model (learnable GTR: the reference's `--model GTR` always learns
+// rates and frequencies, phylomodel.py:69-74, through torch autograd over GTR_p_t, :96-114).  From
+// G[b][e][k] = d lnL_b / d P(r_k t_e) (the pruning kernel in DODO_PRUNE_GMATS mode with device-formed P) to
+//   d lnL_b / d t_e = sum_k r_k sum_m lam_m e^{lam_m r_k t_e} M_mm,           M = U^T G U^-T
+//   W_b            = sum_{e,k} Phi(r_k t_e) o M                               (4 x 4)
+// with Phi_mn(tau) = tau (e^{lam_m tau} - e^{lam_n tau}) / ((lam_m - lam_n) tau), Phi_mm = tau e^{lam_m tau}
+// (Daleckii-Krein: d exp(Q tau) = U [Phi o (U^-1 dQ U)] U^-1), so that d lnL_b / d Q = U^-T W_b U^T; the host
+// carries that 4 x 4 matrix through Q(rates, freqs).  One CTA per sample, one thread per edge, W reduced
+// over the edges in a fixed order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) model_chain_kernel(ModelDev md, const double *__restrict__ blens,
+                                                        const double *__restrict__ gP, int S, int K,
+                                                        double *__restrict__ gbl, double *__restrict__ Wout) {
+    __shared__ double red[128][17];
+    const int b = blockIdx.x, tid = threadIdx.x, E = 2 * S - 2;
+    double W[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) W[i] = 0.0;
+    for (int e = tid; e < E; e += 128) {
+        const double t = blens[(size_t)b * E + e];
+        double gb = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double rk = md.rates[k], tau = t * rk;
+            const double *G = gP + (((size_t)b * E + e) * K + k) * 16;
+            double tmp[16], M[16], ex[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {  // (G U^-T)_in = sum_j G_ij Uinv_nj
+                    double a = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a = fma(G[i * 4 + j], md.Uinv[n * 4 + j], a);
+                    tmp[i * 4 + n] = a;
+                }
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {  // M_mn = sum_i U_im (G U^-T)_in
+                    double a = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a = fma(md.U[i * 4 + m], tmp[i * 4 + n], a);
+                    M[m * 4 + n] = a;
+                }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ex[m] = exp(md.lam[m] * tau);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) gb = fma(rk * md.lam[m] * ex[m], M[m * 4 + m], gb);
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    double phi;
+                    if (m == n) phi = tau * ex[m];
+                    else {
+                        const double d = fmin((md.lam[m] - md.lam[n]) * tau, 700.0);
+                        phi = tau * ex[n] * (fabs(d) < 1e-8 ? 1.0 + 0.5 * d : expm1(d) / d);
+                    }
+                    W[m * 4 + n] = fma(phi, M[m * 4 + n], W[m * 4 + n]);
+                }
+        }
+        gbl[(size_t)b * E + e] = gb;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[tid][i] = W[i];
+    __syncthreads();
+    for (int half = 64; half >= 1; half >>= 1) {  // fixed-order tree
+        if (tid < half)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) red[tid][i] += red[tid + half][i];
+        __syncthreads();
+    }
+    if (tid < 16) Wout[(size_t)b * 16 + tid] = red[0][tid];
+}
+
 typedef void (*prune_fn_t)(PruneArgs, ModelDev);
 template <int MODE, int NP, int PM>
 static prune_fn_t prune_pick(bool small, bool scale) {
@@ -1337,5 +1412,23 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
             A.gm_part, A.gpi_part, B, plan->n_tiles, K, plan->threads / 32, E, d_grad_P, d_grad_pi);
         DODO_LAUNCH_CHECK();
     }
+    return DODO_OK;
+}
+
+extern "C" int dodo_model_chain(const dodo_model_t *model, const double *rates, int K, const double *d_blens,
+                                const double *d_grad_P, int B, int S, double *d_grad_blens, double *d_W, void *stream_) {
+    DODO_CHECK_ARG(model && d_blens && d_grad_P && d_grad_blens && d_W, "dodo_model_chain: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2 && K >= 1 && K <= MAX_K, "dodo_model_chain: need B>=1, S>=2, 1<=K<=%d", MAX_K);
+    DODO_CHECK_ARG(model->kind == DODO_MODEL_EIGEN, "dodo_model_chain: needs an eigen-decomposed (GTR) model");
+    ModelDev md;
+    memcpy(md.U, model->U, sizeof(md.U));
+    memcpy(md.Uinv, model->Uinv, sizeof(md.Uinv));
+    memcpy(md.lam, model->lam, sizeof(md.lam));
+    memcpy(md.Q, model->Q, sizeof(md.Q));
+    memcpy(md.pi, model->pi, sizeof(md.pi));
+    md.kind = model->kind;
+    for (int k = 0; k < MAX_K; ++k) md.rates[k] = (k < K) ? (rates ? rates[k] : 1.0) : 0.0;
+    model_chain_kernel<<<B, 128, 0, (cudaStream_t)stream_>>>(md, d_blens, d_grad_P, S, K, d_grad_blens, d_W);
+    DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

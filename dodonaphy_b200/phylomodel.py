@@ -138,6 +138,17 @@ class PhyloModel:
         return inv_root @ V, lam, torch.linalg.inv(V) @ root
 
     @staticmethod
+    def rate_matrix_from_raw(raw_rates, raw_freqs):
+        """Differentiable map from the unconstrained leaves (5), (3) to the normalised GTR rate matrix (4,4)
+        and the frequencies (4,): compute_Q_martix + norm (phylomodel.py:116-128) on the host."""
+        r, pi = _SIMPLEX(raw_rates), _SIMPLEX(raw_freqs)
+        iu = torch.triu_indices(4, 4, 1)
+        R = torch.zeros((4, 4), dtype=torch.float64).index_put((iu[0], iu[1]), r)
+        Q = (R + R.T) * pi
+        Q = Q - torch.diag(Q.sum(dim=1))
+        return Q / -(torch.diagonal(Q) * pi).sum(), pi
+
+    @staticmethod
     def transition_mats_from_raw(raw_rates, raw_freqs, blens, cat_rates=None):
         """Differentiable P(t) for a batch: unconstrained leaves (5), (3) on the host, blens (B,E) on
         any device, K category rates -> (B,E,K,4,4) on blens' device, and pi (4,) on the host.

@@ -95,7 +95,17 @@ class HotPath:
             dec["grad_x"], dec["grad_curvature"] = self.decode_backward(x, dec, gbl)
         return dec
 
-    def resolve(self, x, out, to_locations=True):
+    def value_and_grad_model(self, x, exhaustive=False):
+        """As ``value_and_grad(to_locations=False)`` with the gradient w.r.t. the (GTR) model next to the one
+        w.r.t. the branch lengths: adds W (B,4,4) and grad_pi (B,4) (``PruneEngine.loglik_model_grad``).
+        Flagged samples are poisoned the same way."""
+        dec = self.decode(x, exhaustive=exhaustive)
+        out = self.prune.loglik_model_grad(dec["peel"], dec["blens"], self.model, rates=self.rates, mix=self.mix)
+        dec["bad"] = engine.nj_guard(dec["flags"], out["lnL"], out["grad_blens"])
+        dec.update(out)
+        return dec
+
+    def resolve(self, x, out, to_locations=True, model=False):
         """Host side of the flag policy (one device->host read of two counters): samples whose exactness
         guard tripped are re-evaluated with the exhaustive N^2 soft argmin -- the reference's result in
         every regime -- and patched into ``out``; an invalid selection raises, as the one-tree route
@@ -106,7 +116,8 @@ class HotPath:
                                f"{n_invalid} sample(s) (temperature too high for these distances)")
         if n_guard:
             idx = ((out["flags"] & 4) != 0).any(dim=1).nonzero().reshape(-1)
-            sub = self.value_and_grad(x[idx].contiguous(), to_locations=to_locations, exhaustive=True)
+            sub = (self.value_and_grad_model(x[idx].contiguous(), exhaustive=True) if model else
+                   self.value_and_grad(x[idx].contiguous(), to_locations=to_locations, exhaustive=True))
             if int(sub["bad"][1]):
                 raise RuntimeError("soft NJ: the soft argmin selected an inactive node")
             for k, v in sub.items():

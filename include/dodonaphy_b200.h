@@ -129,6 +129,16 @@ int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double *d_curvatu
                  int lift, int matsumoto, void *d_ws, const double *d_grad_pdm, double *d_grad_x,
                  double *d_grad_curv, void *stream);
 
+/* Chain rule of a device-formed reversible (GTR) model whose rates and frequencies are being learnt (the
+ * reference's `--model GTR`, dodonaphy/phylomodel.py:69-74: torch autograd through GTR_p_t :96-114 and
+ * calculate_treelikelihood, reached from BaseModel.compute_LL dodonaphy/base_model.py:239-247).  Input: d_grad_P
+ * [B][2S-2][K][16] from dodo_prune(DODO_PRUNE_GMATS) called with branch lengths (P formed on the device from
+ * `model`).  Output: d_grad_blens [B][2S-2] = d lnL_b / d t_e and d_W [B][16] (row-major 4 x 4) with
+ * d lnL_b / d Q = U^-T W_b U^T for the NORMALISED rate matrix Q of `model` at fixed branch lengths; the
+ * caller carries that through Q(rates, freqs) on the host (a 4 x 4 computation). */
+int dodo_model_chain(const dodo_model_t *model, const double *rates, int K, const double *d_blens,
+                     const double *d_grad_P, int B, int S, double *d_grad_blens, double *d_W, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1p: batched POINTWISE hyperbolic distances -- n independent pairs (x1[i], x2[i]) of D-dimensional
  * points (D <= 16) -- and their vector-Jacobian product.  Replaces the single-pair utilities the
