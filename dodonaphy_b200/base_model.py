@@ -45,6 +45,7 @@ class _BatchedLogLik(torch.autograd.Function):
         ctx.devs = (locs.device, curvature_leaf.device)
         ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens", "grad_prior") if k in out}
         ctx.mark_non_differentiable(out["peel"])
+        hot.last_decode = (x, out["peel"], out["flags"])  # for the Jacobian term of the same step (vi.py:376-387)
         return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device), _ln_prior_of(out).to(locs.device)
 
     @staticmethod
@@ -80,6 +81,7 @@ class _BatchedLogLikModel(torch.autograd.Function):
         ctx.save_for_backward(raw_rates.detach(), raw_freqs.detach())
         ctx.model = hot.model
         ctx.mark_non_differentiable(out["peel"])
+        hot.last_decode = (x, out["peel"], out["flags"])  # for the Jacobian term of the same step (vi.py:376-387)
         return out["lnL"].to(locs.device), out["peel"], out["blens"].to(locs.device), _ln_prior_of(out).to(locs.device)
 
     @staticmethod

@@ -184,6 +184,174 @@ __global__ void __launch_bounds__(1024) pdm_bwd_kernel(const double *__restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// d blens / d locations of a whole soft-NJ tree in ONE pass (the reference takes 2S-2
+// autograd passes per sample through its get_pdm -> nj_torch chain, vi.py:376-387).
+//
+// With the selections fixed (they carry no gradient, soft.py:56-61) every distance NJ ever forms is a bilinear
+// form of the tip distance matrix D:  d(u, x) = a_u^T D a_x - c_u - c_x  with a_u = (a_l + a_r) / 2 the
+// averaging weights of the cluster (a_tip = unit vector) and c_u = a_l^T D a_r / 2 (c_tip = 0): induction on
+// d(u, x) = (d(l, x) + d(r, x) - d(l, r)) / 2 (get_new_dist_soft, peeler.py:251-265).  The two branch lengths of a
+// join (peeler.py:199-213) are
+//   d_pl = d_lr / 2 + (r_l - r_r) / (2 (n - 2)),   d_pr = d_lr - d_pl,
+//   d_lr = a_l^T D a_r - c_l - c_r,   r_l - r_r = (a_l - a_r)^T D sigma - (n - 2)(c_l - c_r),
+// sigma = the sum of a_x over the other live nodes.  The gradient of a^T D b w.r.t. the sheet point s_i is
+// a_i Y_b[i] + b_i Y_a[i] with Y_v[i] = sum_j v_j dD_ij/ds_i, and Y is linear in v: Y_u = (Y_l + Y_r) / 2.  So
+// every row of the Jacobian follows from per-node quantities (a, Y, grad c) that are ELEMENTWISE in
+// (taxon i, sheet coordinate d): one thread owns one (i, d), walks the S-1 joins on its own (no barrier, no
+// reduction) and writes its column of all 2S-2 rows -- O(S^2 D) per tree instead of (2S-2) replays of an
+// O(S^2) backward.  A second pass maps the sheet-space rows through the lift to the location coordinates,
+// exactly as pdm_bwd_kernel does.  Clamped branches (flags bit0/bit1) pass no gradient, as in nj_soft_bwd.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t jac_ws_doubles(int S, int D) {
+    // per tree: a, Y, grad c of the S-1 internal nodes and the 2S-2 sheet-space rows, S (D+1) elements each
+    return (size_t)(3 * (S - 1) + 2 * S - 2) * S * (D + 1);
+}
+
+__global__ void __launch_bounds__(1024) blens_jac_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
+                                                        const double *__restrict__ util, int S, int D,
+                                                        const double *__restrict__ curv, int lift, int matsumoto,
+                                                        const int64_t *__restrict__ peel, const int32_t *__restrict__ flags,
+                                                        double *__restrict__ ws, double *__restrict__ J) {
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int D1 = D + 1, NE = S * D1, E = 2 * S - 2;
+    const double kappa = curv[0];
+    const double sc = 1.0 / sqrt(-kappa);
+    const double *sh = sheet + (size_t)b * S * D1;
+    const double *ut = util + (size_t)b * S;
+    const int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    const int32_t *fl = flags + (size_t)b * (S - 1);
+    double *An = ws + (size_t)b * jac_ws_doubles(S, D);  // [S-1][NE] averaging weight a_u[i] (per element)
+    double *Yn = An + (size_t)(S - 1) * NE;               // [S-1][NE] Y_u[i][d]
+    double *Gn = Yn + (size_t)(S - 1) * NE;               // [S-1][NE] d c_u / d s_i[d]
+    double *Js = Gn + (size_t)(S - 1) * NE;               // [2S-2][NE] rows in sheet coordinates
+    for (int el = tid; el < NE; el += T) {
+        const int i = el / D1, dp = el - i * D1;
+        double si[MAX_D + 1];
+        for (int d = 0; d <= D; ++d) si[d] = sh[(size_t)i * D1 + d];
+        const double ui = ut[i];
+        auto tipY = [&](int j) -> double {  // dD_ij / ds_i[dp]  (pdm_bwd_kernel's per-pair term)
+            if (j == i) return 0.0;
+            const double *sj = sh + (size_t)j * D1;
+            const double uj = ut[j];
+            const double Hraw = pair_H(si, sj, D, ui, uj);
+            if (!(Hraw < -TORCH_CLAMP)) return 0.0;  // clamped entry: constant
+            double coef = -sc / sqrt(Hraw * Hraw - 1.0);
+            if (matsumoto) coef *= tanh(sc * acosh(-Hraw));
+            return coef * (sj[dp] - (uj / ui) * si[dp]);
+        };
+        double Ta = 1.0, TY = 0.0;  // sums over the live nodes: a_x[i] (only tip i counts at the start), Y_x[i][dp]
+        for (int j = 0; j < S; ++j) TY += tipY(j);
+        for (int t = 0; t < S - 1; ++t) {
+            const int l = (int)pl[t * 3 + 0], r = (int)pl[t * 3 + 1], u = (int)pl[t * 3 + 2];
+            const int f = fl[t];
+            const int n = S - t;
+            double al, Yl, Gl, ar, Yr, Gr;
+            if (l < S) { al = l == i ? 1.0 : 0.0; Yl = tipY(l); Gl = 0.0; }
+            else { const size_t o = (size_t)(l - S) * NE + el; al = An[o]; Yl = Yn[o]; Gl = Gn[o]; }
+            if (r < S) { ar = r == i ? 1.0 : 0.0; Yr = tipY(r); Gr = 0.0; }
+            else { const size_t o = (size_t)(r - S) * NE + el; ar = An[o]; Yr = Yn[o]; Gr = Gn[o]; }
+            const double A = al * Yr + ar * Yl;  // d (a_l^T D a_r) / d s_i[dp]
+            const double dlr = A - Gl - Gr;
+            const double sig = Ta - al - ar, Ysig = TY - Yl - Yr;
+            // (the last join has no other live node: its two rows are the same half of d d_lr bit for bit, as in
+            // the reference, where both come from one d_lr / 2)
+            const double drr = n == 2 ? 0.0 : (al - ar) * Ysig + sig * (Yl - Yr) - (double)(n - 2) * (Gl - Gr);
+            const double nact = fmax((double)n, 3.0);
+            const double basel = (f & 1) ? 0.0 : 0.5 * dlr + drr / (2.0 * (nact - 2.0));
+            Js[(size_t)l * NE + el] = basel;
+            Js[(size_t)r * NE + el] = (f & 2) ? 0.0 : dlr - basel;
+            const double au = 0.5 * (al + ar), Yu = 0.5 * (Yl + Yr);
+            const size_t o = (size_t)(u - S) * NE + el;
+            An[o] = au; Yn[o] = Yu; Gn[o] = 0.5 * A;
+            Ta += au - al - ar;
+            TY += Yu - Yl - Yr;
+        }
+    }
+    __syncthreads();  // rows complete (written by this CTA): now through the lift, one thread per (row, taxon)
+    double *Jb = J + (size_t)b * E * S * D;
+    for (int w = tid; w < E * S; w += T) {
+        const int e = w / S, i = w - e * S;
+        const double *acc = Js + (size_t)e * NE + (size_t)i * D1;
+        const double *xi = x + ((size_t)b * S + i) * D;
+        double *out = Jb + (size_t)e * S * D + (size_t)i * D;
+        if (lift == DODO_LIFT_UP) {
+            const double s0 = sh[(size_t)i * D1];
+            for (int d = 0; d < D; ++d) out[d] = acc[d + 1] + acc[0] * xi[d] / s0;
+        } else {
+            const double n2 = row_norm2(xi, D);
+            const double r = sqrt(fmax(n2, DBL_EPSILON));
+            const double shr = sinh(r), chr = cosh(r);
+            const double fr = shr / r;
+            double dot = 0.0;
+            for (int d = 0; d < D; ++d) dot = fma(acc[d + 1], xi[d], dot);
+            const double dfdr = (r * chr - shr) / (r * r);
+            const double rad = (n2 > DBL_EPSILON) ? (acc[0] * shr + dot * dfdr) / r : 0.0;
+            for (int d = 0; d < D; ++d) out[d] = fr * acc[d + 1] + rad * xi[d];
+        }
+    }
+}
+
+// log sqrt|det(J J^T)| of the Jacobian of every sample (vi.py:385-387), one CTA per sample: the Gram matrix is
+// formed in shared memory and reduced by Gaussian elimination (one barrier per step).  J J^T is singular for
+// an NJ tree (the last join gives two equal rows), so -- as in the reference -- the value is -inf or rounding
+// noise; what matters is that it costs microseconds instead of a batched LAPACK call.
+__global__ void __launch_bounds__(1024) gram_logdet_kernel(const double *__restrict__ J, int E, int C,
+                                                          double *__restrict__ out) {
+    extern __shared__ __align__(16) double gsm[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int ld = E + 1;
+    double *A = gsm;  // [E][ld]
+    const double *Jb = J + (size_t)b * E * C;
+    // Gram matrix: J is staged 32 columns at a time ([E][33], coalesced loads, conflict-free reads); one thread per
+    // entry e <= f adds its partial dot product, columns in ascending order
+    double *Jc = A + (size_t)E * ld;  // [E][33]
+    const int T = blockDim.x;
+    for (int idx = tid; idx < E * ld; idx += T) A[idx] = 0.0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        __syncthreads();
+        for (int idx = tid; idx < E * 32; idx += T) {
+            const int e = idx >> 5, c = idx & 31;
+            Jc[e * 33 + c] = c0 + c < C ? Jb[(size_t)e * C + c0 + c] : 0.0;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < E * E; idx += T) {
+            const int e = idx / E, f = idx - e * E;
+            if (f < e) continue;
+            const double *re = Jc + e * 33, *rf = Jc + f * 33;
+            double acc = A[e * ld + f];
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) acc = fma(re[c], rf[c], acc);
+            A[e * ld + f] = acc;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < E * E; idx += T) {
+        const int e = idx / E, f = idx - e * E;
+        if (f > e) A[f * ld + e] = A[e * ld + f];
+    }
+    // J J^T is symmetric positive semi-definite: elimination without pivoting (the Cholesky order) is stable.  One
+    // barrier per step; warps take the rows below the pivot, lanes the columns to its right.
+    double logabs = 0.0;
+    for (int k = 0; k < E; ++k) {
+        __syncthreads();
+        const double piv = A[k * ld + k];
+        if (!(piv != 0.0)) {  // exactly singular (or NaN): log|det| = -inf (NaN propagates)
+            if (tid == 0) out[b] = piv == piv ? -INFINITY : piv;
+            return;
+        }
+        if (tid == 0) logabs += log(fabs(piv));
+        const double inv = 1.0 / piv;
+        const double *rowk = A + k * ld;
+        for (int i = k + 1 + warp; i < E; i += nwarp) {
+            double *rowi = A + i * ld;
+            const double l = rowi[k] * inv;
+            for (int j = k + 1 + lane; j < E; j += 32) rowi[j] = fma(-l, rowk[j], rowi[j]);
+        }
+    }
+    if (tid == 0) out[b] = 0.5 * logabs;
+}
+
 }  // namespace dodo
 
 using namespace dodo;
@@ -241,6 +409,43 @@ extern "C" int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double
     const int bwd_threads = B >= 8 * sm_count() ? 256 : (S >= 48 ? 1024 : (S >= 16 ? 512 : 256));
     pdm_bwd_kernel<<<B, bwd_threads, 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_grad_pdm, d_grad_x,
                                           d_grad_curv);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+extern "C" uint64_t dodo_blens_jacobian_workspace_bytes(int B, int S, int D) {
+    return ((uint64_t)B * S * (D + 2) + (uint64_t)B * jac_ws_doubles(S, D)) * sizeof(double);
+}
+
+extern "C" int dodo_blens_jacobian(const double *d_x, int B, int S, int D, const double *d_curvature, int lift,
+                                   int matsumoto, const int64_t *d_peel, const int32_t *d_flags, void *d_ws, double *d_J,
+                                   void *stream_) {
+    DODO_CHECK_ARG(d_x && d_curvature && d_peel && d_flags && d_ws && d_J, "dodo_blens_jacobian: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && S >= 2 && D >= 1 && D <= MAX_D, "dodo_blens_jacobian: need B>=1, S>=2, 1<=D<=%d", MAX_D);
+    DODO_CHECK_ARG(lift == DODO_LIFT_UP || lift == DODO_LIFT_WRAP, "dodo_blens_jacobian: bad lift");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double *sheet, *util;
+    int rc = run_lift(d_x, B, S, D, lift, d_ws, stream, &sheet, &util);
+    if (rc != DODO_OK) return rc;
+    double *ws = util + (size_t)B * S;
+    const int ne = S * (D + 1);
+    const int threads = ne >= 1024 ? 1024 : ((ne + 31) / 32) * 32;
+    blens_jac_kernel<<<B, threads, 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_peel, d_flags, ws, d_J);
+    DODO_LAUNCH_CHECK();
+    return DODO_OK;
+}
+
+extern "C" int dodo_gram_logdet(const double *d_J, int B, int E, int C, double *d_out, void *stream_) {
+    DODO_CHECK_ARG(d_J && d_out, "dodo_gram_logdet: NULL argument");
+    DODO_CHECK_ARG(B >= 1 && E >= 1 && C >= 1, "dodo_gram_logdet: need B, E, C >= 1");
+    const size_t smem = ((size_t)E * (E + 1) + (size_t)E * 33) * sizeof(double);
+    if (smem > 227 * 1024 || E > 192) {
+        set_error("dodo_gram_logdet: %d rows need %zu bytes of shared memory (limit 227 KB)", E, smem);
+        return DODO_ENOTIMPL;
+    }
+    if (smem > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(gram_logdet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = E >= 64 ? 512 : (E >= 24 ? 256 : 64);
+    gram_logdet_kernel<<<B, threads, smem, (cudaStream_t)stream_>>>(d_J, E, C, d_out);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

@@ -385,6 +385,37 @@ def pdm_backward(x, grad_pdm, curvature=-1.0, lift="up", matsumoto=False, ws=Non
     return (gx[0] if squeeze else gx), gc
 
 
+def blens_jacobian(x, peel, flags, curvature=-1.0, lift="up", matsumoto=False, ws=None):
+    """d blens / d locations of soft-NJ trees in one pass: x (B,S,D), peel (B,S-1,3), flags (B,S-1) as returned
+    by ``nj_soft`` -> (B, 2S-2, S*D).  (``dodo_blens_jacobian``; the reference: vi.py:376-387.)"""
+    lib = _lib.load()
+    x, squeeze = _as_batch(x, 3)
+    B, S, D = (int(v) for v in x.shape)
+    peel = peel.reshape(B, S - 1, 3).to(x.device, dtype=torch.int64).contiguous()
+    flags = flags.reshape(B, S - 1).to(x.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(x.device):
+        J = torch.empty((B, 2 * S - 2, S * D), dtype=torch.float64, device=x.device)
+        ws = _workspace("jac", lib.dodo_blens_jacobian_workspace_bytes(B, S, D), x.device, ws)
+        cv = _curv_tensor(curvature, x.device)
+        _lib.check(lib.dodo_blens_jacobian(_ptr(x), B, S, D, _ptr(cv), _lib.LIFT_UP if lift == "up" else _lib.LIFT_WRAP,
+                                           int(bool(matsumoto)), _ptr(peel), _ptr(flags), _ptr(ws), _ptr(J), _stream()))
+    return J[0] if squeeze else J
+
+
+def gram_logdet(J):
+    """0.5 * log|det(J J^T)| for a batch of matrices (B, E, C) on the device (``dodo_gram_logdet``); falls back
+    to the library LU when E (E+1) doubles do not fit in shared memory."""
+    lib = _lib.load()
+    B, E, Cc = (int(v) for v in J.shape)
+    if (E * (E + 1) + E * 33) * 8 > 227 * 1024 or E > 192:
+        return 0.5 * torch.linalg.slogdet(J @ J.transpose(1, 2))[1]
+    J = J.contiguous()
+    with torch.cuda.device(J.device):
+        out = torch.empty(B, dtype=torch.float64, device=J.device)
+        _lib.check(lib.dodo_gram_logdet(_ptr(J), B, E, Cc, _ptr(out), _stream()))
+    return out
+
+
 _DIST_FORMS = {"poincare": _lib.DIST_POINCARE, "lorentz": _lib.DIST_LORENTZ, "sheet_up": _lib.DIST_SHEET_UP}
 
 

@@ -141,13 +141,17 @@ class HotPath:
                 dec[k][idx] = v
         return dec
 
-    def blens_jacobian(self, x, peel=None, flags=None, logdet=True):
+    def blens_jacobian(self, x, peel=None, flags=None, logdet=True, replay=False):
         """d blens / d locations for every sample, (B, 2S-2, S*D), and log sqrt|det(J J^T)| -- the
         change-of-variables term the reference obtains with ``torch.autograd.functional.jacobian``
-        and 2S-2 backward passes per sample (vi.py:376-387; ~3/4 of a reference VI sample).  Here the
-        2S-2 one-hot cotangents of all B samples go through the NJ and distance backward kernels as
-        ONE batch of B*(2S-2) replays.  (The last NJ join splits one distance into two equal halves,
-        so two rows of J coincide and the determinant is numerically ~0 in the reference as well.)"""
+        and 2S-2 backward passes per sample (vi.py:376-387; ~3/4 of a reference VI sample).  For the NJ
+        connector all 2S-2 rows of a tree come out of ONE pass over its joins (``engine.blens_jacobian``:
+        every NJ distance is a bilinear form of the tip distances, so the rows follow from per-node
+        quantities that are elementwise in (taxon, coordinate)).  ``replay=True`` (and the geodesic connector)
+        takes the 2S-2 one-hot cotangents through the backward kernels as ONE batch of B*(2S-2) replays --
+        the literal batched form of the reference's loop, kept as a cross-check.  (The last NJ join splits
+        one distance into two equal halves, so two rows of J coincide and the determinant is numerically ~0
+        in the reference as well.)"""
         B, S, D = (int(v) for v in x.shape)
         E = 2 * S - 2
         if self.connector == "geodesics":
@@ -155,27 +159,35 @@ class HotPath:
             cot = torch.eye(E, dtype=torch.float64, device=x.device).repeat(B, 1)
             rep = {k: dec[k].repeat_interleave(E, 0) for k in ("peel", "slots", "tape")}
             gx, _ = self.decode_backward(None, rep, cot)
+            J = gx.reshape(B, E, S * D)
         else:
             if peel is None:
                 dec = self.decode_checked(x)
                 peel, flags = dec["peel"], dec["flags"]
-            # every replay needs an S x S adjoint workspace: chunk the B*E replays to a memory budget
-            # (2000 taxa: 32 MB per replay) instead of asking for all of them at once
-            per = max(1, int(engine._lib.load().dodo_nj_workspace_bytes(1, S)))
-            chunk = max(1, min(B, int((2 << 30) // (per * E))))
-            parts = []
-            eye = torch.eye(E, dtype=torch.float64, device=x.device)
-            for lo in range(0, B, chunk):
-                hi = min(B, lo + chunk)
-                rep = dict(peel=peel[lo:hi].repeat_interleave(E, 0), flags=flags[lo:hi].repeat_interleave(E, 0))
-                g, _ = self.decode_backward(x[lo:hi].repeat_interleave(E, 0), rep, eye.repeat(hi - lo, 1))
-                parts.append(g)
-            gx = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
-        J = gx.reshape(B, E, S * D)
+            if not replay:
+                # the workspace is ~ (5S) x S(D+1) doubles per tree: chunk the batch to a memory budget
+                per = max(1, int(engine._lib.load().dodo_blens_jacobian_workspace_bytes(1, S, D)) + 8 * E * S * D)
+                chunk = max(1, min(B, int((4 << 30) // per)))
+                parts = [engine.blens_jacobian(x[lo:lo + chunk], peel[lo:lo + chunk], flags[lo:lo + chunk], self.curvature,
+                                               self.lift, self.matsumoto, ws=self.ws) for lo in range(0, B, chunk)]
+                J = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+            else:
+                # every replay needs an S x S adjoint workspace: chunk the B*E replays to a memory budget
+                # (2000 taxa: 32 MB per replay) instead of asking for all of them at once
+                per = max(1, int(engine._lib.load().dodo_nj_workspace_bytes(1, S)))
+                chunk = max(1, min(B, int((2 << 30) // (per * E))))
+                parts = []
+                eye = torch.eye(E, dtype=torch.float64, device=x.device)
+                for lo in range(0, B, chunk):
+                    hi = min(B, lo + chunk)
+                    rep = dict(peel=peel[lo:hi].repeat_interleave(E, 0), flags=flags[lo:hi].repeat_interleave(E, 0))
+                    g, _ = self.decode_backward(x[lo:hi].repeat_interleave(E, 0), rep, eye.repeat(hi - lo, 1))
+                    parts.append(g)
+                gx = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+                J = gx.reshape(B, E, S * D)
         if not logdet:
             return J
-        sign, logabs = torch.linalg.slogdet(J @ J.transpose(1, 2))
-        return J, 0.5 * logabs
+        return J, engine.gram_logdet(J)
 
     def value(self, x):
         """Gradient-free MCMC path (Chyp_np.get_pdm -> Cpeeler.nj_np -> Cphylo.compute_LL_np)."""

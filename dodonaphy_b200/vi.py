@@ -68,7 +68,8 @@ class DodonaphyVI(BaseModel):
             ln_prior = priors.compute_prior_exponential(blens, rate=10.0)
         if self.include_jacobian:
             hot = self._hotpath()
-            _, jac = hot.blens_jacobian(x.detach().to(hot.device), logdet=True)
+            xd, peel_d, flags_d = hot.last_decode  # the trees just decoded for the likelihood: not decoded again
+            _, jac = hot.blens_jacobian(xd, peel_d, flags_d, logdet=True)
             jac = torch.where(torch.isfinite(jac), jac, torch.zeros_like(jac)).to(x.device)  # vi.py:199-201
         else:
             jac = torch.zeros_like(ln_p)

@@ -161,6 +161,20 @@ int dodo_hypdist_bwd(const double *d_x1, const double *d_x2, int64_t n, int D, c
                      double *d_grad_curv, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * d blens / d locations of a soft-NJ tree in one pass: the (2S-2) x (S D) Jacobian the reference obtains with
+ * torch.autograd.functional.jacobian over its get_pdm -> nj_torch chain, 2S-2 backward passes per sample
+ * (dodonaphy/vi.py:376-387).  d_peel / d_flags: the outputs of dodo_nj_soft for the same locations.
+ * d_J [B][2S-2][S*D].  Selections carry no gradient (dodonaphy/soft.py:56-61); clamped branches pass none.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t dodo_blens_jacobian_workspace_bytes(int B, int S, int D);
+int dodo_blens_jacobian(const double *d_x, int B, int S, int D, const double *d_curvature, int lift, int matsumoto,
+                        const int64_t *d_peel, const int32_t *d_flags, void *d_ws, double *d_J, void *stream);
+
+/* log sqrt|det(J J^T)| for B row-major matrices J [B][E][C] (the change-of-variables term of
+ * dodonaphy/vi.py:385-387): d_out [B]; -inf when J J^T is exactly singular.  E (E+1) doubles of shared memory. */
+int dodo_gram_logdet(const double *d_J, int B, int E, int C, double *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2: batched neighbour joining, one tree per CTA.
  * dodo_nj_hard replaces Cpeeler.nj_np (dodonaphy/cython/Cpeeler.pyx:15-125): bit-identical peel
  * and blens (same operation order, no FMA contraction, first strict minimum in pool order).

@@ -265,7 +265,7 @@ def test_vi_jacobian_term_follows_the_reference_policy(monkeypatch):
     vi.set_params_optim(prob["x"], np.full((S, D), -9.0))
     x = torch.tensor(prob["xs"][:3])
     for fake, want in ((float("-inf"), 0.0), (-34.4, -34.4)):
-        monkeypatch.setattr(HotPath, "blens_jacobian", lambda self, xx, logdet=True, v=fake: (None, torch.full((xx.shape[0],), v, dtype=torch.float64, device=xx.device)))
+        monkeypatch.setattr(HotPath, "blens_jacobian", lambda self, xx, *a, v=fake, **kw: (None, torch.full((xx.shape[0],), v, dtype=torch.float64, device=xx.device)))
         _, _, jac, _, _ = vi.elbo_terms(x)
         assert jac.tolist() == [want] * 3 and not jac.requires_grad
 
@@ -677,3 +677,51 @@ def test_gamma_dirichlet_prior_kernel_and_nj_epilogue():
     peel, blens, (lp, g) = engine.nj_hard(pdm, prior=engine.GammaDirPrior(variant="numpy", grad=False))
     assert g is None
     np.testing.assert_allclose(lp.cpu().numpy(), [Cphylo.compute_prior_gamma_dir_np(b) for b in blens.cpu().numpy()], rtol=1e-12)
+
+
+def test_one_pass_jacobian_equals_the_batched_replays():
+    """engine.blens_jacobian (all 2S-2 rows of a tree from one pass over its joins) against the literal batched
+    form of the reference's loop (one NJ + distance backward replay per row): both lifts, the Matsumoto
+    adjustment, another curvature, and trees with clamped branches (flags bit0 / bit1 set)."""
+    from dodonaphy_b200 import engine, synth
+    from dodonaphy_b200.engine import SubstModel
+    from dodonaphy_b200.pipeline import HotPath
+
+    rng = np.random.default_rng(5)
+    seen_clamped = False
+    for S, D, lift, mats, kappa, scale in ((5, 2, "up", False, -1.0, 0.1), (9, 3, "wrap", False, -1.0, 0.1),
+                                           (17, 5, "up", True, -0.7, 1.0), (33, 4, "wrap", True, -1.3, 1.0),
+                                           (64, 5, "up", False, -1.0, 0.05), (12, 3, "up", False, -1.0, None)):
+        prob = synth.make_problem(S, 16, 3, D=D, seed=S)
+        hp = HotPath(prob["masks"], prob["weights"], SubstModel.jc69(), tau=1e-8, curvature=kappa, lift=lift, matsumoto=mats)
+        x = torch.tensor(rng.normal(0, scale or 0.1, (3, S, D))).cuda()
+        if scale is None:
+            x[:, 3] = x[:, 1]  # coincident taxa: zero-length branches are clamped
+        dec = hp.decode(x)
+        good = ((dec["flags"] & 12) == 0).all(dim=1)  # (log cosh shrinks small distances below the temperature: the
+        assert bool(good.any())                        # reference's soft argmin then selects a masked node, too)
+        x, dec = x[good].contiguous(), {k: v[good].contiguous() for k, v in dec.items()}
+        seen_clamped = seen_clamped or bool((dec["flags"] & 3).any())
+        J1 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False)
+        J0 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False, replay=True)
+        ref = J0.cpu().numpy()
+        np.testing.assert_allclose(J1.cpu().numpy(), ref, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(ref).max()), err_msg=f"S={S} {lift}")
+    assert seen_clamped
+
+
+def test_gram_logdet_kernel():
+    """0.5 log|det(J J^T)| by the one-CTA-per-matrix elimination kernel against LAPACK (NumPy) on well-conditioned
+    matrices, and -inf on an exactly singular one (vi.py:385-387 / :199-201)."""
+    from dodonaphy_b200 import engine
+
+    rng = np.random.default_rng(8)
+    for E, C in ((1, 3), (5, 9), (30, 40), (126, 320), (126, 126)):
+        J = rng.normal(size=(4, E, C))
+        got = engine.gram_logdet(torch.tensor(J).cuda()).cpu().numpy()
+        want = [0.5 * np.linalg.slogdet(j @ j.T)[1] for j in J]
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10)
+    J = np.zeros((1, 4, 6))
+    J[0, 0, 0] = J[0, 1, 1] = 1.0
+    J[0, 2, 0] = 1.0  # row 2 == row 0: exactly representable duplicate
+    J[0, 3, 3] = 2.0
+    assert engine.gram_logdet(torch.tensor(J).cuda()).item() == float("-inf")
