@@ -125,11 +125,15 @@ __global__ void prior_kernel(const double *__restrict__ blens, int B, int S, Pri
 #endif
 __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
                                                        int64_t *__restrict__ peel, double *__restrict__ blens,
-                                                       PriorDev prior) {
+                                                       PriorDev prior, int lean_first) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     double *Dm = ws + (size_t)b * nj_ws_doubles(S);
+    if (lean_first) {  // nj_hard_lean_kernel ran first: only the trees it handed over are done here
+        const int todo = *reinterpret_cast<const int *>(Dm);
+        if (__syncthreads_or(0) || todo == 0) return;
+    }
     const int LD = nj_ld(S);
     double *Dalt = Dm + (size_t)LD * LD;  // second matrix of the workspace: target of the next repack
     int ld = LD;                          // row stride of the current matrix
@@ -974,13 +978,11 @@ __global__ void __launch_bounds__(32 * W) nj_soft_lean_kernel(const double *__re
                     const double dij = dv[j];
                     const double qa = (nm2 * dij - rsr[j]) - rsc;
                     const double qb = (nm2 * dij - rsc) - rsr[j];
-                    double q = 0.5 * (qa + qb);
-                    if (!(rj < n && c < rj)) q = DBL_MAX;
-                    const bool lt1 = q < m1, lt2 = q < m2;
-                    m2 = lt1 ? m1 : (lt2 ? q : m2);
-                    m1 = lt1 ? q : m1;
-                    dmin = lt1 ? dij : dmin;
-                    key = lt1 ? (((unsigned)rj << 16) | (unsigned)c) : key;
+                    const double q = 0.5 * (qa + qb);
+                    if ((rj < n && c < rj) && q < m2) {  // rare once the two running minima have settled
+                        if (q < m1) { m2 = m1; m1 = q; dmin = dij; key = ((unsigned)rj << 16) | (unsigned)c; }
+                        else m2 = q;
+                    }
                 }
             }
         }
@@ -999,11 +1001,16 @@ __global__ void __launch_bounds__(32 * W) nj_soft_lean_kernel(const double *__re
         if (W > 1) {
             if (lane == 0) { red[3 * warp] = m1; red[3 * warp + 1] = m2; red[3 * warp + 2] = dmin; redk[warp] = key; }
             __syncthreads();
-            m1 = red[0]; m2 = red[1]; dmin = red[2]; key = redk[0];
+            // every warp folds the W per-warp results for itself: lane w takes entry w, then the same butterfly
+            m1 = lane < W ? red[3 * lane] : DBL_MAX;
+            m2 = lane < W ? red[3 * lane + 1] : DBL_MAX;
+            dmin = lane < W ? red[3 * lane + 2] : 0.0;
+            key = lane < W ? redk[lane] : 0x00010000u;
 #pragma unroll
-            for (int w = 1; w < W; ++w) {
-                const double o1 = red[3 * w], o2 = red[3 * w + 1], od = red[3 * w + 2];
-                const unsigned ok = redk[w];
+            for (int m = W / 2; m >= 1; m >>= 1) {
+                const double o1 = __shfl_xor_sync(0xffffffffu, m1, m), o2 = __shfl_xor_sync(0xffffffffu, m2, m);
+                const double od = __shfl_xor_sync(0xffffffffu, dmin, m);
+                const unsigned ok = __shfl_xor_sync(0xffffffffu, key, m);
                 const bool lt = o1 < m1;
                 const double lo1 = lt ? o1 : m1, hi1 = lt ? m1 : o1, oth = lt ? o2 : m2;
                 m2 = oth < hi1 ? oth : hi1;
@@ -1011,6 +1018,10 @@ __global__ void __launch_bounds__(32 * W) nj_soft_lean_kernel(const double *__re
                 dmin = lt ? od : dmin;
                 key = lt ? ok : key;
             }
+            // (on an exact tie of the minimum the lanes may hold different keys, but then m2 == m1 everywhere and the
+            // key is not used; otherwise every lane of the group holds the same result: take lane 0's)
+            m1 = __shfl_sync(0xffffffffu, m1, 0); m2 = __shfl_sync(0xffffffffu, m2, 0);
+            dmin = __shfl_sync(0xffffffffu, dmin, 0); key = __shfl_sync(0xffffffffu, key, 0);
         }
         // m = min(min Q, 0) (the strict upper triangle of the padded matrix holds zeros, torch.tril).  The
         // usual case is soft_argmin_fast's one-candidate branch: m is attained by exactly one live pair and
@@ -1125,6 +1136,213 @@ __global__ void __launch_bounds__(32 * W) nj_soft_lean_kernel(const double *__re
         cur = nxt;
     }
     if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);  // epilogue: bl written by lane 0
+}
+
+// ------------------------------------------------------------------------------------------ lean hard
+// Hard NJ for trees whose lower triangle fits in shared memory (<= NJ_HARD_LEAN_MAX taxa): the same construction
+// as nj_soft_lean_kernel -- dense slots, the matrix resident (triangular: D(i,j), i > j, at i(i-1)/2 + j), per-slot
+// scalars double-buffered, three barriers per join -- with Cpeeler.nj_np's arithmetic kept to the bit:
+// explicitly rounded q = ((n-2) d - x_a) - x_b with a the pool-first node, FIRST strict minimum in pool order
+// (pool order = ascending node id, so ties go to the smaller id pair), running row sums updated in the
+// reference's operation order, the new node's row sum accumulated sequentially in pool order (`ord` keeps the
+// slots sorted by node id).  Asymmetric input or an all-NaN matrix: todo = 1, the general kernel redoes the tree.
+constexpr int NJ_HARD_LEAN_MAX = 224;
+__host__ __device__ inline size_t nj_hard_lean_smem_bytes(int S, int W) {
+    return ((size_t)S * (S - 1) / 2 + 1 + 3 * (size_t)S + 2 * (size_t)W + 2) * sizeof(double) +
+           (6 * (size_t)S + 2 * (size_t)W + 4) * sizeof(int);
+}
+__device__ __forceinline__ int tri_at(int i, int j) { return i > j ? i * (i - 1) / 2 + j : j * (j - 1) / 2 + i; }
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
+                                                            int64_t *__restrict__ peel, double *__restrict__ blens,
+                                                            PriorDev prior) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T = 32 * W;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *tri = reinterpret_cast<double *>(smem_raw);  // [S (S-1) / 2]
+    double *xsb = tri + (((size_t)S * (S - 1) / 2 + 1) & ~(size_t)1);  // [2][S] running row sums by slot, double-buffered (16-byte aligned)
+    double *newd = xsb + 2 * S;                          // [S] new distances in pool order
+    double *red = newd + S;                              // [2 W] per-warp (q, d)
+    int *sidb = reinterpret_cast<int *>(red + 2 * W + 2);    // [2][S] slot -> node id
+    int *posb = sidb + 2 * S;                            // [2][S] slot -> pool position
+    int *ordb = posb + 2 * S;                            // [2][S] pool position -> slot
+    unsigned *redk = reinterpret_cast<unsigned *>(ordb + 2 * S);  // [2 W] (id pair, slot pair)
+    int *todo = reinterpret_cast<int *>(ws + (size_t)b * nj_ws_doubles(S));
+    const double *P = pdm + (size_t)b * S * S;
+    int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    double *bl = blens + (size_t)b * (2 * S - 2);
+
+    if (tid == 0) *todo = 0;
+    int asym = 0;
+    for (int i = tid; i < S * S; i += T) {
+        const int r = i / S, c = i - r * S;
+        if (r > c) {
+            const double v = P[i];
+            tri[r * (r - 1) / 2 + c] = v;
+            if (v != P[(size_t)c * S + r]) asym = 1;
+        }
+    }
+    for (int s = tid; s < S; s += T) {
+        sidb[s] = s; posb[s] = s; ordb[s] = s;
+        // Cpeeler.pyx:46-54: sequential sum over the other pool members, in pool order
+        double acc = 0.0;
+        const double *row = P + (size_t)s * S;
+        for (int j = 0; j < S; ++j)
+            if (j != s) acc = __dadd_rn(acc, row[j]);
+        xsb[s] = acc;
+    }
+    if (__syncthreads_or(asym)) {
+        if (tid == 0) *todo = 1;
+        return;
+    }
+    int cur = 0;
+    for (int n = S; n > 1; --n) {
+        const double *xs = xsb + cur * S;
+        const int *sid = sidb + cur * S, *pos = posb + cur * S, *ord = ordb + cur * S;
+        const int nxt = cur ^ 1;
+        const double nm2 = (double)n - 2.0;
+        // ---- first strict minimum of q in pool order (Cpeeler.pyx:58-66); four rows per trip share the column
+        double bq = DBL_MAX, bd = 0.0;
+        unsigned bkey = ~0u, bslot = 0u;
+        for (int r0 = 1 + warp; r0 < n; r0 += 4 * W) {
+            double xr[4];
+            int ir[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rj = r0 + j * W;
+                xr[j] = rj < n ? xs[rj] : 0.0;
+                ir[j] = rj < n ? sid[rj] : 0;
+            }
+            const int rtop = min(r0 + 3 * W, n - 1);
+            for (int c = lane; c < rtop; c += 32) {
+                const double xc = xs[c];
+                const int ic = sid[c];
+                double dv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rj = r0 + j * W;
+                    dv[j] = (rj < n && c < rj) ? tri[rj * (rj - 1) / 2 + c] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rj = r0 + j * W;
+                    const bool rfirst = ir[j] < ic;
+                    const double xa = rfirst ? xr[j] : xc, xb = rfirst ? xc : xr[j];
+                    const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, dv[j]), xa), xb);
+                    if ((rj < n && c < rj) && q <= bq) {  // rare once the running minimum has settled
+                        const unsigned key = rfirst ? (((unsigned)ir[j] << 16) | (unsigned)ic) : (((unsigned)ic << 16) | (unsigned)ir[j]);
+                        if (q < bq || key < bkey) {
+                            bq = q;
+                            bd = dv[j];
+                            bkey = key;
+                            bslot = ((unsigned)rj << 16) | (unsigned)c;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const double oq = __shfl_xor_sync(0xffffffffu, bq, m), od = __shfl_xor_sync(0xffffffffu, bd, m);
+            const unsigned ok = __shfl_xor_sync(0xffffffffu, bkey, m), os = __shfl_xor_sync(0xffffffffu, bslot, m);
+            const bool take = oq < bq || (oq == bq && ok < bkey);
+            bq = take ? oq : bq; bd = take ? od : bd; bkey = take ? ok : bkey; bslot = take ? os : bslot;
+        }
+        if (lane == 0) { red[2 * warp] = bq; red[2 * warp + 1] = bd; redk[2 * warp] = bkey; redk[2 * warp + 1] = bslot; }
+        __syncthreads();
+        // every warp folds the W per-warp results for itself: lane w takes entry w, then the same butterfly
+        bq = lane < W ? red[2 * lane] : DBL_MAX;
+        bd = lane < W ? red[2 * lane + 1] : 0.0;
+        bkey = lane < W ? redk[2 * lane] : ~0u;
+        bslot = lane < W ? redk[2 * lane + 1] : 0u;
+#pragma unroll
+        for (int m = W / 2; m >= 1; m >>= 1) {
+            const double oq = __shfl_xor_sync(0xffffffffu, bq, m), od = __shfl_xor_sync(0xffffffffu, bd, m);
+            const unsigned ok = __shfl_xor_sync(0xffffffffu, bkey, m), os = __shfl_xor_sync(0xffffffffu, bslot, m);
+            const bool take = oq < bq || (oq == bq && ok < bkey);
+            bq = take ? oq : bq; bd = take ? od : bd; bkey = take ? ok : bkey; bslot = take ? os : bslot;
+        }
+        bq = __shfl_sync(0xffffffffu, bq, 0); bd = __shfl_sync(0xffffffffu, bd, 0);
+        bkey = __shfl_sync(0xffffffffu, bkey, 0); bslot = __shfl_sync(0xffffffffu, bslot, 0);
+        if (bkey == ~0u) {  // all-NaN distances: the general kernel's memory-safe fallback decides
+            if (tid == 0) *todo = 1;
+            return;
+        }
+        const int n1 = (int)(bkey >> 16), n2 = (int)(bkey & 0xffffu);  // node ids; n1 comes first in the pool
+        const int s_hi = (int)(bslot >> 16), s_lo = (int)(bslot & 0xffffu);
+        const int sa = sid[s_hi] == n1 ? s_hi : s_lo, sb = sid[s_hi] == n1 ? s_lo : s_hi;
+        const int pa = pos[sa], pb = pos[sb];
+        const int keep = s_lo, freed = s_hi, last = n - 1;
+        const int parent = S + (S - n);
+        const double d12 = bd;  // == D(sa, sb), carried by the reduction: the pass below overwrites that entry
+        // ---- one pass over the pool: distances of the new node (into slot `keep`), the last live slot moved into
+        // `freed`, running row sums (Cpeeler.pyx:81-95), the survivors' new pool positions.  Thread p only touches
+        // column sx = ord[p] of rows sa, sb, last, keep, freed: no two threads meet.
+        for (int p = tid; p < n; p += T) {
+            if (p == pa || p == pb) continue;
+            const int sx = ord[p];
+            const double dsa = tri[tri_at(sx, sa)], dsb = tri[tri_at(sx, sb)];
+            const double v1 = __dadd_rn(__dadd_rn(0.0, dsa), dsb);
+            const double dist = __dmul_rn(0.5, __dsub_rn(v1, d12));
+            double x = __dadd_rn(xs[sx], dist);
+            x = __dsub_rn(x, dsa);
+            x = __dsub_rn(x, dsb);
+            const int dx = sx == last ? freed : sx;
+            if (sx != last && freed != last) tri[tri_at(freed, sx)] = tri[tri_at(last, sx)];
+            tri[tri_at(keep, dx)] = dist;
+            const int pc = p - (p > pa) - (p > pb);
+            xsb[nxt * S + dx] = x;
+            sidb[nxt * S + dx] = sid[sx];
+            posb[nxt * S + dx] = pc;
+            ordb[nxt * S + pc] = dx;
+            newd[pc] = dist;  // dense, in pool order: summed sequentially below
+        }
+        if (tid == 32 % T) {
+            // branch lengths (Cpeeler.pyx:98-112) with the joined nodes' row sums as they stand
+            double df, dg;
+            if (n > 2) {
+                const double v1 = __dmul_rn(0.5, d12);
+                const double v4 = __dmul_rn(__ddiv_rn(1.0, __dmul_rn(2.0, nm2)), __dsub_rn(xs[sa], xs[sb]));
+                df = __dadd_rn(v1, v4);
+                dg = __dsub_rn(d12, df);
+            } else {
+                df = __ddiv_rn(d12, 2.0);
+                dg = df;
+            }
+            bl[n1] = fmax(df, DBL_EPSILON);  // Cpeeler.pyx:124
+            bl[n2] = fmax(dg, DBL_EPSILON);
+            pl[(S - n) * 3 + 0] = n1;
+            pl[(S - n) * 3 + 1] = n2;
+            pl[(S - n) * 3 + 2] = parent;
+            sidb[nxt * S + keep] = parent;
+            posb[nxt * S + keep] = n - 2;
+            ordb[nxt * S + n - 2] = keep;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // new node's row sum: sequential in pool order (Cpeeler.pyx:92), loads running ahead of the adds
+            double acc = 0.0;
+            const int m = n - 2;
+            int p = 0;
+#pragma unroll 2
+            for (; p + 8 <= m; p += 8) {
+                const double2 u0 = *reinterpret_cast<const double2 *>(newd + p);
+                const double2 u1 = *reinterpret_cast<const double2 *>(newd + p + 2);
+                const double2 u2 = *reinterpret_cast<const double2 *>(newd + p + 4);
+                const double2 u3 = *reinterpret_cast<const double2 *>(newd + p + 6);
+                acc = __dadd_rn(acc, u0.x); acc = __dadd_rn(acc, u0.y);
+                acc = __dadd_rn(acc, u1.x); acc = __dadd_rn(acc, u1.y);
+                acc = __dadd_rn(acc, u2.x); acc = __dadd_rn(acc, u2.y);
+                acc = __dadd_rn(acc, u3.x); acc = __dadd_rn(acc, u3.y);
+            }
+            for (; p < m; ++p) acc = __dadd_rn(acc, newd[p]);
+            xsb[nxt * S + keep] = acc;
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);
 }
 
 // reverse replay: adjoint of blens w.r.t. the input distance matrix
@@ -1672,7 +1890,21 @@ extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64
     size_t smem = 2 * (size_t)nj_ld(S) * sizeof(double) + 3 * (size_t)nj_ld(S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr);
+    int lean_first = 0;
+    if (S <= NJ_HARD_LEAN_MAX && S >= 3 && !getenv("DODO_NJ_NO_LEAN")) {
+        int W = S <= 64 ? 8 : 16;  // measured (profiles/tools/nj_sweep.py): 64 taxa 0.147 ms at W = 8, 200 taxa 0.93 ms at W = 16
+        if (const char *e = getenv("DODO_NJ_LEAN_W")) {  // tuning sweeps
+            const int w = atoi(e);
+            if (w == 8 || w == 16 || w == 32) W = w;
+        }
+        const size_t lsm = nj_hard_lean_smem_bytes(S, W);
+        auto fn = W == 8 ? nj_hard_lean_kernel<8> : (W == 16 ? nj_hard_lean_kernel<16> : nj_hard_lean_kernel<32>);
+        if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+        fn<<<B, 32 * W, lsm, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr);
+        DODO_LAUNCH_CHECK();
+        lean_first = 1;
+    }
+    nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr, lean_first);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
 }

@@ -21,7 +21,11 @@ p1, b1, f1 = engine.nj_soft(pdm, 1e-8, return_flags=True)
 os.environ["DODO_NJ_NO_LEAN"] = "1"
 gen = t(lambda: engine.nj_soft(pdm, 1e-8))
 p0, b0, f0 = engine.nj_soft(pdm, 1e-8, return_flags=True)
+hard_gen = t(lambda: engine.nj_hard(pdm_np))
+hp0, hb0 = engine.nj_hard(pdm_np)
 del os.environ["DODO_NJ_NO_LEAN"]
+hp1, hb1 = engine.nj_hard(pdm_np)
+same_hard = bool(torch.equal(hp0, hp1)) and bool(torch.equal(hb0, hb1))
 same = bool(torch.equal(p0, p1)), float((b0 - b1).abs().max()), bool(torch.equal(f0, f1))
-print(S, B, "soft ms %.3f (general %.3f) hard ms %.3f" % (lean, gen, t(lambda: engine.nj_hard(pdm_np))), "lean==general:", same,
+print(S, B, "soft ms %.3f (general %.3f) hard ms %.3f (general %.3f, identical %s)" % (lean, gen, t(lambda: engine.nj_hard(pdm_np)), hard_gen, same_hard), "lean==general:", same,
       "W", os.environ.get("DODO_NJ_LEAN_W", "auto"))

@@ -200,3 +200,28 @@ def test_lean_soft_nj_agrees_with_the_general_kernel(monkeypatch):
         monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
         p0, b0, f0 = engine.nj_soft(pdm, tau, return_flags=True)
         assert torch.equal(p0, p1) and torch.equal(f0, f1) and torch.equal(b0, b1)
+
+
+@pytest.mark.gpu
+def test_lean_hard_nj_is_bit_identical_to_the_general_kernel(monkeypatch):
+    """Trees of up to 224 taxa go through nj_hard_lean_kernel (lower triangle resident in shared memory); peel AND
+    branch lengths must equal the general kernel's -- and hence Cpeeler.nj_np's -- bit for bit, ties included."""
+    from dodonaphy_b200 import engine, synth
+
+    rng = np.random.default_rng(12)
+    cases = [torch.tensor(rng.normal(0, 0.08, (B, S, 4))).cuda() for S, B in ((3, 4), (4, 4), (5, 3), (17, 5), (48, 3), (49, 3), (129, 2), (200, 3), (224, 2))]
+    dup = rng.normal(0, 0.08, (2, 12, 3))
+    dup[:, 5] = dup[:, 2]
+    dup[:, 9] = dup[:, 2]
+    cases.append(torch.tensor(dup).cuda())
+    mats = [engine.pdm_forward(x, -1.0, "numpy") for x in cases]
+    mats.append(torch.tensor(np.stack([synth.det_distances(60, 3, seed) for seed in (1, 2)])).cuda())  # bit-reproducible distances
+    asym = mats[3].clone()
+    asym[:, 1, 2] += 1e-3  # handed over to the general kernel as a whole
+    mats.append(asym)
+    for pdm in mats:
+        monkeypatch.delenv("DODO_NJ_NO_LEAN", raising=False)
+        p1, b1 = engine.nj_hard(pdm)
+        monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
+        p0, b0 = engine.nj_hard(pdm)
+        assert torch.equal(p0, p1) and torch.equal(b0, b1)
