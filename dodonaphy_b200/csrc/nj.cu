@@ -591,9 +591,110 @@ __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, doubl
     return true;
 }
 
+// Active-pair scan with TWO running minima per thread (the test nj_soft_lean_kernel uses): one coalesced sweep
+// finds the smallest and the second smallest Q of the live pairs; when the smallest stands alone inside the 750 tau
+// window (and clear of the zeros / 1e9 of the padded matrix) its flat index IS the soft argmin -- soft_argmin_fast's
+// one-candidate branch -- and nothing else has to be remembered during the sweep: per entry one load, four
+// flops, one compare.  (The window bookkeeping of soft_argmin_fast costs 1.9x the instructions of the hard scan
+// at the kernel's 64-register cap: ncu, 2000 taxa.)  Otherwise a second sweep gathers the entries inside the
+// window and soft_eval_candidates evaluates them; more than CAND_CAP of them: false, the caller goes on.
+#ifndef SOFT_MLP
+#define SOFT_MLP 8
+#endif
+__device__ bool soft_argmin_two_minima(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
+    __shared__ double t_m1[32], t_m2[32], t_cs[CAND_CAP], t_cf[CAND_CAP];
+    __shared__ int t_row[32], t_col[32], t_n;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const double W = 750.0 * tau, Wsure = W * (1.0 + 1e-9);
+    double m1 = DBL_MAX, m2 = DBL_MAX;
+    int brow = 0, bcol = 0;
+    auto sweep = [&](auto &&visit) {
+        for (int prow = 1 + warp; prow < c.n; prow += nwarp) {
+            const int srow = c.act[prow];
+            const double *rowp = c.Dm + (size_t)srow * c.S;
+            const double rsr = c.rs[srow];
+            auto entry = [&](int scol, double dij, double dji) {
+                const double rsc = c.rs[scol];
+                const double a = (c.nm2 * dij - rsr) - rsc;
+                const double b = (c.nm2 * dji - rsc) - rsr;
+                visit(0.5 * (a + b), srow, scol);
+            };
+            int pcol = lane;
+            for (; pcol + 32 * (SOFT_MLP - 1) < prow; pcol += 32 * SOFT_MLP) {  // independent loads in flight per lane
+                int sc[SOFT_MLP];
+                double d[SOFT_MLP];
+#pragma unroll
+                for (int k = 0; k < SOFT_MLP; ++k) sc[k] = c.act[pcol + 32 * k];
+#pragma unroll
+                for (int k = 0; k < SOFT_MLP; ++k) d[k] = rowp[sc[k]];
+#pragma unroll
+                for (int k = 0; k < SOFT_MLP; ++k) entry(sc[k], d[k], c.symmetric ? d[k] : c.Dm[(size_t)sc[k] * c.S + srow]);
+            }
+            for (; pcol < prow; pcol += 32) {
+                const int scol = c.act[pcol];
+                const double dij = rowp[scol];
+                entry(scol, dij, c.symmetric ? dij : c.Dm[(size_t)scol * c.S + srow]);
+            }
+        }
+    };
+    sweep([&](double q, int srow, int scol) {
+        if (q < m2) {  // rare once the two running minima have settled
+            if (q < m1) { m2 = m1; m1 = q; brow = srow; bcol = scol; }
+            else m2 = q;
+        }
+    });
+    auto fold = [&](int m) {
+        const double o1 = __shfl_xor_sync(0xffffffffu, m1, m), o2 = __shfl_xor_sync(0xffffffffu, m2, m);
+        const int orow = __shfl_xor_sync(0xffffffffu, brow, m), ocol = __shfl_xor_sync(0xffffffffu, bcol, m);
+        const bool lt = o1 < m1;  // an exact tie leaves m2 == m1: not the one-candidate regime
+        const double lo1 = lt ? o1 : m1, hi1 = lt ? m1 : o1, oth = lt ? o2 : m2;
+        m2 = oth < hi1 ? oth : hi1;
+        m1 = lo1;
+        brow = lt ? orow : brow;
+        bcol = lt ? ocol : bcol;
+    };
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) fold(m);
+    __syncthreads();  // (the buffers below may still be read from the previous join)
+    if (lane == 0) { t_m1[warp] = m1; t_m2[warp] = m2; t_row[warp] = brow; t_col[warp] = bcol; }
+    if (tid == 0) t_n = 0;
+    __syncthreads();
+    m1 = lane < nwarp ? t_m1[lane] : DBL_MAX;
+    m2 = lane < nwarp ? t_m2[lane] : DBL_MAX;
+    brow = lane < nwarp ? t_row[lane] : 0;
+    bcol = lane < nwarp ? t_col[lane] : 0;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) fold(m);
+    m1 = __shfl_sync(0xffffffffu, m1, 0); m2 = __shfl_sync(0xffffffffu, m2, 0);
+    brow = __shfl_sync(0xffffffffu, brow, 0); bcol = __shfl_sync(0xffffffffu, bcol, 0);
+    if (1.0 / tau > 750.0 && m1 < 0.0 && m2 > m1 + W && -m1 > Wsure && LARGE - m1 > Wsure) {
+        idx_out = (double)c.id_of[brow] * (double)c.N + (double)c.id_of[bcol];  // row id > column id (tril order)
+        guard_ok = true;
+        return true;
+    }
+    const double mm = fmin(m1, 0.0);  // the strict upper triangle holds zeros (torch.tril)
+    sweep([&](double q, int srow, int scol) {
+        if (q <= mm + W) {
+            const int slot = atomicAdd(&t_n, 1);
+            if (slot < CAND_CAP) { t_cs[slot] = q; t_cf[slot] = (double)c.id_of[srow] * (double)c.N + (double)c.id_of[scol]; }
+        }
+    });
+    __syncthreads();
+    const int nc = t_n;
+    if (nc < 1 || nc > CAND_CAP) return false;
+    if (tid == 0) soft_eval_candidates(t_cs, t_cf, nc, mm, tau, (double)c.N * (double)c.N, false, sh[0], sh[1]);
+    __syncthreads();
+    idx_out = sh[0];
+    guard_ok = sh[1] != 0.0;
+    return true;
+}
+
 template <int MODE>
 __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
-    if (soft_argmin_fast<MODE>(c, tau, sh, idx_out, guard_ok)) return;
+    if (MODE == 0) {
+        if (soft_argmin_two_minima(c, tau, sh, idx_out, guard_ok)) return;
+    } else if (soft_argmin_fast<MODE>(c, tau, sh, idx_out, guard_ok)) return;
     constexpr bool FULL = MODE != 0;
     const int tid = threadIdx.x, T = blockDim.x;
     const long long P = MODE == 2 ? c.dense_n : (FULL ? (long long)c.N * c.N : (long long)c.n * (c.n - 1) / 2);
