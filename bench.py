@@ -53,7 +53,28 @@ SIDE = {
     "c3": dict(S=200, L=50000, B=64, D=5, desc="MCMC, 64 chains, 200 taxa x 50k patterns, JC69, forward only (configs[2])"),
     "c4": dict(S=2000, B=256, D=5, desc="pairwise distance + batched NJ, 2000 taxa x 256 embeddings (configs[3])"),
     "c5": dict(S=500, L=1000000, B=1, D=5, desc="long alignment, 500 taxa x 1M patterns, fwd+grad (configs[4]; one GPU holds L/world)"),
+    "gtr": dict(S=64, L=10000, B=128, D=5, desc="configs[1] with the GTR rates and frequencies LEARNT (the reference's --model GTR always learns them, phylomodel.py:69-74): lnL + gradients to locations, curvature, rate and frequency leaves"),
+    "jac": dict(S=64, L=10000, B=128, D=5, desc="configs[1]: the change-of-variables term of every sample (vi.py:376-387): d blens / d locations (126 x 320 per sample) + log sqrt det(J J^T)"),
 }
+
+
+def config_dict(cfg, world):
+    """The `config` object of the JSON line -- identical for both arms (the reference arm's bounded sample is
+    described in its cpu_baseline.sample, not here)."""
+    return {"workload": cfg["desc"], "taxa": cfg["S"], "site_patterns": cfg["L"], "samples_per_step_per_gpu": cfg["B"],
+            "global_samples_per_step": cfg["B"] * world, "rate_categories": cfg["K"], "model": "GTR+G4",
+            "embedding_dim": cfg["D"], "soft_nj_tau": cfg["tau"],
+            "sharding": "by sample; all_gather of per-sample lnL" if world > 1 else "single GPU",
+            "l2": "pruning scratch streams ~20 GB/step through HBM (>> 126 MB L2); no flush needed"}
+
+
+def kernel_source_sha():
+    """sha256 of the pruning kernel's source: profiles/roofline_traffic.json records the one its ncu capture was
+    taken with, so a stale DRAM-traffic figure is never quoted for a changed kernel."""
+    import hashlib
+
+    with open(os.path.join(ROOT, "dodonaphy_b200", "csrc", "prune.cu"), "rb") as fh:
+        return hashlib.sha256(fh.read()).hexdigest()
 
 
 def algorithmic_bytes_fwd_bwd(S, K):
@@ -187,8 +208,7 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "taxa": cfg["S"], "site_patterns": cfg["L"], "samples_per_step": n_trees,
-                       "rate_categories": cfg["K"], "model": "GTR+G4"},
+            "config": config_dict(cfg, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -304,27 +324,27 @@ def run_ours(args, cfg):
         alg_bytes = algorithmic_bytes_fwd_bwd(S, K) * L * B
         k_ms = sum(kern_ms) / len(kern_ms)
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_note = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 tj = json.load(fh)
-            if tj.get("workload") == args.workload:
+            if tj.get("workload") == args.workload and tj.get("prune_cu_sha256") == kernel_source_sha():
                 traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = tj.get("source")
+            else:
+                traffic_note = "profiles/roofline_traffic.json was captured for another kernel source or workload: not quoted"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": cfg["desc"], "taxa": S, "site_patterns": L, "samples_per_step_per_gpu": B,
-                           "global_samples_per_step": B * world, "rate_categories": K, "model": "GTR+G4", "embedding_dim": D,
-                           "soft_nj_tau": cfg["tau"], "sharding": "by sample; all_gather of per-sample lnL" if world > 1 else "single GPU",
-                           "l2": "pruning scratch streams ~20 GB/step through HBM (>> 126 MB L2); no flush needed"},
+                "config": config_dict(cfg, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 8),
                         "d2h_bytes_per_step": int((ll_pin.numel() + gx_pin.numel()) * 8), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "dodo::prune_kernel<1,true,false,1,0> (MODE=grad, resident tables, no rescaling, 1 pattern/thread, generic P: fused P(t)+pruning forward + branch-length gradient)", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
-                             "kernel_share_of_step": k_ms / ms_step, "traffic": traffic},
+                             "kernel_share_of_step": k_ms / ms_step, "traffic": traffic, "traffic_source": traffic_note},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu:
             from dodonaphy_b200 import synth as _s  # noqa: F401
@@ -535,6 +555,35 @@ def run_side(args):
         out["mcmc_sweep_graph_ms"] = timed(lambda: g_mcmc.run(chains), 200)
         out["vi_step_ms"] = timed(lambda: hp.value_and_grad(samples), 200)
         out["vi_step_graph_ms"] = timed(lambda: g_vi.run(samples), 200)
+    elif args.side in ("gtr", "jac"):
+        c2 = WORKLOADS["c2"]
+        prob = synth.make_problem(S, cfg["L"], B, D=D, seed=c2["seed"])
+        grates = SubstModel.discrete_gamma(c2["alpha"], c2["K"])
+        hp = HotPath(prob["masks"], prob["weights"], SubstModel.gtr(prob["rates"], prob["freqs"]), rates=grates, mix=True, tau=c2["tau"])
+        x = torch.as_tensor(prob["xs"]).cuda()
+        out["fixed_model_step_ms"] = timed(lambda: hp.value_and_grad(x), 10)
+        if args.side == "gtr":
+            from dodonaphy_b200.base_model import BaseModel
+
+            tips = [torch.tensor(np.stack([(m >> j) & 1 for j in range(4)]).astype(np.float64)) for m in prob["masks"]]
+            m = BaseModel("vi", tips, torch.tensor(prob["weights"]), D, soft_temp=c2["tau"], model_name="GTR", gamma_shape=c2["alpha"],
+                          n_rate_categories=c2["K"])
+            m.phylomodel.sub_rates = torch.tensor(prob["rates"])
+            m.phylomodel.freqs = torch.tensor(prob["freqs"])
+            xl = x.clone().requires_grad_(True)
+
+            def learn_step():
+                ll, _, _ = m.log_likelihood_batch(xl)
+                ll.sum().backward()
+
+            out["learnable_gtr_step_ms"] = timed(learn_step, 10)
+            out["device_part_ms"] = timed(lambda: m._hotpath().value_and_grad_model(x), 10)
+            out["ratio_to_fixed_model"] = out["learnable_gtr_step_ms"] / out["fixed_model_step_ms"]
+        else:
+            dec = hp.decode_checked(x)
+            out["jacobian_ms"] = timed(lambda: hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False), 10)
+            out["jacobian_logdet_ms"] = timed(lambda: hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=True), 10)
+            out["jacobian_by_replays_ms"] = timed(lambda: hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False, replay=True), 3)
     elif args.side == "c4":
         lo, hi = ddist.shard_bounds(B, rank, world)
         xs = torch.as_tensor(rng.normal(0, 0.05, (B, S, D))[lo:hi]).cuda()

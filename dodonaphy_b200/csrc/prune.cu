@@ -735,8 +735,15 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             }
         };
         auto tab_at = [&](unsigned off) -> const double * { return SMALL ? sptr(sbase + off * 8u) : tabg + off; };
-        auto tipmsg = [&](int t, int q) -> V4 {
-            const unsigned sel = SMALL ? (unsigned)SEL(t, q) : encode_sel(__ldg(tm[q] + (size_t)t * A.ld_mask));
+        // LARGE (tip masks in global memory): the mask byte of a tip is fetched ONE JOIN AHEAD of its use (the
+        // schedule in shared memory names the tips of the next join), so the table-row load that depends on it
+        // does not wait for an L2 round trip first: ncu showed 47 % of all stall samples on that byte at 200
+        // taxa (two dependent global loads per tip on the critical path of every join).
+        auto load_mask = [&](int code, int q) -> unsigned {  // child code < 0 -> tip ~code
+            return (!SMALL && code < 0) ? (unsigned)__ldg(tm[q] + (size_t)(~code) * A.ld_mask) : 0u;
+        };
+        auto tipmsg = [&](int t, int q, unsigned mask) -> V4 {
+            const unsigned sel = SMALL ? (unsigned)SEL(t, q) : encode_sel(mask);
             return tip_message<SMALL>(tab_at(o_T + (unsigned)t * 20u), sel);
         };
         // tabulated cherry: one 32-byte row of its 5 x 5 table instead of two tip rows and a mat-vec
@@ -752,11 +759,11 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             return true;
         };
         // message of a cherry, recomputed exactly as the forward sweep formed it (oc = the cherry's op)
-        auto cherry_msg = [&](const int4 &oc, int q, int &cnt) -> V4 {
+        auto cherry_msg = [&](const int4 &oc, int q, int &cnt, unsigned mx, unsigned my) -> V4 {
             cnt = 0;
             V4 t;
             if (cherry_lookup(oc, q, t)) return t;
-            V4 x[1] = {vmul(tipmsg(~oc.x, q), tipmsg(~oc.y, q))}, y[1];
+            V4 x[1] = {vmul(tipmsg(~oc.x, q, mx), tipmsg(~oc.y, q, my))}, y[1];
             if (SCALE) scale_up(x[0], cnt);
             apply_P<SMALL, 1, false>(pmode, md, tab_at((unsigned)oc.z * 16u), x, y);
             return y[0];
@@ -775,12 +782,18 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             int bc[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) { Bv[q] = V4{0, 0, 0, 0}; bc[q] = 0; }
+            unsigned cmx[NP], cmy[NP];  // masks of the current join's tip children (LARGE; see load_mask)
+            {
+                const int4 o1 = OPS(1);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) { cmx[q] = load_mask(o1.x, q); cmy[q] = load_mask(o1.y, q); }
+            }
             auto join = [&](const int4 &o, V4 (&Lv)[NP], int (&cnt)[NP]) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     cnt[q] = 0;
                     if (o.x < 0) {
-                        Lv[q] = tipmsg(~o.x, q);
+                        Lv[q] = tipmsg(~o.x, q, cmx[q]);
                     } else {
                         Lv[q] = ldg256(SCR(o.x, q));
                         if (SCALE) cnt[q] = __ldcg(CSCR(o.x, q));
@@ -788,7 +801,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 }
                 if (o.y < 0) {  // both children are tips: Bv is free
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) { Bv[q] = tipmsg(~o.y, q); bc[q] = 0; }
+                    for (int q = 0; q < NP; ++q) { Bv[q] = tipmsg(~o.y, q, cmy[q]); bc[q] = 0; }
                 }
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
@@ -800,6 +813,12 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll 1
             for (int i = 1; i < nops; ++i) {
                 const int4 o = OPS(i);
+                unsigned nmx[NP], nmy[NP];
+                if (!SMALL) {
+                    const int4 on = OPS(i + 1);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) { nmx[q] = load_mask(on.x, q); nmy[q] = load_mask(on.y, q); }
+                }
                 V4 Lv[NP];
                 int cnt[NP];
                 bool tabulated = false;
@@ -825,7 +844,10 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     apply_P<SMALL, NP, false>(pmode, md, tab_at((unsigned)o.z * 16u), Lv, Bv);
                 }
 #pragma unroll
-                for (int q = 0; q < NP; ++q) bc[q] = cnt[q];
+                for (int q = 0; q < NP; ++q) {
+                    bc[q] = cnt[q];
+                    if (!SMALL) { cmx[q] = nmx[q]; cmy[q] = nmy[q]; }
+                }
                 if ((MODE != 0 && !(RECOMP && (o.w & FL_NO_STORE))) || (o.w & FL_A_CHILD)) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
@@ -889,9 +911,21 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 double pend_ga = 0.0, pend_gb = 0.0;
                 int pend_x = 0, pend_y = 0;
                 bool have_pending = false;
+                unsigned cmx[NP], cmy[NP];  // masks of the current join's tip children (LARGE; see load_mask)
+                {
+                    const int4 o1 = OPS(nops);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) { cmx[q] = load_mask(o1.x, q); cmy[q] = load_mask(o1.y, q); }
+                }
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
+                    unsigned nmx[NP], nmy[NP];  // ... and of the join that comes next in this (reversed) order
+                    if (!SMALL) {
+                        const int4 on = OPS(i - 1);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) { nmx[q] = load_mask(on.x, q); nmy[q] = load_mask(on.y, q); }
+                    }
 #if DODO_PF_L2_DIST > 0
                     {
                         // pull what the join a few steps ahead needs out of HBM into L2
@@ -931,10 +965,10 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         ac[q] = 0; bcn[q] = 0;
-                        if (o.x < 0) av[q] = tipmsg(~o.x, q);
+                        if (o.x < 0) av[q] = tipmsg(~o.x, q, cmx[q]);
                         else { av[q] = ldg256_bwd(SCR(o.x, q)); if (SCALE) ac[q] = __ldcg(CSCR(o.x, q)); }
-                        if (o.y < 0) bv[q] = tipmsg(~o.y, q);
-                        else if (RECOMP && (o.w & FL_B_CHERRY)) bv[q] = cherry_msg(OPS(i - 1), q, bcn[q]);
+                        if (o.y < 0) bv[q] = tipmsg(~o.y, q, cmy[q]);
+                        else if (RECOMP && (o.w & FL_B_CHERRY)) bv[q] = cherry_msg(OPS(i - 1), q, bcn[q], SMALL ? 0u : nmx[q], SMALL ? 0u : nmy[q]);
                         else { bv[q] = ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
                         ua[q] = vmul(Wv[q], bv[q]);
                         ub[q] = vmul(Wv[q], av[q]);
@@ -986,6 +1020,10 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                             if (SCALE) { int neg = -we[q]; scale_both(Wv[q], neg); we[q] = -neg; }
                         }
                     }
+                    if (!SMALL) {
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) { cmx[q] = nmx[q]; cmy[q] = nmy[q]; }
+                    }
                 }
                 if (PAIR && have_pending) {  // odd number of joins: the last pair goes alone
                     const double g2 = warp_sum2(pend_ga, pend_gb, lane);
@@ -1016,10 +1054,12 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
                     const int4 o = OPS(i);
-                    const V4 av = o.x < 0 ? tipmsg(~o.x, 0) : ldg256(SCR(o.x, 0));
+                    const V4 av = o.x < 0 ? tipmsg(~o.x, 0, load_mask(o.x, 0)) : ldg256(SCR(o.x, 0));
                     int unused_cnt;
-                    const V4 bv = o.y < 0 ? tipmsg(~o.y, 0)
-                                          : ((RECOMP && (o.w & FL_B_CHERRY)) ? cherry_msg(OPS(i - 1), 0, unused_cnt) : ldg256(SCR(o.y, 0)));
+                    const int4 oc = OPS(i - 1);
+                    const V4 bv = o.y < 0 ? tipmsg(~o.y, 0, load_mask(o.y, 0))
+                                          : ((RECOMP && (o.w & FL_B_CHERRY)) ? cherry_msg(oc, 0, unused_cnt, load_mask(oc.x, 0), load_mask(oc.y, 0))
+                                                                             : ldg256(SCR(o.y, 0)));
                     const V4 Lv = vmul(av, bv);
                     V4 w;
                     if (i == nops) {

@@ -34,13 +34,14 @@ def timed(fn, n=10, warm=3):
 
 def main():
     which = sys.argv[1:] or ["c2", "c3", "c5"]
+    NS = tuple(int(v) for v in os.environ.get("SHARDS", "1,2,4,8").split(","))  # which N to emulate
     out = {}
     if "c2" in which:
         prob = synth.make_problem(64, 10000, 128, D=5, seed=1002)
         hp = HotPath(prob["masks"], prob["weights"], SubstModel.gtr(prob["rates"], prob["freqs"]),
                      rates=SubstModel.discrete_gamma(0.5, 4), mix=True, tau=1e-8)
         rows = []
-        for n in (1, 2, 4, 8):
+        for n in NS:
             x = torch.as_tensor(prob["xs"][:128 // n]).cuda()
             g = GraphedStep(hp, x, grad=True)
             pdm = engine.pdm_forward(x, -1.0, "torch")
@@ -57,7 +58,7 @@ def main():
         weights = np.tile(prob["weights"], 3)[:50000]
         hp = HotPath(masks, weights, SubstModel.jc69())
         rows = []
-        for n in (1, 2, 4, 8):
+        for n in NS:
             x = torch.as_tensor(prob["xs"][:64 // n]).cuda()
             g = GraphedStep(hp, x, grad=False)
             pdm = engine.pdm_forward(x, -1.0, "numpy")
@@ -75,7 +76,7 @@ def main():
         weights = np.tile(prob["weights"], 50)[:L]
         peel, blens = engine.nj_hard(engine.pdm_forward(torch.as_tensor(prob["xs"][0]).cuda(), -1.0, "numpy"))
         rows = []
-        for n in (1, 2, 4, 8):
+        for n in NS:
             eng = PruneEngine(np.ascontiguousarray(masks[:, :L // n]), weights[:L // n])
             rows.append(dict(n=n, patterns=L // n, eval_ms=timed(lambda: eng.loglik(peel, blens, SubstModel.jc69(), grad=True), n=5)))
             del eng
