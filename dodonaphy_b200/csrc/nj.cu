@@ -1521,6 +1521,107 @@ __global__ void __launch_bounds__(1024) nj_soft_bwd_kernel(const int64_t *__rest
     }
 }
 
+// The same vector-Jacobian product without a replay, for trees whose per-join weight vectors fit in shared memory
+// (<= NJ_BWD_LEAN_MAX taxa).  With the selections fixed every NJ distance is a bilinear form of the tip distance
+// matrix D (see blens_jac_kernel, csrc/pdm.cu): d(u, x) = a_u^T D a_x - c_u - c_x, a_u = (a_l + a_r) / 2,
+// c_u = F_u / 2 with F_t = a_l^T D a_r the form of the join that made u.  A join contributes
+//   g_lr d_lr + kappa_t (r_l - r_r),  d_lr = F_t - c_l - c_r,  r_l - r_r = (a_l - a_r)^T D sigma_t - (n-2)(c_l - c_r)
+// to sum_e g_e blens_e (g_lr, kappa_t from the two cotangents and the clamp flags exactly as in the replay), so
+//   d / d D = sum_t [ A_t a_l (x) a_r + kappa_t (a_l - a_r) (x) sigma_t ]  =  a (S x 2(S-1)) (2(S-1) x S) product,
+// A_t = g_lr(t) plus what the parent join of node S+t puts on c.  Prologue: one thread per taxon fills its column of
+// a_l, a_r, sigma_t (a column only depends on itself), one thread forms the scalars; then every thread
+// accumulates a 2 x 2 tile of the product.  No barrier per join, no reduction (the replay needs four barriers and
+// a block-wide sum per un-join: 78 us for 128 x 64 taxa, latency-bound).
+constexpr int NJ_BWD_LEAN_MAX = 80;
+__host__ __device__ inline size_t nj_bwd_lean_smem_bytes(int S) {
+    return (3 * (size_t)(S - 1) * S + (size_t)S * S + 4 * (size_t)S) * sizeof(double) + 3 * (size_t)S * sizeof(int);
+}
+
+__global__ void __launch_bounds__(1024) nj_soft_bwd_lean_kernel(const int64_t *__restrict__ peel,
+                                                                const int32_t *__restrict__ flags,
+                                                                const double *__restrict__ gblens, int S,
+                                                                double *__restrict__ gpdm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int nJ = S - 1;
+    double *U = reinterpret_cast<double *>(smem_raw);  // [S-1][S] a_l of join t
+    double *V = U + (size_t)nJ * S;                    // [S-1][S] a_r
+    double *Sg = V + (size_t)nJ * S;                   // [S-1][S] sigma_t: sum of a_x over the other live nodes
+    double *G = Sg + (size_t)nJ * S;                   // [S][S]
+    double *Ac = G + (size_t)S * S;                    // [S] coefficient of F_t
+    double *kap = Ac + S;                              // [S] coefficient of r_l - r_r
+    double *gbs = kap + S;                             // [2S] the cotangents, staged (one thread walks them)
+    int *cl = reinterpret_cast<int *>(gbs + 2 * S);    // [S] left child of join t
+    int *cr = cl + S;                                  // [S] right child
+    int *fls = cr + S;                                 // [S] clamp flags
+    const int64_t *pl = peel + (size_t)b * nJ * 3;
+    const int32_t *fl = flags + (size_t)b * nJ;
+    const double *gb = gblens + (size_t)b * (2 * S - 2);
+    double *out = gpdm + (size_t)b * S * S;
+    for (int t = tid; t < nJ; t += T) {
+        cl[t] = (int)pl[t * 3 + 0];
+        cr[t] = (int)pl[t * 3 + 1];
+        fls[t] = fl[t];
+        Ac[t] = 0.0;
+    }
+    for (int e = tid; e < 2 * S - 2; e += T) gbs[e] = gb[e];
+    __syncthreads();
+    if (tid < S) {  // column tid of a_l, a_r, sigma_t, join by join
+        const int i = tid;
+        double Ti = 1.0;  // sum of a_x[i] over the live nodes
+        for (int t = 0; t < nJ; ++t) {
+            const int l = cl[t], r = cr[t];
+            const double al = l < S ? (l == i ? 1.0 : 0.0) : 0.5 * (U[(size_t)(l - S) * S + i] + V[(size_t)(l - S) * S + i]);
+            const double ar = r < S ? (r == i ? 1.0 : 0.0) : 0.5 * (U[(size_t)(r - S) * S + i] + V[(size_t)(r - S) * S + i]);
+            U[(size_t)t * S + i] = al;
+            V[(size_t)t * S + i] = ar;
+            Sg[(size_t)t * S + i] = Ti - al - ar;
+            Ti += 0.5 * (al + ar) - al - ar;
+        }
+    } else if (tid == ((S + 31) & ~31)) {  // one thread of another warp: the per-join scalars (parents first)
+        for (int t = nJ - 1; t >= 0; --t) {
+            const int l = cl[t], r = cr[t], f = fls[t];
+            const int n = S - t;
+            const double nact = fmax((double)n, 3.0);
+            double g_pl = gbs[l], g_pr = gbs[r], g_lr = 0.0;
+            if (!(f & 2)) { g_lr += g_pr; g_pl -= g_pr; }
+            double kp = 0.0;
+            if (!(f & 1)) { g_lr += 0.5 * g_pl; kp = g_pl / (2.0 * (nact - 2.0)); }
+            kap[t] = kp;
+            Ac[t] += g_lr;  // (Ac[t] already holds what the parent of node S+t put on c_{S+t} = F_t / 2)
+            const double w = kp * (double)(n - 2);
+            if (l >= S) Ac[l - S] += 0.5 * (-g_lr - w);
+            if (r >= S) Ac[r - S] += 0.5 * (-g_lr + w);
+        }
+    }
+    __syncthreads();
+    const int H = (S + 1) / 2;  // 2 x 2 tiles
+    for (int w = tid; w < H * H; w += T) {
+        const int i0 = 2 * (w / H), j0 = 2 * (w - (w / H) * H);
+        const int i1 = min(i0 + 1, S - 1), j1 = min(j0 + 1, S - 1);
+        double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0;
+        for (int t = 0; t < nJ; ++t) {
+            const double *u = U + (size_t)t * S, *v = V + (size_t)t * S, *sg = Sg + (size_t)t * S;
+            const double a = Ac[t], k = kap[t];
+            const double p0 = a * u[i0], p1 = a * u[i1], q0 = k * (u[i0] - v[i0]), q1 = k * (u[i1] - v[i1]);
+            const double vj0 = v[j0], vj1 = v[j1], s0 = sg[j0], s1 = sg[j1];
+            g00 = fma(q0, s0, fma(p0, vj0, g00));
+            g01 = fma(q0, s1, fma(p0, vj1, g01));
+            g10 = fma(q1, s0, fma(p1, vj0, g10));
+            g11 = fma(q1, s1, fma(p1, vj1, g11));
+        }
+        G[(size_t)i0 * S + j0] = g00;
+        if (j0 + 1 < S) G[(size_t)i0 * S + j0 + 1] = g01;
+        if (i0 + 1 < S) G[(size_t)(i0 + 1) * S + j0] = g10;
+        if (i0 + 1 < S && j0 + 1 < S) G[(size_t)(i0 + 1) * S + j0 + 1] = g11;
+    }
+    __syncthreads();
+    for (int e = tid; e < S * S; e += T) {
+        const int i = e / S, j = e - i * S;
+        out[e] = (i == j) ? 0.0 : 0.5 * (G[e] + G[(size_t)j * S + i]);
+    }
+}
+
 // soft.argmin on arbitrary matrices (dodonaphy/soft.py:38-53), one CTA per matrix
 __global__ void __launch_bounds__(256) soft_argmin_kernel(const double *__restrict__ Q, int rows, int cols, double tau,
                                                           double *__restrict__ out) {
@@ -2054,6 +2155,15 @@ extern "C" int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, c
     size_t smem = 32 * sizeof(double) + (2 * (size_t)S + (size_t)S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (S <= NJ_BWD_LEAN_MAX && S >= 2 && !getenv("DODO_NJ_NO_LEAN")) {
+        const size_t lsm = nj_bwd_lean_smem_bytes(S);
+        if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+        int lt = ((S + 1) / 2 * ((S + 1) / 2) + 31) / 32 * 32;  // one 2 x 2 tile per thread, and one warp beyond the S column threads
+        lt = lt < ((S + 31) / 32 + 1) * 32 ? ((S + 31) / 32 + 1) * 32 : (lt > 1024 ? 1024 : lt);
+        nj_soft_bwd_lean_kernel<<<B, lt, lsm, stream>>>(d_peel, d_flags, d_grad_blens, S, d_grad_pdm);
+        DODO_LAUNCH_CHECK();
+        return DODO_OK;
+    }
     nj_soft_bwd_kernel<<<B, bwd_threads, smem, stream>>>(d_peel, d_flags, d_grad_blens, S, (double *)d_ws, d_grad_pdm);
     DODO_LAUNCH_CHECK();
     return DODO_OK;

@@ -225,3 +225,33 @@ def test_lean_hard_nj_is_bit_identical_to_the_general_kernel(monkeypatch):
         monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
         p0, b0 = engine.nj_hard(pdm)
         assert torch.equal(p0, p1) and torch.equal(b0, b1)
+
+
+@pytest.mark.gpu
+def test_lean_soft_nj_backward_equals_the_replay(monkeypatch):
+    """nj_soft_bwd_lean_kernel (trees up to 96 taxa: d blens / d pdm from the bilinear-form structure, one thread per
+    matrix entry) against the reverse replay of the joins (nj_soft_bwd_kernel), incl. clamped branches."""
+    from dodonaphy_b200 import engine
+
+    rng = np.random.default_rng(21)
+    seen_clamped = False
+    for S, B in ((2, 3), (3, 4), (4, 4), (7, 5), (33, 4), (64, 6), (80, 2), (96, 2)):
+        x = rng.normal(0, 0.08, (B, S, 4))
+        if S >= 7:
+            x[:, 3] = x[:, 1]  # coincident taxa: clamped branches (flags bit0 / bit1)
+        pdm = engine.pdm_forward(torch.tensor(x).cuda(), -1.0, "torch")
+        peel, blens, flags = engine.nj_soft(pdm, 1e-8, return_flags=True)
+        if S >= 4:  # the clamp flags are inputs of the backward: set some by hand (a clamped branch passes no gradient)
+            flags = flags.clone()
+            flags[:, 1] |= 1
+            flags[:, 2] |= 2
+            flags[0, S - 2] |= 3
+        seen_clamped = seen_clamped or bool((flags & 3).any())
+        g = torch.tensor(rng.normal(size=(B, 2 * S - 2))).cuda()
+        monkeypatch.delenv("DODO_NJ_NO_LEAN", raising=False)
+        g1 = engine.nj_soft_backward(peel, flags, g)
+        monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
+        g0 = engine.nj_soft_backward(peel, flags, g)
+        ref = g0.cpu().numpy()
+        np.testing.assert_allclose(g1.cpu().numpy(), ref, rtol=1e-10, atol=1e-13 * max(1.0, np.abs(ref).max()))
+    assert seen_clamped
