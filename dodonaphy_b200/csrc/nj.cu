@@ -2155,7 +2155,10 @@ extern "C" int dodo_nj_soft_bwd(const int64_t *d_peel, const int32_t *d_flags, c
     size_t smem = 32 * sizeof(double) + (2 * (size_t)S + (size_t)S) * sizeof(int);
     if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default as well
         DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (S <= NJ_BWD_LEAN_MAX && S >= 2 && !getenv("DODO_NJ_NO_LEAN")) {
+    // (latency-bound batches only: with many more trees than SMs the replay's per-tree latency is hidden by the
+    // other trees of the SM and its O(S^2) work per tree wins over the product's O(S^3): 16 128 replays of the
+    // batched-Jacobian cross-check take 2.8 ms by replay, 7.3 ms by product)
+    if (S <= NJ_BWD_LEAN_MAX && S >= 2 && B <= 2 * sm_count() && !getenv("DODO_NJ_NO_LEAN")) {
         const size_t lsm = nj_bwd_lean_smem_bytes(S);
         if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(nj_soft_bwd_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
         int lt = ((S + 1) / 2 * ((S + 1) / 2) + 31) / 32 * 32;  // one 2 x 2 tile per thread, and one warp beyond the S column threads

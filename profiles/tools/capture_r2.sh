@@ -11,12 +11,13 @@ NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/r2_launches_c2.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-strong > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:prune_kernel -s 3 -c 1 -o $O/prof_prune_r2 -f python bench.py --steps 2 --warmup 3 --no-cpu --no-strong > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:nj_soft_lean -s 3 -c 1 -o $O/prof_njsoftlean_r2 -f python bench.py --steps 2 --warmup 3 --no-cpu --no-strong > /dev/null 2>&1
-$NCU --set full --import-source on -k regex:nj_soft_bwd -s 3 -c 1 -o $O/prof_njsoftbwd_r2 -f python bench.py --steps 2 --warmup 3 --no-cpu --no-strong > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:nj_soft_bwd_lean -s 3 -c 1 -o $O/prof_njsoftbwd_r2 -f python bench.py --steps 2 --warmup 3 --no-cpu --no-strong > /dev/null 2>&1
 # the other pruning variants: C3 (large tables, rescaling, JC69, forward only), C5 (+ gradient), learnable GTR (d lnL/d P)
 $NCU --set full --import-source on -k regex:prune_kernel -s 2 -c 1 -o $O/prof_prune_c3_r2 -f python bench.py --side c3 > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:prune_kernel -s 2 -c 1 -o $O/prof_prune_c5_r2 -f python bench.py --side c5 > /dev/null 2>&1
-$NCU --set full --import-source on -k regex:prune_kernel\<2 -s 1 -c 1 -o $O/prof_prune_gmats_r2 -f python bench.py --side gtr > /dev/null 2>&1
+$NCU --set full --import-source on -k 'regex:prune_kernel<2' -s 1 -c 1 -o $O/prof_prune_gmats_r2 -f python bench.py --side gtr > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:blens_jac -s 1 -c 1 -o $O/prof_jac_r2 -f python bench.py --side jac > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:gram_logdet -s 1 -c 1 -o $O/prof_logdet_r2 -f python bench.py --side jac > /dev/null 2>&1
+$NCU --set full --import-source on -k regex:nj_hard_lean -s 2 -c 1 -o $O/prof_njhardlean_r2 -f python bench.py --side c3 > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:geo_soft -c 2 -o $O/prof_geo_r2 -f python -m pytest tests/test_geodesic_gpu.py -m gpu -q -x > /dev/null 2>&1
 ls -la $O/*_r2*
