@@ -385,9 +385,15 @@ extern "C" int dodo_pdm_fwd(const double *d_x, int B, int S, int D, const double
     double *sheet, *util;
     int rc = run_lift(d_x, B, S, D, lift, d_ws, stream, &sheet, &util);
     if (rc != DODO_OK) return rc;
-    dim3 blk(32, 8), grd((S + 31) / 32, (S + 7) / 8, B);
-    pdm_fwd_kernel<<<grd, blk, 0, stream>>>(d_x, sheet, util, S, D, d_curvature, variant, matsumoto, d_pdm);
-    DODO_LAUNCH_CHECK();
+    // gridDim.z is limited to 65535: larger batches go in slices (the batched Jacobian cross-check asks for
+    // B * (2S-2) matrices)
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = B - b0 < 65535 ? B - b0 : 65535;
+        dim3 blk(32, 8), grd((S + 31) / 32, (S + 7) / 8, nb);
+        pdm_fwd_kernel<<<grd, blk, 0, stream>>>(d_x + (size_t)b0 * S * D, sheet + (size_t)b0 * S * (D + 1), util + (size_t)b0 * S, S, D,
+                                                d_curvature, variant, matsumoto, d_pdm + (size_t)b0 * S * S);
+        DODO_LAUNCH_CHECK();
+    }
     return DODO_OK;
 }
 
