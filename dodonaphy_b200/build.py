@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "_C")
 LIB = os.path.join(OUT_DIR, "libdodonaphy_b200.so")
 STAMP = os.path.join(OUT_DIR, "build.stamp")
-SOURCES = ["common.cu", "prune.cu", "pdm.cu", "hypdist.cu", "nj.cu"]
+SOURCES = ["common.cu", "prune.cu", "pdm.cu", "hypdist.cu", "nj.cu", "align.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--fmad=true", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 # tuning knobs (compile-time), e.g. DODO_DEFINES="-DDODO_PRUNE_MINBLOCKS=3"

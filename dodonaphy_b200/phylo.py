@@ -44,23 +44,37 @@ def compress_alignment(alignment, get_namespace=False, get_freqs=False):
 
 def compress_alignment_device(sequences, device="cuda"):
     """Alignment ingestion on the device: the same unique-sorted-pattern compression as
-    ``compress_alignment`` (phylo.py:16-58) for a list of equal-length strings, but the column
-    sort/unique runs on the GPU and the result is what the kernels consume directly:
+    ``compress_alignment`` (phylo.py:16-58) for a list of equal-length strings, with the column sort / unique
+    done by the library's radix-sort kernels (``dodo_alignment_sort`` / ``dodo_alignment_gather``,
+    csrc/align.cu); the result is what the pruning kernel consumes directly:
     (tip masks uint8 (S, L) on ``device``, pattern weights int64 (L,) on ``device``).
     Patterns are ordered like the reference's ``sorted(Counter(zip(*sequences)))`` (byte order of the
     raw characters); the character -> state-set map is case-insensitive."""
+    from . import _lib
+
     S = len(sequences)
     n = len(sequences[0])
     if any(len(q) != n for q in sequences):
         raise ValueError("sequences must have equal length")
-    raw = torch.frombuffer(bytearray("".join(sequences), "ascii"), dtype=torch.uint8).reshape(S, n).to(device)
-    cols, counts = torch.unique(raw.T.contiguous(), dim=0, return_counts=True)  # lexicographic, like sorted()
+    _lib.require_cuda()
+    lib = _lib.load()
+    raw = torch.frombuffer(bytearray("".join(sequences), "ascii"), dtype=torch.uint8).reshape(S, n).to(device).contiguous()
     lut = torch.full((256,), 15, dtype=torch.uint8)
     for ch, m in _IUPAC.items():
         lut[ord(ch)] = m
         lut[ord(ch.lower())] = m
-    masks = lut.to(device)[cols.T.contiguous().long()]
-    return masks.contiguous(), counts.to(torch.int64)
+    lut = lut.to(raw.device)
+    with torch.cuda.device(raw.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        ws = torch.empty(int(lib.dodo_alignment_workspace_bytes(S, n)), dtype=torch.uint8, device=raw.device)
+        n_unique = torch.zeros(1, dtype=torch.int32, device=raw.device)
+        _lib.check(lib.dodo_alignment_sort(raw.data_ptr(), S, n, ws.data_ptr(), n_unique.data_ptr(), stream))
+        U = int(n_unique.item())
+        masks = torch.empty((S, U), dtype=torch.uint8, device=raw.device)
+        weights = torch.empty(U, dtype=torch.int64, device=raw.device)
+        _lib.check(lib.dodo_alignment_gather(raw.data_ptr(), S, n, ws.data_ptr(), U, lut.data_ptr(), masks.data_ptr(),
+                                             weights.data_ptr(), stream))
+    return masks, weights
 
 
 # ------------------------------------------------------------------------------------------------

@@ -140,6 +140,20 @@ int dodo_model_chain(const dodo_model_t *model, const double *rates, int K, cons
                      const double *d_grad_P, int B, int S, double *d_grad_blens, double *d_W, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Alignment ingestion on the device: the unique site patterns of an S x n character matrix in sorted order with
+ * their multiplicities -- phylo.compress_alignment (dodonaphy/phylo.py:16-58: Counter(zip(*sequences)), sorted) --
+ * by an LSD radix sort of the columns (stable counting-sort passes over groups of taxa), boundary flags and a scan.
+ * d_raw uint8 [S][n]: the raw characters, one row per taxon.  dodo_alignment_sort leaves the sorted order in d_ws and
+ * writes the number of patterns to d_n_unique (device int32; it synchronises the stream once to read the alphabet
+ * size, the caller reads d_n_unique to size the outputs); dodo_alignment_gather then fills d_masks uint8 [S][U]
+ * (through d_lut uint8 [256]: character -> IUPAC mask) and d_weights int64 [U].
+ * ------------------------------------------------------------------------------------------ */
+uint64_t dodo_alignment_workspace_bytes(int S, int64_t n);
+int dodo_alignment_sort(const uint8_t *d_raw, int S, int64_t n, void *d_ws, int32_t *d_n_unique, void *stream);
+int dodo_alignment_gather(const uint8_t *d_raw, int S, int64_t n, void *d_ws, int32_t n_unique, const uint8_t *d_lut,
+                          uint8_t *d_masks, int64_t *d_weights, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K1p: batched POINTWISE hyperbolic distances -- n independent pairs (x1[i], x2[i]) of D-dimensional
  * points (D <= 16) -- and their vector-Jacobian product.  Replaces the single-pair utilities the
  * reference calls in Python loops over a tree's branches (BaseModel.compute_branch_lengths,

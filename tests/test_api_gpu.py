@@ -271,7 +271,8 @@ def test_vi_jacobian_term_follows_the_reference_policy(monkeypatch):
 
 
 def test_compress_alignment_on_device():
-    """phylo.compress_alignment (phylo.py:16-58) with the sort/unique on the GPU."""
+    """phylo.compress_alignment (phylo.py:16-58) with the column sort / unique done by the library's radix-sort
+    kernels (csrc/align.cu): masks, weights and pattern ORDER equal to sorted(Counter(zip(*sequences)))."""
     from dodonaphy_b200 import phylo
     from oracle import phylo as ophylo
 
@@ -286,6 +287,21 @@ def test_compress_alignment_on_device():
     assert np.array_equal(masks.cpu().numpy(), m_ref)
     from dodonaphy_b200.engine import PruneEngine, SubstModel
 
+    # the radix sort itself: several pass structures (alphabet sizes 2 .. > 32 -> 1 .. 10 bits per taxon, taxa counts
+    # that are not multiples of the group size, more columns than one warp segment, all columns equal / all distinct)
+    for S2, n2, letters in ((1, 50, "AC"), (3, 5000, "ACGT"), (7, 9001, "ACGT-N"), (11, 3000, "ACGTRYMWSKBDHVN?-acgt"),
+                            (4, 700, "".join(chr(c) for c in range(48, 112))), (40, 20000, "ACGT"), (2, 4, "A"), (3, 6000, "AC")):
+        mat = rng.choice(np.array(list(letters)), size=(S2, n2))
+        if n2 == 20000:
+            mat[:, 10000:] = mat[:, :10000]  # heavy duplication
+        if S2 == 3 and letters == "AC":
+            mat[:] = "A"
+            mat[:, ::2] = "C"
+        seqs2 = ["".join(row) for row in mat]
+        m2, w2 = phylo.compress_alignment_device(seqs2)
+        _, w_ref2, m_ref2 = ophylo.compress_alignment(seqs2)
+        assert np.array_equal(w2.cpu().numpy(), w_ref2), (S2, n2, letters)
+        assert np.array_equal(m2.cpu().numpy(), m_ref2), (S2, n2, letters)
     eng = PruneEngine(masks, weights)
     peel = torch.tensor([[0, 1, 5], [2, 3, 6], [5, 6, 7], [4, 7, 8]]).cuda()
     ll, _ = eng.loglik(peel, torch.full((8,), 0.1, dtype=torch.float64).cuda(), SubstModel.jc69())
