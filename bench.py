@@ -16,9 +16,10 @@ e2e     = the same through the public API with HOST buffers: pinned H2D of the s
           D2H of lnL + gradients inside the timed region.
 roofline= algorithmic bytes of the pruning fwd+bwd kernel (V(5S-8)+2S per pattern and
           sample, V = 32K) / that kernel's duration measured with CUDA events around the launch.
-cpu_baseline / --impl reference = the reference's CPU arithmetic (oracle port of its torch path, its
-          own compiled Cython modules from oracle/_ref where they exist) on this box's host cores,
-          on a bounded sample of the same workload.
+cpu_baseline / --impl reference = the reference's own modules from oracle/_ref (compiled Cython + its Python
+          package: Chyp_np.get_pdm, Cpeeler.nj_np, PhyloModel.get_transition_mats, phylo.calculate_treelikelihood,
+          torch autograd; kind "reference") on this box's host cores, on a bounded sample of the same workload;
+          the torch port of those lines (kind "port") only where oracle/_ref is absent.
 
 N > 1 (torchrun, one rank per GPU): samples are sharded, every rank holds its own 128 samples (weak
 scaling); the only exchange is an all_gather of the per-sample lnL (the IWAE logsumexp needs all of
@@ -163,7 +164,18 @@ def cpu_reference(prob, cfg, n_trees, repeats=1, threads=None):
     w = torch.tensor(prob["weights"])
     sub = torch.tensor(prob["rates"])
     fr = torch.tensor(prob["freqs"])
-    kind = "port"
+    # The REAL reference where its package travelled (oracle/_ref: compiled Cython modules + its Python modules):
+    # Chyp_np.get_pdm -> Cpeeler.nj_np -> PhyloModel("GTR").get_transition_mats with the K category rates as the
+    # reference's own category axis -> phylo.calculate_treelikelihood -> torch autograd.  The reference has no gamma
+    # MIXTURE: with a category axis its broadcasting sums the per-category lnL (phylo.py:137-139) -- the same
+    # arithmetic as the mixture minus one per-site logsumexp.  Otherwise the torch port of those lines.
+    real = bool(ref.compiled and ref.python)
+    kind = "reference" if real else "port"
+    if real:
+        pm = ref.phylomodel.PhyloModel("GTR")
+        pm._freqs = pm.freqs_transform.inv(fr).clone().detach()
+        pm._sub_rates = pm.sub_rates_transform.inv(sub).clone().detach()
+        L = int(prob["masks"].shape[1])
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -176,14 +188,25 @@ def cpu_reference(prob, cfg, n_trees, repeats=1, threads=None):
             else:
                 peel, blens = nj.nj_hard(hyp.get_pdm_np(x))
             bt = torch.tensor(blens, requires_grad=True)
-            mats = phylo.gtr_p_t_torch(bt[:, None] * rates[None, :], sub, fr)
-            ll = phylo.treelikelihood_torch(tips, w, peel, mats, fr, gamma_mix=cfg["K"] > 1)
+            if real:
+                parts = list(tips) + [torch.zeros((1, 4, L)) for _ in range(cfg["S"] - 1)]  # BaseModel.__init__, base_model.py:86-101
+                mats = pm.get_transition_mats(bt[:, None] * rates[None, :])
+                ll = ref.phylo.calculate_treelikelihood(parts, w, peel, mats, pm.freqs)
+            else:
+                mats = phylo.gtr_p_t_torch(bt[:, None] * rates[None, :], sub, fr)
+                ll = phylo.treelikelihood_torch(tips, w, peel, mats, fr, gamma_mix=cfg["K"] > 1)
             ll.backward()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    desc = (f"{n_trees} of {cfg['B']} samples: pdm + hard NJ ({'reference Cython modules (oracle/_ref)' if ref.compiled else 'oracle port'}; "
-            f"the reference's soft NJ is infeasible at {cfg['S']} taxa) + GTR P(t) + pruning lnL + autograd gradient "
-            f"(torch float64 port of phylo.py:132-139 / phylomodel.py:96-114), {torch.get_num_threads()} threads")
+    if real:
+        how = ("the reference's own modules (oracle/_ref): Chyp_np.get_pdm, Cpeeler.nj_np, PhyloModel.get_transition_mats with the "
+               f"{cfg['K']} gamma rates as its category axis, phylo.calculate_treelikelihood, torch autograd (per-category lnL summed: "
+               "the reference has no gamma mixture)")
+    else:
+        how = (f"pdm + hard NJ ({'reference Cython modules (oracle/_ref)' if ref.compiled else 'oracle port'}) + GTR P(t) + pruning "
+               "lnL + autograd gradient (torch float64 port of phylo.py:132-139 / phylomodel.py:96-114)")
+    desc = (f"{n_trees} of {cfg['B']} samples: {how}; hard NJ stands in for the reference's soft NJ (209 s and 18.8 GB per "
+            f"{cfg['S']}-taxon tree); {torch.get_num_threads()} threads")
     return best, desc, kind, torch.get_num_threads()
 
 
@@ -355,6 +378,9 @@ def run_ours(args, cfg):
                 "config": config_dict(cfg, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 8),
                         "d2h_bytes_per_step": int((ll_pin.numel() + gx_pin.numel()) * 8), "ms_per_step": ms_e2e / args.steps},
+                "notes": ("K = 4 discrete-gamma MIXTURE (lnL = sum_p w_p log mean_k f_pk) does not exist in the reference (no rate "
+                          "heterogeneity): parity of that mode is pinned to the restatement only; K = 1 and the reference's summed "
+                          "category axis are pinned to the reference itself at this size (tests/golden/prune_c2.npz, chain_c2.npz)"),
                 "gpu_launches": int(launches),
                 "launch_mode": "one CUDA graph replay per step (pipeline.GraphedStep); gpu_launches counts the kernels of the K steps, counted from the same steps launched directly",
                 "roofline": {"bound": "hbm", "kernel": "dodo::prune_kernel<1,true,false,1,0> (MODE=grad, resident tables, no rescaling, 1 pattern/thread, generic P: fused P(t)+pruning forward + branch-length gradient)", "achieved": achieved,
