@@ -93,6 +93,15 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
+    path = os.environ.get("DODO_LIB", LIB_PATH)  # an alternative build of the same library (A/B timing runs)
+    if path != LIB_PATH:
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     if not os.path.exists(LIB_PATH):
         if not build_if_missing:
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -m dodonaphy_b200.build`")

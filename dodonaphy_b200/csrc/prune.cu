@@ -667,6 +667,23 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
     const unsigned o_T = (unsigned)(S - 1) * 16u;                                   // Ttip inside the slab
     const unsigned o_C = o_T + (unsigned)S * 20u;                                   // Cher inside the slab
 #define GACC(i) smd[o_gacc + (i)]
+#ifndef DODO_GACC_SHARED
+#define DODO_GACC_SHARED 1
+#endif
+#if DODO_GACC_SHARED
+    // the per-join accumulation goes through explicit shared-window addresses (ld/st.shared from `sbase`): addressed
+    // from the `smd` symbol every lane-dependent access re-derives the window base (S2UR + conversions per join)
+#define GACC_ADD(i, v)                                                              \
+    do {                                                                            \
+        const unsigned a__ = sbase + (o_gacc + (i)) * 8u;                            \
+        double r__;                                                                 \
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r__) : "r"(a__) : "memory");  \
+        r__ += (v);                                                                 \
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(a__), "d"(r__) : "memory");    \
+    } while (0)
+#else
+#define GACC_ADD(i, v) GACC(i) += (v)
+#endif
 #define FX(k, q) smd[o_fx + ((unsigned)(k) * NP + (q)) * nthr + tid]
 #define RED(i) smd[o_red + (i)]
 #define CX(k, q) (reinterpret_cast<int *>(&smd[o_cx])[((unsigned)(k) * NP + (q)) * nthr + tid])
@@ -991,13 +1008,13 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         const double g2 = warp_sum2(ga, gb, lane);
                         if ((lane & 15u) == 0u) {
                             const int c = lane ? o.y : o.x;
-                            GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
+                            GACC_ADD(gw + (unsigned)(c < 0 ? ~c : c + S), g2);
                         }
                     } else if (have_pending) {  // warp-uniform: every second join reduces its own and the parked pair
                         const double g4 = warp_sum4(pend_ga, pend_gb, ga, gb, lane);
                         if ((lane & 7u) == 0u) {
                             const int c = lane == 0u ? pend_x : (lane == 8u ? pend_y : (lane == 16u ? o.x : o.y));
-                            GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g4;
+                            GACC_ADD(gw + (unsigned)(c < 0 ? ~c : c + S), g4);
                         }
                         have_pending = false;
                     } else {
@@ -1034,7 +1051,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                     const double g2 = warp_sum2(pend_ga, pend_gb, lane);
                     if ((lane & 15u) == 0u) {
                         const int c = lane ? pend_y : pend_x;
-                        GACC(gw + (unsigned)(c < 0 ? ~c : c + S)) += g2;
+                        GACC_ADD(gw + (unsigned)(c < 0 ? ~c : c + S), g2);
                     }
                 }
             }
@@ -1112,6 +1129,7 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
         item = s_next_item;
     }
 #undef GACC
+#undef GACC_ADD
 #undef FX
 #undef RED
 #undef CX

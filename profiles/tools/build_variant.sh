@@ -1,14 +1,14 @@
 #!/bin/bash
 # build_variant.sh NAME "-DFOO=1 ..."  ->  _variants/NAME.so  (load with DODO_LIB=_variants/NAME.so)
+# every source is compiled with the extra flags; A/B timing runs compare two builds on the same GPU box
 set -e
 ROOT=$(cd "$(dirname "$0")/../.." && pwd)
 mkdir -p $ROOT/_variants/$1
-for f in common prune pdm nj; do
-  if [ "$f" = "prune" ] || [ ! -f $ROOT/_variants/base_$f.o ]; then
-    out=$ROOT/_variants/$1/$f.o
-    [ "$f" != "prune" ] && out=$ROOT/_variants/base_$f.o
-    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=true -Xcompiler -fPIC -Xcompiler -O2 --expt-relaxed-constexpr $2 -c $ROOT/dodonaphy_b200/csrc/$f.cu -o $out
-  fi
+objs=""
+for f in common prune pdm hypdist nj align; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=true -Xcompiler -fPIC -Xcompiler -O2 --expt-relaxed-constexpr $2 -c $ROOT/dodonaphy_b200/csrc/$f.cu -o $ROOT/_variants/$1/$f.o &
+  objs="$objs $ROOT/_variants/$1/$f.o"
 done
-nvcc -shared -o $ROOT/_variants/$1.so $ROOT/_variants/$1/prune.o $ROOT/_variants/base_common.o $ROOT/_variants/base_pdm.o $ROOT/_variants/base_nj.o -lcudart
+wait
+nvcc -shared -o $ROOT/_variants/$1.so $objs -lcudart
 echo $ROOT/_variants/$1.so
