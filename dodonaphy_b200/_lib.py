@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("DODO_LIB") or os.path.join(_PKG, "_C", "libdodonaphy_
 
 DODO_OK, DODO_EINVAL, DODO_ECUDA, DODO_ENOTIMPL, DODO_EINEXACT = 0, -1, -2, -3, -4
 MODEL_JC69, MODEL_EIGEN = 0, 1
-PRUNE_GRAD, PRUNE_MIX, PRUNE_SCALE, PRUNE_GMATS = 1, 2, 4, 8
+PRUNE_GRAD, PRUNE_MIX, PRUNE_SCALE, PRUNE_GMATS, PRUNE_GMODEL = 1, 2, 4, 8, 16
 PDM_TORCH, PDM_NUMPY = 0, 1
 LIFT_UP, LIFT_WRAP = 0, 1
 DIST_POINCARE, DIST_LORENTZ, DIST_SHEET_UP = 0, 1, 2
@@ -49,6 +49,9 @@ _SIGNATURES = {
     "dodo_prune": (C.c_int, [C.POINTER(PrunePlan), C.POINTER(Model), C.POINTER(C.c_double), C.c_void_p,
                              C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dodo_prune_model": (C.c_int, [C.POINTER(PrunePlan), C.POINTER(Model), C.POINTER(C.c_double), C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dodo_pdm_workspace_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
     "dodo_pdm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

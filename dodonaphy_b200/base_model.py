@@ -20,7 +20,7 @@ import torch
 
 from . import Chyp_np, Chyp_torch, Cpeeler, peeler
 from .phylo import LikelihoodInstance, TreeLikelihood, calculate_treelikelihood
-from .phylomodel import PhyloModel
+from .phylomodel import PhyloModel, rate_matrix_jacobian_np
 from .pipeline import HotPath
 
 
@@ -65,20 +65,25 @@ class _BatchedLogLikModel(torch.autograd.Function):
     """As ``_BatchedLogLik`` with a learnable GTR model: gradient also reaches the unconstrained
     rate / frequency leaves (phylomodel.py:19-45) -- the batched form of the reference's non-bito branch
     (base_model.py:239-247: explicit ``get_transition_mats`` + ``calculate_treelikelihood`` under autograd).
-    P(t) is formed on the device from the current eigen-system; the pruning kernel returns d lnL/d P per edge
-    and category (DODO_PRUNE_GMATS) and d lnL/d pi; ``dodo_model_chain`` contracts them on the device into
-    d lnL/d blens and one 4 x 4 matrix per sample, W_b with d lnL_b/d Q = U^-T W_b U^T.  What is left for the
-    host is the 4 x 4 map (rates, freqs) -> normalised Q, differentiated by autograd on 16 numbers."""
+    P(t) is formed on the device from the current eigen-system; ONE pruning launch (``dodo_prune_model``) returns
+    lnL, d lnL/d blens, d lnL/d pi and one 4 x 4 matrix per sample, W_b with d lnL_b/d Q = U^-T W_b U^T.  What
+    is left for the host is the 4 x 4 map (rates, freqs) -> normalised Q: its 20 x 8 Jacobian is formed in closed
+    form (``phylomodel.rate_matrix_jacobian_np``) while the device is busy, so the backward pass is one 20-number
+    device->host read and a matrix-vector product."""
 
     @staticmethod
     def forward(ctx, locs, curvature_leaf, raw_rates, raw_freqs, hot):
         hot.curvature = -float(torch.exp(curvature_leaf.detach().reshape(-1)[0]))
         x = locs.detach().to(hot.device, dtype=torch.float64).contiguous()
-        out = hot.resolve(x, hot.value_and_grad_model(x), model=True)
+        out = hot.value_and_grad_model(x)  # launched; the host carries on
+        # while the device works: the Jacobian of the 4 x 4 map (rates, freqs) -> (normalised Q, pi), 20 x (5 + 3)
+        # numbers on the host in closed form -- all the backward pass needs besides W and d lnL / d pi
+        ctx.jac = rate_matrix_jacobian_np(raw_rates.detach().cpu().numpy(), raw_freqs.detach().cpu().numpy())[2]
+        ctx.n_rates, ctx.leaf_like = int(raw_rates.numel()), (raw_rates, raw_freqs)
+        out = hot.resolve(x, out, model=True)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
         ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens", "grad_prior", "W", "grad_pi") if k in out}
-        ctx.save_for_backward(raw_rates.detach(), raw_freqs.detach())
         ctx.model = hot.model
         ctx.mark_non_differentiable(out["peel"])
         hot.last_decode = (x, out["peel"], out["flags"])  # for the Jacobian term of the same step (vi.py:376-387)
@@ -86,7 +91,6 @@ class _BatchedLogLikModel(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_ll, _g_peel, g_blens, g_prior):
-        raw_rates, raw_freqs = ctx.saved_tensors
         x, hot = ctx.x, ctx.hot
         w = g_ll.to(x.device).reshape(-1)
         gb = w.reshape(-1, 1) * ctx.dec["grad_blens"]
@@ -95,15 +99,14 @@ class _BatchedLogLikModel(torch.autograd.Function):
         if g_prior is not None and ctx.dec.get("grad_prior") is not None:
             gb = gb + g_prior.to(x.device).reshape(-1, 1) * ctx.dec["grad_prior"]
         # model leaves: sum_b w_b (U^-T W_b U^T) : dQ  +  sum_b w_b grad_pi_b : d pi  -- 20 numbers to the host
-        packed = torch.cat([(w.reshape(-1, 1, 1) * ctx.dec["W"]).sum(0).reshape(-1), (w.reshape(-1, 1) * ctx.dec["grad_pi"]).sum(0)]).cpu()
-        U, Uinv = torch.as_tensor(ctx.model.U), torch.as_tensor(ctx.model.Uinv)
-        GQ = Uinv.T @ packed[:16].reshape(4, 4) @ U.T
-        with torch.enable_grad():
-            rr, rf = raw_rates.clone().requires_grad_(True), raw_freqs.clone().requires_grad_(True)
-            Q, pi = PhyloModel.rate_matrix_from_raw(rr, rf)
-            g_rates, g_freqs = torch.autograd.grad((Q * GQ).sum() + (pi * packed[16:]).sum(), (rr, rf))
+        packed = torch.cat([(w.reshape(-1, 1, 1) * ctx.dec["W"]).sum(0).reshape(-1), (w.reshape(-1, 1) * ctx.dec["grad_pi"]).sum(0)])
         hot.curvature = ctx.kappa
-        gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())
+        gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())  # launched before the host waits for `packed`
+        packed = packed.cpu().numpy()
+        v = np.concatenate([(ctx.model.Uinv.T @ packed[:16].reshape(4, 4) @ ctx.model.U.T).reshape(-1), packed[16:]])
+        g = torch.as_tensor(v @ ctx.jac)
+        g_rates, g_freqs = (t.to(device=like.device, dtype=like.dtype)
+                            for t, like in zip((g[:ctx.n_rates], g[ctx.n_rates:]), ctx.leaf_like))
         return (gx.to(ctx.devs[0]), (gc.sum() * ctx.kappa).reshape(ctx.cshape).to(ctx.devs[1]),
                 g_rates, g_freqs, None)
 

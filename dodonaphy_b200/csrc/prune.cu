@@ -152,12 +152,15 @@ __global__ void schedule_kernel(const int64_t *__restrict__ peel, int nb, int S,
 __host__ __device__ __forceinline__ unsigned cherry_entry(unsigned ja, unsigned jb) {  // rows 0..3 one-hot, 4 = any
     return (ja < 4u && jb < 4u) ? ja * 4u + jb : (ja == 4u ? 16u + jb : 21u + ja);
 }
-__host__ __device__ inline size_t tab_doubles(int S, int chmax) {
-    return (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)chmax * 100;
+//                 Phi[2S-2][16] (model-gradient launches only, `gm`): per edge the divided differences
+//                                 Phi'_mn = tau expm1((lam_m - lam_n) tau) / ((lam_m - lam_n) tau), Phi'_mm = tau,
+//                                 tau = r_k t_e, of the Daleckii-Krein form of d exp(Q tau) (see model_edge) }
+__host__ __device__ inline size_t tab_doubles(int S, int chmax, int gm = 0) {
+    return (size_t)(S - 1) * 16 + (size_t)S * 20 + (size_t)chmax * 100 + (gm ? (size_t)(2 * S - 2) * 16 : 0);
 }
 
 __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens, const double *__restrict__ P_in,
-                                  int B, int S, int K, int eig, int chmax, double *__restrict__ tab) {
+                                  int B, int S, int K, int eig, int chmax, int gm, double *__restrict__ tab) {
     const int E = 2 * S - 2;
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)B * E * K;
@@ -193,7 +196,22 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
                 }
         }
     }
-    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax);
+    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax, gm);
+    if (gm) {  // eigen models only (checked by the host)
+        const double tau = blens[(size_t)b * E + e] * md.rates[k];
+        double2 *ph = reinterpret_cast<double2 *>(slab + tab_doubles(S, chmax) + (size_t)e * 16);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            double row[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const double d = fmin((md.lam[m] - md.lam[n]) * tau, 700.0);
+                row[n] = (m == n) ? tau : tau * (fabs(d) < 1e-8 ? 1.0 + 0.5 * d : expm1(d) / d);
+            }
+            ph[2 * m] = make_double2(row[0], row[1]);
+            ph[2 * m + 1] = make_double2(row[2], row[3]);
+        }
+    }
     if (e >= S) {
         double2 *out = reinterpret_cast<double2 *>(slab + (size_t)(e - S) * 16);
 #pragma unroll
@@ -248,13 +266,13 @@ constexpr int NT = 256;  // threads per CTA = site patterns per work item
 
 // Shared memory.  SMALL (tables and tip selectors resident): tables | gacc | fx | red | cx | ops | sel.
 // LARGE (big S: tables and masks stay in global memory, read through L1): gacc | fx | red | cx | ops.
-__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np, int chmax) {
+__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np, int chmax, int gm = 0) {
     const size_t nwarp = NT / 32, E = 2 * (size_t)S - 2;
-    size_t dbl = nwarp * E + (size_t)K * NT * np + nwarp + (small ? tab_doubles(S, chmax) : 0);
+    size_t dbl = nwarp * E + (size_t)K * NT * np + nwarp + (gm ? nwarp * 20 : 0) + (small ? tab_doubles(S, chmax, gm) : 0);
     return (dbl + 1) & ~(size_t)1;  // keep what follows 16-byte aligned
 }
-__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np, int chmax) {
-    return prune_smem_dbl(S, K, small, np, chmax) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
+__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np, int chmax, int gm = 0) {
+    return prune_smem_dbl(S, K, small, np, chmax, gm) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
            (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT * np : 0);
 }
 
@@ -413,6 +431,7 @@ __device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, dou
 
 // sum over the warp of the 4x4 outer products u (x) v; entry (i,j) ends in lane 2*(4i+j) and is
 // written to dst[4i+j].  Halving butterfly: 16 double shuffles instead of 80, fixed order.
+__device__ __forceinline__ void reduce16_store(const double (&x)[16], double *dst, unsigned lane);
 __device__ __forceinline__ void outer_reduce_store(const V4 &u, const V4 &v, double *dst, unsigned lane) {
     double x[16];
     const double uu[4] = {u.a, u.b, u.c, u.d}, vv[4] = {v.a, v.b, v.c, v.d};
@@ -420,6 +439,10 @@ __device__ __forceinline__ void outer_reduce_store(const V4 &u, const V4 &v, dou
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[i * 4 + j] = uu[i] * vv[j];
+    reduce16_store(x, dst, lane);
+}
+// sum over the warp of 16 values per lane: entry i ends in lane 2 i and is written to dst[i]
+__device__ __forceinline__ void reduce16_store(const double (&x)[16], double *dst, unsigned lane) {
     double y[8];
     {
         const bool hi = lane & 16u;
@@ -581,6 +604,48 @@ __device__ __forceinline__ void matvecT_n(const double *P, const V4 (&x)[NP], V4
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Learnable reversible model (MODE 3): per edge c with upper message u (parent side) and message msg = P_c L_c,
+//   a = U^T u,  bt = U^-1 msg = e o (U^-1 L_c)                       (e_m = exp(lam_m tau), tau = r_k t_c)
+//   d lnL / d t_c        += r_k sum_m lam_m a_m bt_m                  (= r_k u . Q msg)
+//   W_mn                 += Phi'_mn a_m bt_n                          (Phi' from the slab, see tab_doubles)
+// so that d lnL / d Q = U^-T W U^T (Daleckii-Krein: d exp(Q tau) = U [Phi o (U^-1 dQ U)] U^-1 with
+// Phi_mn = e_n Phi'_mn).  W is accumulated PER THREAD over all edges and categories of the walk and reduced
+// over the warp once per work item -- the explicit-matrix mode (GMATS) reduces 16 values per edge instead.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ V4 matvec_cT(const double *M, const V4 &v) {  // M^T v, M in the constant bank
+    return V4{fma(M[12], v.d, fma(M[8], v.c, fma(M[4], v.b, M[0] * v.a))),
+              fma(M[13], v.d, fma(M[9], v.c, fma(M[5], v.b, M[1] * v.a))),
+              fma(M[14], v.d, fma(M[10], v.c, fma(M[6], v.b, M[2] * v.a))),
+              fma(M[15], v.d, fma(M[11], v.c, fma(M[7], v.b, M[3] * v.a)))};
+}
+__device__ __forceinline__ V4 matvec_c(const double *M, const V4 &v) {  // M v
+    return V4{fma(M[3], v.d, fma(M[2], v.c, fma(M[1], v.b, M[0] * v.a))),
+              fma(M[7], v.d, fma(M[6], v.c, fma(M[5], v.b, M[4] * v.a))),
+              fma(M[11], v.d, fma(M[10], v.c, fma(M[9], v.b, M[8] * v.a))),
+              fma(M[15], v.d, fma(M[14], v.c, fma(M[13], v.b, M[12] * v.a)))};
+}
+template <bool SMALL>
+__device__ __forceinline__ double model_edge(const ModelDev &md, const double *Phi, const V4 &u, const V4 &msg,
+                                             const double (&rl)[4], const double sf, double (&W)[16]) {
+    V4 a = matvec_cT(md.U, u);
+    a = V4{a.a * sf, a.b * sf, a.c * sf, a.d * sf};  // sf: exact power of two (1 without rescaling)
+    const V4 bt = matvec_c(md.Uinv, msg);
+    V4 ph = ld4t<SMALL, 0>(Phi);
+    W[0] = fma(ph.a, a.a * bt.a, W[0]); W[1] = fma(ph.b, a.a * bt.b, W[1]);
+    W[2] = fma(ph.c, a.a * bt.c, W[2]); W[3] = fma(ph.d, a.a * bt.d, W[3]);
+    ph = ld4t<SMALL, 4>(Phi);
+    W[4] = fma(ph.a, a.b * bt.a, W[4]); W[5] = fma(ph.b, a.b * bt.b, W[5]);
+    W[6] = fma(ph.c, a.b * bt.c, W[6]); W[7] = fma(ph.d, a.b * bt.d, W[7]);
+    ph = ld4t<SMALL, 8>(Phi);
+    W[8] = fma(ph.a, a.c * bt.a, W[8]); W[9] = fma(ph.b, a.c * bt.b, W[9]);
+    W[10] = fma(ph.c, a.c * bt.c, W[10]); W[11] = fma(ph.d, a.c * bt.d, W[11]);
+    ph = ld4t<SMALL, 12>(Phi);
+    W[12] = fma(ph.a, a.d * bt.a, W[12]); W[13] = fma(ph.b, a.d * bt.b, W[13]);
+    W[14] = fma(ph.c, a.d * bt.c, W[14]); W[15] = fma(ph.d, a.d * bt.d, W[15]);
+    return fma(rl[3], a.d * bt.d, fma(rl[2], a.c * bt.c, fma(rl[1], a.b * bt.b, rl[0] * (a.a * bt.a))));
+}
+
 enum { PM_GENERIC = 0, PM_JC = 1, PM_EIG = 2 };
 // PM_EIG measured slower at 64 taxa x 10k x 128 x 4 (5.7 ms against 4.7 ms): U and U^-1 do not fit the
 // uniform register file next to Q, pi and the rates, so every use reloads them (+50 % instructions).
@@ -602,7 +667,7 @@ __device__ __forceinline__ void apply_P(const int pmode, const ModelDev &md, con
 // bit for bit.  One thread per (sample, category, cherry, pair).
 // ------------------------------------------------------------------------------------------
 __global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restrict__ chop, int ops_batch, int B, int S,
-                              int K, int chmax, int pmode, ModelDev md, double *__restrict__ tab) {
+                              int K, int chmax, int gm, int pmode, ModelDev md, double *__restrict__ tab) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)B * K * chmax * 25) return;
     const int pair = gid % 25;
@@ -613,7 +678,7 @@ __global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restric
     const int pos = chop[(size_t)ob * (S / 2) + c];
     if (pos < 0) return;
     const int4 o = ops[(size_t)ob * (S - 1) + pos];  // {left tip, right tip, node, flags}
-    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax);
+    double *slab = tab + ((size_t)b * K + k) * tab_doubles(S, chmax, gm);
     const double *P = slab + (size_t)(o.z - S) * 16;
     const double *Tl = slab + (size_t)(S - 1) * 16 + (size_t)o.x * 20 + (pair / 5) * 2;  // split rows: see Ttip
     const double *Tr = slab + (size_t)(S - 1) * 16 + (size_t)o.y * 20 + (pair % 5) * 2;
@@ -623,7 +688,8 @@ __global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restric
     out[0] = y[0].a; out[25] = y[0].b; out[50] = y[0].c; out[75] = y[0].d;
 }
 
-// MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi
+// MODE 0: lnL only; 1: lnL + d lnL/d blens; 2: lnL + d lnL/d P (per edge and category) + d lnL/d pi;
+// 3: lnL + d lnL/d blens + the 4 x 4 matrix W of the model chain rule (see model_edge) + d lnL/d pi
 // NP: site patterns per thread (1 or 2).  With NP = 2 the schedule decode, the branches, the address
 // arithmetic and -- above all -- the warp-wide fills of registers with the (warp-uniform) entries of P
 // are shared by two independent patterns, which also doubles the instruction-level parallelism.
@@ -636,9 +702,12 @@ __global__ void cherry_kernel(const int4 *__restrict__ ops, const int *__restric
 // Latency is hidden by the resident warps plus an L2 prefetch three joins ahead in the backward
 // sweep; a register-level software pipeline was measured slower (more instructions).
 template <int MODE, bool SMALL, bool SCALE, int NP, int PM>
-__global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kernel(PruneArgs A, ModelDev md) {
-    constexpr bool GRAD = MODE == 1;
+__global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS : 2) prune_kernel(PruneArgs A, ModelDev md) {
+    constexpr bool GMODEL = MODE == 3;  // the branch-length sweep + per-thread accumulation of W (16 more doubles: 2 CTAs/SM)
+    constexpr bool GRAD = MODE == 1 || GMODEL;
     constexpr bool GMATS = MODE == 2;
+    constexpr int GM = GMODEL ? 1 : 0;
+    static_assert(!(GMODEL && NP != 1), "the model gradient handles one pattern per thread");
     static_assert(!(GMATS && SCALE), "GMATS is built without rescaling");
     static_assert(!(GMATS && NP != 1), "GMATS handles one pattern per thread");
     extern __shared__ __align__(16) double smd[];  // indexed from the symbol: keeps LDS addressing direct
@@ -656,16 +725,18 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
 #define DODO_PRUNE_RECOMP_LARGE 1
 #endif
     constexpr bool RECOMP = SMALL || DODO_PRUNE_RECOMP_LARGE;
-    const unsigned tabn = (unsigned)tab_doubles(S, A.ch_max);
-    // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] | cx | ops | sel
+    const unsigned tabn = (unsigned)tab_doubles(S, A.ch_max, GM);
+    // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] wred[nwarp][20] (GMODEL) | cx | ops | sel
     const unsigned o_gacc = SMALL ? tabn : 0u;
     const unsigned o_fx = o_gacc + nwarp * (unsigned)E;
     const unsigned o_red = o_fx + (unsigned)K * npt;
-    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP, A.ch_max);      // int [K][npt]
+    const unsigned o_wred = o_red + nwarp;                                          // per-warp W (16) + d/d pi (4)
+    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP, A.ch_max, GM);  // int [K][npt]
     const unsigned o_ops = o_cx + ((unsigned)K * npt) / 2u;                         // int4 [S+2]
     const unsigned o_sel = o_ops + 2u * (unsigned)(S + 2);                          // u8 [S][npt]
     const unsigned o_T = (unsigned)(S - 1) * 16u;                                   // Ttip inside the slab
     const unsigned o_C = o_T + (unsigned)S * 20u;                                   // Cher inside the slab
+    const unsigned o_X = o_C + (unsigned)A.ch_max * 100u;                           // Phi' inside the slab (GMODEL)
 #define GACC(i) smd[o_gacc + (i)]
 #ifndef DODO_GACC_SHARED
 #define DODO_GACC_SHARED 1
@@ -724,7 +795,11 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
             tm[q] = A.tipmask + (valid ? p : A.L - 1);
         }
         const double *tab_b = A.tab + (size_t)b * K * tabn;
+        double Wm[16];  // GMODEL: this thread's share of W, over every edge and category of the walk (else unused)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Wm[i] = 0.0;
         __syncthreads();
+        if (GMODEL && lane < 4) smd[o_wred + warp * 20u + 16u + lane] = 0.0;  // d lnL / d pi of this warp
         {
             // schedule of this sample, re-encoded: child code < 0 -> tip ~code, else internal index
             const int4 *ops_b = A.ops + (size_t)(A.ops_batch == 1 ? 0 : b) * nops;
@@ -919,17 +994,23 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 V4 *scr = scr0 + (size_t)k * (S - 1) * npt;
                 int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * npt : nullptr;
                 const double rate_k = md.rates[k];
+                const double rl[4] = {rate_k * md.lam[0], rate_k * md.lam[1], rate_k * md.lam[2], rate_k * md.lam[3]};
+                double sc0 = 0.0;
                 V4 Wv[NP];
                 int we[NP];  // true w = Wv * 2^(256 we)
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     const double sc = A.mix ? wt[q] / (f[q] * (double)K) : wt[q] / FX(k, q);
+                    sc0 = sc;
                     Wv[q] = V4{md.pi[0] * sc, md.pi[1] * sc, md.pi[2] * sc, md.pi[3] * sc};
                     we[q] = SCALE ? (A.mix ? cmin[q] : CX(k, q)) : 0;
                 }
                 // edge gradients of two consecutive joins share one reduction (resident tables only:
                 // the large-tree variants have no registers to park a pair in)
-                constexpr bool PAIR = DODO_PRUNE_PAIR_REDUCE && SMALL;
+#ifndef DODO_GM_PAIR
+#define DODO_GM_PAIR 0
+#endif
+                constexpr bool PAIR = DODO_PRUNE_PAIR_REDUCE && SMALL && (!GMODEL || DODO_GM_PAIR);
                 double pend_ga = 0.0, pend_gb = 0.0;
                 int pend_x = 0, pend_y = 0;
                 bool have_pending = false;
@@ -996,11 +1077,24 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                         ub[q] = vmul(Wv[q], av[q]);
                         // explicitly rounded: the result must not depend on whether the (exact)
                         // rescaling factor sits between the product and the accumulation
-                        double gaq = __dmul_rn(rate_k, uQx(md.Q, ua[q], av[q]));
-                        double gbq = __dmul_rn(rate_k, uQx(md.Q, ub[q], bv[q]));
-                        if (SCALE) {
-                            const double sf = pow2_256(we[q] - ac[q] - bcn[q]);
-                            gaq = __dmul_rn(gaq, sf); gbq = __dmul_rn(gbq, sf);
+                        double gaq, gbq;
+                        if (GMODEL) {
+                            const double sf = SCALE ? pow2_256(we[q] - ac[q] - bcn[q]) : 1.0;
+                            gaq = model_edge<SMALL>(md, tab_at(o_X + (unsigned)(o.x < 0 ? ~o.x : o.x + S) * 16u), ua[q], av[q], rl, sf, Wm);
+                            gbq = model_edge<SMALL>(md, tab_at(o_X + (unsigned)(o.y < 0 ? ~o.y : o.y + S) * 16u), ub[q], bv[q], rl, sf, Wm);
+                            if (i == nops) {  // root: d lnL / d pi_j = sum_k sc_k (msg_a * msg_b)_j
+                                const double s2 = sc0 * sf;
+                                const double g4 = warp_sum4(s2 * (av[q].a * bv[q].a), s2 * (av[q].b * bv[q].b),
+                                                            s2 * (av[q].c * bv[q].c), s2 * (av[q].d * bv[q].d), lane);
+                                if ((lane & 7u) == 0u) smd[o_wred + warp * 20u + 16u + (lane >> 3)] += g4;
+                            }
+                        } else {
+                            gaq = __dmul_rn(rate_k, uQx(md.Q, ua[q], av[q]));
+                            gbq = __dmul_rn(rate_k, uQx(md.Q, ub[q], bv[q]));
+                            if (SCALE) {
+                                const double sf = pow2_256(we[q] - ac[q] - bcn[q]);
+                                gaq = __dmul_rn(gaq, sf); gbq = __dmul_rn(gbq, sf);
+                            }
                         }
                         ga = __dadd_rn(ga, gaq); gb = __dadd_rn(gb, gbq);
                     }
@@ -1106,11 +1200,17 @@ __global__ void __launch_bounds__(NT, NP == 1 ? DODO_PRUNE_CTAS : 2) prune_kerne
                 gq[0] = gpi0; gq[1] = gpi1; gq[2] = gpi2; gq[3] = gpi3;
             }
         }
+        if (GMODEL) reduce16_store(Wm, &smd[o_wred + warp * 20u], lane);
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
             for (unsigned w2 = 0; w2 < nwarp; ++w2) s += RED(w2);
             A.ll_part[item] = s;
+        }
+        if (GMODEL && tid >= 32u && tid < 52u) {  // W (16) and d lnL / d pi (4) of this item, warps in index order
+            double s = 0.0;
+            for (unsigned w2 = 0; w2 < nwarp; ++w2) s += smd[o_wred + w2 * 20u + (tid - 32u)];
+            A.gm_part[(size_t)item * 20 + (tid - 32u)] = s;
         }
         if (GRAD) {
             double *gp = A.g_part + (size_t)item * E;
@@ -1183,6 +1283,18 @@ __global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, co
             for (int w = 0; w < nwarp; ++w) s += gpi_part[(((size_t)b * n_tiles + t) * nwarp + w) * 4 + i];
         grad_pi[(size_t)b * 4 + i] = s;
     }
+}
+
+// model-gradient launches: W [B][16] and d lnL / d pi [B][4] from the per-item partials, tiles in index order
+__global__ void prune_reduce_model_kernel(const double *__restrict__ part, int B, int n_tiles, double *__restrict__ W,
+                                          double *__restrict__ grad_pi) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * 20) return;
+    const int b = gid / 20, i = gid - b * 20;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += part[((size_t)b * n_tiles + t) * 20 + i];
+    if (i < 16) W[(size_t)b * 16 + i] = s;
+    else grad_pi[(size_t)b * 4 + (i - 16)] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1275,6 +1387,7 @@ static prune_fn_t prune_pick_pm(bool small, bool scale, int pm) {
     return prune_pick<MODE, NP, PM_GENERIC>(small, scale);
 }
 static prune_fn_t prune_entry(int mode, bool small, bool scale, int np, int pm) {
+    if (mode == 3) return prune_pick<3, 1, PM_GENERIC>(small, scale);  // eigen models only
     if (mode == 2) {  // d lnL/d P reads P itself: generic or JC69 forward, generic reverse sweep
         if (pm == PM_JC) return small ? prune_kernel<2, true, false, 1, PM_JC> : prune_kernel<2, false, false, 1, PM_JC>;
         return small ? prune_kernel<2, true, false, 1, PM_GENERIC> : prune_kernel<2, false, false, 1, PM_GENERIC>;
@@ -1289,17 +1402,17 @@ static prune_fn_t prune_entry(int mode, bool small, bool scale, int np, int pm) 
 #ifndef DODO_PRUNE_SMEM_KB
 #define DODO_PRUNE_SMEM_KB 74
 #endif
-static size_t prune_small_budget(int np) { return (size_t)(np == 2 ? 110 : DODO_PRUNE_SMEM_KB) * 1024; }
-static bool prune_small(int S, int K, int np) { return prune_smem_bytes(S, K, true, np, 0) <= prune_small_budget(np); }
+static size_t prune_small_budget(int np, int gm) { return (size_t)((np == 2 || gm) ? 110 : DODO_PRUNE_SMEM_KB) * 1024; }  // 2 or 3 CTAs per SM
+static bool prune_small(int S, int K, int np, int gm) { return prune_smem_bytes(S, K, true, np, 0, gm) <= prune_small_budget(np, gm); }
 // Tabulated cherries per tree: whatever shared memory is left inside the budget that keeps the CTA
 // count per SM (100 doubles per cherry); none with rescaling (counters are not tabulated) or when
 // the tables are not resident.
-static int prune_cherry_slots(int S, int K, int np, bool small, bool scale) {
+static int prune_cherry_slots(int S, int K, int np, int gm, bool small, bool scale) {
 #ifdef DODO_PRUNE_NO_CHERRY_TABLE
     return 0;
 #endif
     if (!small || scale) return 0;
-    const size_t left = prune_small_budget(np) - prune_smem_bytes(S, K, true, np, 0);
+    const size_t left = prune_small_budget(np, gm) - prune_smem_bytes(S, K, true, np, 0, gm);
     const int fit = (int)(left / 800);
     return fit < S / 2 ? fit : S / 2;
 }
@@ -1308,14 +1421,16 @@ static int prune_cherry_slots(int S, int K, int np, bool small, bool scale) {
 // 4.75 ms at 64 taxa x 10k patterns x 128 samples x 4 categories, so one per thread is the default.
 static int prune_np(int B, int L, uint32_t flags) {
     (void)B; (void)L;
-    if (flags & DODO_PRUNE_GMATS) return 1;
+    if (flags & (DODO_PRUNE_GMATS | DODO_PRUNE_GMODEL)) return 1;
 #ifdef DODO_PRUNE_NP
     return DODO_PRUNE_NP;
 #else
     return 1;
 #endif
 }
-static int prune_mode(uint32_t flags) { return (flags & DODO_PRUNE_GMATS) ? 2 : ((flags & DODO_PRUNE_GRAD) ? 1 : 0); }
+static int prune_mode(uint32_t flags) {
+    return (flags & DODO_PRUNE_GMODEL) ? 3 : ((flags & DODO_PRUNE_GMATS) ? 2 : ((flags & DODO_PRUNE_GRAD) ? 1 : 0));
+}
 
 }  // namespace dodo
 
@@ -1330,16 +1445,20 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
                    "dodo_prune_plan: GRAD and GMATS are separate calls");
     DODO_CHECK_ARG(!((flags & DODO_PRUNE_GMATS) && (flags & DODO_PRUNE_SCALE)),
                    "dodo_prune_plan: GMATS is not available with rescaling");
+    DODO_CHECK_ARG(!((flags & DODO_PRUNE_GMODEL) && (flags & DODO_PRUNE_GMATS)),
+                   "dodo_prune_plan: GMODEL and GMATS are separate calls");
+    if (flags & DODO_PRUNE_GMODEL) flags |= DODO_PRUNE_GRAD;  // the model gradient comes with the branch-length gradient
     memset(plan, 0, sizeof(*plan));
     plan->B = B; plan->S = S; plan->L = L; plan->K = K; plan->flags = flags;
     (void)threads_hint;
     const int threads = NT;
     const int np = prune_np(B, L, flags);
-    const bool small = prune_small(S, K, np);
+    const int gm = (flags & DODO_PRUNE_GMODEL) ? 1 : 0;
+    const bool small = prune_small(S, K, np, gm);
     const bool scale = (flags & DODO_PRUNE_SCALE) != 0;
-    const int chmax = prune_cherry_slots(S, K, np, small, scale);
+    const int chmax = prune_cherry_slots(S, K, np, gm, small, scale);
     plan->cherry_slots = chmax;
-    const size_t smem = prune_smem_bytes(S, K, small, np, chmax);
+    const size_t smem = prune_smem_bytes(S, K, small, np, chmax, gm);
     if (smem > 227 * 1024) {
         set_error("dodo_prune_plan: %d taxa need %zu bytes of shared memory per CTA (limit 227 KB)", S, smem);
         return DODO_ENOTIMPL;
@@ -1369,7 +1488,7 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     uint64_t off = 0;
     plan->off_ops = off;     off = align_up(off + (uint64_t)B * nI * sizeof(int4), 256);
     plan->off_sched = off;   off = align_up(off + (uint64_t)B * 6 * S * sizeof(int), 256);
-    plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S, chmax) * sizeof(double), 256);
+    plan->off_pmat = off;    off = align_up(off + (uint64_t)B * K * tab_doubles(S, chmax, gm) * sizeof(double), 256);
     plan->off_scratch = off; off = align_up(off + (uint64_t)grid * K * nI * threads * np * 32, 256);
     plan->off_tiptab = off;  // rescaling counters (int32 per stored message)
     if (scale) off = align_up(off + (uint64_t)grid * K * nI * threads * np * sizeof(int), 256);
@@ -1382,15 +1501,16 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
         off = align_up(off + (uint64_t)plan->n_items * K * nwarp * E * 16 * sizeof(double), 256);
         off = align_up(off + (uint64_t)plan->n_items * nwarp * 4 * sizeof(double), 256);
     }
+    if (gm) off = align_up(off + (uint64_t)plan->n_items * 20 * sizeof(double), 256);  // per-item W (16) + d/d pi (4)
     plan->ws_bytes = off;
     return DODO_OK;
 }
 
-extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
-                          const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights,
-                          const int64_t *d_peel, int peel_batch, const double *d_blens, const double *d_P_in,
-                          void *d_ws, double *d_loglik, double *d_grad_blens, double *d_grad_P,
-                          double *d_grad_pi, void *stream_) {
+static int prune_launch(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
+                        const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights,
+                        const int64_t *d_peel, int peel_batch, const double *d_blens, const double *d_P_in,
+                        void *d_ws, double *d_loglik, double *d_grad_blens, double *d_grad_P,
+                        double *d_grad_pi, double *d_W, void *stream_) {
     DODO_CHECK_ARG(plan && model && d_tipmask && d_weights && d_peel && d_ws && d_loglik, "dodo_prune: NULL argument");
     DODO_CHECK_ARG(d_blens || d_P_in, "dodo_prune: need blens or explicit transition matrices");
     const int B = plan->B, S = plan->S, L = plan->L, K = plan->K;
@@ -1401,6 +1521,10 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     DODO_CHECK_ARG(!(grad && d_P_in), "dodo_prune: blens gradient needs device-formed P(t) (use GMATS for explicit mats)");
     const bool gmats = plan->flags & DODO_PRUNE_GMATS;
     DODO_CHECK_ARG(!gmats || (d_grad_P && d_grad_pi), "dodo_prune: GMATS requested but d_grad_P / d_grad_pi is NULL");
+    const int gm = (plan->flags & DODO_PRUNE_GMODEL) ? 1 : 0;
+    DODO_CHECK_ARG(!gm || (d_W && d_grad_pi), "dodo_prune_model: d_W / d_grad_pi is NULL");
+    DODO_CHECK_ARG(!gm || model->kind == DODO_MODEL_EIGEN, "dodo_prune_model: needs an eigen-decomposed (GTR) model");
+    DODO_CHECK_ARG(gm || !d_W, "dodo_prune: the plan was not made with DODO_PRUNE_GMODEL");
     cudaStream_t stream = (cudaStream_t)stream_;
     char *ws = (char *)d_ws;
     const int E = 2 * S - 2;
@@ -1432,11 +1556,11 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     {
         size_t total = (size_t)B * E * K;
         transition_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(md, d_blens, d_P_in, B, S, K,
-                                                                               pmode == PM_EIG ? 1 : 0, chmax, tab);
+                                                                               pmode == PM_EIG ? 1 : 0, chmax, gm, tab);
         DODO_LAUNCH_CHECK();
         if (chmax > 0) {
             size_t tc = (size_t)B * K * chmax * 25;
-            cherry_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, stream>>>(ops, chop, peel_batch, B, S, K, chmax, pmode, md, tab);
+            cherry_kernel<<<(unsigned)((tc + 127) / 128), 128, 0, stream>>>(ops, chop, peel_batch, B, S, K, chmax, gm, pmode, md, tab);
             DODO_LAUNCH_CHECK();
         }
     }
@@ -1458,8 +1582,8 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
     A.pmode = pmode;
     A.ch_max = chmax;
     const int np = plan->tile_patterns / plan->threads;
-    const bool small = prune_small(S, K, np);
-    size_t smem = prune_smem_bytes(S, K, small, np, chmax);
+    const bool small = prune_small(S, K, np, gm);
+    size_t smem = prune_smem_bytes(S, K, small, np, chmax, gm);
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
@@ -1482,7 +1606,31 @@ extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *mod
             A.gm_part, A.gpi_part, B, plan->n_tiles, K, plan->threads / 32, E, d_grad_P, d_grad_pi);
         DODO_LAUNCH_CHECK();
     }
+    if (gm) {
+        prune_reduce_model_kernel<<<(B * 20 + 127) / 128, 128, 0, stream>>>(A.gm_part, B, plan->n_tiles, d_W, d_grad_pi);
+        DODO_LAUNCH_CHECK();
+    }
     return DODO_OK;
+}
+
+extern "C" int dodo_prune(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
+                          const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights,
+                          const int64_t *d_peel, int peel_batch, const double *d_blens, const double *d_P_in,
+                          void *d_ws, double *d_loglik, double *d_grad_blens, double *d_grad_P,
+                          double *d_grad_pi, void *stream_) {
+    DODO_CHECK_ARG(plan && !(plan->flags & DODO_PRUNE_GMODEL), "dodo_prune: a DODO_PRUNE_GMODEL plan goes through dodo_prune_model");
+    return prune_launch(plan, model, rates, d_tipmask, ld_mask, d_weights, d_peel, peel_batch, d_blens, d_P_in, d_ws,
+                        d_loglik, d_grad_blens, d_grad_P, d_grad_pi, nullptr, stream_);
+}
+
+extern "C" int dodo_prune_model(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
+                                const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights,
+                                const int64_t *d_peel, int peel_batch, const double *d_blens, void *d_ws,
+                                double *d_loglik, double *d_grad_blens, double *d_W, double *d_grad_pi, void *stream_) {
+    DODO_CHECK_ARG(plan && (plan->flags & DODO_PRUNE_GMODEL), "dodo_prune_model: the plan was not made with DODO_PRUNE_GMODEL");
+    DODO_CHECK_ARG(d_blens && d_grad_blens, "dodo_prune_model: NULL argument");
+    return prune_launch(plan, model, rates, d_tipmask, ld_mask, d_weights, d_peel, peel_batch, d_blens, nullptr, d_ws,
+                        d_loglik, d_grad_blens, nullptr, d_grad_pi, d_W, stream_);
 }
 
 extern "C" int dodo_model_chain(const dodo_model_t *model, const double *rates, int K, const double *d_blens,

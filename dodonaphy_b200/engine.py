@@ -214,12 +214,14 @@ class PruneEngine:
                                            _ptr(mats), _ptr(ws), _ptr(ll), _ptr(g), None, None, _stream()))
             return ll, g
 
-    def loglik_model_grad(self, peel, blens, model, rates=None, mix=False):
+    def loglik_model_grad(self, peel, blens, model, rates=None, mix=False, scale=None, via_mats=False):
         """lnL and its gradient w.r.t. the branch lengths AND the (GTR) model, P(t) formed on the device:
         returns dict(lnL (B,), grad_blens (B, 2S-2), W (B, 4, 4), grad_pi (B, 4)) with
-        d lnL_b / d Q = U^-T W_b U^T for the model's normalised rate matrix (see ``dodo_model_chain``) and
-        grad_pi the gradient w.r.t. the root frequencies.  The learnable-GTR step of VI / MAP: the pruning
-        kernel emits d lnL / d P per edge and category, a small chain kernel contracts it on the device."""
+        d lnL_b / d Q = U^-T W_b U^T for the model's normalised rate matrix and grad_pi the gradient w.r.t. the
+        root frequencies.  The learnable-GTR step of VI / MAP in one pruning launch (``dodo_prune_model``): every
+        thread accumulates its pattern's share of W over the edges and categories of its walk.
+        ``via_mats``: the round-1 route (d lnL / d P per edge and category from ``DODO_PRUNE_GMATS``, contracted by
+        ``dodo_model_chain``), kept as the cross-check."""
         with torch.cuda.device(self.device):
             blens_t = blens.to(self.device, dtype=torch.float64)
             if blens_t.dim() == 1:
@@ -234,20 +236,29 @@ class PruneEngine:
             peel_t = peel_t.contiguous()
             if tuple(peel_t.shape[1:]) != (self.S - 1, 3) or peel_t.shape[0] not in (1, B):
                 raise ValueError("peel must have shape (B or 1, S-1, 3)")
-            flags = _lib.PRUNE_GMATS | (_lib.PRUNE_MIX if (mix and K > 1) else 0)
-            plan, ws = self._plan(B, K, flags)
             ll = torch.empty(B, dtype=torch.float64, device=self.device)
-            gP = self._buffer(("gP", B, K), (B, self.E, K, 4, 4))
             gpi = torch.empty((B, 4), dtype=torch.float64, device=self.device)
             gbl = torch.empty((B, self.E), dtype=torch.float64, device=self.device)
             W = torch.empty((B, 4, 4), dtype=torch.float64, device=self.device)
             cm = model.c_struct()
             rates_c = (C.c_double * K)(*rates_arr.tolist())
-            _lib.check(self.lib.dodo_prune(C.byref(plan), C.byref(cm), rates_c, _ptr(self.tipmask), self.L,
-                                           _ptr(self.weights), _ptr(peel_t), int(peel_t.shape[0]), _ptr(blens_t),
-                                           None, _ptr(ws), _ptr(ll), None, _ptr(gP), _ptr(gpi), _stream()))
-            _lib.check(self.lib.dodo_model_chain(C.byref(cm), rates_c, K, _ptr(blens_t), _ptr(gP), B, self.S, _ptr(gbl), _ptr(W),
-                                                 _stream()))
+            if via_mats:
+                flags = _lib.PRUNE_GMATS | (_lib.PRUNE_MIX if (mix and K > 1) else 0)
+                plan, ws = self._plan(B, K, flags)
+                gP = self._buffer(("gP", B, K), (B, self.E, K, 4, 4))
+                _lib.check(self.lib.dodo_prune(C.byref(plan), C.byref(cm), rates_c, _ptr(self.tipmask), self.L,
+                                               _ptr(self.weights), _ptr(peel_t), int(peel_t.shape[0]), _ptr(blens_t),
+                                               None, _ptr(ws), _ptr(ll), None, _ptr(gP), _ptr(gpi), _stream()))
+                _lib.check(self.lib.dodo_model_chain(C.byref(cm), rates_c, K, _ptr(blens_t), _ptr(gP), B, self.S, _ptr(gbl),
+                                                     _ptr(W), _stream()))
+                return dict(lnL=ll, grad_blens=gbl, W=W, grad_pi=gpi)
+            if scale is None:
+                scale = self.S >= 200
+            flags = _lib.PRUNE_GMODEL | (_lib.PRUNE_MIX if (mix and K > 1) else 0) | (_lib.PRUNE_SCALE if scale else 0)
+            plan, ws = self._plan(B, K, flags)
+            _lib.check(self.lib.dodo_prune_model(C.byref(plan), C.byref(cm), rates_c, _ptr(self.tipmask), self.L,
+                                                 _ptr(self.weights), _ptr(peel_t), int(peel_t.shape[0]), _ptr(blens_t),
+                                                 _ptr(ws), _ptr(ll), _ptr(gbl), _ptr(W), _ptr(gpi), _stream()))
             return dict(lnL=ll, grad_blens=gbl, W=W, grad_pi=gpi)
 
     def _buffer(self, key, shape):

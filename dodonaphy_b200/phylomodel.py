@@ -8,6 +8,7 @@ The likelihood kernels never consume P(t) tensors: they form P(t) on the device 
 reference (and its tests, test/test_phylo.py:276-300) keep working; they are 4x4 host arithmetic.
 Priors, file output and the rest of the reference class are outside the hot path.
 """
+import numpy as np
 import torch
 from torch.distributions.transforms import StickBreakingTransform
 
@@ -15,6 +16,67 @@ from .engine import SubstModel
 
 _SIMPLEX = StickBreakingTransform()
 _EYE4 = torch.eye(4, dtype=torch.float64)
+
+
+_IU = np.triu_indices(4, 1)
+
+
+def _stick_np(raw):
+    """StickBreakingTransform (the map behind the reference's unconstrained leaves, phylomodel.py:19-45) and its
+    Jacobian in NumPy: raw (n-1,) -> simplex y (n,), dy/draw (n, n-1).  z_i = sigmoid(raw_i - log(n-1-i)),
+    y_i = z_i prod_{j<i} (1 - z_j), y_n = prod_j (1 - z_j)."""
+    raw = np.asarray(raw, dtype=np.float64)
+    n1 = raw.shape[0]
+    z = 1.0 / (1.0 + np.exp(-(raw - np.log(n1 - np.arange(n1)))))
+    rest = np.concatenate([[1.0], np.cumprod(1.0 - z)])  # rest[i] = prod_{j<i} (1 - z_j)
+    y = np.concatenate([z * rest[:-1], rest[-1:]])
+    J = np.zeros((n1 + 1, n1))
+    dz = z * (1.0 - z)
+    for j in range(n1):
+        J[j, j] = dz[j] * rest[j]
+        J[j + 1:, j] = -y[j + 1:] * z[j]  # d log(1 - z_j) / d raw_j = -z_j for every later factor
+    return y, J
+
+
+def rate_matrix_jacobian_np(raw_rates, raw_freqs):
+    """Host side of the learnable-GTR chain rule, closed form: the normalised rate matrix Q (4,4), pi (4,) and
+    the Jacobian (20, 5 + 3) of [vec(Q), pi] w.r.t. the unconstrained leaves (compute_Q_martix + norm,
+    phylomodel.py:116-128, composed with the stick-breaking maps).  A few microseconds of NumPy instead of an
+    autograd pass over sixteen numbers; pinned to ``rate_matrix_from_raw`` under autograd in the tests."""
+    r, Jr = _stick_np(raw_rates)
+    pi, Jp = _stick_np(raw_freqs)
+    R = np.zeros((4, 4))
+    R[_IU] = r
+    R = R + R.T
+    dR = np.zeros((4, 4, 6))  # d R / d r
+    dR[_IU[0], _IU[1], np.arange(6)] = 1.0
+    dR[_IU[1], _IU[0], np.arange(6)] = 1.0
+    A = R * pi[None, :]  # off-diagonal part of the unnormalised matrix
+    dA_r = dR * pi[None, :, None]
+    dA_p = np.zeros((4, 4, 4))
+    for j in range(4):
+        dA_p[:, j, j] = R[:, j]
+
+    def with_diag(M):  # rows sum to zero
+        M = M.copy()
+        idx = np.arange(4)
+        M[idx, idx] = M[idx, idx] - M.sum(axis=1)
+        return M
+
+    Qt = with_diag(A)
+    dQt_r = np.stack([with_diag(dA_r[:, :, k]) for k in range(6)], axis=-1)
+    dQt_p = np.stack([with_diag(dA_p[:, :, k]) for k in range(4)], axis=-1)
+    norm = -(np.diagonal(Qt) * pi).sum()
+    dn_r = -np.einsum("ik,i->k", dQt_r[np.arange(4), np.arange(4), :], pi)
+    dn_p = -np.einsum("ik,i->k", dQt_p[np.arange(4), np.arange(4), :], pi) - np.diagonal(Qt)
+    Q = Qt / norm
+    dQ_r = dQt_r / norm - Qt[:, :, None] * dn_r[None, None, :] / norm ** 2
+    dQ_p = dQt_p / norm - Qt[:, :, None] * dn_p[None, None, :] / norm ** 2
+    J = np.zeros((20, Jr.shape[1] + Jp.shape[1]))
+    J[:16, :Jr.shape[1]] = dQ_r.reshape(16, 6) @ Jr
+    J[:16, Jr.shape[1]:] = dQ_p.reshape(16, 4) @ Jp
+    J[16:, Jr.shape[1]:] = Jp
+    return Q, pi, J
 
 
 class _SimplexLeaf:

@@ -72,6 +72,8 @@ typedef struct {
 #define DODO_PRUNE_SCALE 4u    /* power-of-two rescaling (bit-identical where the unscaled       */
                                /* computation stays finite)                                       */
 #define DODO_PRUNE_GMATS 8u    /* also produce d lnL / d P[b,e,k,:,:] and d lnL / d pi          */
+#define DODO_PRUNE_GMODEL 16u  /* plan for dodo_prune_model: d lnL / d blens, the 4 x 4 matrix W  */
+                               /* of the model chain rule and d lnL / d pi (implies GRAD)         */
 
 typedef struct {
     int32_t B, S, L, K;
@@ -129,7 +131,22 @@ int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double *d_curvatu
                  int lift, int matsumoto, void *d_ws, const double *d_grad_pdm, double *d_grad_x,
                  double *d_grad_curv, void *stream);
 
-/* Chain rule of a device-formed reversible (GTR) model whose rates and frequencies are being learnt (the
+/* The learnable-GTR step in ONE pruning launch (the reference's `--model GTR` always learns rates and frequencies,
+ * dodonaphy/phylomodel.py:69-74: torch autograd through GTR_p_t :96-114 and calculate_treelikelihood
+ * dodonaphy/phylo.py:132-139, reached from BaseModel.compute_LL dodonaphy/base_model.py:239-247).  `plan` must be made
+ * with DODO_PRUNE_GMODEL, `model` must be an eigen-decomposed model (DODO_MODEL_EIGEN).  Outputs: d_loglik [B],
+ * d_grad_blens [B][2S-2], d_grad_pi [B][4] (w.r.t. the root frequencies) and d_W [B][16] (row-major 4 x 4) with
+ * d lnL_b / d Q = U^-T W_b U^T for the NORMALISED rate matrix Q of `model` at fixed branch lengths; the caller
+ * carries that through Q(rates, freqs) on the host (a 4 x 4 computation).  Every thread accumulates its pattern's
+ * share of W over all edges and categories of its walk; nothing per edge leaves the kernel.  Other arguments as
+ * dodo_prune. */
+int dodo_prune_model(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
+                     const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights, const int64_t *d_peel,
+                     int peel_batch, const double *d_blens, void *d_ws, double *d_loglik, double *d_grad_blens,
+                     double *d_W, double *d_grad_pi, void *stream);
+
+/* The same chain rule from explicit per-edge matrices (kept as the cross-check of dodo_prune_model and for callers
+ * that already hold d lnL / d P): a device-formed reversible (GTR) model whose rates and frequencies are being learnt (the
  * reference's `--model GTR`, dodonaphy/phylomodel.py:69-74: torch autograd through GTR_p_t :96-114 and
  * calculate_treelikelihood, reached from BaseModel.compute_LL dodonaphy/base_model.py:239-247).  Input: d_grad_P
  * [B][2S-2][K][16] from dodo_prune(DODO_PRUNE_GMATS) called with branch lengths (P formed on the device from

@@ -235,3 +235,59 @@ def test_tabulated_recomputed_and_stored_cherries_agree_bit_for_bit(seed):
         assert a[i].item() == pytest.approx(ll.item(), rel=1e-9)
         g = bt.grad.numpy()
         np.testing.assert_allclose(ga[i].cpu().numpy(), g, rtol=1e-9, atol=1e-9 * np.abs(g).max())
+
+
+@pytest.mark.parametrize("S,L,K", [(5, 40, 1), (27, 300, 1), (64, 700, 4), (130, 260, 2), (230, 100, 3)])
+def test_model_gradient_in_one_launch(S, L, K):
+    """The learnable-GTR launch (dodo_prune_model: per-thread accumulation of the 4 x 4 matrix W of the
+    Daleckii-Krein chain rule) against (1) the branch-length kernel (lnL bit for bit, d lnL / d blens 1e-11),
+    (2) the explicit route d lnL / d P per edge -> dodo_model_chain (W, d lnL / d pi: 1e-10 of the largest
+    entry), (3) torch autograd through the oracle's GTR_p_t restatement down to the rate / frequency leaves.
+    Small-table, large-table and rescaled variants, both rate-category semantics."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import phylo
+
+    prob = synth.make_problem(S, L, 3, D=3, seed=500 + S)
+    peels, blens = _nj_batch(prob)
+    eng = _engine(prob["masks"], prob["weights"])
+    m = SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(0.5, K)
+    for mix in ((False, True) if K > 1 else (False,)):
+        for scale in (False, True):
+            new = eng.loglik_model_grad(_dev(peels), _dev(blens), m, rates=rates, mix=mix, scale=scale)
+            ll, g = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=mix, grad=True, scale=scale)
+            assert torch.equal(new["lnL"], ll)
+            _assert_grad_tol(new["grad_blens"].cpu().numpy(), g.cpu().numpy(), 1e-11)
+            if not scale:
+                old = eng.loglik_model_grad(_dev(peels), _dev(blens), m, rates=rates, mix=mix, via_mats=True)
+                for key in ("W", "grad_pi", "grad_blens"):
+                    _assert_grad_tol(new[key].cpu().numpy(), old[key].cpu().numpy(), 1e-10)
+    # autograd through the reference's arithmetic (phylomodel.py:96-114 restated), one sample, down to Q
+    rr = torch.tensor(prob["rates"], requires_grad=True)
+    ff = torch.tensor(prob["freqs"], requires_grad=True)
+    bt = torch.tensor(blens[0])
+    mats = phylo.gtr_p_t_torch(bt[:, None] * torch.tensor(rates)[None, :], rr, ff)
+    ref = phylo.treelikelihood_torch([torch.tensor(phylo.mask_to_partial(x)) for x in prob["masks"]], torch.tensor(prob["weights"]),
+                                     peels[0], mats, ff.detach(), gamma_mix=(K > 1))
+    ref.backward()
+    new = eng.loglik_model_grad(_dev(peels), _dev(blens), m, rates=rates, mix=(K > 1), scale=False)
+    U, Ui = torch.tensor(m.U), torch.tensor(m.Uinv)
+    dQ = Ui.T @ new["W"][0].cpu() @ U.T
+    rr2 = torch.tensor(prob["rates"], requires_grad=True)
+    ff2 = torch.tensor(prob["freqs"], requires_grad=True)
+    iu = torch.triu_indices(4, 4, 1)
+    Q = torch.zeros((4, 4), dtype=torch.float64)
+    Q[iu[0], iu[1]] = rr2
+    Q[iu[1], iu[0]] = rr2
+    Q = Q * ff2.unsqueeze(0)
+    Q = Q + torch.diag(-torch.sum(Q, dim=1))
+    Q = Q / (-torch.sum(torch.diagonal(Q) * ff2))  # phylomodel.py:116-128
+    (Q * dQ).sum().backward()
+    _assert_grad_tol(rr2.grad.numpy(), rr.grad.numpy(), 1e-8)
+    _assert_grad_tol(ff2.grad.numpy(), ff.grad.numpy(), 1e-8)
+
+
+def _assert_grad_tol(ours, ref, tol):
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(ours, ref, rtol=0, atol=tol * scale)
