@@ -48,6 +48,22 @@ __device__ __forceinline__ QKey warp_qmin(QKey v) {
     return v;
 }
 
+// Row prefetch of the streaming scans (general kernels: the matrix lives in HBM and every join reads all of it
+// once).  A scan is one warp per matrix row; its loads are issued a trip at a time (8 per lane), so between trips a
+// warp has nothing in flight and the scan ends up bound by HBM latency, not bandwidth (ncu, 2000 taxa: long-scoreboard
+// stalls 10.8 warps per issue, DRAM 47 %).  The TMA unit's bulk L2 prefetch takes a whole row segment in ONE
+// instruction by one lane -- no registers, no shared memory, no completion barrier: each warp asks for the row it
+// will scan NJ_PF_ROWS rows from now, and the scan's own loads then find their sectors in L2.
+#ifndef NJ_PF_ROWS
+#define NJ_PF_ROWS 0
+#endif
+__device__ __forceinline__ void prefetch_l2_bulk(const double *p, int n_doubles) {
+    if (n_doubles <= 0) return;
+    const unsigned long long a = (unsigned long long)p, a0 = a & ~15ull;  // 16-byte granules; rows are 128-byte aligned
+    const unsigned bytes = ((unsigned)(a - a0) + (unsigned)n_doubles * 8u + 15u) & ~15u;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+}
+
 // Storage scheme of the NJ kernels.  A new node always takes a FRESH slot at the end of the matrix, so
 // slot order == pool order (survivors in their order, then new nodes in creation order) and a row scan
 // in pool order walks memory monotonically.  Every join retires two slots; once the spare slots are
@@ -186,7 +202,16 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
         QKey best;
         best.q = DBL_MAX;
         best.key = ~0ull;
+        auto prefetch_row = [&](int pr) {  // columns pr+1 .. n-1 of pool row pr: slots act[pr+1] .. act[n-1], contiguous
+            if (NJ_PF_ROWS > 0 && lane == 0 && pr < n - 1) {
+                const int s0 = act[pr + 1];
+                prefetch_l2_bulk(Dm + (size_t)act[pr] * ld + s0, act[n - 1] + 1 - s0);
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < NJ_PF_ROWS; ++k) prefetch_row(warp + k * nwarp);
         for (int pa = warp; pa < n - 1; pa += nwarp) {
+            prefetch_row(pa + NJ_PF_ROWS * nwarp);
             const int sa = act[pa];
             const double xa = xs[sa];
             const double *row = Dm + (size_t)sa * ld;
@@ -609,8 +634,14 @@ __device__ bool soft_argmin_two_minima(const SoftCtx &c, double tau, double *sh,
     const double W = 750.0 * tau, Wsure = W * (1.0 + 1e-9);
     double m1 = DBL_MAX, m2 = DBL_MAX;
     int brow = 0, bcol = 0;
+    auto prefetch_row = [&](int pr) {  // columns 0 .. pr-1 of pool row pr: slots 0 .. act[pr-1]
+        if (NJ_PF_ROWS > 0 && lane == 0 && pr < c.n) prefetch_l2_bulk(c.Dm + (size_t)c.act[pr] * c.S, c.act[pr - 1] + 1);
+    };
     auto sweep = [&](auto &&visit) {
+#pragma unroll
+        for (int k = 0; k < NJ_PF_ROWS; ++k) prefetch_row(1 + warp + k * nwarp);
         for (int prow = 1 + warp; prow < c.n; prow += nwarp) {
+            prefetch_row(prow + NJ_PF_ROWS * nwarp);
             const int srow = c.act[prow];
             const double *rowp = c.Dm + (size_t)srow * c.S;
             const double rsr = c.rs[srow];
@@ -1246,34 +1277,66 @@ __global__ void __launch_bounds__(32 * W) nj_soft_lean_kernel(const double *__re
 // (pool order = ascending node id, so ties go to the smaller id pair), running row sums updated in the
 // reference's operation order, the new node's row sum accumulated sequentially in pool order (`ord` keeps the
 // slots sorted by node id).  Asymmetric input or an all-NaN matrix: todo = 1, the general kernel redoes the tree.
+//
+// CL > 1: one tree per thread-block CLUSTER of CL CTAs (a shard of a sharded MCMC run leaves most SMs without a tree:
+// 8 chains on 148 SMs).  The scan -- the issue-bound part of a join -- is split over the CL x W warps of the cluster;
+// every warp writes its (q, d, id pair, slot pair) straight into the exchange buffers of all CL CTAs through
+// distributed shared memory (mapa + st.shared::cluster), ONE cluster barrier (arrive.release / wait.acquire) replaces
+// the block barrier, and every warp folds the CL x W results for itself.  Everything else of a join (new distances,
+// slot move, row sums, the sequential sum) is done redundantly by every CTA on its own copy of the matrix, so no
+// other exchange is needed and the arithmetic -- hence the result -- is the one-CTA kernel's bit for bit.
 constexpr int NJ_HARD_LEAN_MAX = 224;
-__host__ __device__ inline size_t nj_hard_lean_smem_bytes(int S, int W) {
-    return ((size_t)S * (S - 1) / 2 + 1 + 3 * (size_t)S + 2 * (size_t)W + 2) * sizeof(double) +
-           (6 * (size_t)S + 2 * (size_t)W + 4) * sizeof(int);
+__host__ __device__ inline size_t nj_hard_lean_smem_bytes(int S, int W, int CL = 1) {
+    const size_t nx = CL > 1 ? 2 * (size_t)CL * W : (size_t)W;  // exchange buffers are double-buffered across joins
+    return ((size_t)S * (S - 1) / 2 + 1 + 3 * (size_t)S + 2 * nx + 2) * sizeof(double) +
+           (6 * (size_t)S + 2 * nx + 4) * sizeof(int);
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_map(const void *p, unsigned rank) {  // shared::cluster address of p in CTA `rank`
+    unsigned a = (unsigned)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_st(unsigned addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_st(unsigned addr, unsigned v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ int tri_at(int i, int j) { return i > j ? i * (i - 1) / 2 + j : j * (j - 1) / 2 + i; }
 
-template <int W>
+template <int W, int CL>
 __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__restrict__ pdm, int S, double *__restrict__ ws,
                                                             int64_t *__restrict__ peel, double *__restrict__ blens,
                                                             PriorDev prior) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int T = 32 * W;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int TW = W * CL;                           // warps per tree
+    constexpr int NX = CL > 1 ? 2 * TW : W;              // per-warp results (CL > 1: all warps of the cluster, two joins)
+    const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int mw = warp * CL + rank;                     // this warp among the TW warps of the tree (rows interleaved)
     double *tri = reinterpret_cast<double *>(smem_raw);  // [S (S-1) / 2]
     double *xsb = tri + (((size_t)S * (S - 1) / 2 + 1) & ~(size_t)1);  // [2][S] running row sums by slot, double-buffered (16-byte aligned)
     double *newd = xsb + 2 * S;                          // [S] new distances in pool order
-    double *red = newd + S;                              // [2 W] per-warp (q, d)
-    int *sidb = reinterpret_cast<int *>(red + 2 * W + 2);    // [2][S] slot -> node id
+    double *red = newd + S;                              // [2 NX] per-warp (q, d)
+    int *sidb = reinterpret_cast<int *>(red + 2 * NX + 2);   // [2][S] slot -> node id
     int *posb = sidb + 2 * S;                            // [2][S] slot -> pool position
     int *ordb = posb + 2 * S;                            // [2][S] pool position -> slot
-    unsigned *redk = reinterpret_cast<unsigned *>(ordb + 2 * S);  // [2 W] (id pair, slot pair)
+    unsigned *redk = reinterpret_cast<unsigned *>(ordb + 2 * S);  // [2 NX] (id pair, slot pair)
     int *todo = reinterpret_cast<int *>(ws + (size_t)b * nj_ws_doubles(S));
     const double *P = pdm + (size_t)b * S * S;
     int64_t *pl = peel + (size_t)b * (S - 1) * 3;
     double *bl = blens + (size_t)b * (2 * S - 2);
 
-    if (tid == 0) *todo = 0;
+    if (tid == 0 && rank == 0) *todo = 0;
     int asym = 0;
     for (int i = tid; i < S * S; i += T) {
         const int r = i / S, c = i - r * S;
@@ -1292,41 +1355,44 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
             if (j != s) acc = __dadd_rn(acc, row[j]);
         xsb[s] = acc;
     }
-    if (__syncthreads_or(asym)) {
-        if (tid == 0) *todo = 1;
+    if (__syncthreads_or(asym)) {  // (every CTA of a cluster sees the same matrix: they leave together)
+        if (tid == 0 && rank == 0) *todo = 1;
         return;
     }
+    if (CL > 1) cluster_barrier();  // every CTA of the cluster is resident before the first remote store
     int cur = 0;
     for (int n = S; n > 1; --n) {
         const double *xs = xsb + cur * S;
         const int *sid = sidb + cur * S, *pos = posb + cur * S, *ord = ordb + cur * S;
         const int nxt = cur ^ 1;
         const double nm2 = (double)n - 2.0;
-        // ---- first strict minimum of q in pool order (Cpeeler.pyx:58-66); four rows per trip share the column
+        // ---- first strict minimum of q in pool order (Cpeeler.pyx:58-66); RU rows per trip share the column
+        // (a cluster leaves a warp one or two rows per join: there a trip over four rows is mostly masked lanes)
+        constexpr int RU = CL > 1 ? 1 : 4;
         double bq = DBL_MAX, bd = 0.0;
         unsigned bkey = ~0u, bslot = 0u;
-        for (int r0 = 1 + warp; r0 < n; r0 += 4 * W) {
-            double xr[4];
-            int ir[4];
+        for (int r0 = 1 + mw; r0 < n; r0 += RU * TW) {
+            double xr[RU];
+            int ir[RU];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int rj = r0 + j * W;
+            for (int j = 0; j < RU; ++j) {
+                const int rj = r0 + j * TW;
                 xr[j] = rj < n ? xs[rj] : 0.0;
                 ir[j] = rj < n ? sid[rj] : 0;
             }
-            const int rtop = min(r0 + 3 * W, n - 1);
+            const int rtop = min(r0 + (RU - 1) * TW, n - 1);
             for (int c = lane; c < rtop; c += 32) {
                 const double xc = xs[c];
                 const int ic = sid[c];
-                double dv[4];
+                double dv[RU];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rj = r0 + j * W;
+                for (int j = 0; j < RU; ++j) {
+                    const int rj = r0 + j * TW;
                     dv[j] = (rj < n && c < rj) ? tri[rj * (rj - 1) / 2 + c] : 0.0;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rj = r0 + j * W;
+                for (int j = 0; j < RU; ++j) {
+                    const int rj = r0 + j * TW;
                     const bool rfirst = ir[j] < ic;
                     const double xa = rfirst ? xr[j] : xc, xb = rfirst ? xc : xr[j];
                     const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, dv[j]), xa), xb);
@@ -1349,15 +1415,36 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
             const bool take = oq < bq || (oq == bq && ok < bkey);
             bq = take ? oq : bq; bd = take ? od : bd; bkey = take ? ok : bkey; bslot = take ? os : bslot;
         }
-        if (lane == 0) { red[2 * warp] = bq; red[2 * warp + 1] = bd; redk[2 * warp] = bkey; redk[2 * warp + 1] = bslot; }
-        __syncthreads();
-        // every warp folds the W per-warp results for itself: lane w takes entry w, then the same butterfly
-        bq = lane < W ? red[2 * lane] : DBL_MAX;
-        bd = lane < W ? red[2 * lane + 1] : 0.0;
-        bkey = lane < W ? redk[2 * lane] : ~0u;
-        bslot = lane < W ? redk[2 * lane + 1] : 0u;
+        if (CL == 1) {
+            if (lane == 0) { red[2 * warp] = bq; red[2 * warp + 1] = bd; redk[2 * warp] = bkey; redk[2 * warp + 1] = bslot; }
+            __syncthreads();
+            // every warp folds the W per-warp results for itself: lane w takes entry w, then the same butterfly
+            bq = lane < W ? red[2 * lane] : DBL_MAX;
+            bd = lane < W ? red[2 * lane + 1] : 0.0;
+            bkey = lane < W ? redk[2 * lane] : ~0u;
+            bslot = lane < W ? redk[2 * lane + 1] : 0u;
+        } else {
+            // lane l hands this warp's result to CTA l of the cluster (slot `mw` of the buffer of this join's parity);
+            // the release/acquire pair of the cluster barrier orders the remote stores before the reads below
+            const int px = (n & 1) * TW;
+            if (lane < CL) {
+                const unsigned aq = cluster_map(red + 2 * (px + mw), (unsigned)lane);
+                const unsigned ak = cluster_map(redk + 2 * (px + mw), (unsigned)lane);
+                cluster_st(aq, bq); cluster_st(aq + 8u, bd);
+                cluster_st(ak, bkey); cluster_st(ak + 4u, bslot);
+            }
+            cluster_barrier();
+            bq = DBL_MAX; bd = 0.0; bkey = ~0u; bslot = 0u;
 #pragma unroll
-        for (int m = W / 2; m >= 1; m >>= 1) {
+            for (int e = lane; e < TW; e += 32) {
+                const double oq = red[2 * (px + e)], od = red[2 * (px + e) + 1];
+                const unsigned ok = redk[2 * (px + e)], os = redk[2 * (px + e) + 1];
+                const bool take = oq < bq || (oq == bq && ok < bkey);
+                bq = take ? oq : bq; bd = take ? od : bd; bkey = take ? ok : bkey; bslot = take ? os : bslot;
+            }
+        }
+#pragma unroll
+        for (int m = (TW < 32 ? TW : 32) / 2; m >= 1; m >>= 1) {
             const double oq = __shfl_xor_sync(0xffffffffu, bq, m), od = __shfl_xor_sync(0xffffffffu, bd, m);
             const unsigned ok = __shfl_xor_sync(0xffffffffu, bkey, m), os = __shfl_xor_sync(0xffffffffu, bslot, m);
             const bool take = oq < bq || (oq == bq && ok < bkey);
@@ -1366,7 +1453,7 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
         bq = __shfl_sync(0xffffffffu, bq, 0); bd = __shfl_sync(0xffffffffu, bd, 0);
         bkey = __shfl_sync(0xffffffffu, bkey, 0); bslot = __shfl_sync(0xffffffffu, bslot, 0);
         if (bkey == ~0u) {  // all-NaN distances: the general kernel's memory-safe fallback decides
-            if (tid == 0) *todo = 1;
+            if (tid == 0 && rank == 0) *todo = 1;
             return;
         }
         const int n1 = (int)(bkey >> 16), n2 = (int)(bkey & 0xffffu);  // node ids; n1 comes first in the pool
@@ -1410,11 +1497,13 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
                 df = __ddiv_rn(d12, 2.0);
                 dg = df;
             }
-            bl[n1] = fmax(df, DBL_EPSILON);  // Cpeeler.pyx:124
-            bl[n2] = fmax(dg, DBL_EPSILON);
-            pl[(S - n) * 3 + 0] = n1;
-            pl[(S - n) * 3 + 1] = n2;
-            pl[(S - n) * 3 + 2] = parent;
+            if (rank == 0) {
+                bl[n1] = fmax(df, DBL_EPSILON);  // Cpeeler.pyx:124
+                bl[n2] = fmax(dg, DBL_EPSILON);
+                pl[(S - n) * 3 + 0] = n1;
+                pl[(S - n) * 3 + 1] = n2;
+                pl[(S - n) * 3 + 2] = parent;
+            }
             sidb[nxt * S + keep] = parent;
             posb[nxt * S + keep] = n - 2;
             ordb[nxt * S + n - 2] = keep;
@@ -1425,6 +1514,9 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
             double acc = 0.0;
             const int m = n - 2;
             int p = 0;
+#ifdef NJ_TIMING_NO_SEQSUM  // timing experiment only (wrong row sums): what the dependent adds cost
+            p = m > 8 ? ((m - 8) & ~1) : 0;
+#endif
 #pragma unroll 2
             for (; p + 8 <= m; p += 8) {
                 const double2 u0 = *reinterpret_cast<const double2 *>(newd + p);
@@ -1442,7 +1534,7 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
         __syncthreads();
         cur = nxt;
     }
-    if (prior.ln_prior != nullptr && warp == 0) prior_warp(bl, S, prior, b, lane);
+    if (prior.ln_prior != nullptr && warp == 0 && rank == 0) prior_warp(bl, S, prior, b, lane);
 }
 
 // reverse replay: adjoint of blens w.r.t. the input distance matrix
@@ -2081,6 +2173,37 @@ extern "C" int dodo_prior_gamma_dir(const double *d_blens, int B, int S, const d
     return DODO_OK;
 }
 
+// how many clusters of CL CTAs of the 16-warp lean hard kernel the device holds at once (0: this size cannot launch)
+typedef void (*hard_lean_fn_t)(const double *, int, double *, int64_t *, double *, PriorDev);
+static hard_lean_fn_t hard_lean_cluster_fn(int W, int CL) {
+    if (W == 8) return CL == 8 ? nj_hard_lean_kernel<8, 8> : (CL == 4 ? nj_hard_lean_kernel<8, 4> : nj_hard_lean_kernel<8, 2>);
+    return CL == 8 ? nj_hard_lean_kernel<16, 8> : (CL == 4 ? nj_hard_lean_kernel<16, 4> : nj_hard_lean_kernel<16, 2>);
+}
+static int hard_lean_max_clusters(int S, int W, int CL) {
+    static int cache[NJ_HARD_LEAN_MAX + 1][2][9];  // 0 = not asked yet, else 1 + answer
+    int &slot = cache[S][W == 8 ? 0 : 1][CL];
+    if (slot) return slot - 1;
+    hard_lean_fn_t fn = hard_lean_cluster_fn(W, CL);
+    const size_t lsm = nj_hard_lean_smem_bytes(S, W, CL);
+    int n = 0;
+    if (lsm <= 227 * 1024 && (lsm <= 48 * 1024 ||
+                              cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm) == cudaSuccess)) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(148 * CL);
+        cfg.blockDim = dim3(32 * W);
+        cfg.dynamicSmemBytes = lsm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    slot = n + 1;
+    return n;
+}
+
 extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64_t *d_peel, double *d_blens,
                             const dodo_prior_t *prior, void *stream_) {
     DODO_CHECK_ARG(d_pdm && d_ws && d_peel && d_blens, "dodo_nj_hard: NULL argument");
@@ -2098,11 +2221,44 @@ extern "C" int dodo_nj_hard(const double *d_pdm, int B, int S, void *d_ws, int64
             const int w = atoi(e);
             if (w == 8 || w == 16 || w == 32) W = w;
         }
-        const size_t lsm = nj_hard_lean_smem_bytes(S, W);
-        auto fn = W == 8 ? nj_hard_lean_kernel<8> : (W == 16 ? nj_hard_lean_kernel<16> : nj_hard_lean_kernel<32>);
-        if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-        fn<<<B, 32 * W, lsm, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr);
-        DODO_LAUNCH_CHECK();
+        // Few trees on this GPU (a shard of a sharded run, or fewer chains than SMs): a cluster of CL CTAs per tree
+        // splits the scans; trees above 100 taxa only (below, a join is bound by its barriers, not by the scan).
+        // Measured at 200 taxa (profiles/tools/nj_cluster.py, one CTA per tree: 0.94 ms): 8 CTAs of 8 warps 0.68 ms
+        // while the clusters take at most half of the SMs, 4 CTAs of 16 warps 0.73 ms and 2 CTAs 0.85 ms while all
+        // clusters are resident at once -- a second wave of clusters costs more than the split saves.
+        int CL = 1;
+        if (S > 100 && W == 16) {
+            if (B * 16 <= sm_count() && B <= hard_lean_max_clusters(S, 8, 8)) { W = 8; CL = 8; }
+            else if (B <= hard_lean_max_clusters(S, 16, 4)) CL = 4;
+            else if (B <= hard_lean_max_clusters(S, 16, 2)) CL = 2;
+        }
+        if (const char *e = getenv("DODO_NJ_CLUSTER")) {  // tuning sweeps
+            const int c = atoi(e);
+            if ((c == 1 || c == 2 || c == 4 || c == 8) && W <= 16) CL = c;
+        }
+        if (CL > 1) {
+            hard_lean_fn_t fn = hard_lean_cluster_fn(W, CL);
+            const size_t lsm = nj_hard_lean_smem_bytes(S, W, CL);
+            if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)B * CL);
+            cfg.blockDim = dim3(32 * W);
+            cfg.dynamicSmemBytes = lsm;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            DODO_CUDA(cudaLaunchKernelEx(&cfg, fn, d_pdm, S, (double *)d_ws, d_peel, d_blens, pr));
+            count_launch();
+        } else {
+            const size_t lsm = nj_hard_lean_smem_bytes(S, W);
+            hard_lean_fn_t fn = W == 8 ? nj_hard_lean_kernel<8, 1> : (W == 16 ? nj_hard_lean_kernel<16, 1> : nj_hard_lean_kernel<32, 1>);
+            if (lsm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            fn<<<B, 32 * W, lsm, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr);
+            DODO_LAUNCH_CHECK();
+        }
         lean_first = 1;
     }
     nj_hard_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, (double *)d_ws, d_peel, d_blens, pr, lean_first);

@@ -228,6 +228,32 @@ def test_lean_hard_nj_is_bit_identical_to_the_general_kernel(monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("S,B", [(101, 3), (200, 8), (200, 20), (224, 40)])
+def test_hard_nj_on_thread_block_clusters_is_bit_identical(monkeypatch, S, B):
+    """Above 100 taxa and with few trees per GPU one tree is joined by a thread-block CLUSTER (2, 4 or 8 CTAs: the
+    scan split over the cluster, results exchanged through distributed shared memory, one cluster barrier per join).
+    Every cluster size -- forced, and the library's own choice -- must return the one-CTA kernel's peel and branch
+    lengths bit for bit, exact ties (duplicated taxa) included."""
+    from dodonaphy_b200 import engine
+
+    x = np.random.default_rng(100 + S).normal(0, 0.06, (B, S, 3))
+    x[:, 7] = x[:, 3]  # duplicated taxon: q ties broken by node id
+    pdm = engine.pdm_forward(torch.tensor(x).cuda(), -1.0, "numpy")
+    monkeypatch.setenv("DODO_NJ_CLUSTER", "1")
+    p0, b0 = engine.nj_hard(pdm)
+    for cl in ("2", "4", "8", None):
+        if cl is None:
+            monkeypatch.delenv("DODO_NJ_CLUSTER")
+        else:
+            monkeypatch.setenv("DODO_NJ_CLUSTER", cl)
+        p1, b1 = engine.nj_hard(pdm)
+        assert torch.equal(p0, p1) and torch.equal(b0, b1), cl
+    monkeypatch.setenv("DODO_NJ_NO_LEAN", "1")
+    p2, b2 = engine.nj_hard(pdm)
+    assert torch.equal(p0, p2) and torch.equal(b0, b2)
+
+
+@pytest.mark.gpu
 def test_lean_soft_nj_backward_equals_the_replay(monkeypatch):
     """nj_soft_bwd_lean_kernel (trees up to 96 taxa: d blens / d pdm from the bilinear-form structure, one thread per
     matrix entry) against the reverse replay of the joins (nj_soft_bwd_kernel), incl. clamped branches."""
