@@ -1361,8 +1361,23 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
     }
     if (CL > 1) cluster_barrier();  // every CTA of the cluster is resident before the first remote store
     int cur = 0;
+#ifdef NJ_PHASE_CLOCKS  // debugging aid: cycles per phase of a join, summed over the joins, printed by one thread
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
+#define NJ_PHASE(i) do { const long long t__ = clock64(); ph[i] += t__ - tc; tc = t__; } while (0)
+#else
+#define NJ_PHASE(i) do { } while (0)
+#endif
+    // The new node's row sum is a SEQUENTIAL sum in pool order (Cpeeler.pyx:92: one dependent fp64 add per survivor,
+    // ~18 cycles each: 28 % of a join at 200 taxa when it stands alone between two barriers).  It is only needed by
+    // the NEXT join, and there only by the pairs that involve the new node.  So it runs on lane 0 of warp 0 WHILE
+    // the other warps scan the next join's pairs (phase A); the new node's slot `ks` carries the row sum -DBL_MAX
+    // meanwhile, which makes every q that involves it +huge, i.e. never the minimum; after the barrier all threads
+    // visit the n - 1 pairs of the new node with its real row sum (phase B).  Same candidates, same arithmetic.
+    constexpr int WS = W - 1, TWS = WS * CL;             // scanning warps per CTA / per tree (phase A)
+    const int mws = (warp - 1) * CL + rank;
+    int ks = -1, pend = 0;                               // slot of the node the previous join created; its survivors
     for (int n = S; n > 1; --n) {
-        const double *xs = xsb + cur * S;
+        double *xs = xsb + cur * S;
         const int *sid = sidb + cur * S, *pos = posb + cur * S, *ord = ordb + cur * S;
         const int nxt = cur ^ 1;
         const double nm2 = (double)n - 2.0;
@@ -1371,28 +1386,52 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
         constexpr int RU = CL > 1 ? 1 : 4;
         double bq = DBL_MAX, bd = 0.0;
         unsigned bkey = ~0u, bslot = 0u;
-        for (int r0 = 1 + mw; r0 < n; r0 += RU * TW) {
+        if (warp == 0) {
+            if (lane == 0 && ks >= 0) {
+                // the previous join's new node: sequential in pool order (Cpeeler.pyx:92), loads running ahead of the adds
+                double acc = 0.0;
+                const int m = pend;
+                int p = 0;
+#ifdef NJ_TIMING_NO_SEQSUM  // timing experiment only (wrong row sums): what the dependent adds cost
+                p = m > 8 ? ((m - 8) & ~1) : 0;
+#endif
+#pragma unroll 2
+                for (; p + 8 <= m; p += 8) {
+                    const double2 u0 = *reinterpret_cast<const double2 *>(newd + p);
+                    const double2 u1 = *reinterpret_cast<const double2 *>(newd + p + 2);
+                    const double2 u2 = *reinterpret_cast<const double2 *>(newd + p + 4);
+                    const double2 u3 = *reinterpret_cast<const double2 *>(newd + p + 6);
+                    acc = __dadd_rn(acc, u0.x); acc = __dadd_rn(acc, u0.y);
+                    acc = __dadd_rn(acc, u1.x); acc = __dadd_rn(acc, u1.y);
+                    acc = __dadd_rn(acc, u2.x); acc = __dadd_rn(acc, u2.y);
+                    acc = __dadd_rn(acc, u3.x); acc = __dadd_rn(acc, u3.y);
+                }
+                for (; p < m; ++p) acc = __dadd_rn(acc, newd[p]);
+                xs[ks] = acc;
+            }
+        } else
+        for (int r0 = 1 + mws; r0 < n; r0 += RU * TWS) {
             double xr[RU];
             int ir[RU];
 #pragma unroll
             for (int j = 0; j < RU; ++j) {
-                const int rj = r0 + j * TW;
+                const int rj = r0 + j * TWS;
                 xr[j] = rj < n ? xs[rj] : 0.0;
                 ir[j] = rj < n ? sid[rj] : 0;
             }
-            const int rtop = min(r0 + (RU - 1) * TW, n - 1);
+            const int rtop = min(r0 + (RU - 1) * TWS, n - 1);
             for (int c = lane; c < rtop; c += 32) {
                 const double xc = xs[c];
                 const int ic = sid[c];
                 double dv[RU];
 #pragma unroll
                 for (int j = 0; j < RU; ++j) {
-                    const int rj = r0 + j * TW;
+                    const int rj = r0 + j * TWS;
                     dv[j] = (rj < n && c < rj) ? tri[rj * (rj - 1) / 2 + c] : 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < RU; ++j) {
-                    const int rj = r0 + j * TW;
+                    const int rj = r0 + j * TWS;
                     const bool rfirst = ir[j] < ic;
                     const double xa = rfirst ? xr[j] : xc, xb = rfirst ? xc : xr[j];
                     const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, dv[j]), xa), xb);
@@ -1408,6 +1447,31 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
                 }
             }
         }
+        NJ_PHASE(0);
+        if (ks >= 0) {  // ---- phase B: the pairs of the new node, once its row sum is there
+            __syncthreads();
+            const double xk = xs[ks];
+            const int ik = sid[ks];
+            for (int c = rank * T + tid; c < n; c += T * CL) {
+                if (c == ks) continue;
+                const double xc = xs[c];
+                const int ic = sid[c];
+                const double dkc = tri[tri_at(ks, c)];
+                const bool kfirst = ik < ic;
+                const double xa = kfirst ? xk : xc, xb = kfirst ? xc : xk;
+                const double q = __dsub_rn(__dsub_rn(__dmul_rn(nm2, dkc), xa), xb);
+                if (q <= bq) {
+                    const unsigned key = kfirst ? (((unsigned)ik << 16) | (unsigned)ic) : (((unsigned)ic << 16) | (unsigned)ik);
+                    if (q < bq || key < bkey) {
+                        bq = q;
+                        bd = dkc;
+                        bkey = key;
+                        bslot = ((unsigned)max(ks, c) << 16) | (unsigned)min(ks, c);
+                    }
+                }
+            }
+        }
+        NJ_PHASE(6);
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             const double oq = __shfl_xor_sync(0xffffffffu, bq, m), od = __shfl_xor_sync(0xffffffffu, bd, m);
@@ -1415,6 +1479,7 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
             const bool take = oq < bq || (oq == bq && ok < bkey);
             bq = take ? oq : bq; bd = take ? od : bd; bkey = take ? ok : bkey; bslot = take ? os : bslot;
         }
+        NJ_PHASE(1);
         if (CL == 1) {
             if (lane == 0) { red[2 * warp] = bq; red[2 * warp + 1] = bd; redk[2 * warp] = bkey; redk[2 * warp + 1] = bslot; }
             __syncthreads();
@@ -1434,6 +1499,7 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
                 cluster_st(ak, bkey); cluster_st(ak + 4u, bslot);
             }
             cluster_barrier();
+            NJ_PHASE(2);
             bq = DBL_MAX; bd = 0.0; bkey = ~0u; bslot = 0u;
 #pragma unroll
             for (int e = lane; e < TW; e += 32) {
@@ -1452,6 +1518,7 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
         }
         bq = __shfl_sync(0xffffffffu, bq, 0); bd = __shfl_sync(0xffffffffu, bd, 0);
         bkey = __shfl_sync(0xffffffffu, bkey, 0); bslot = __shfl_sync(0xffffffffu, bslot, 0);
+        NJ_PHASE(3);
         if (bkey == ~0u) {  // all-NaN distances: the general kernel's memory-safe fallback decides
             if (tid == 0 && rank == 0) *todo = 1;
             return;
@@ -1485,6 +1552,7 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
             ordb[nxt * S + pc] = dx;
             newd[pc] = dist;  // dense, in pool order: summed sequentially below
         }
+        NJ_PHASE(4);
         if (tid == 32 % T) {
             // branch lengths (Cpeeler.pyx:98-112) with the joined nodes' row sums as they stand
             double df, dg;
@@ -1507,33 +1575,21 @@ __global__ void __launch_bounds__(32 * W) nj_hard_lean_kernel(const double *__re
             sidb[nxt * S + keep] = parent;
             posb[nxt * S + keep] = n - 2;
             ordb[nxt * S + n - 2] = keep;
+            xsb[nxt * S + keep] = -DBL_MAX;  // until the next join's phase A has summed the new row
         }
         __syncthreads();
-        if (tid == 0) {
-            // new node's row sum: sequential in pool order (Cpeeler.pyx:92), loads running ahead of the adds
-            double acc = 0.0;
-            const int m = n - 2;
-            int p = 0;
-#ifdef NJ_TIMING_NO_SEQSUM  // timing experiment only (wrong row sums): what the dependent adds cost
-            p = m > 8 ? ((m - 8) & ~1) : 0;
-#endif
-#pragma unroll 2
-            for (; p + 8 <= m; p += 8) {
-                const double2 u0 = *reinterpret_cast<const double2 *>(newd + p);
-                const double2 u1 = *reinterpret_cast<const double2 *>(newd + p + 2);
-                const double2 u2 = *reinterpret_cast<const double2 *>(newd + p + 4);
-                const double2 u3 = *reinterpret_cast<const double2 *>(newd + p + 6);
-                acc = __dadd_rn(acc, u0.x); acc = __dadd_rn(acc, u0.y);
-                acc = __dadd_rn(acc, u1.x); acc = __dadd_rn(acc, u1.y);
-                acc = __dadd_rn(acc, u2.x); acc = __dadd_rn(acc, u2.y);
-                acc = __dadd_rn(acc, u3.x); acc = __dadd_rn(acc, u3.y);
-            }
-            for (; p < m; ++p) acc = __dadd_rn(acc, newd[p]);
-            xsb[nxt * S + keep] = acc;
-        }
-        __syncthreads();
+        NJ_PHASE(5);
+        ks = keep;
+        pend = n - 2;
+        NJ_PHASE(7);
         cur = nxt;
     }
+#ifdef NJ_PHASE_CLOCKS
+    if (tid == 0 && blockIdx.x == 0)
+        printf("nj_hard_lean W=%d CL=%d S=%d cycles: scan %lld | butterfly %lld | exchange+barrier %lld | fold %lld | update %lld | "
+               "blens+sync %lld | phase B (incl. wait for the row sum) %lld | - %lld\n", W, CL, S, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+#endif
+#undef NJ_PHASE
     if (prior.ln_prior != nullptr && warp == 0 && rank == 0) prior_warp(bl, S, prior, b, lane);
 }
 
