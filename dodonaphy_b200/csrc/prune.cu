@@ -33,6 +33,7 @@ constexpr int MAX_K = 8;
 struct ModelDev {
     double U[16], Uinv[16], lam[4], Q[16], pi[4];
     double rates[MAX_K];
+    double rlam[MAX_K][4];  // rates[k] * lam[m] (model-gradient launches)
     int kind;
 };
 
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                 V4 *scr = scr0 + (size_t)k * (S - 1) * npt;
                 int *cscr = SCALE ? cscr0 + (size_t)k * (S - 1) * npt : nullptr;
                 const double rate_k = md.rates[k];
-                const double rl[4] = {rate_k * md.lam[0], rate_k * md.lam[1], rate_k * md.lam[2], rate_k * md.lam[3]};
+                const double rl[4] = {md.rlam[k][0], md.rlam[k][1], md.rlam[k][2], md.rlam[k][3]};
                 double sc0 = 0.0;
                 V4 Wv[NP];
                 int we[NP];  // true w = Wv * 2^(256 we)
@@ -1537,6 +1538,8 @@ static int prune_launch(const dodo_prune_plan_t *plan, const dodo_model_t *model
     memcpy(md.pi, model->pi, sizeof(md.pi));
     md.kind = model->kind;
     for (int k = 0; k < MAX_K; ++k) md.rates[k] = (k < K) ? (rates ? rates[k] : 1.0) : 0.0;
+    for (int k = 0; k < MAX_K; ++k)
+        for (int m = 0; m < 4; ++m) md.rlam[k][m] = md.rates[k] * md.lam[m];
 
     const int pmode = d_P_in != nullptr ? PM_GENERIC
                       : (model->kind == DODO_MODEL_JC69 ? PM_JC
