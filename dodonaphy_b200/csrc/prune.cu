@@ -626,25 +626,28 @@ __device__ __forceinline__ V4 matvec_c(const double *M, const V4 &v) {  // M v
               fma(M[11], v.d, fma(M[10], v.c, fma(M[9], v.b, M[8] * v.a))),
               fma(M[15], v.d, fma(M[14], v.c, fma(M[13], v.b, M[12] * v.a)))};
 }
+// The eigenvalue 0 of a rate matrix sits LAST here (the host permutes the eigen-system if need be): its right
+// eigenvector is the constant vector, so column 3 of W only ever multiplies the ROW SUMS of a perturbation dQ
+// (d lnL / d Q = U^-T W U^T, U^T[3, :] = const), which are zero for every rate matrix.  That column is not
+// accumulated: 12 accumulators instead of 16, bt needs three components, and r_k lam_3 = 0 drops out of d/dt.
 template <bool SMALL>
 __device__ __forceinline__ double model_edge(const ModelDev &md, const double *Phi, const V4 &u, const V4 &msg,
-                                             const double (&rl)[4], const double sf, double (&W)[16]) {
+                                             const double (&rl)[4], const double sf, double (&W)[12]) {
     V4 a = matvec_cT(md.U, u);
     a = V4{a.a * sf, a.b * sf, a.c * sf, a.d * sf};  // sf: exact power of two (1 without rescaling)
-    const V4 bt = matvec_c(md.Uinv, msg);
+    const double *M = md.Uinv;
+    const double b0 = fma(M[3], msg.d, fma(M[2], msg.c, fma(M[1], msg.b, M[0] * msg.a)));
+    const double b1 = fma(M[7], msg.d, fma(M[6], msg.c, fma(M[5], msg.b, M[4] * msg.a)));
+    const double b2 = fma(M[11], msg.d, fma(M[10], msg.c, fma(M[9], msg.b, M[8] * msg.a)));
     V4 ph = ld4t<SMALL, 0>(Phi);
-    W[0] = fma(ph.a, a.a * bt.a, W[0]); W[1] = fma(ph.b, a.a * bt.b, W[1]);
-    W[2] = fma(ph.c, a.a * bt.c, W[2]); W[3] = fma(ph.d, a.a * bt.d, W[3]);
+    W[0] = fma(ph.a, a.a * b0, W[0]); W[1] = fma(ph.b, a.a * b1, W[1]); W[2] = fma(ph.c, a.a * b2, W[2]);
     ph = ld4t<SMALL, 4>(Phi);
-    W[4] = fma(ph.a, a.b * bt.a, W[4]); W[5] = fma(ph.b, a.b * bt.b, W[5]);
-    W[6] = fma(ph.c, a.b * bt.c, W[6]); W[7] = fma(ph.d, a.b * bt.d, W[7]);
+    W[3] = fma(ph.a, a.b * b0, W[3]); W[4] = fma(ph.b, a.b * b1, W[4]); W[5] = fma(ph.c, a.b * b2, W[5]);
     ph = ld4t<SMALL, 8>(Phi);
-    W[8] = fma(ph.a, a.c * bt.a, W[8]); W[9] = fma(ph.b, a.c * bt.b, W[9]);
-    W[10] = fma(ph.c, a.c * bt.c, W[10]); W[11] = fma(ph.d, a.c * bt.d, W[11]);
+    W[6] = fma(ph.a, a.c * b0, W[6]); W[7] = fma(ph.b, a.c * b1, W[7]); W[8] = fma(ph.c, a.c * b2, W[8]);
     ph = ld4t<SMALL, 12>(Phi);
-    W[12] = fma(ph.a, a.d * bt.a, W[12]); W[13] = fma(ph.b, a.d * bt.b, W[13]);
-    W[14] = fma(ph.c, a.d * bt.c, W[14]); W[15] = fma(ph.d, a.d * bt.d, W[15]);
-    return fma(rl[3], a.d * bt.d, fma(rl[2], a.c * bt.c, fma(rl[1], a.b * bt.b, rl[0] * (a.a * bt.a))));
+    W[9] = fma(ph.a, a.d * b0, W[9]); W[10] = fma(ph.b, a.d * b1, W[10]); W[11] = fma(ph.c, a.d * b2, W[11]);
+    return fma(rl[2], a.c * b2, fma(rl[1], a.b * b1, rl[0] * (a.a * b0)));
 }
 
 enum { PM_GENERIC = 0, PM_JC = 1, PM_EIG = 2 };
@@ -796,9 +799,9 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
             tm[q] = A.tipmask + (valid ? p : A.L - 1);
         }
         const double *tab_b = A.tab + (size_t)b * K * tabn;
-        double Wm[16];  // GMODEL: this thread's share of W, over every edge and category of the walk (else unused)
+        double Wm[12];  // GMODEL: this thread's share of W (columns 0..2), over every edge and category of the walk
 #pragma unroll
-        for (int i = 0; i < 16; ++i) Wm[i] = 0.0;
+        for (int i = 0; i < 12; ++i) Wm[i] = 0.0;
         __syncthreads();
         if (GMODEL && lane < 4) smd[o_wred + warp * 20u + 16u + lane] = 0.0;  // d lnL / d pi of this warp
         {
@@ -1201,7 +1204,10 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                 gq[0] = gpi0; gq[1] = gpi1; gq[2] = gpi2; gq[3] = gpi3;
             }
         }
-        if (GMODEL) reduce16_store(Wm, &smd[o_wred + warp * 20u], lane);
+        if (GMODEL) {  // [m][n] with n < 3 -> the 4 x 4 slot layout of the per-warp buffer (column 3 stays zero)
+            const double x16[16] = {Wm[0], Wm[1], Wm[2], 0.0, Wm[3], Wm[4], Wm[5], 0.0, Wm[6], Wm[7], Wm[8], 0.0, Wm[9], Wm[10], Wm[11], 0.0};
+            reduce16_store(x16, &smd[o_wred + warp * 20u], lane);
+        }
         __syncthreads();
         if (tid == 0) {
             double s = 0.0;
@@ -1287,15 +1293,19 @@ __global__ void prune_reduce_gmats_kernel(const double *__restrict__ gm_part, co
 }
 
 // model-gradient launches: W [B][16] and d lnL / d pi [B][4] from the per-item partials, tiles in index order
-__global__ void prune_reduce_model_kernel(const double *__restrict__ part, int B, int n_tiles, double *__restrict__ W,
-                                          double *__restrict__ grad_pi) {
+// (W comes back in the caller's eigenvector order: `zero` = the position of the eigenvalue 0 there, swapped with 3 here)
+__global__ void prune_reduce_model_kernel(const double *__restrict__ part, int B, int n_tiles, int zero,
+                                          double *__restrict__ W, double *__restrict__ grad_pi) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= B * 20) return;
     const int b = gid / 20, i = gid - b * 20;
     double s = 0.0;
     for (int t = 0; t < n_tiles; ++t) s += part[((size_t)b * n_tiles + t) * 20 + i];
-    if (i < 16) W[(size_t)b * 16 + i] = s;
-    else grad_pi[(size_t)b * 4 + (i - 16)] = s;
+    if (i < 16) {
+        const int m = i >> 2, n = i & 3;
+        const int pm = m == 3 ? zero : (m == zero ? 3 : m), pn = n == 3 ? zero : (n == zero ? 3 : n);
+        W[(size_t)b * 16 + pm * 4 + pn] = s;
+    } else grad_pi[(size_t)b * 4 + (i - 16)] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1538,6 +1548,21 @@ static int prune_launch(const dodo_prune_plan_t *plan, const dodo_model_t *model
     memcpy(md.pi, model->pi, sizeof(md.pi));
     md.kind = model->kind;
     for (int k = 0; k < MAX_K; ++k) md.rates[k] = (k < K) ? (rates ? rates[k] : 1.0) : 0.0;
+    int zero = 3;
+    if (gm) {  // the eigenvalue 0 goes last (see model_edge); W is handed back in the caller's order
+        double big = 0.0;
+        for (int m = 0; m < 4; ++m) big = fmax(big, fabs(md.lam[m]));
+        for (int m = 0; m < 4; ++m)
+            if (fabs(md.lam[m]) < fabs(md.lam[zero])) zero = m;
+        DODO_CHECK_ARG(fabs(md.lam[zero]) <= 1e-9 * big, "dodo_prune_model: the model has no zero eigenvalue (not a rate matrix)");
+        if (zero != 3) {
+            for (int i = 0; i < 4; ++i) {
+                const double u = md.U[i * 4 + zero]; md.U[i * 4 + zero] = md.U[i * 4 + 3]; md.U[i * 4 + 3] = u;
+                const double v = md.Uinv[zero * 4 + i]; md.Uinv[zero * 4 + i] = md.Uinv[3 * 4 + i]; md.Uinv[3 * 4 + i] = v;
+            }
+            const double l = md.lam[zero]; md.lam[zero] = md.lam[3]; md.lam[3] = l;
+        }
+    }
     for (int k = 0; k < MAX_K; ++k)
         for (int m = 0; m < 4; ++m) md.rlam[k][m] = md.rates[k] * md.lam[m];
 
@@ -1610,7 +1635,7 @@ static int prune_launch(const dodo_prune_plan_t *plan, const dodo_model_t *model
         DODO_LAUNCH_CHECK();
     }
     if (gm) {
-        prune_reduce_model_kernel<<<(B * 20 + 127) / 128, 128, 0, stream>>>(A.gm_part, B, plan->n_tiles, d_W, d_grad_pi);
+        prune_reduce_model_kernel<<<(B * 20 + 127) / 128, 128, 0, stream>>>(A.gm_part, B, plan->n_tiles, zero, d_W, d_grad_pi);
         DODO_LAUNCH_CHECK();
     }
     return DODO_OK;

@@ -136,10 +136,11 @@ int dodo_pdm_bwd(const double *d_x, int B, int S, int D, const double *d_curvatu
  * dodonaphy/phylo.py:132-139, reached from BaseModel.compute_LL dodonaphy/base_model.py:239-247).  `plan` must be made
  * with DODO_PRUNE_GMODEL, `model` must be an eigen-decomposed model (DODO_MODEL_EIGEN).  Outputs: d_loglik [B],
  * d_grad_blens [B][2S-2], d_grad_pi [B][4] (w.r.t. the root frequencies) and d_W [B][16] (row-major 4 x 4) with
- * d lnL_b / d Q = U^-T W_b U^T for the NORMALISED rate matrix Q of `model` at fixed branch lengths; the caller
- * carries that through Q(rates, freqs) on the host (a 4 x 4 computation).  Every thread accumulates its pattern's
- * share of W over all edges and categories of its walk; nothing per edge leaves the kernel.  Other arguments as
- * dodo_prune. */
+ * d lnL_b / d Q = U^-T W_b U^T for the NORMALISED rate matrix Q of `model` at fixed branch lengths, for every
+ * perturbation dQ with zero row sums (any change of a rate matrix): the column of W that belongs to the eigenvalue 0
+ * only multiplies the row sums of dQ and is returned as zero.  The caller carries W through Q(rates, freqs) on the
+ * host (a 4 x 4 computation).  Every thread accumulates its pattern's share of W over all edges and categories of
+ * its walk; nothing per edge leaves the kernel.  Other arguments as dodo_prune. */
 int dodo_prune_model(const dodo_prune_plan_t *plan, const dodo_model_t *model, const double *rates,
                      const uint8_t *d_tipmask, int64_t ld_mask, const double *d_weights, const int64_t *d_peel,
                      int peel_batch, const double *d_blens, void *d_ws, double *d_loglik, double *d_grad_blens,

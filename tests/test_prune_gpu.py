@@ -261,8 +261,18 @@ def test_model_gradient_in_one_launch(S, L, K):
             _assert_grad_tol(new["grad_blens"].cpu().numpy(), g.cpu().numpy(), 1e-11)
             if not scale:
                 old = eng.loglik_model_grad(_dev(peels), _dev(blens), m, rates=rates, mix=mix, via_mats=True)
-                for key in ("W", "grad_pi", "grad_blens"):
+                for key in ("grad_pi", "grad_blens"):
                     _assert_grad_tol(new[key].cpu().numpy(), old[key].cpu().numpy(), 1e-10)
+                # W: all but the column of the eigenvalue 0 (eigh: the last), which only meets the row sums of dQ
+                _assert_grad_tol(new["W"][..., :3].cpu().numpy(), old["W"][..., :3].cpu().numpy(), 1e-10)
+                assert float(new["W"][..., 3].abs().max()) == 0.0
+                assert abs(m.lam[3]) < 1e-12
+    # an eigen-system handed over in another order (zero eigenvalue first): W comes back in that order
+    perm = [3, 0, 1, 2]
+    m2 = SubstModel(m.kind, m.U[:, perm], m.lam[perm], m.Uinv[perm, :], m.Q, m.pi)
+    w1 = eng.loglik_model_grad(_dev(peels), _dev(blens), m, rates=rates, mix=(K > 1), scale=False)["W"].cpu().numpy()
+    w2 = eng.loglik_model_grad(_dev(peels), _dev(blens), m2, rates=rates, mix=(K > 1), scale=False)["W"].cpu().numpy()
+    _assert_grad_tol(w2, w1[:, perm][:, :, perm], 1e-12)
     # autograd through the reference's arithmetic (phylomodel.py:96-114 restated), one sample, down to Q
     rr = torch.tensor(prob["rates"], requires_grad=True)
     ff = torch.tensor(prob["freqs"], requires_grad=True)
