@@ -218,10 +218,10 @@ __global__ void __launch_bounds__(1024, 1) nj_hard_kernel(const double *__restri
             int pb = pa + 1 + lane;
             // HARD_MLP independent loads in flight per lane (the scan is otherwise latency-bound)
             for (; pb + 32 * (HARD_MLP - 1) < n; pb += 32 * HARD_MLP) {
-                int sb[HARD_MLP];
+                unsigned sb[HARD_MLP];  // unsigned: one IMAD.WIDE per address instead of a sign-extended 64-bit add
                 double d[HARD_MLP];
 #pragma unroll
-                for (int k = 0; k < HARD_MLP; ++k) sb[k] = act[pb + 32 * k];
+                for (int k = 0; k < HARD_MLP; ++k) sb[k] = (unsigned)act[pb + 32 * k];
 #pragma unroll
                 for (int k = 0; k < HARD_MLP; ++k) d[k] = row[sb[k]];
 #pragma unroll
@@ -626,6 +626,7 @@ __device__ bool soft_argmin_fast(const SoftCtx &c, double tau, double *sh, doubl
 #ifndef SOFT_MLP
 #define SOFT_MLP 8
 #endif
+template <bool SYM>  // SYM: the matrix is symmetric bit for bit (compile-time: the per-entry test and the transposed load drop out of the scan)
 __device__ bool soft_argmin_two_minima(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
     __shared__ double t_m1[32], t_m2[32], t_cs[CAND_CAP], t_cf[CAND_CAP];
     __shared__ int t_row[32], t_col[32], t_n;
@@ -655,7 +656,20 @@ __device__ bool soft_argmin_two_minima(const SoftCtx &c, double tau, double *sh,
             // of single loads was 15 % of the stall samples at 2000 taxa, one dependent L2/HBM latency per trip
             // (148 trees: 476 -> 427 ms; costs ~10 % at a few hundred taxa, where the lean kernel or the hard
             // variant are the ones in use)
-            for (int pcol = lane; pcol < prow; pcol += 32 * SOFT_MLP) {
+            // Full trips carry no predicates and index with unsigned slots (one IMAD.WIDE per address instead of a
+            // sign-extended 64-bit add); only the last trip of a row is predicated.
+            int pcol = lane;
+            for (; pcol + 32 * (SOFT_MLP - 1) < prow; pcol += 32 * SOFT_MLP) {
+                unsigned sc[SOFT_MLP];
+                double d[SOFT_MLP];
+#pragma unroll
+                for (int k = 0; k < SOFT_MLP; ++k) sc[k] = (unsigned)c.act[pcol + 32 * k];
+#pragma unroll
+                for (int k = 0; k < SOFT_MLP; ++k) d[k] = rowp[sc[k]];
+#pragma unroll
+                for (int k = 0; k < SOFT_MLP; ++k) entry((int)sc[k], d[k], SYM ? d[k] : c.Dm[(size_t)sc[k] * c.S + srow]);
+            }
+            if (pcol < prow) {
                 int sc[SOFT_MLP];
                 double d[SOFT_MLP];
 #pragma unroll
@@ -664,7 +678,7 @@ __device__ bool soft_argmin_two_minima(const SoftCtx &c, double tau, double *sh,
                 for (int k = 0; k < SOFT_MLP; ++k) d[k] = sc[k] >= 0 ? rowp[sc[k]] : 0.0;
 #pragma unroll
                 for (int k = 0; k < SOFT_MLP; ++k)
-                    if (sc[k] >= 0) entry(sc[k], d[k], c.symmetric ? d[k] : c.Dm[(size_t)sc[k] * c.S + srow]);
+                    if (sc[k] >= 0) entry(sc[k], d[k], SYM ? d[k] : c.Dm[(size_t)sc[k] * c.S + srow]);
             }
         }
     };
@@ -723,7 +737,8 @@ __device__ bool soft_argmin_two_minima(const SoftCtx &c, double tau, double *sh,
 template <int MODE>
 __device__ void soft_argmin_block(const SoftCtx &c, double tau, double *sh, double &idx_out, bool &guard_ok) {
     if (MODE == 0) {
-        if (soft_argmin_two_minima(c, tau, sh, idx_out, guard_ok)) return;
+        if (c.symmetric ? soft_argmin_two_minima<true>(c, tau, sh, idx_out, guard_ok)
+                        : soft_argmin_two_minima<false>(c, tau, sh, idx_out, guard_ok)) return;
     } else if (soft_argmin_fast<MODE>(c, tau, sh, idx_out, guard_ok)) return;
     constexpr bool FULL = MODE != 0;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -822,7 +837,10 @@ __device__ __forceinline__ void dd_add_dd(double &hi, double &lo, double xh, dou
     lo = __dsub_rn(e, __dsub_rn(hi, s));
 }
 
-__global__ void __launch_bounds__(1024, 1) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
+#ifndef NJ_SOFT_MAXT
+#define NJ_SOFT_MAXT 1024  // tuning: a smaller bound gives the scan more registers per thread (more loads in flight per lane)
+#endif
+__global__ void __launch_bounds__(NJ_SOFT_MAXT, 1) nj_soft_kernel(const double *__restrict__ pdm, int S, double tau, int full,
                                                        double *__restrict__ ws, int64_t *__restrict__ peel,
                                                        double *__restrict__ blens, int32_t *__restrict__ flags,
                                                        PriorDev prior, int lean_first) {
@@ -2349,7 +2367,7 @@ extern "C" int dodo_nj_soft(const double *d_pdm, int B, int S, double tau, void 
         DODO_LAUNCH_CHECK();
         lean_first = 1;
     }
-    nj_soft_kernel<<<B, nj_threads(S, B), smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags, pr,
+    nj_soft_kernel<<<B, nj_threads(S, B) < NJ_SOFT_MAXT ? nj_threads(S, B) : NJ_SOFT_MAXT, smem, stream>>>(d_pdm, S, t, full, (double *)d_ws, d_peel, d_blens, d_flags, pr,
                                                           lean_first);
     DODO_LAUNCH_CHECK();
     return DODO_OK;
