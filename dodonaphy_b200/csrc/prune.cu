@@ -205,10 +205,11 @@ __global__ void transition_kernel(ModelDev md, const double *__restrict__ blens,
         for (int m = 0; m < 4; ++m) {
             double row[4];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            for (int n = 0; n < 3; ++n) {
                 const double d = fmin((md.lam[m] - md.lam[n]) * tau, 700.0);
                 row[n] = (m == n) ? tau : tau * (fabs(d) < 1e-8 ? 1.0 + 0.5 * d : expm1(d) / d);
             }
+            row[3] = exp(md.lam[m] * tau);  // column 3 of Phi' is never used (model_edge): it carries e_m for P^T u = U^-T (e o a)
             ph[2 * m] = make_double2(row[0], row[1]);
             ph[2 * m + 1] = make_double2(row[2], row[3]);
         }
@@ -632,21 +633,27 @@ __device__ __forceinline__ V4 matvec_c(const double *M, const V4 &v) {  // M v
 // accumulated: 12 accumulators instead of 16, bt needs three components, and r_k lam_3 = 0 drops out of d/dt.
 template <bool SMALL>
 __device__ __forceinline__ double model_edge(const ModelDev &md, const double *Phi, const V4 &u, const V4 &msg,
-                                             const double (&rl)[4], const double sf, double (&W)[12]) {
+                                             const double (&rl)[4], const double sf, double (&W)[12], V4 &z) {
     V4 a = matvec_cT(md.U, u);
+    const V4 a0 = a;
     a = V4{a.a * sf, a.b * sf, a.c * sf, a.d * sf};  // sf: exact power of two (1 without rescaling)
     const double *M = md.Uinv;
     const double b0 = fma(M[3], msg.d, fma(M[2], msg.c, fma(M[1], msg.b, M[0] * msg.a)));
     const double b1 = fma(M[7], msg.d, fma(M[6], msg.c, fma(M[5], msg.b, M[4] * msg.a)));
     const double b2 = fma(M[11], msg.d, fma(M[10], msg.c, fma(M[9], msg.b, M[8] * msg.a)));
+    // z = e o (U^T u): the downward message of an internal edge is P^T u = U^-T z -- no second pass over a table of P
     V4 ph = ld4t<SMALL, 0>(Phi);
     W[0] = fma(ph.a, a.a * b0, W[0]); W[1] = fma(ph.b, a.a * b1, W[1]); W[2] = fma(ph.c, a.a * b2, W[2]);
+    z.a = ph.d * a0.a;
     ph = ld4t<SMALL, 4>(Phi);
     W[3] = fma(ph.a, a.b * b0, W[3]); W[4] = fma(ph.b, a.b * b1, W[4]); W[5] = fma(ph.c, a.b * b2, W[5]);
+    z.b = ph.d * a0.b;
     ph = ld4t<SMALL, 8>(Phi);
     W[6] = fma(ph.a, a.c * b0, W[6]); W[7] = fma(ph.b, a.c * b1, W[7]); W[8] = fma(ph.c, a.c * b2, W[8]);
+    z.c = ph.d * a0.c;
     ph = ld4t<SMALL, 12>(Phi);
     W[9] = fma(ph.a, a.d * b0, W[9]); W[10] = fma(ph.b, a.d * b1, W[10]); W[11] = fma(ph.c, a.d * b2, W[11]);
+    z.d = ph.d * a0.d;
     return fma(rl[2], a.c * b2, fma(rl[1], a.b * b1, rl[0] * (a.a * b0)));
 }
 
@@ -1014,6 +1021,9 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
 #ifndef DODO_GM_PAIR
 #define DODO_GM_PAIR 0
 #endif
+#ifndef DODO_GM_EIG_DOWN  // model-gradient sweep: downward messages as U^-T (e o U^T u), U^T u being there already
+#define DODO_GM_EIG_DOWN 1
+#endif
                 constexpr bool PAIR = DODO_PRUNE_PAIR_REDUCE && SMALL && (!GMODEL || DODO_GM_PAIR);
                 double pend_ga = 0.0, pend_gb = 0.0;
                 int pend_x = 0, pend_y = 0;
@@ -1067,6 +1077,7 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                         if (o.y >= 0) ab_b = load_ab<SMALL>(tab_at((unsigned)o.y * 16u));
                     }
                     V4 av[NP], bv[NP], ua[NP], ub[NP];
+                    V4 za = V4{0, 0, 0, 0}, zb = za;  // GMODEL: e o (U^T u) of the two child edges
                     int ac[NP], bcn[NP];
                     double ga = 0.0, gb = 0.0;
 #pragma unroll
@@ -1084,8 +1095,8 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                         double gaq, gbq;
                         if (GMODEL) {
                             const double sf = SCALE ? pow2_256(we[q] - ac[q] - bcn[q]) : 1.0;
-                            gaq = model_edge<SMALL>(md, tab_at(o_X + (unsigned)(o.x < 0 ? ~o.x : o.x + S) * 16u), ua[q], av[q], rl, sf, Wm);
-                            gbq = model_edge<SMALL>(md, tab_at(o_X + (unsigned)(o.y < 0 ? ~o.y : o.y + S) * 16u), ub[q], bv[q], rl, sf, Wm);
+                            gaq = model_edge<SMALL>(md, tab_at(o_X + (unsigned)(o.x < 0 ? ~o.x : o.x + S) * 16u), ua[q], av[q], rl, sf, Wm, za);
+                            gbq = model_edge<SMALL>(md, tab_at(o_X + (unsigned)(o.y < 0 ? ~o.y : o.y + S) * 16u), ub[q], bv[q], rl, sf, Wm, zb);
                             if (i == nops) {  // root: d lnL / d pi_j = sum_k sc_k (msg_a * msg_b)_j
                                 const double s2 = sc0 * sf;
                                 const double g4 = warp_sum4(s2 * (av[q].a * bv[q].a), s2 * (av[q].b * bv[q].b),
@@ -1121,7 +1132,8 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                     }
                     if (o.x >= 0) {
                         V4 wa[NP];
-                        if (pmode == PM_JC) matvec_jc_ab<NP>(ab_a, ua, wa);
+                        if (GMODEL && DODO_GM_EIG_DOWN) wa[0] = matvec_cT(md.Uinv, za);
+                        else if (pmode == PM_JC) matvec_jc_ab<NP>(ab_a, ua, wa);
                         else apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.x * 16u), ua, wa);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
@@ -1132,7 +1144,8 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                         }
                     }
                     if (o.y >= 0) {  // the next join (in this reversed order) is exactly node b
-                        if (pmode == PM_JC) matvec_jc_ab<NP>(ab_b, ub, Wv);
+                        if (GMODEL && DODO_GM_EIG_DOWN) Wv[0] = matvec_cT(md.Uinv, zb);
+                        else if (pmode == PM_JC) matvec_jc_ab<NP>(ab_b, ub, Wv);
                         else apply_P<SMALL, NP, true>(pmode, md, tab_at((unsigned)o.y * 16u), ub, Wv);
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
