@@ -83,7 +83,8 @@ class _BatchedLogLikModel(torch.autograd.Function):
         out = hot.resolve(x, out, model=True)
         ctx.hot, ctx.kappa, ctx.cshape = hot, hot.curvature, curvature_leaf.shape
         ctx.devs = (locs.device, curvature_leaf.device)
-        ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens", "grad_prior", "W", "grad_pi") if k in out}
+        ctx.x, ctx.dec = x, {k: out[k] for k in ("peel", "flags", "slots", "tape", "grad_blens", "grad_prior") if k in out}
+        ctx.wg = torch.cat([out["W"].reshape(-1, 16), out["grad_pi"]], dim=1)  # (B, 20): one contraction in backward
         ctx.model = hot.model
         ctx.mark_non_differentiable(out["peel"])
         hot.last_decode = (x, out["peel"], out["flags"])  # for the Jacobian term of the same step (vi.py:376-387)
@@ -99,7 +100,7 @@ class _BatchedLogLikModel(torch.autograd.Function):
         if g_prior is not None and ctx.dec.get("grad_prior") is not None:
             gb = gb + g_prior.to(x.device).reshape(-1, 1) * ctx.dec["grad_prior"]
         # model leaves: sum_b w_b (U^-T W_b U^T) : dQ  +  sum_b w_b grad_pi_b : d pi  -- 20 numbers to the host
-        packed = torch.cat([(w.reshape(-1, 1, 1) * ctx.dec["W"]).sum(0).reshape(-1), (w.reshape(-1, 1) * ctx.dec["grad_pi"]).sum(0)])
+        packed = (w.reshape(-1, 1) * ctx.wg).sum(0)
         hot.curvature = ctx.kappa
         gx, gc = hot.decode_backward(x, ctx.dec, gb.contiguous())  # launched before the host waits for `packed`
         packed = packed.cpu().numpy()
@@ -197,8 +198,10 @@ class BaseModel:
         return peel, blens, pdm
 
     # -- a batch of trees -------------------------------------------------------------------------
-    def _hotpath(self):
-        model = self.phylomodel.device_model()
+    def _hotpath(self, defer_model=False):
+        """``defer_model``: a learnable model is eigen-decomposed on the host every step (0.2 ms); the caller then sets
+        ``hot.model_fn`` and the decomposition runs after the distance / NJ kernels are launched, in their shadow."""
+        model = self._hot.model if (defer_model and self._hot is not None) else self.phylomodel.device_model()
         if self._hot is None:
             self._hot = HotPath.from_engine(self._inst.engine, model, rates=self.rates, mix=self.rates is not None,
                                             tau=self.soft_temp, lift=self.embedder, matsumoto=self.matsumoto,
@@ -214,9 +217,11 @@ class BaseModel:
         item, ln prior (B,), comes from the epilogue of the same NJ kernel launch (base_model.py:475-527
         evaluated where the branch lengths are produced) and is differentiable like lnL."""
         pm = self.phylomodel
-        hot = self._hotpath()
+        learn = not (pm.fix_sub_rates and pm.fix_freqs)
+        hot = self._hotpath(defer_model=learn)
         hot.prior = prior
-        if not (pm.fix_sub_rates and pm.fix_freqs):
+        if learn:
+            hot.model_fn = pm.device_model
             out = _BatchedLogLikModel.apply(locs, self._curvature, pm._sub_rates, pm._freqs, hot)
         else:
             out = _BatchedLogLik.apply(locs, self._curvature, hot)

@@ -100,6 +100,9 @@ class HotPath:
         w.r.t. the branch lengths: adds W (B,4,4) and grad_pi (B,4) (``PruneEngine.loglik_model_grad``).
         Flagged samples are poisoned the same way."""
         dec = self.decode(x, exhaustive=exhaustive)
+        fn = getattr(self, "model_fn", None)
+        if fn is not None:  # the current eigen-system, formed on the host while the device decodes the trees
+            self.model, self.model_fn = fn(), None
         out = self.prune.loglik_model_grad(dec["peel"], dec["blens"], self.model, rates=self.rates, mix=self.mix)
         dec["bad"] = engine.nj_guard(dec["flags"], out["lnL"], out["grad_blens"])
         dec.update(out)

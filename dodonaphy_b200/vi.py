@@ -67,7 +67,7 @@ class DodonaphyVI(BaseModel):
             ln_p, peel, blens = self.log_likelihood_batch(x)
             ln_prior = priors.compute_prior_exponential(blens, rate=10.0)
         if self.include_jacobian:
-            hot = self._hotpath()
+            hot = self._hotpath(defer_model=True)  # (exists: the likelihood call above made it)
             xd, peel_d, flags_d = hot.last_decode  # the trees just decoded for the likelihood: not decoded again
             _, jac = hot.blens_jacobian(xd, peel_d, flags_d, logdet=True)
             jac = torch.where(torch.isfinite(jac), jac, torch.zeros_like(jac)).to(x.device)  # vi.py:199-201

@@ -301,3 +301,48 @@ def test_model_gradient_in_one_launch(S, L, K):
 def _assert_grad_tol(ours, ref, tol):
     scale = np.abs(ref).max()
     np.testing.assert_allclose(ours, ref, rtol=0, atol=tol * scale)
+
+
+def test_model_gradient_where_the_reference_underflows():
+    """Learnable GTR on 400 taxa with long branches: the unscaled product underflows (the reference returns -inf and
+    the explicit d lnL / d P route has no rescaling); the rescaled model-gradient launch must agree with the
+    log-space oracle under autograd: lnL, d lnL / d blens and the gradient to the rate / frequency parameters."""
+    from dodonaphy_b200 import synth
+    from dodonaphy_b200.engine import SubstModel
+    from oracle import phylo
+
+    S, L, K = 400, 40, 2
+    prob = synth.make_problem(S, L, 1, D=4, seed=77)
+    rng = np.random.default_rng(5)
+    masks = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    peels, blens = _nj_batch(prob)
+    blens = blens * 40.0 + 0.5
+    eng = _engine(masks, prob["weights"])
+    m = SubstModel.gtr(prob["rates"], prob["freqs"])
+    rates = SubstModel.discrete_gamma(0.5, K)
+    raw, _ = eng.loglik(_dev(peels), _dev(blens), m, rates=rates, mix=True, grad=False, scale=False)
+    assert not torch.isfinite(raw).all(), "test input no longer underflows without rescaling"
+    out = eng.loglik_model_grad(_dev(peels), _dev(blens), m, rates=rates, mix=True, scale=True)
+    rr = torch.tensor(prob["rates"], requires_grad=True)
+    ff = torch.tensor(prob["freqs"], requires_grad=True)
+    bt = torch.tensor(blens[0], requires_grad=True)
+    mats = phylo.gtr_p_t_torch(bt[:, None] * torch.tensor(rates)[None, :], rr, ff)
+    ref = phylo.treelikelihood_rescaled_torch([torch.tensor(phylo.mask_to_partial(x)) for x in masks], torch.tensor(prob["weights"]),
+                                              peels[0], mats, ff.detach(), gamma_mix=True)
+    ref.backward()
+    assert torch.isfinite(out["lnL"]).all()
+    assert out["lnL"].item() == pytest.approx(ref.item(), rel=RTOL)
+    _assert_grad(out["grad_blens"][0].cpu().numpy(), bt.grad.numpy())
+    dQ = torch.tensor(m.Uinv).T @ out["W"][0].cpu() @ torch.tensor(m.U).T
+    rr2 = torch.tensor(prob["rates"], requires_grad=True)
+    ff2 = torch.tensor(prob["freqs"], requires_grad=True)
+    iu = torch.triu_indices(4, 4, 1)
+    Q = torch.zeros((4, 4), dtype=torch.float64)
+    Q[iu[0], iu[1]] = rr2
+    Q[iu[1], iu[0]] = rr2
+    Q = Q * ff2.unsqueeze(0)
+    Q = Q + torch.diag(-torch.sum(Q, dim=1))
+    Q = Q / (-torch.sum(torch.diagonal(Q) * ff2))
+    (Q * dQ).sum().backward()
+    _assert_grad_tol(rr2.grad.numpy(), rr.grad.numpy(), 1e-7)
+    _assert_grad_tol(ff2.grad.numpy(), ff.grad.numpy(), 1e-7)
