@@ -69,6 +69,15 @@ def config_dict(cfg, world):
             "l2": "pruning scratch streams ~20 GB/step through HBM (>> 126 MB L2); no flush needed"}
 
 
+def quiet_nccl():
+    """Rank 0 prints ONE JSON line on stdout.  NCCL writes its version banner to stdout at the VERSION and WARN levels
+    and honours NCCL_DEBUG_FILE only above VERSION: so VERSION becomes WARN, and whatever NCCL logs goes to a file."""
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dodonaphy_b200_nccl.%h.%p.log")
+
+
 def kernel_source_sha():
     """sha256 of the pruning kernel's source: profiles/roofline_traffic.json records the one its ncu capture was
     taken with, so a stale DRAM-traffic figure is never quoted for a changed kernel."""
@@ -252,8 +261,7 @@ def run_ours(args, cfg):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from dodonaphy_b200 import _lib, synth
@@ -568,6 +576,7 @@ def run_side(args):
     if world > 1:
         import torch.distributed as dist
 
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
 
     def timed(fn, n):
