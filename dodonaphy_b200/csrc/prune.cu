@@ -261,7 +261,10 @@ struct PruneArgs {
     int *next_item;  // work counter (zeroed before the launch): items beyond the first gridDim.x are claimed dynamically
 };
 
-constexpr int NT = 256;  // threads per CTA = site patterns per work item
+#ifndef DODO_PRUNE_NT
+#define DODO_PRUNE_NT 256
+#endif
+constexpr int NT = DODO_PRUNE_NT;  // threads per CTA = site patterns per work item (a multiple of 32)
 #ifndef DODO_PRUNE_CTAS
 #define DODO_PRUNE_CTAS 3
 #endif
@@ -1025,14 +1028,32 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
 #define DODO_GM_EIG_DOWN 1
 #endif
                 constexpr bool PAIR = DODO_PRUNE_PAIR_REDUCE && SMALL && (!GMODEL || DODO_GM_PAIR);
+#ifndef DODO_PRUNE_HOIST
+#define DODO_PRUNE_HOIST 0
+#endif
+                constexpr bool HOIST = (DODO_PRUNE_HOIST & 1) && SMALL && !SCALE && NP == 1 && (MODE == 1 || ((DODO_PRUNE_HOIST & 2) && GMODEL));
+                constexpr bool HOIST_B = HOIST && !(DODO_PRUNE_HOIST & 4), HOIST_W = HOIST && !(DODO_PRUNE_HOIST & 8);
                 double pend_ga = 0.0, pend_gb = 0.0;
                 int pend_x = 0, pend_y = 0;
                 bool have_pending = false;
                 unsigned cmx[NP], cmy[NP];  // masks of the current join's tip children (LARGE; see load_mask)
+                // HOIST: the stored operands of a join (messages of its internal children, the parked upper message of
+                // an a-child) are requested in the MIDDLE of the join before it -- right after the last use of that
+                // join's own av / bv, into the registers they leave free -- instead of at the top of their own join,
+                // where their first use follows at once and the L2 round trip is exposed (11 % + 4 % of all stall
+                // samples on those two uses, profiles/r2/prune.txt).
+                V4 nav[NP], nbv[NP];
                 {
                     const int4 o1 = OPS(nops);
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) { cmx[q] = load_mask(o1.x, q); cmy[q] = load_mask(o1.y, q); }
+                    for (int q = 0; q < NP; ++q) {
+                        cmx[q] = load_mask(o1.x, q); cmy[q] = load_mask(o1.y, q);
+                        nav[q] = nbv[q] = V4{0, 0, 0, 0};
+                        if (HOIST) {
+                            if (o1.x >= 0) nav[q] = ldg256_bwd(SCR(o1.x, q));
+                            if (HOIST_B && o1.y >= 0 && !(RECOMP && (o1.w & FL_B_CHERRY))) nbv[q] = ldg256_bwd(SCR(o1.y, q));
+                        }
+                    }
                 }
 #pragma unroll 1
                 for (int i = nops; i >= 1; --i) {
@@ -1064,7 +1085,7 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                         }
                     }
 #endif
-                    if (o.w & FL_A_CHILD) {  // a-child: its upper message was parked in its own slot by the parent
+                    if (!HOIST_W && (o.w & FL_A_CHILD)) {  // a-child: its upper message was parked in its own slot by the parent
 #pragma unroll
                         for (int q = 0; q < NP; ++q) {
                             Wv[q] = ldg256(SCR(o.z, q));
@@ -1084,10 +1105,10 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                     for (int q = 0; q < NP; ++q) {
                         ac[q] = 0; bcn[q] = 0;
                         if (o.x < 0) av[q] = tipmsg(~o.x, q, cmx[q]);
-                        else { av[q] = ldg256_bwd(SCR(o.x, q)); if (SCALE) ac[q] = __ldcg(CSCR(o.x, q)); }
+                        else { av[q] = HOIST ? nav[q] : ldg256_bwd(SCR(o.x, q)); if (SCALE) ac[q] = __ldcg(CSCR(o.x, q)); }
                         if (o.y < 0) bv[q] = tipmsg(~o.y, q, cmy[q]);
                         else if (RECOMP && (o.w & FL_B_CHERRY)) bv[q] = cherry_msg(OPS(i - 1), q, bcn[q], SMALL ? 0u : nmx[q], SMALL ? 0u : nmy[q]);
-                        else { bv[q] = ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
+                        else { bv[q] = HOIST_B ? nbv[q] : ldg256_bwd(SCR(o.y, q)); if (SCALE) bcn[q] = __ldcg(CSCR(o.y, q)); }
                         ua[q] = vmul(Wv[q], bv[q]);
                         ub[q] = vmul(Wv[q], av[q]);
                         // explicitly rounded: the result must not depend on whether the (exact)
@@ -1112,6 +1133,16 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                             }
                         }
                         ga = __dadd_rn(ga, gaq); gb = __dadd_rn(gb, gbq);
+                    }
+                    if (HOIST) {  // av / bv are dead from here on: the next join's operands take their place
+                        const int4 on = OPS(i - 1);  // (entry 0 is a sentinel without internal children or flags)
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            if (on.x >= 0) nav[q] = ldg256_bwd(SCR(on.x, q));
+                            if (HOIST_B && on.y >= 0 && !(RECOMP && (on.w & FL_B_CHERRY))) nbv[q] = ldg256_bwd(SCR(on.y, q));
+                            // an a-child follows a join without internal children: Wv is not produced below
+                            if (HOIST_W && (on.w & FL_A_CHILD)) Wv[q] = ldg256(SCR(on.z, q));
+                        }
                     }
                     if (!PAIR) {
                         const double g2 = warp_sum2(ga, gb, lane);
