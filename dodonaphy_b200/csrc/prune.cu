@@ -261,6 +261,10 @@ struct PruneArgs {
     int *next_item;  // work counter (zeroed before the launch): items beyond the first gridDim.x are claimed dynamically
 };
 
+#ifndef DODO_PRUNE_FWD_UNROLL
+#define DODO_PRUNE_FWD_UNROLL 1
+#endif
+constexpr int FWD_UNROLL = DODO_PRUNE_FWD_UNROLL;  // forward join loop (2: the loop-carried result needs no register copies)
 #ifndef DODO_PRUNE_NT
 #define DODO_PRUNE_NT 256
 #endif
@@ -921,7 +925,7 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
                     if (SCALE) scale_up(Lv[q], cnt[q]);
                 }
             };
-#pragma unroll 1
+#pragma unroll FWD_UNROLL
             for (int i = 1; i < nops; ++i) {
                 const int4 o = OPS(i);
                 unsigned nmx[NP], nmy[NP];

@@ -290,7 +290,7 @@ def test_compress_alignment_on_device():
     # the radix sort itself: several pass structures (alphabet sizes 2 .. > 32 -> 1 .. 10 bits per taxon, taxa counts
     # that are not multiples of the group size, more columns than one warp segment, all columns equal / all distinct)
     for S2, n2, letters in ((1, 50, "AC"), (3, 5000, "ACGT"), (7, 9001, "ACGT-N"), (11, 3000, "ACGTRYMWSKBDHVN?-acgt"),
-                            (4, 700, "".join(chr(c) for c in range(48, 112))), (40, 20000, "ACGT"), (2, 4, "A"), (3, 6000, "AC")):
+                            (4, 700, "".join(chr(c) for c in range(48, 112))), (40, 20000, "ACGT"), (2, 4, "A"), (3, 6000, "AC"), (6, 70001, "ACGT"), (9, 131072, "ACGTN")):
         mat = rng.choice(np.array(list(letters)), size=(S2, n2))
         if n2 == 20000:
             mat[:, 10000:] = mat[:, :10000]  # heavy duplication
