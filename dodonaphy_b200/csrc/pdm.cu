@@ -352,6 +352,164 @@ __global__ void __launch_bounds__(1024) gram_logdet_kernel(const double *__restr
     if (tid == 0) out[b] = 0.5 * logabs;
 }
 
+
+// The same quantity for up to 128 rows (trees up to 65 taxa: the headline size) with the matrix in REGISTERS: thread
+// t owns the 8 x 8 tile (ti, tj), tj <= ti, of the lower triangle (136 tiles -> 160 threads for 126 rows).
+//   Gram phase: J is staged 32 columns at a time, transposed ([column][row], so a tile's eight rows are 64 contiguous
+// bytes: four 16-byte loads per operand and column, 64 multiply-adds per 8 loads -- the first kernel spends two loads
+// per multiply-add and is bound by them: 209 of its 372 us at 126 x 320).
+//   Elimination: symmetric (the Schur complement of a symmetric matrix is symmetric: A_ij -= A_ik A_jk / A_kk for
+// i >= j > k), so a step only needs COLUMN k: its owners publish it (double-buffered: one barrier per step), every
+// tile at or right of it updates its 64 entries from 16 published values.  Diagonal tiles keep both triangles
+// (the upper one is never read).  Pivot order and singular-pivot behaviour as above.
+constexpr int GT_LD = 130;  // row stride of the transposed chunk (even: 16-byte loads stay aligned)
+// Position of row e = 8 t + 2 h + p inside a column of the chunk (and inside the published pivot column): [h][t][p].
+// A thread reads the eight rows of its tile as four 16-byte pairs; with the rows in their natural order consecutive
+// tiles are 64 bytes apart and a quarter-warp's loads fall into two bank groups (16 wavefronts per load, measured:
+// the Gram phase took 460 cycles per column where the multiply-adds need 256); in this order they are contiguous.
+__device__ __forceinline__ int gt_pos(int e) { return ((e >> 1) & 3) * 32 + ((e >> 3) << 1) + (e & 1); }
+__global__ void __launch_bounds__(160) gram_logdet_tile_kernel(const double *__restrict__ J, int E, int C,
+                                                               double *__restrict__ out) {
+    extern __shared__ __align__(16) double gt_sm[];  // Jc[2][32][GT_LD]: the chunk in use and the one in flight
+    __shared__ __align__(16) double colk[2][128];
+    __shared__ double pivs[2], part[16], s_val;
+    __shared__ int s_stop;
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int nt = (E + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+    const bool active = tid < ntiles;
+    int ti = 0, tj = 0;
+    if (active) {
+        ti = (int)((sqrt(8.0 * (double)tid + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+        while (ti * (ti + 1) / 2 > tid) --ti;
+        tj = tid - ti * (ti + 1) / 2;
+    }
+    if (tid == 0) s_stop = 0;
+    double A[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) A[r][c] = 0.0;
+    const double *Jb = J + (size_t)b * E * C;
+    // 8-byte asynchronous copies (global reads coalesced along the columns, written transposed; rows and columns
+    // outside the matrix are zero-filled through the source size): chunk n + 1 lands while chunk n is consumed
+    auto stage = [&](int c0, double *dst) {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(dst);
+        for (int idx = tid; idx < 128 * 32; idx += T) {
+            const int e = idx >> 5, c = idx & 31;
+            const bool in = e < E && c0 + c < C;
+            const double *src = in ? Jb + (size_t)e * C + c0 + c : Jb;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(base + (unsigned)(c * GT_LD + gt_pos(e)) * 8u), "l"(src),
+                         "r"(in ? 8 : 0)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, gt_sm);
+    int cur = 0;
+    for (int c0 = 0; c0 < C; c0 += 32, cur ^= 1) {
+        const double *Jc = gt_sm + cur * (32 * GT_LD);
+        if (c0 + 32 < C) {
+            stage(c0 + 32, gt_sm + (cur ^ 1) * (32 * GT_LD));  // (its previous readers passed the barrier below one round ago)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (active) {
+            const double *pa = Jc + 2 * ti, *pb = Jc + 2 * tj;
+#pragma unroll 2
+            for (int c = 0; c < 32; ++c) {
+                double a[8], bb[8];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const double2 x = *reinterpret_cast<const double2 *>(pa + c * GT_LD + 32 * h);
+                    const double2 y = *reinterpret_cast<const double2 *>(pb + c * GT_LD + 32 * h);
+                    a[2 * h] = x.x; a[2 * h + 1] = x.y;
+                    bb[2 * h] = y.x; bb[2 * h + 1] = y.y;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) A[r][q] = fma(a[r], bb[q], A[r][q]);
+            }
+        }
+        __syncthreads();  // everyone is done with this chunk before the round after next refills its buffer
+    }
+    double pv[8];  // pivots of this thread's diagonal tile (their logarithms are taken after the elimination)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) pv[r] = 1.0;
+    for (int kb = 0; kb < nt; ++kb) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const int k = 8 * kb + kk;
+            if (k >= E) break;
+            double *ck = colk[kk & 1];
+            if (active && tj == kb) {  // owners of column k
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    *reinterpret_cast<double2 *>(ck + 32 * h + 2 * ti) = make_double2(A[2 * h][kk], A[2 * h + 1][kk]);
+                if (ti == kb) {
+                    const double piv = A[kk][kk];
+                    pivs[kk & 1] = piv;
+                    if (!(piv != 0.0)) {  // exactly singular (or NaN): log|det| = -inf (NaN propagates)
+                        s_val = piv == piv ? -INFINITY : piv;
+                        s_stop = 1;
+                    } else {
+                        pv[kk] = piv;
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_stop) {
+                if (tid == 0) out[b] = s_val;
+                return;
+            }
+            if (active && tj >= kb) {
+                const double inv = 1.0 / pivs[kk & 1];
+                double l[8], cj[8];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const double2 x = *reinterpret_cast<const double2 *>(ck + 32 * h + 2 * ti);
+                    const double2 y = *reinterpret_cast<const double2 *>(ck + 32 * h + 2 * tj);
+                    l[2 * h] = x.x * inv; l[2 * h + 1] = x.y * inv;
+                    cj[2 * h] = y.x; cj[2 * h + 1] = y.y;
+                }
+                if (tj > kb) {  // every row and column of the tile lies beyond k
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) A[r][q] = fma(-l[r], cj[q], A[r][q]);
+                } else if (ti > kb) {  // the tile column that holds k: columns beyond k only
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q > kk) A[r][q] = fma(-l[r], cj[q], A[r][q]);
+                } else {  // the diagonal tile that holds k
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (r > kk && q > kk) A[r][q] = fma(-l[r], cj[q], A[r][q]);
+                }
+            }
+        }
+    }
+    if (active && ti == tj) {
+        double logabs = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) logabs += log(fabs(pv[r]));  // (rows beyond E keep the neutral 1.0)
+        part[ti] = logabs;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nt; ++i) s += part[i];
+        out[b] = 0.5 * s;
+    }
+}
+
 }  // namespace dodo
 
 using namespace dodo;
@@ -444,6 +602,14 @@ extern "C" int dodo_blens_jacobian(const double *d_x, int B, int S, int D, const
 extern "C" int dodo_gram_logdet(const double *d_J, int B, int E, int C, double *d_out, void *stream_) {
     DODO_CHECK_ARG(d_J && d_out, "dodo_gram_logdet: NULL argument");
     DODO_CHECK_ARG(B >= 1 && E >= 1 && C >= 1, "dodo_gram_logdet: need B, E, C >= 1");
+    if (E <= 128) {  // the matrix in registers, 8 x 8 tiles of the lower triangle
+        const int ntiles = ((E + 7) / 8) * ((E + 7) / 8 + 1) / 2;
+        const int gsm = 2 * 32 * GT_LD * (int)sizeof(double);
+        DODO_CUDA(cudaFuncSetAttribute(gram_logdet_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+        gram_logdet_tile_kernel<<<B, (ntiles + 31) / 32 * 32, gsm, (cudaStream_t)stream_>>>(d_J, E, C, d_out);
+        DODO_LAUNCH_CHECK();
+        return DODO_OK;
+    }
     const size_t smem = ((size_t)E * (E + 1) + (size_t)E * 33) * sizeof(double);
     if (smem > 227 * 1024 || E > 192) {
         set_error("dodo_gram_logdet: %d rows need %zu bytes of shared memory (limit 227 KB)", E, smem);
