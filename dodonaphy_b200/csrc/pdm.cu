@@ -9,6 +9,7 @@
 // Tiny next to the pruning kernel (8 S^2 bytes written per tree); one thread per matrix entry,
 // rows of the sheet staged in shared memory.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -208,6 +209,36 @@ __host__ __device__ inline size_t jac_ws_doubles(int S, int D) {
     return (size_t)(3 * (S - 1) + 2 * S - 2) * S * (D + 1);
 }
 
+// second pass of the Jacobian kernels: the sheet-space rows Js [2S-2][S (D+1)] of tree b through the lift to the
+// location coordinates, one thread per (row, taxon), exactly as pdm_bwd_kernel does
+__device__ __forceinline__ void jac_rows_through_lift(const double *__restrict__ x, const double *__restrict__ sh,
+                                                      const double *__restrict__ Js, double *__restrict__ J, int b, int S, int D,
+                                                      int lift, int tid, int T) {
+    const int D1 = D + 1, NE = S * D1, E = 2 * S - 2;
+    double *Jb = J + (size_t)b * E * S * D;
+    for (int w = tid; w < E * S; w += T) {
+        const int e = w / S, i = w - e * S;
+        const double *acc = Js + (size_t)e * NE + (size_t)i * D1;
+        const double *xi = x + ((size_t)b * S + i) * D;
+        double *out = Jb + (size_t)e * S * D + (size_t)i * D;
+        if (lift == DODO_LIFT_UP) {
+            const double s0 = sh[(size_t)i * D1];
+            for (int d = 0; d < D; ++d) out[d] = acc[d + 1] + acc[0] * xi[d] / s0;
+        } else {
+            const double n2 = row_norm2(xi, D);
+            const double r = sqrt(fmax(n2, DBL_EPSILON));
+            const double shr = sinh(r), chr = cosh(r);
+            const double fr = shr / r;
+            double dot = 0.0;
+            for (int d = 0; d < D; ++d) dot = fma(acc[d + 1], xi[d], dot);
+            const double dfdr = (r * chr - shr) / (r * r);
+            const double rad = (n2 > DBL_EPSILON) ? (acc[0] * shr + dot * dfdr) / r : 0.0;
+            for (int d = 0; d < D; ++d) out[d] = fr * acc[d + 1] + rad * xi[d];
+        }
+    }
+}
+
+
 __global__ void __launch_bounds__(1024) blens_jac_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
                                                         const double *__restrict__ util, int S, int D,
                                                         const double *__restrict__ curv, int lift, int matsumoto,
@@ -269,26 +300,140 @@ __global__ void __launch_bounds__(1024) blens_jac_kernel(const double *__restric
         }
     }
     __syncthreads();  // rows complete (written by this CTA): now through the lift, one thread per (row, taxon)
-    double *Jb = J + (size_t)b * E * S * D;
-    for (int w = tid; w < E * S; w += T) {
-        const int e = w / S, i = w - e * S;
-        const double *acc = Js + (size_t)e * NE + (size_t)i * D1;
-        const double *xi = x + ((size_t)b * S + i) * D;
-        double *out = Jb + (size_t)e * S * D + (size_t)i * D;
-        if (lift == DODO_LIFT_UP) {
-            const double s0 = sh[(size_t)i * D1];
-            for (int d = 0; d < D; ++d) out[d] = acc[d + 1] + acc[0] * xi[d] / s0;
-        } else {
-            const double n2 = row_norm2(xi, D);
-            const double r = sqrt(fmax(n2, DBL_EPSILON));
-            const double shr = sinh(r), chr = cosh(r);
-            const double fr = shr / r;
-            double dot = 0.0;
-            for (int d = 0; d < D; ++d) dot = fma(acc[d + 1], xi[d], dot);
-            const double dfdr = (r * chr - shr) / (r * r);
-            const double rad = (n2 > DBL_EPSILON) ? (acc[0] * shr + dot * dfdr) / r : 0.0;
-            for (int d = 0; d < D; ++d) out[d] = fr * acc[d + 1] + rad * xi[d];
+    jac_rows_through_lift(x, sh, Js, J, b, S, D, lift, tid, T);
+}
+
+// The same walk for trees whose S^2 pair terms fit in shared memory (up to 118 taxa), restructured around what the
+// first kernel spends its time on (ncu: 39k dependent instructions per thread at 64 taxa, 0.12 instructions per cycle
+// and warp -- a serial chain of fp64 and L2 latencies, 170 us for 128 trees):
+//   * the expensive part of a tip term -- the pair's Lorentz product, sqrt, division (tanh / acosh with the Matsumoto
+//     adjustment) -- does not depend on the coordinate and is needed twice per (i, j) (initial sum, and when tip j is
+//     joined): all S^2 of them are formed first, by all threads, as independent evaluations that pipeline, and kept
+//     in shared memory ([j][i]: conflict-free for the walk) as coef_ij (0 = "no gradient") and u_j / u_i;
+//   * the peel is staged in shared memory (no dependent global load per join);
+//   * the per-node quantities of the NEXT join's children are requested before the current join is evaluated (they
+//     come back from L2: a thread reads what it wrote itself, and stores do not allocate in L1) unless the child is
+//     the node being formed, which is taken from registers;
+//   * the rows go through the lift in a kernel of their own with one thread per (tree, row, taxon).
+// Same expressions in the same order per (taxon, coordinate): rows bit-identical to blens_jac_kernel's.
+__global__ void __launch_bounds__(512) blens_jac_cached_kernel(const double *__restrict__ sheet, const double *__restrict__ util,
+                                                               int S, int D, const double *__restrict__ curv, int matsumoto,
+                                                               const int64_t *__restrict__ peel, const int32_t *__restrict__ flags,
+                                                               double *__restrict__ ws) {
+    extern __shared__ __align__(16) double jc_smd[];  // coefT [S][S] | qT [S][S] | {l, r, u, flags} of the S-1 joins
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int D1 = D + 1, NE = S * D1;
+    const double kappa = curv[0];
+    const double sc = 1.0 / sqrt(-kappa);
+    const double *sh = sheet + (size_t)b * S * D1;
+    const double *ut = util + (size_t)b * S;
+    const int64_t *pl = peel + (size_t)b * (S - 1) * 3;
+    const int32_t *fl = flags + (size_t)b * (S - 1);
+    double *An = ws + (size_t)b * jac_ws_doubles(S, D);
+    double *Yn = An + (size_t)(S - 1) * NE;
+    double *Gn = Yn + (size_t)(S - 1) * NE;
+    double *Js = Gn + (size_t)(S - 1) * NE;
+    double *coefT = jc_smd, *qT = jc_smd + (size_t)S * S;
+    int *pj = reinterpret_cast<int *>(qT + (size_t)S * S);
+    for (int t = tid; t < S - 1; t += T) {
+        pj[4 * t + 0] = (int)pl[t * 3 + 0];
+        pj[4 * t + 1] = (int)pl[t * 3 + 1];
+        pj[4 * t + 2] = (int)pl[t * 3 + 2];
+        pj[4 * t + 3] = fl[t];
+    }
+    for (int p = tid; p < S * S; p += T) {
+        const int j = p / S, i = p - j * S;
+        const double ui = ut[i], uj = ut[j];
+        double coef = 0.0;
+        if (j != i) {
+            const double Hraw = pair_H(sh + (size_t)i * D1, sh + (size_t)j * D1, D, ui, uj);
+            if (Hraw < -TORCH_CLAMP) {  // (clamped entries are constants)
+                coef = -sc / sqrt(Hraw * Hraw - 1.0);
+                if (matsumoto) coef *= tanh(sc * acosh(-Hraw));
+            }
         }
+        coefT[p] = coef;
+        qT[p] = uj / ui;
+    }
+    __syncthreads();
+    for (int el = tid; el < NE; el += T) {
+        const int i = el / D1, dp = el - i * D1;
+        const double sidp = sh[(size_t)i * D1 + dp];
+        auto tipY = [&](int j) -> double {  // dD_ij / ds_i[dp]  (pdm_bwd_kernel's per-pair term)
+            const double coef = coefT[(size_t)j * S + i];
+            return coef != 0.0 ? coef * (sh[(size_t)j * D1 + dp] - qT[(size_t)j * S + i] * sidp) : 0.0;
+        };
+        auto fetch = [&](int node, double &a, double &Y, double &G) {
+            if (node < S) { a = node == i ? 1.0 : 0.0; Y = tipY(node); G = 0.0; }
+            else { const size_t o = (size_t)(node - S) * NE + el; a = An[o]; Y = Yn[o]; G = Gn[o]; }
+        };
+        double Ta = 1.0, TY = 0.0;  // sums over the live nodes: a_x[i] (only tip i counts at the start), Y_x[i][dp]
+        for (int j = 0; j < S; ++j) TY += tipY(j);
+        int4 o4 = *reinterpret_cast<const int4 *>(pj);
+        double al, Yl, Gl, ar, Yr, Gr;
+        fetch(o4.x, al, Yl, Gl);
+        fetch(o4.y, ar, Yr, Gr);
+        for (int t = 0; t < S - 1; ++t) {
+            const int l = o4.x, r = o4.y, u = o4.z, f = o4.w;
+            const int n = S - t;
+            // the next join's children, requested now (the node formed below is handed over in registers)
+            int4 on = make_int4(0, 0, 0, 0);
+            double aln = 0.0, Yln = 0.0, Gln = 0.0, arn = 0.0, Yrn = 0.0, Grn = 0.0;
+            if (t + 1 < S - 1) {
+                on = *reinterpret_cast<const int4 *>(pj + 4 * (t + 1));
+                if (on.x != u) fetch(on.x, aln, Yln, Gln);
+                if (on.y != u) fetch(on.y, arn, Yrn, Grn);
+            }
+            const double A = al * Yr + ar * Yl;  // d (a_l^T D a_r) / d s_i[dp]
+            const double dlr = A - Gl - Gr;
+            const double sig = Ta - al - ar, Ysig = TY - Yl - Yr;
+            // (the last join has no other live node: its two rows are the same half of d d_lr bit for bit, as in
+            // the reference, where both come from one d_lr / 2)
+            const double drr = n == 2 ? 0.0 : (al - ar) * Ysig + sig * (Yl - Yr) - (double)(n - 2) * (Gl - Gr);
+            const double nact = fmax((double)n, 3.0);
+            const double basel = (f & 1) ? 0.0 : 0.5 * dlr + drr / (2.0 * (nact - 2.0));
+            Js[(size_t)l * NE + el] = basel;
+            Js[(size_t)r * NE + el] = (f & 2) ? 0.0 : dlr - basel;
+            const double au = 0.5 * (al + ar), Yu = 0.5 * (Yl + Yr), Gu = 0.5 * A;
+            const size_t o = (size_t)(u - S) * NE + el;
+            An[o] = au; Yn[o] = Yu; Gn[o] = Gu;
+            Ta += au - al - ar;
+            TY += Yu - Yl - Yr;
+            if (on.x == u) { aln = au; Yln = Yu; Gln = Gu; }
+            if (on.y == u) { arn = au; Yrn = Yu; Grn = Gu; }
+            al = aln; Yl = Yln; Gl = Gln; ar = arn; Yr = Yrn; Gr = Grn;
+            o4 = on;
+        }
+    }
+}
+
+// the rows of every tree through the lift: one thread per (tree, row, taxon)
+__global__ void __launch_bounds__(256) jac_lift_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
+                                                       const double *__restrict__ ws, int B, int S, int D, int lift,
+                                                       double *__restrict__ J) {
+    const int E = 2 * S - 2, D1 = D + 1, NE = S * D1;
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (size_t)B * E * S) return;
+    const int b = (int)(w / ((size_t)E * S));
+    const int rem = (int)(w - (size_t)b * E * S);
+    const int e = rem / S, i = rem - e * S;
+    const double *Js = ws + (size_t)b * jac_ws_doubles(S, D) + (size_t)3 * (S - 1) * NE;
+    const double *acc = Js + (size_t)e * NE + (size_t)i * D1;
+    const double *xi = x + ((size_t)b * S + i) * D;
+    double *out = J + ((size_t)b * E + e) * S * D + (size_t)i * D;
+    if (lift == DODO_LIFT_UP) {
+        const double s0 = sheet[((size_t)b * S + i) * D1];
+        for (int d = 0; d < D; ++d) out[d] = acc[d + 1] + acc[0] * xi[d] / s0;
+    } else {
+        const double n2 = row_norm2(xi, D);
+        const double r = sqrt(fmax(n2, DBL_EPSILON));
+        const double shr = sinh(r), chr = cosh(r);
+        const double fr = shr / r;
+        double dot = 0.0;
+        for (int d = 0; d < D; ++d) dot = fma(acc[d + 1], xi[d], dot);
+        const double dfdr = (r * chr - shr) / (r * r);
+        const double rad = (n2 > DBL_EPSILON) ? (acc[0] * shr + dot * dfdr) / r : 0.0;
+        for (int d = 0; d < D; ++d) out[d] = fr * acc[d + 1] + rad * xi[d];
     }
 }
 
@@ -593,6 +738,19 @@ extern "C" int dodo_blens_jacobian(const double *d_x, int B, int S, int D, const
     if (rc != DODO_OK) return rc;
     double *ws = util + (size_t)B * S;
     const int ne = S * (D + 1);
+    // trees whose S^2 pair terms fit in shared memory (up to 118 taxa): cached pair terms, staged peel, operand
+    // requests one join ahead, the lift as a kernel of its own
+    const size_t sm = (size_t)2 * S * S * sizeof(double) + (size_t)(S - 1) * 4 * sizeof(int);
+    if (sm <= 220 * 1024 && !getenv("DODO_JAC_PER_ELEMENT")) {
+        const int th = ne >= 512 ? 512 : ((ne + 31) / 32) * 32;
+        if (sm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(blens_jac_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        blens_jac_cached_kernel<<<B, th, sm, stream>>>(sheet, util, S, D, d_curvature, matsumoto, d_peel, d_flags, ws);
+        DODO_LAUNCH_CHECK();
+        const size_t items = (size_t)B * (2 * S - 2) * S;
+        jac_lift_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(d_x, sheet, ws, B, S, D, lift, d_J);
+        DODO_LAUNCH_CHECK();
+        return DODO_OK;
+    }
     const int threads = ne >= 1024 ? 1024 : ((ne + 31) / 32) * 32;
     blens_jac_kernel<<<B, threads, 0, stream>>>(d_x, sheet, util, S, D, d_curvature, lift, matsumoto, d_peel, d_flags, ws, d_J);
     DODO_LAUNCH_CHECK();

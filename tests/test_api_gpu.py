@@ -1,6 +1,8 @@
 """GPU parity through the reference-shaped Python API (same names/arguments as the reference's
 modules): these read like the reference's own tests (test/test_phylo.py, test/test_peeler.py,
 test/test_bito.py, test/test_chyp_np.py) with the CUDA path underneath."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -722,6 +724,14 @@ def test_one_pass_jacobian_equals_the_batched_replays():
         J0 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False, replay=True)
         ref = J0.cpu().numpy()
         np.testing.assert_allclose(J1.cpu().numpy(), ref, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(ref).max()), err_msg=f"S={S} {lift}")
+        # the one-thread-per-taxon kernel (D = 2, 3, 5) and the one-thread-per-(taxon, coordinate) kernel evaluate the
+        # same expressions in the same order: identical bits
+        os.environ["DODO_JAC_PER_ELEMENT"] = "1"
+        try:
+            J2 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False)
+        finally:
+            del os.environ["DODO_JAC_PER_ELEMENT"]
+        assert torch.equal(J1, J2), f"S={S} D={D} {lift}"
     assert seen_clamped
 
 
