@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(1024) blens_jac_kernel(const double *__restric
                                                         const int64_t *__restrict__ peel, const int32_t *__restrict__ flags,
                                                         double *__restrict__ ws, double *__restrict__ J) {
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    const int D1 = D + 1, NE = S * D1, E = 2 * S - 2;
+    const int D1 = D + 1, NE = S * D1;
     const double kappa = curv[0];
     const double sc = 1.0 / sqrt(-kappa);
     const double *sh = sheet + (size_t)b * S * D1;

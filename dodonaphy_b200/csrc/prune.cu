@@ -275,13 +275,16 @@ constexpr int NT = DODO_PRUNE_NT;  // threads per CTA = site patterns per work i
 
 // Shared memory.  SMALL (tables and tip selectors resident): tables | gacc | fx | red | cx | ops | sel.
 // LARGE (big S: tables and masks stay in global memory, read through L1): gacc | fx | red | cx | ops.
-__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np, int chmax, int gm = 0) {
+// (LARGE launches without a branch-length gradient carry no per-warp accumulators: at 200 taxa that is 25 KB per CTA
+// which go to L1 instead, where the transition tables of the three resident CTAs -- 57 KB each -- have to live)
+__host__ __device__ inline size_t prune_smem_dbl(int S, int K, bool small, int np, int chmax, int gm = 0, int nograd = 0) {
     const size_t nwarp = NT / 32, E = 2 * (size_t)S - 2;
-    size_t dbl = nwarp * E + (size_t)K * NT * np + nwarp + (gm ? nwarp * 20 : 0) + (small ? tab_doubles(S, chmax, gm) : 0);
+    size_t dbl = ((small || !nograd) ? nwarp * E : 0) + (size_t)K * NT * np + nwarp + (gm ? nwarp * 20 : 0) +
+                 (small ? tab_doubles(S, chmax, gm) : 0);
     return (dbl + 1) & ~(size_t)1;  // keep what follows 16-byte aligned
 }
-__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np, int chmax, int gm = 0) {
-    return prune_smem_dbl(S, K, small, np, chmax, gm) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
+__host__ __device__ inline size_t prune_smem_bytes(int S, int K, bool small, int np, int chmax, int gm = 0, int nograd = 0) {
+    return prune_smem_dbl(S, K, small, np, chmax, gm, nograd) * sizeof(double) + (size_t)K * NT * np * sizeof(int) +
            (size_t)(S + 2) * sizeof(int4) + (small ? (size_t)S * NT * np : 0);
 }
 
@@ -330,6 +333,9 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 #endif
 #ifndef DODO_PF_L2_DIST
 #define DODO_PF_L2_DIST 3
+#endif
+#ifndef DODO_MASK_NOALLOC
+#define DODO_MASK_NOALLOC 1
 #endif
 #ifndef DODO_PF_L1
 #define DODO_PF_L1 0
@@ -746,10 +752,10 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
     const unsigned tabn = (unsigned)tab_doubles(S, A.ch_max, GM);
     // offsets in doubles: [tables (SMALL)] gacc[nwarp][E] fx[K][npt] red[nwarp] wred[nwarp][20] (GMODEL) | cx | ops | sel
     const unsigned o_gacc = SMALL ? tabn : 0u;
-    const unsigned o_fx = o_gacc + nwarp * (unsigned)E;
+    const unsigned o_fx = o_gacc + ((SMALL || GRAD) ? nwarp * (unsigned)E : 0u);
     const unsigned o_red = o_fx + (unsigned)K * npt;
     const unsigned o_wred = o_red + nwarp;                                          // per-warp W (16) + d/d pi (4)
-    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP, A.ch_max, GM);  // int [K][npt]
+    const unsigned o_cx = (unsigned)prune_smem_dbl(S, K, SMALL, NP, A.ch_max, GM, GRAD ? 0 : 1);  // int [K][npt]
     const unsigned o_ops = o_cx + ((unsigned)K * npt) / 2u;                         // int4 [S+2]
     const unsigned o_sel = o_ops + 2u * (unsigned)(S + 2);                          // u8 [S][npt]
     const unsigned o_T = (unsigned)(S - 1) * 16u;                                   // Ttip inside the slab
@@ -855,7 +861,15 @@ __global__ void __launch_bounds__(NT, (NP == 1 && MODE != 3) ? DODO_PRUNE_CTAS :
         // does not wait for an L2 round trip first: ncu showed 47 % of all stall samples on that byte at 200
         // taxa (two dependent global loads per tip on the critical path of every join).
         auto load_mask = [&](int code, int q) -> unsigned {  // child code < 0 -> tip ~code
-            return (!SMALL && code < 0) ? (unsigned)__ldg(tm[q] + (size_t)(~code) * A.ld_mask) : 0u;
+            if (SMALL || code >= 0) return 0u;
+#if DODO_MASK_NOALLOC
+            // a mask byte is used once per sweep: it streams past L1 (which holds the tables) instead of through it
+            unsigned m;
+            asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(m) : "l"(tm[q] + (size_t)(~code) * A.ld_mask));
+            return m;
+#else
+            return (unsigned)__ldg(tm[q] + (size_t)(~code) * A.ld_mask);
+#endif
         };
         auto tipmsg = [&](int t, int q, unsigned mask) -> V4 {
             const unsigned sel = SMALL ? (unsigned)SEL(t, q) : encode_sel(mask);
@@ -1517,7 +1531,7 @@ extern "C" int dodo_prune_plan(int B, int S, int L, int K, uint32_t flags, int g
     const bool scale = (flags & DODO_PRUNE_SCALE) != 0;
     const int chmax = prune_cherry_slots(S, K, np, gm, small, scale);
     plan->cherry_slots = chmax;
-    const size_t smem = prune_smem_bytes(S, K, small, np, chmax, gm);
+    const size_t smem = prune_smem_bytes(S, K, small, np, chmax, gm, (flags & DODO_PRUNE_GRAD) ? 0 : 1);
     if (smem > 227 * 1024) {
         set_error("dodo_prune_plan: %d taxa need %zu bytes of shared memory per CTA (limit 227 KB)", S, smem);
         return DODO_ENOTIMPL;
@@ -1659,7 +1673,7 @@ static int prune_launch(const dodo_prune_plan_t *plan, const dodo_model_t *model
     A.ch_max = chmax;
     const int np = plan->tile_patterns / plan->threads;
     const bool small = prune_small(S, K, np, gm);
-    size_t smem = prune_smem_bytes(S, K, small, np, chmax, gm);
+    size_t smem = prune_smem_bytes(S, K, small, np, chmax, gm, (plan->flags & DODO_PRUNE_GRAD) ? 0 : 1);
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0 && ev1) DODO_CUDA(cudaEventRecord(ev0, stream));
