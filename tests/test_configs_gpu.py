@@ -325,3 +325,56 @@ def test_c4_shape_distances_against_the_reference_itself():
     np.testing.assert_allclose(dt[ii, jj], g["torch_vals"], rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose((dn.sum(1) - np.diag(dn))[:16], g["np_row_sum"] - 0.0, rtol=1e-9, atol=1e-6)
     assert float(dt.sum()) == pytest.approx(float(g["torch_total"]), rel=1e-10)
+
+
+def test_c5_shape_alignment_ingestion_properties():
+    """configs[4], the step before the path: 500 taxa x 1M sites through the radix-sort kernels (csrc/align.cu;
+    phylo.compress_alignment, phylo.py:16-58).  Too large for the host oracle, so size-independent properties: the
+    weights add up to the number of sites, the patterns come out strictly increasing in the reference's order
+    (lexicographic, taxon 0 most significant), they are exactly the distinct columns the input was tiled from, and
+    ingesting the patterns themselves returns them unchanged with weight 1 (idempotence)."""
+    from dodonaphy_b200 import _lib
+
+    S, n, n_base = 500, 1_000_000, 20_000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    letters = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")  # A C G T
+    base = letters[torch.randint(0, 4, (S, n_base), generator=g, device="cuda")]
+    raw = base.repeat(1, n // n_base).contiguous()
+    lut = torch.full((256,), 15, dtype=torch.uint8)
+    lut[65], lut[67], lut[71], lut[84] = 1, 2, 4, 8
+    lut = lut.cuda()
+    lib = _lib.load()
+
+    def ingest(cols):
+        m = int(cols.shape[1])
+        ws = torch.empty(int(lib.dodo_alignment_workspace_bytes(S, m)), dtype=torch.uint8, device="cuda")
+        nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.dodo_alignment_sort(cols.data_ptr(), S, m, ws.data_ptr(), nu.data_ptr(), st))
+        U = int(nu.item())
+        masks = torch.empty((S, U), dtype=torch.uint8, device="cuda")
+        w = torch.empty(U, dtype=torch.int64, device="cuda")
+        _lib.check(lib.dodo_alignment_gather(cols.data_ptr(), S, m, ws.data_ptr(), U, lut.data_ptr(), masks.data_ptr(), w.data_ptr(), st))
+        return masks, w
+
+    masks, w = ingest(raw)
+    U = int(masks.shape[1])
+    assert int(w.sum().item()) == n
+    # strictly increasing: at the first taxon where neighbouring patterns differ the left one is smaller
+    # (the mask codes 1, 2, 4, 8 keep the order of the bytes A < C < G < T)
+    differ = masks[:, 1:] != masks[:, :-1]
+    assert bool(differ.any(dim=0).all())
+    first = differ.to(torch.uint8).argmax(dim=0)
+    left = masks[:, :-1].gather(0, first[None])[0]
+    right = masks[:, 1:].gather(0, first[None])[0]
+    assert bool((left < right).all())
+    # exactly the distinct columns of the tile, each with the right multiplicity
+    ref_cols, ref_counts = torch.unique(lut[base.long()].T.contiguous(), dim=0, return_counts=True)
+    assert U == int(ref_cols.shape[0])
+    assert torch.equal(masks, ref_cols.T.contiguous())
+    assert torch.equal(w, ref_counts * (n // n_base))
+    # idempotence
+    inv = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    inv[1], inv[2], inv[4], inv[8] = 65, 67, 71, 84
+    again, w1 = ingest(inv[masks.long()].contiguous())
+    assert torch.equal(again, masks) and bool((w1 == 1).all())
