@@ -316,10 +316,17 @@ __global__ void __launch_bounds__(1024) blens_jac_kernel(const double *__restric
 //     the node being formed, which is taken from registers;
 //   * the rows go through the lift in a kernel of their own with one thread per (tree, row, taxon).
 // Same expressions in the same order per (taxon, coordinate): rows bit-identical to blens_jac_kernel's.
-__global__ void __launch_bounds__(512) blens_jac_cached_kernel(const double *__restrict__ sheet, const double *__restrict__ util,
+//   * FUSE_UP ("up" lift): the D+1 coordinates of a taxon sit in neighbouring lanes of ONE warp (32 / (D+1) taxa per
+//     warp), so a row goes through the lift where it is formed -- d blens / d x_i[d] = row[d+1] + row[0] x_i[d] / s_i[0],
+//     row[0] by one shuffle -- and is written straight into J: no sheet-space rows in memory, no second kernel
+//     (29 us for 90 MB of rows in and out at 128 x 64 taxa).  x_i[d] / s_i[0] is formed once per thread, so an entry
+//     differs from the two-kernel path in the last bit.
+template <bool FUSE_UP>
+__global__ void __launch_bounds__(512) blens_jac_cached_kernel(const double *__restrict__ x, const double *__restrict__ sheet,
+                                                               const double *__restrict__ util,
                                                                int S, int D, const double *__restrict__ curv, int matsumoto,
                                                                const int64_t *__restrict__ peel, const int32_t *__restrict__ flags,
-                                                               double *__restrict__ ws) {
+                                                               double *__restrict__ ws, double *__restrict__ J) {
     extern __shared__ __align__(16) double jc_smd[];  // coefT [S][S] | qT [S][S] | {l, r, u, flags} of the S-1 joins
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int D1 = D + 1, NE = S * D1;
@@ -356,9 +363,32 @@ __global__ void __launch_bounds__(512) blens_jac_cached_kernel(const double *__r
         qT[p] = uj / ui;
     }
     __syncthreads();
-    for (int el = tid; el < NE; el += T) {
-        const int i = el / D1, dp = el - i * D1;
+    // element -> thread: el = tid (+ k T) in the two-kernel form; with the fused lift warp w, lane g (D+1) + dp owns
+    // taxon (w + k nwarps) (32 / (D+1)) + g, coordinate dp (the last 32 mod (D+1) lanes of a warp walk along idle)
+    const int lane = tid & 31, G = 32 / D1, nwarps = T >> 5;
+    const int n_rounds = FUSE_UP ? (S + G * nwarps - 1) / (G * nwarps) : (NE + T - 1) / T;
+    for (int k = 0; k < n_rounds; ++k) {
+        int i, dp;
+        bool live;
+        if (FUSE_UP) {
+            const int g = lane / D1;
+            dp = lane - g * D1;
+            i = ((tid >> 5) + k * nwarps) * G + g;
+            live = g < G && i < S;
+            if (!live) { i = 0; dp = 0; }  // (reads stay in range; nothing is written)
+        } else {
+            const int e0 = tid + k * T;
+            live = e0 < NE;
+            if (!live) break;
+            i = e0 / D1;
+            dp = e0 - i * D1;
+        }
+        const int el = i * D1 + dp;
         const double sidp = sh[(size_t)i * D1 + dp];
+        // fused lift: column (i, dp - 1) of J; r0 = x_i[dp - 1] / s_i[0]
+        const double r0 = (FUSE_UP && dp >= 1) ? x[((size_t)b * S + i) * D + (dp - 1)] / sh[(size_t)i * D1] : 0.0;
+        double *Jcol = FUSE_UP ? J + (size_t)b * (2 * S - 2) * S * D + (size_t)i * D + (dp - 1) : nullptr;
+        const int lane0 = lane - dp;  // the lane that holds coordinate 0 of this taxon
         auto tipY = [&](int j) -> double {  // dD_ij / ds_i[dp]  (pdm_bwd_kernel's per-pair term)
             const double coef = coefT[(size_t)j * S + i];
             return coef != 0.0 ? coef * (sh[(size_t)j * D1 + dp] - qT[(size_t)j * S + i] * sidp) : 0.0;
@@ -392,11 +422,20 @@ __global__ void __launch_bounds__(512) blens_jac_cached_kernel(const double *__r
             const double drr = n == 2 ? 0.0 : (al - ar) * Ysig + sig * (Yl - Yr) - (double)(n - 2) * (Gl - Gr);
             const double nact = fmax((double)n, 3.0);
             const double basel = (f & 1) ? 0.0 : 0.5 * dlr + drr / (2.0 * (nact - 2.0));
-            Js[(size_t)l * NE + el] = basel;
-            Js[(size_t)r * NE + el] = (f & 2) ? 0.0 : dlr - basel;
+            const double baser = (f & 2) ? 0.0 : dlr - basel;
+            if (FUSE_UP) {
+                const double l0 = __shfl_sync(0xffffffffu, basel, lane0), r0v = __shfl_sync(0xffffffffu, baser, lane0);
+                if (live && dp >= 1) {
+                    Jcol[(size_t)l * S * D] = fma(l0, r0, basel);
+                    Jcol[(size_t)r * S * D] = fma(r0v, r0, baser);
+                }
+            } else {
+                Js[(size_t)l * NE + el] = basel;
+                Js[(size_t)r * NE + el] = baser;
+            }
             const double au = 0.5 * (al + ar), Yu = 0.5 * (Yl + Yr), Gu = 0.5 * A;
             const size_t o = (size_t)(u - S) * NE + el;
-            An[o] = au; Yn[o] = Yu; Gn[o] = Gu;
+            if (live) { An[o] = au; Yn[o] = Yu; Gn[o] = Gu; }
             Ta += au - al - ar;
             TY += Yu - Yl - Yr;
             if (on.x == u) { aln = au; Yln = Yu; Gln = Gu; }
@@ -742,9 +781,17 @@ extern "C" int dodo_blens_jacobian(const double *d_x, int B, int S, int D, const
     // requests one join ahead, the lift as a kernel of its own
     const size_t sm = (size_t)2 * S * S * sizeof(double) + (size_t)(S - 1) * 4 * sizeof(int);
     if (sm <= 220 * 1024 && !getenv("DODO_JAC_PER_ELEMENT")) {
+        if (lift == DODO_LIFT_UP && D + 1 <= 16 && !getenv("DODO_JAC_TWO_KERNELS")) {  // the lift inside the walk
+            const int G = 32 / (D + 1), nw = (S + G - 1) / G;
+            const int th = nw >= 16 ? 512 : nw * 32;
+            if (sm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(blens_jac_cached_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            blens_jac_cached_kernel<true><<<B, th, sm, stream>>>(d_x, sheet, util, S, D, d_curvature, matsumoto, d_peel, d_flags, ws, d_J);
+            DODO_LAUNCH_CHECK();
+            return DODO_OK;
+        }
         const int th = ne >= 512 ? 512 : ((ne + 31) / 32) * 32;
-        if (sm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(blens_jac_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        blens_jac_cached_kernel<<<B, th, sm, stream>>>(sheet, util, S, D, d_curvature, matsumoto, d_peel, d_flags, ws);
+        if (sm > 48 * 1024) DODO_CUDA(cudaFuncSetAttribute(blens_jac_cached_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        blens_jac_cached_kernel<false><<<B, th, sm, stream>>>(d_x, sheet, util, S, D, d_curvature, matsumoto, d_peel, d_flags, ws, d_J);
         DODO_LAUNCH_CHECK();
         const size_t items = (size_t)B * (2 * S - 2) * S;
         jac_lift_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(d_x, sheet, ws, B, S, D, lift, d_J);

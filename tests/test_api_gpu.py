@@ -724,14 +724,24 @@ def test_one_pass_jacobian_equals_the_batched_replays():
         J0 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False, replay=True)
         ref = J0.cpu().numpy()
         np.testing.assert_allclose(J1.cpu().numpy(), ref, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(ref).max()), err_msg=f"S={S} {lift}")
-        # the one-thread-per-taxon kernel (D = 2, 3, 5) and the one-thread-per-(taxon, coordinate) kernel evaluate the
-        # same expressions in the same order: identical bits
+        # the first kernel (no cached pair terms, peel from global memory) and the cached kernel followed by the lift
+        # kernel evaluate the same expressions in the same order: identical bits; with the lift fused into the walk
+        # ("up") x_i[d] / s_i[0] is formed once per thread: last-bit differences
         os.environ["DODO_JAC_PER_ELEMENT"] = "1"
         try:
             J2 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False)
         finally:
             del os.environ["DODO_JAC_PER_ELEMENT"]
-        assert torch.equal(J1, J2), f"S={S} D={D} {lift}"
+        os.environ["DODO_JAC_TWO_KERNELS"] = "1"
+        try:
+            J3 = hp.blens_jacobian(x, dec["peel"], dec["flags"], logdet=False)
+        finally:
+            del os.environ["DODO_JAC_TWO_KERNELS"]
+        assert torch.equal(J3, J2), f"S={S} D={D} {lift}"
+        if lift == "up":
+            np.testing.assert_allclose(J1.cpu().numpy(), J2.cpu().numpy(), rtol=1e-13, atol=1e-15 * max(1.0, np.abs(ref).max()))
+        else:
+            assert torch.equal(J1, J2), f"S={S} D={D} {lift}"
     assert seen_clamped
 
 
