@@ -552,28 +552,32 @@ constexpr int GT_LD = 130;  // row stride of the transposed chunk (even: 16-byte
 // tiles are 64 bytes apart and a quarter-warp's loads fall into two bank groups (16 wavefronts per load, measured:
 // the Gram phase took 460 cycles per column where the multiply-adds need 256); in this order they are contiguous.
 __device__ __forceinline__ int gt_pos(int e) { return ((e >> 1) & 3) * 32 + ((e >> 3) << 1) + (e & 1); }
-__global__ void __launch_bounds__(160) gram_logdet_tile_kernel(const double *__restrict__ J, int E, int C,
+__global__ void __launch_bounds__(288) gram_logdet_tile_kernel(const double *__restrict__ J, int E, int C,
                                                                double *__restrict__ out) {
+    // Two threads per tile, each with an 8 x 4 half (columns 4 h .. 4 h + 3 of the tile): 272 threads in 9 warps at 126
+    // rows.  One thread per whole tile is 5 warps on 4 schedulers, and the scheduler that gets two of them paces both
+    // phases (an fp64 warp instruction takes the pipe for two cycles whatever the number of active lanes).
     extern __shared__ __align__(16) double gt_sm[];  // Jc[2][32][GT_LD]: the chunk in use and the one in flight
     __shared__ __align__(16) double colk[2][128];
-    __shared__ double pivs[2], part[16], s_val;
+    __shared__ double pivs[2], part[32], s_val;
     __shared__ int s_stop;
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const int nt = (E + 7) >> 3, ntiles = nt * (nt + 1) / 2;
-    const bool active = tid < ntiles;
+    const int tile = tid >> 1, h = tid & 1;
+    const bool active = tile < ntiles;
     int ti = 0, tj = 0;
     if (active) {
-        ti = (int)((sqrt(8.0 * (double)tid + 1.0) - 1.0) * 0.5);
-        while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
-        while (ti * (ti + 1) / 2 > tid) --ti;
-        tj = tid - ti * (ti + 1) / 2;
+        ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+        while (ti * (ti + 1) / 2 > tile) --ti;
+        tj = tile - ti * (ti + 1) / 2;
     }
     if (tid == 0) s_stop = 0;
-    double A[8][8];
+    double A[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) A[r][c] = 0.0;
+        for (int c = 0; c < 4; ++c) A[r][c] = 0.0;
     const double *Jb = J + (size_t)b * E * C;
     // 8-byte asynchronous copies (global reads coalesced along the columns, written transposed; rows and columns
     // outside the matrix are zero-filled through the source size): chunk n + 1 lands while chunk n is consumed
@@ -601,46 +605,52 @@ __global__ void __launch_bounds__(160) gram_logdet_tile_kernel(const double *__r
         }
         __syncthreads();
         if (active) {
-            const double *pa = Jc + 2 * ti, *pb = Jc + 2 * tj;
+            // rows 8 ti + 2 m + p sit at plane m (m = 0..3), columns 8 tj + 4 h + 2 m' + p at plane 2 h + m' (m' = 0, 1)
+            const double *pa = Jc + 2 * ti, *pb = Jc + 2 * tj + 64 * h;
 #pragma unroll 2
             for (int c = 0; c < 32; ++c) {
-                double a[8], bb[8];
+                double a[8], bb[4];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const double2 x = *reinterpret_cast<const double2 *>(pa + c * GT_LD + 32 * h);
-                    const double2 y = *reinterpret_cast<const double2 *>(pb + c * GT_LD + 32 * h);
-                    a[2 * h] = x.x; a[2 * h + 1] = x.y;
-                    bb[2 * h] = y.x; bb[2 * h + 1] = y.y;
+                for (int m = 0; m < 4; ++m) {
+                    const double2 x = *reinterpret_cast<const double2 *>(pa + c * GT_LD + 32 * m);
+                    a[2 * m] = x.x; a[2 * m + 1] = x.y;
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const double2 y = *reinterpret_cast<const double2 *>(pb + c * GT_LD + 32 * m);
+                    bb[2 * m] = y.x; bb[2 * m + 1] = y.y;
                 }
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) A[r][q] = fma(a[r], bb[q], A[r][q]);
+                    for (int q = 0; q < 4; ++q) A[r][q] = fma(a[r], bb[q], A[r][q]);
             }
         }
         __syncthreads();  // everyone is done with this chunk before the round after next refills its buffer
     }
-    double pv[8];  // pivots of this thread's diagonal tile (their logarithms are taken after the elimination)
+    double pv[4];  // pivots held by this thread (diagonal tiles: columns 4 h .. 4 h + 3); logarithms after the elimination
 #pragma unroll
-    for (int r = 0; r < 8; ++r) pv[r] = 1.0;
+    for (int r = 0; r < 4; ++r) pv[r] = 1.0;
     for (int kb = 0; kb < nt; ++kb) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             const int k = 8 * kb + kk;
             if (k >= E) break;
+            const int hk = kk >> 2;     // which half of the tile column holds column k
+            const int qk = kk & 3;      // ... and where in it
             double *ck = colk[kk & 1];
-            if (active && tj == kb) {  // owners of column k
+            if (active && tj == kb && h == hk) {  // owners of column k
 #pragma unroll
-                for (int h = 0; h < 4; ++h)
-                    *reinterpret_cast<double2 *>(ck + 32 * h + 2 * ti) = make_double2(A[2 * h][kk], A[2 * h + 1][kk]);
+                for (int m = 0; m < 4; ++m)
+                    *reinterpret_cast<double2 *>(ck + 32 * m + 2 * ti) = make_double2(A[2 * m][qk], A[2 * m + 1][qk]);
                 if (ti == kb) {
-                    const double piv = A[kk][kk];
+                    const double piv = A[kk][qk];
                     pivs[kk & 1] = piv;
                     if (!(piv != 0.0)) {  // exactly singular (or NaN): log|det| = -inf (NaN propagates)
                         s_val = piv == piv ? -INFINITY : piv;
                         s_stop = 1;
                     } else {
-                        pv[kk] = piv;
+                        pv[qk] = piv;
                     }
                 }
             }
@@ -651,31 +661,30 @@ __global__ void __launch_bounds__(160) gram_logdet_tile_kernel(const double *__r
             }
             if (active && tj >= kb) {
                 const double inv = 1.0 / pivs[kk & 1];
-                double l[8], cj[8];
+                double l[8], cj[4];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const double2 x = *reinterpret_cast<const double2 *>(ck + 32 * h + 2 * ti);
-                    const double2 y = *reinterpret_cast<const double2 *>(ck + 32 * h + 2 * tj);
-                    l[2 * h] = x.x * inv; l[2 * h + 1] = x.y * inv;
-                    cj[2 * h] = y.x; cj[2 * h + 1] = y.y;
+                for (int m = 0; m < 4; ++m) {
+                    const double2 x = *reinterpret_cast<const double2 *>(ck + 32 * m + 2 * ti);
+                    l[2 * m] = x.x * inv; l[2 * m + 1] = x.y * inv;
                 }
-                if (tj > kb) {  // every row and column of the tile lies beyond k
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const double2 y = *reinterpret_cast<const double2 *>(ck + 64 * h + 32 * m + 2 * tj);
+                    cj[2 * m] = y.x; cj[2 * m + 1] = y.y;
+                }
+                if (tj > kb) {  // every row and column of the half lies beyond k
 #pragma unroll
                     for (int r = 0; r < 8; ++r)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) A[r][q] = fma(-l[r], cj[q], A[r][q]);
-                } else if (ti > kb) {  // the tile column that holds k: columns beyond k only
+                        for (int q = 0; q < 4; ++q) A[r][q] = fma(-l[r], cj[q], A[r][q]);
+                } else if (h >= hk) {  // the tile column that holds k: columns beyond k only (none in the half left of it)
+                    const bool whole = h > hk;        // the half right of the one that holds k
+                    const bool below = ti > kb;       // (otherwise the diagonal tile: rows beyond k only)
 #pragma unroll
                     for (int r = 0; r < 8; ++r)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q > kk) A[r][q] = fma(-l[r], cj[q], A[r][q]);
-                } else {  // the diagonal tile that holds k
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (r > kk && q > kk) A[r][q] = fma(-l[r], cj[q], A[r][q]);
+                        for (int q = 0; q < 4; ++q)
+                            if ((whole || q > qk) && (below || r > kk)) A[r][q] = fma(-l[r], cj[q], A[r][q]);
                 }
             }
         }
@@ -683,13 +692,13 @@ __global__ void __launch_bounds__(160) gram_logdet_tile_kernel(const double *__r
     if (active && ti == tj) {
         double logabs = 0.0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) logabs += log(fabs(pv[r]));  // (rows beyond E keep the neutral 1.0)
-        part[ti] = logabs;
+        for (int r = 0; r < 4; ++r) logabs += log(fabs(pv[r]));  // (columns beyond E keep the neutral 1.0)
+        part[2 * ti + h] = logabs;
     }
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
-        for (int i = 0; i < nt; ++i) s += part[i];
+        for (int i = 0; i < 2 * nt; ++i) s += part[i];
         out[b] = 0.5 * s;
     }
 }
@@ -811,7 +820,7 @@ extern "C" int dodo_gram_logdet(const double *d_J, int B, int E, int C, double *
         const int ntiles = ((E + 7) / 8) * ((E + 7) / 8 + 1) / 2;
         const int gsm = 2 * 32 * GT_LD * (int)sizeof(double);
         DODO_CUDA(cudaFuncSetAttribute(gram_logdet_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
-        gram_logdet_tile_kernel<<<B, (ntiles + 31) / 32 * 32, gsm, (cudaStream_t)stream_>>>(d_J, E, C, d_out);
+        gram_logdet_tile_kernel<<<B, (2 * ntiles + 31) / 32 * 32, gsm, (cudaStream_t)stream_>>>(d_J, E, C, d_out);
         DODO_LAUNCH_CHECK();
         return DODO_OK;
     }
