@@ -227,8 +227,17 @@ class HotPath:
         """Host buffers in, host buffers out: pinned (B,S,D) locations -> lnL (B,) and d lnL/d locations
         (B,S,D) written into the caller's pinned buffers (asynchronously on the current stream).
         The device part of the step is captured once per (shape, model, settings) as a CUDA graph and
-        replayed, so a caller that synchronises every step pays ~3 API calls instead of the Python
-        launch sequence; ``graph=False`` launches kernel by kernel."""
+        replayed -- with pinned buffers the three copies are nodes of that graph, so a caller that synchronises
+        every step pays ONE launch instead of the Python launch sequence; ``graph=False`` launches kernel by kernel."""
+        if graph and x_pinned.is_pinned() and out_ll_pinned.is_pinned() and out_gx_pinned.is_pinned():
+            # the three copies are nodes of the captured graph as well (one launch per step); a capture belongs to
+            # one triple of host buffers, which it keeps alive
+            bufs = (x_pinned, out_ll_pinned, out_gx_pinned)
+            key = (self._fingerprint(x_pinned.shape),) + tuple(t.data_ptr() for t in bufs)
+            hit = self.__dict__.get("_host_graph")
+            if hit is None or hit[0] != key:
+                hit = self.__dict__["_host_graph"] = (key, GraphedStep(self, x_pinned.to(self.device), grad=True, host=bufs))
+            return hit[1].run_host()
         if graph:
             r = self.graphed(x_pinned, grad=True).run(x_pinned)
         else:
@@ -251,7 +260,7 @@ class GraphedStep:
     overwritten by every replay.
     """
 
-    def __init__(self, hot, x_example, grad=True):
+    def __init__(self, hot, x_example, grad=True, host=None):
         # the graph addresses its scratch by raw pointer: give it workspaces of its own (a private
         # view of the HotPath sharing the tips and the prune plans, which are never reallocated), so that
         # nothing the owner does later -- a bigger batch, the batched Jacobian -- can free them
@@ -261,6 +270,8 @@ class GraphedStep:
         hot.ws = engine.Workspaces()
         hot.ws.freeze()
         hot.__dict__.pop("_graphs", None)
+        hot.__dict__.pop("_host_graph", None)
+        self.host = host  # (x, lnL, grad_x) pinned host buffers whose copies are part of the graph, or None
         self.x = x_example.detach().to(hot.device, dtype=torch.float64).contiguous().clone()
         fn = hot.value_and_grad if grad else hot.value
         side = torch.cuda.Stream(device=hot.device)
@@ -271,7 +282,17 @@ class GraphedStep:
         torch.cuda.current_stream(hot.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if host is not None:
+                self.x.copy_(host[0], non_blocking=True)
             self.out = fn(self.x)
+            if host is not None:  # flagged samples arrive as NaN (see value_and_grad); out["bad"] holds their counts
+                host[1].copy_(self.out["lnL"], non_blocking=True)
+                host[2].copy_(self.out["grad_x"], non_blocking=True)
+
+    def run_host(self):
+        """Replay with the captured host buffers: host[0] -> device, the step, results -> host[1], host[2]."""
+        self.graph.replay()
+        return self.out
 
     def run(self, x):
         self.x.copy_(x, non_blocking=True)

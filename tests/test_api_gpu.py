@@ -623,6 +623,21 @@ def test_host_buffer_entry_point_graph_and_plain_agree():
             assert torch.equal(ll, runs[0][0]) and torch.equal(gx, runs[0][1])
     kinds = list(outs)
     assert not torch.equal(outs[kinds[0]][0][0], outs[kinds[1]][0][0])  # the model change was picked up
+    # the same three host buffers again with other locations in them: the replay (copies included) picks them up
+    ll = torch.empty(B, dtype=torch.float64).pin_memory()
+    gx = torch.empty((B, S, D), dtype=torch.float64).pin_memory()
+    hp.value_and_grad_host(x, ll, gx)
+    torch.cuda.synchronize()
+    first = (ll.clone(), gx.clone())
+    x.mul_(1.5)
+    hp.value_and_grad_host(x, ll, gx)
+    torch.cuda.synchronize()
+    assert not torch.equal(ll, first[0])
+    ll2 = torch.empty(B, dtype=torch.float64).pin_memory()
+    gx2 = torch.empty((B, S, D), dtype=torch.float64).pin_memory()
+    hp.value_and_grad_host(x, ll2, gx2, graph=False)
+    torch.cuda.synchronize()
+    assert torch.equal(ll, ll2) and torch.equal(gx, gx2)
 
 
 def test_pointwise_hyperbolic_distances_against_the_reference():
